@@ -1,0 +1,844 @@
+// api.cu -- the extern "C" boundary of libqipb200 (include/qipb200.h).
+//
+// Host runtime above the kernels: owns the device amplitude buffer and the gate
+// schedule, exactly the role of the fold in LocalBuilder::calculate_state_with_init
+// (qip/src/builder.rs:400-519).  No CPU fallback: every compute entry needs a
+// context, and a context needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/qipb200.h"
+#include "dist.cuh"
+#include "kernels.cuh"
+#include "opcompile.h"
+#include "schedule.h"
+#include "state.h"
+
+using namespace qipb200;
+
+namespace {
+
+thread_local std::string g_tls_err = "";
+
+int set_err(const qipb200_ctx *ctx, int status, const std::string &msg) {
+  if (ctx)
+    const_cast<qipb200_ctx *>(ctx)->err = msg;
+  else
+    g_tls_err = msg;
+  return status;
+}
+
+int cuda_fail(const qipb200_ctx *ctx, cudaError_t e, const char *what) {
+  std::string m = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  cudaGetLastError();  // clear sticky-free errors
+  return set_err(ctx, e == cudaErrorMemoryAllocation ? QIPB200_ERR_OOM : QIPB200_ERR_CUDA, m);
+}
+
+#define CU(ctx, call)                                          \
+  do {                                                         \
+    cudaError_t e__ = (call);                                  \
+    if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+  } while (0)
+
+int grow(qipb200_ctx *ctx, void **p, size_t *have, size_t need) {
+  if (*have >= need) return QIPB200_OK;
+  if (*p) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+  }
+  cudaError_t e = cudaMalloc(p, need);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(staging)");
+  *have = need;
+  return QIPB200_OK;
+}
+
+bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+int ilog2(int x) {
+  int l = 0;
+  while ((1 << l) < x) ++l;
+  return l;
+}
+
+}  // namespace
+
+// ===================================================================================
+// library / context
+// ===================================================================================
+
+extern "C" int qipb200_abi_version(void) { return 1000; }
+
+extern "C" int qipb200_init(qipb200_ctx **out, int device_id) {
+  if (!out) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "qipb200_init: ctx out-pointer is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return set_err(nullptr, QIPB200_ERR_CUDA,
+                   std::string("qipb200_init: no CUDA device (") + cudaGetErrorString(e) +
+                       "); libqipb200 has no CPU path");
+  }
+  if (device_id < 0 || device_id >= count)
+    return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "qipb200_init: device_id out of range");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device_id);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    return set_err(nullptr, QIPB200_ERR_CUDA,
+                   std::string("qipb200_init: device '") + prop.name +
+                       "' is not sm_100 (Blackwell B200); this library ships sm_100a code only");
+  e = cudaSetDevice(device_id);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+  qipb200_ctx *ctx = new (std::nothrow) qipb200_ctx();
+  if (!ctx) return set_err(nullptr, QIPB200_ERR_OOM, "qipb200_init: out of host memory");
+  ctx->device = device_id;
+  ctx->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&ctx->d_scalar, 64);
+  if (e != cudaSuccess) {
+    int st = cuda_fail(nullptr, e, "qipb200_init");
+    delete ctx;
+    return st;
+  }
+  *out = ctx;
+  return QIPB200_OK;
+}
+
+extern "C" void qipb200_shutdown(qipb200_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->d_in) cudaFree(ctx->d_in);
+  if (ctx->d_out) cudaFree(ctx->d_out);
+  if (ctx->d_scalar) cudaFree(ctx->d_scalar);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char *qipb200_last_error(const qipb200_ctx *ctx) {
+  return ctx ? ctx->err.c_str() : g_tls_err.c_str();
+}
+
+extern "C" uint64_t qipb200_kernel_launches(const qipb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int qipb200_validate_op(const qipb200_ctx *ctx, qip_prec prec, uint32_t n_qubits, const qip_op *op) {
+  std::string err;
+  int st = validate_op(op, prec, n_qubits, &err);
+  if (st != QIPB200_OK) return set_err(ctx, st, err);
+  return QIPB200_OK;
+}
+
+// ===================================================================================
+// stateless drop-ins (host buffers)
+// ===================================================================================
+
+namespace {
+
+int host_apply(qipb200_ctx *ctx, qip_prec prec, uint32_t n, const qip_op *op, const void *input,
+               uint64_t input_len, void *output, uint64_t output_len, uint64_t input_offset,
+               uint64_t output_offset, bool accumulate) {
+  if (!ctx) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "ctx is NULL (call qipb200_init first; there is no CPU path)");
+  if ((!input && input_len) || (!output && output_len))
+    return set_err(ctx, QIPB200_ERR_INVALID_ARG, "apply_op: NULL amplitude buffer");
+  FlatOp f;
+  std::string err;
+  int st = compile_op(op, prec, n, &f, &err);
+  if (st != QIPB200_OK) return set_err(ctx, st, err);
+  CU(ctx, cudaSetDevice(ctx->device));
+  const size_t ab = amp_bytes(prec);
+  if ((st = grow(ctx, &ctx->d_in, &ctx->d_in_bytes, std::max<size_t>(input_len * ab, 16))) != QIPB200_OK) return st;
+  if ((st = grow(ctx, &ctx->d_out, &ctx->d_out_bytes, std::max<size_t>(output_len * ab, 16))) != QIPB200_OK) return st;
+  if (input_len) CU(ctx, cudaMemcpyAsync(ctx->d_in, input, input_len * ab, cudaMemcpyHostToDevice, ctx->stream));
+  if (accumulate && output_len)
+    CU(ctx, cudaMemcpyAsync(ctx->d_out, output, output_len * ab, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, launch_gather(prec, f, n, ctx->d_in, input_len, input_offset, ctx->d_out, output_len, output_offset,
+                        accumulate, ctx->stream, &ctx->launches));
+  if (output_len) CU(ctx, cudaMemcpyAsync(output, ctx->d_out, output_len * ab, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return QIPB200_OK;
+}
+
+}  // namespace
+
+extern "C" int qipb200_apply_op(qipb200_ctx *ctx, qip_prec prec, uint32_t n, const qip_op *op, const void *input,
+                                uint64_t input_len, void *output, uint64_t output_len, uint64_t input_offset,
+                                uint64_t output_offset) {
+  return host_apply(ctx, prec, n, op, input, input_len, output, output_len, input_offset, output_offset, true);
+}
+
+extern "C" int qipb200_apply_op_overwrite(qipb200_ctx *ctx, qip_prec prec, uint32_t n, const qip_op *op,
+                                          const void *input, uint64_t input_len, void *output,
+                                          uint64_t output_len, uint64_t input_offset, uint64_t output_offset) {
+  return host_apply(ctx, prec, n, op, input, input_len, output, output_len, input_offset, output_offset, false);
+}
+
+// ===================================================================================
+// device-resident state
+// ===================================================================================
+
+namespace {
+
+int state_alloc(qipb200_ctx *ctx, qip_prec prec, uint32_t n, int rank, int world, qipb200_state **out) {
+  if (!ctx) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "ctx is NULL (call qipb200_init first; there is no CPU path)");
+  if (!out) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "state out-pointer is NULL");
+  *out = nullptr;
+  if (prec != QIP_F32 && prec != QIP_F64) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "precision must be QIP_F32 or QIP_F64");
+  if (!is_pow2(world) || world > kMaxWorld || rank < 0 || rank >= world)
+    return set_err(ctx, QIPB200_ERR_INVALID_ARG, "world_size must be a power of two <= 16 and 0 <= rank < world_size");
+  const int g = ilog2(world);
+  if (n == 0 || n > 40 || (int)n - g < 2 * (world > 1))
+    return set_err(ctx, QIPB200_ERR_INVALID_ARG, "n_qubits out of range for this world size");
+  CU(ctx, cudaSetDevice(ctx->device));
+  qipb200_state *s = new (std::nothrow) qipb200_state();
+  if (!s) return set_err(ctx, QIPB200_ERR_OOM, "out of host memory");
+  s->ctx = ctx;
+  s->prec = prec;
+  s->n = n;
+  s->n_local = n - g;
+  s->rank = rank;
+  s->world = world;
+  s->bytes = amp_bytes(prec) << s->n_local;
+  s->phys_of_logical.resize(n);
+  for (uint32_t b = 0; b < n; ++b) s->phys_of_logical[b] = b;
+  cudaError_t e = cudaMalloc(&s->buf, s->bytes);
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->buf, 0, s->bytes, ctx->stream);
+  if (e == cudaSuccess && world > 1) {
+    e = cudaMalloc((void **)&s->flags, kFlagWords * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->flags, 0, kFlagWords * sizeof(uint32_t), ctx->stream);
+  }
+  if (e != cudaSuccess) {
+    int st = cuda_fail(ctx, e, "qipb200_state_new");
+    if (s->buf) cudaFree(s->buf);
+    if (s->flags) cudaFree(s->flags);
+    delete s;
+    return st;
+  }
+  *out = s;
+  return QIPB200_OK;
+}
+
+bool layout_is_identity(const qipb200_state *s) {
+  for (uint32_t b = 0; b < s->n; ++b)
+    if (s->phys_of_logical[b] != b) return false;
+  return true;
+}
+
+int check_barrier_error(qipb200_state *s) {
+  uint32_t flag = 0;
+  CU(s->ctx, cudaMemcpyAsync(&flag, s->flags + kFlagErrorSlot, sizeof(flag), cudaMemcpyDeviceToHost, s->ctx->stream));
+  CU(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+  if (flag) return set_err(s->ctx, QIPB200_ERR_COMM, "multi-GPU flag barrier timed out (a peer rank is not participating)");
+  return QIPB200_OK;
+}
+
+// Swap physical rank bit R (>= n_local) with local bit l: NVLink pair exchange.
+int exchange_bits(qipb200_state *s, uint32_t R, uint32_t l) {
+  qipb200_ctx *ctx = s->ctx;
+  if (!s->ipc_ready)
+    return set_err(ctx, QIPB200_ERR_COMM, "sharded state: peers not mapped (call qipb200_state_ipc_import)");
+  const uint32_t r = R - s->n_local;
+  const int partner = s->rank ^ (1 << r);
+  const int rb = (s->rank >> r) & 1;
+  uint32_t s_bit = s->n_local - 1;
+  if (s_bit == l) s_bit = s->n_local - 2;
+  CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch,
+                              s->flags + kFlagErrorSlot, ctx->stream, &ctx->launches));
+  CU(ctx, launch_pair_exchange(s->prec, s->buf, s->peer_buf[partner], s->n_local, l, s_bit, rb, ctx->stream,
+                               &ctx->launches));
+  CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch,
+                              s->flags + kFlagErrorSlot, ctx->stream, &ctx->launches));
+  s->exchange_bytes += (uint64_t)amp_bytes(s->prec) << (s->n_local - 1);
+  // update the map: the logical bits living at R and l trade places
+  for (uint32_t b = 0; b < s->n; ++b) {
+    if (s->phys_of_logical[b] == R)
+      s->phys_of_logical[b] = l;
+    else if (s->phys_of_logical[b] == l)
+      s->phys_of_logical[b] = R;
+  }
+  return QIPB200_OK;
+}
+
+// Swap two physical bits (any kind) so that the layout can be restored.
+int swap_physical_bits(qipb200_state *s, uint32_t p, uint32_t q) {
+  qipb200_ctx *ctx = s->ctx;
+  if (p == q) return QIPB200_OK;
+  if (p < q) std::swap(p, q);  // p > q
+  const uint32_t nl = s->n_local;
+  if (p < nl) {
+    CU(ctx, launch_bitswap(s->prec, s->buf, nl, 0, q, p, ctx->stream, &ctx->launches));
+    for (uint32_t b = 0; b < s->n; ++b) {
+      if (s->phys_of_logical[b] == p)
+        s->phys_of_logical[b] = q;
+      else if (s->phys_of_logical[b] == q)
+        s->phys_of_logical[b] = p;
+    }
+    return QIPB200_OK;
+  }
+  if (q < nl) return exchange_bits(s, p, q);
+  // both rank bits: route through a local bit
+  const uint32_t l = nl - 1;
+  int st;
+  if ((st = exchange_bits(s, p, l)) != QIPB200_OK) return st;
+  if ((st = exchange_bits(s, q, l)) != QIPB200_OK) return st;
+  return exchange_bits(s, p, l);
+}
+
+int restore_layout(qipb200_state *s) {
+  for (int p = (int)s->n - 1; p >= 0; --p) {
+    const uint32_t where = s->phys_of_logical[p];
+    if (where == (uint32_t)p) continue;
+    int st = swap_physical_bits(s, (uint32_t)p, where);
+    if (st != QIPB200_OK) return st;
+  }
+  return QIPB200_OK;
+}
+
+}  // namespace
+
+namespace qipb200 {
+
+// Non-diagonal target bits of a compiled op (the ones that must be local).
+static void nondiag_bits(const FlatOp &f, std::vector<uint32_t> *out) {
+  out->clear();
+  switch (f.cls) {
+    case CLASS_DENSE:
+    case CLASS_FLIP:
+      *out = f.tgt_sorted;
+      break;
+    case CLASS_BITSWAP:
+      for (size_t i = 0; i < f.swaps.size(); ++i) {
+        out->push_back(f.swaps[i].first);
+        out->push_back(f.swaps[i].second);
+      }
+      break;
+    case CLASS_GENERAL:
+      for (uint32_t j = f.nc; j < f.k; ++j) out->push_back(f.idx_bits[j]);
+      break;
+    default:
+      break;
+  }
+}
+
+// Apply a compiled op whose non-diagonal targets are all local.  Rank bits may
+// still appear as controls (a rank applies the inner op or nothing) or as diagonal
+// bits (a rank picks its slice of the diagonal): no communication.
+int apply_flat_local(qipb200_state *s, const FlatOp &f_in) {
+  qipb200_ctx *ctx = s->ctx;
+  const uint32_t nl = s->n_local;
+  const uint64_t lo_mask = (nl >= 64) ? ~0ull : ((1ull << nl) - 1ull);
+  const uint64_t rank_val = (uint64_t)s->rank << nl;
+  const uint64_t hc = f_in.ctrl_mask & ~lo_mask;
+  if ((rank_val & hc) != hc) return QIPB200_OK;  // a control held by the rank index is 0 here
+  const uint64_t cm = f_in.ctrl_mask & lo_mask;
+  switch (f_in.cls) {
+    case CLASS_IDENTITY:
+      return QIPB200_OK;
+    case CLASS_DIAGONAL: {
+      std::vector<uint32_t> bits;
+      std::vector<cplx> d = f_in.diag;
+      // fix the rank-held diagonal bits to this rank's values (highest first keeps indices valid)
+      std::vector<uint32_t> all = f_in.diag_bits;
+      for (int i = (int)all.size() - 1; i >= 0; --i) {
+        if (all[i] < nl) continue;
+        const int v = (int)((rank_val >> all[i]) & 1ull);
+        std::vector<cplx> nd;
+        for (uint64_t u = 0; u < d.size(); ++u)
+          if ((int)((u >> i) & 1) == v) nd.push_back(d[u]);
+        d.swap(nd);
+        all.erase(all.begin() + i);
+      }
+      bits = all;
+      if (bits.size() > (size_t)kMaxDiagParamK) {
+        // wide diagonal: run it as a dense-diagonal through the row kernel (single GPU only)
+        break;
+      }
+      bool all_one = true;
+      for (size_t u = 0; u < d.size(); ++u)
+        if (!(d[u].real() == 1.0 && d[u].imag() == 0.0)) all_one = false;
+      if (all_one) return QIPB200_OK;
+      CU(ctx, launch_diag(s->prec, s->buf, nl, cm, bits, d, ctx->stream, &ctx->launches));
+      return QIPB200_OK;
+    }
+    case CLASS_FLIP:
+      CU(ctx, launch_flip(s->prec, s->buf, nl, cm, f_in.tgt_sorted[0], ctx->stream, &ctx->launches));
+      return QIPB200_OK;
+    case CLASS_BITSWAP:
+      for (size_t i = 0; i < f_in.swaps.size(); ++i)
+        CU(ctx, launch_bitswap(s->prec, s->buf, nl, cm, f_in.swaps[i].first, f_in.swaps[i].second, ctx->stream,
+                               &ctx->launches));
+      return QIPB200_OK;
+    case CLASS_DENSE:
+      if (f_in.tgt_sorted.size() <= (size_t)kMaxRegK && __builtin_popcountll(cm) + f_in.tgt_sorted.size() <= (size_t)kMaxIns) {
+        FlatOp f = f_in;
+        f.ctrl_mask = cm;
+        CU(ctx, launch_dense(s->prec, s->buf, nl, f, ctx->stream, &ctx->launches));
+        return QIPB200_OK;
+      }
+      break;
+    default:
+      break;
+  }
+  // Fallback: out-of-place row kernel with the reference's gather semantics.
+  if (s->world > 1)
+    return set_err(ctx, QIPB200_ERR_UNSUPPORTED,
+                   "this op needs the out-of-place row kernel, which is not available on a sharded state");
+  if (!s->scratch) {
+    cudaError_t e = cudaMalloc(&s->scratch, s->bytes);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(scratch arena)");
+  }
+  const uint64_t len = 1ull << nl;
+  CU(ctx, launch_gather(s->prec, f_in, s->n, s->buf, len, 0, s->scratch, len, 0, false, ctx->stream, &ctx->launches));
+  std::swap(s->buf, s->scratch);  // `Ok((arena, state, ..))`, builder.rs:514
+  return QIPB200_OK;
+}
+
+// Compile `op` against the current layout and migrate rank-held target bits to
+// local bits if needed.  `next_use` (optional, n entries indexed by logical bit):
+// position in the schedule of the next non-diagonal use, used to pick the victim.
+int compile_and_localize(qipb200_state *s, const qip_op *op, FlatOp *f, const uint64_t *next_use) {
+  qipb200_ctx *ctx = s->ctx;
+  std::string err;
+  int st = compile_op(op, s->prec, s->n, f, &err, s->phys_of_logical.data());
+  if (st != QIPB200_OK) return set_err(ctx, st, err);
+  if (s->world == 1) return QIPB200_OK;
+  if (f->cls == CLASS_BITSWAP && f->ctrl_mask == 0) {
+    // An uncontrolled Swap is a relabelling of index bits: update the map, move nothing.
+    for (size_t i = 0; i < f->swaps.size(); ++i) {
+      const uint32_t p = f->swaps[i].first, q = f->swaps[i].second;
+      for (uint32_t b = 0; b < s->n; ++b) {
+        if (s->phys_of_logical[b] == p)
+          s->phys_of_logical[b] = q;
+        else if (s->phys_of_logical[b] == q)
+          s->phys_of_logical[b] = p;
+      }
+    }
+    f->cls = CLASS_IDENTITY;
+    return QIPB200_OK;
+  }
+  std::vector<uint32_t> nd;
+  nondiag_bits(*f, &nd);
+  bool moved = false;
+  for (size_t i = 0; i < nd.size(); ++i) {
+    if (nd[i] < s->n_local) continue;
+    // choose the local bit to evict: not used by this op, next non-diagonal use furthest away
+    uint64_t used = f->ctrl_mask;
+    for (uint32_t j = 0; j < f->k; ++j) used |= 1ull << f->idx_bits[j];
+    int best = -1;
+    uint64_t best_key = 0;
+    for (uint32_t l = 0; l < s->n_local; ++l) {
+      if ((used >> l) & 1ull) continue;
+      uint64_t key = 1;
+      if (next_use) {
+        uint32_t logical = 0;
+        for (uint32_t b = 0; b < s->n; ++b)
+          if (s->phys_of_logical[b] == l) logical = b;
+        key = next_use[logical] + 1;
+      }
+      // prefer high bits on ties: low bits give the exchange its coalescing
+      if (best < 0 || key > best_key || (key == best_key && l > (uint32_t)best)) {
+        best = (int)l;
+        best_key = key;
+      }
+    }
+    if (best < 0) return set_err(ctx, QIPB200_ERR_UNSUPPORTED, "op touches every local bit: cannot migrate a rank bit");
+    if ((st = exchange_bits(s, nd[i], (uint32_t)best)) != QIPB200_OK) return st;
+    moved = true;
+    // recompile after every move so later decisions see the new layout
+    st = compile_op(op, s->prec, s->n, f, &err, s->phys_of_logical.data());
+    if (st != QIPB200_OK) return set_err(ctx, st, err);
+    nondiag_bits(*f, &nd);
+    i = (size_t)-1;  // restart scan
+  }
+  (void)moved;
+  return QIPB200_OK;
+}
+
+}  // namespace qipb200
+
+extern "C" int qipb200_state_new(qipb200_ctx *ctx, qip_prec prec, uint32_t n_qubits, qipb200_state **state) {
+  return state_alloc(ctx, prec, n_qubits, 0, 1, state);
+}
+
+extern "C" int qipb200_state_new_sharded(qipb200_ctx *ctx, qip_prec prec, uint32_t n_qubits, int rank,
+                                         int world_size, qipb200_state **state) {
+  return state_alloc(ctx, prec, n_qubits, rank, world_size, state);
+}
+
+extern "C" void qipb200_state_free(qipb200_state *s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  for (int t = 0; t < (int)s->peer_buf.size(); ++t) {
+    if (t == s->rank) continue;
+    if (s->peer_buf[t]) cudaIpcCloseMemHandle(s->peer_buf[t]);
+    if (s->peer_flags[t]) cudaIpcCloseMemHandle(s->peer_flags[t]);
+  }
+  if (s->buf) cudaFree(s->buf);
+  if (s->scratch) cudaFree(s->scratch);
+  if (s->flags) cudaFree(s->flags);
+  delete s;
+}
+
+extern "C" int qipb200_state_set_basis(qipb200_state *s, uint64_t index) {
+  if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
+  qipb200_ctx *ctx = s->ctx;
+  if (index >> s->n) return set_err(ctx, QIPB200_ERR_BAD_INDEX, "initial index out of range");
+  CU(ctx, cudaSetDevice(ctx->device));
+  for (uint32_t b = 0; b < s->n; ++b) s->phys_of_logical[b] = b;  // a fresh state has the canonical layout
+  const uint64_t len = 1ull << s->n_local;
+  const bool owns = (index >> s->n_local) == (uint64_t)s->rank;
+  CU(ctx, launch_set_basis(s->prec, s->buf, len, index & (len - 1), owns, ctx->stream, &ctx->launches));
+  return QIPB200_OK;
+}
+
+extern "C" int qipb200_state_upload(qipb200_state *s, const void *host, uint64_t offset, uint64_t len) {
+  if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
+  qipb200_ctx *ctx = s->ctx;
+  if (!host && len) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "upload: host pointer is NULL");
+  if (offset + len > (1ull << s->n_local)) return set_err(ctx, QIPB200_ERR_SIZE_MISMATCH, "upload: range exceeds the local state");
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (!layout_is_identity(s)) {
+    int st = restore_layout(s);
+    if (st != QIPB200_OK) return st;
+  }
+  const size_t ab = amp_bytes(s->prec);
+  CU(ctx, cudaMemcpyAsync((char *)s->buf + offset * ab, host, len * ab, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return QIPB200_OK;
+}
+
+extern "C" int qipb200_state_download(qipb200_state *s, void *host, uint64_t offset, uint64_t len) {
+  if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
+  qipb200_ctx *ctx = s->ctx;
+  if (!host && len) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "download: host pointer is NULL");
+  if (offset + len > (1ull << s->n_local)) return set_err(ctx, QIPB200_ERR_SIZE_MISMATCH, "download: range exceeds the local state");
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (!layout_is_identity(s)) {
+    int st = restore_layout(s);
+    if (st != QIPB200_OK) return st;
+  }
+  const size_t ab = amp_bytes(s->prec);
+  CU(ctx, cudaMemcpyAsync(host, (const char *)s->buf + offset * ab, len * ab, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (s->world > 1) return check_barrier_error(s);
+  return QIPB200_OK;
+}
+
+extern "C" int qipb200_state_apply_op(qipb200_state *s, const qip_op *op) {
+  if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
+  CU(s->ctx, cudaSetDevice(s->ctx->device));
+  FlatOp f;
+  int st = compile_and_localize(s, op, &f, nullptr);
+  if (st != QIPB200_OK) return st;
+  return apply_flat_local(s, f);
+}
+
+extern "C" int qipb200_state_apply_schedule(qipb200_state *s, const qip_op *ops, size_t n_ops, uint32_t flags) {
+  if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
+  if (!ops && n_ops) return set_err(s->ctx, QIPB200_ERR_INVALID_ARG, "schedule: ops is NULL");
+  CU(s->ctx, cudaSetDevice(s->ctx->device));
+  return run_schedule(s, ops, n_ops, flags);
+}
+
+extern "C" int qipb200_state_norm2(qipb200_state *s, double *out) {
+  if (!s || !out) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "norm2: NULL argument");
+  qipb200_ctx *ctx = s->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, launch_norm2(s->prec, s->buf, 1ull << s->n_local, ctx->d_scalar, ctx->stream, &ctx->launches));
+  CU(ctx, cudaMemcpyAsync(out, ctx->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return QIPB200_OK;
+}
+
+extern "C" int qipb200_state_sync(qipb200_state *s) {
+  if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
+  CU(s->ctx, cudaSetDevice(s->ctx->device));
+  CU(s->ctx, cudaStreamSynchronize(s->ctx->stream));
+  if (s->world > 1 && s->ipc_ready) return check_barrier_error(s);
+  return QIPB200_OK;
+}
+
+extern "C" int qipb200_calculate_state(qipb200_ctx *ctx, qip_prec prec, uint32_t n_qubits, uint64_t init_index,
+                                       const qip_op *ops, size_t n_ops, uint32_t flags, void *host_out) {
+  if (!ctx) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "ctx is NULL (call qipb200_init first; there is no CPU path)");
+  if (!host_out) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "calculate_state: host_out is NULL");
+  qipb200_state *s = nullptr;
+  int st = qipb200_state_new(ctx, prec, n_qubits, &s);
+  if (st != QIPB200_OK) return st;
+  st = qipb200_state_set_basis(s, init_index);
+  if (st == QIPB200_OK) st = qipb200_state_apply_schedule(s, ops, n_ops, flags);
+  if (st == QIPB200_OK) st = qipb200_state_download(s, host_out, 0, 1ull << n_qubits);
+  qipb200_state_free(s);
+  return st;
+}
+
+extern "C" int qipb200_apply_ops(qipb200_ctx *ctx, qip_prec prec, uint32_t n, const qip_op *ops, size_t n_ops,
+                                 const void *input, uint64_t input_len, void *output, uint64_t output_len,
+                                 uint64_t input_offset, uint64_t output_offset) {
+  if (!ctx) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "ctx is NULL (call qipb200_init first; there is no CPU path)");
+  const size_t ab = amp_bytes(prec);
+  if (n_ops == 0) {
+    // matrix_ops.rs:170-183: copy of the overlapping index range
+    const uint64_t lower = std::max(input_offset, output_offset);
+    const uint64_t upper = std::min(input_offset + input_len, output_offset + output_len);
+    if (upper > lower) {
+      if (!input || !output) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "apply_ops: NULL amplitude buffer");
+      memcpy((char *)output + (lower - output_offset) * ab, (const char *)input + (lower - input_offset) * ab,
+             (upper - lower) * ab);
+    }
+    return QIPB200_OK;
+  }
+  if (n_ops == 1)  // matrix_ops.rs:167
+    return qipb200_apply_op(ctx, prec, n, ops, input, input_len, output, output_len, input_offset, output_offset);
+  // Sequential product on the full state, accumulated into `output` (see header: Q5).
+  if (input_offset != 0 || output_offset != 0 || input_len != (1ull << n) || output_len != (1ull << n))
+    return set_err(ctx, QIPB200_ERR_UNSUPPORTED, "apply_ops with several ops needs full-length buffers and zero offsets");
+  qipb200_state *s = nullptr;
+  int st = qipb200_state_new(ctx, prec, n, &s);
+  if (st != QIPB200_OK) return st;
+  st = qipb200_state_upload(s, input, 0, input_len);
+  if (st == QIPB200_OK) st = qipb200_state_apply_schedule(s, ops, n_ops, QIPB200_SCHED_DEFAULT);
+  std::vector<char> tmp;
+  if (st == QIPB200_OK) {
+    tmp.resize(output_len * ab);
+    st = qipb200_state_download(s, tmp.data(), 0, output_len);
+  }
+  qipb200_state_free(s);
+  if (st != QIPB200_OK) return st;
+  if (prec == QIP_F32) {
+    float *o = (float *)output;
+    const float *t = (const float *)tmp.data();
+    for (uint64_t i = 0; i < 2 * output_len; ++i) o[i] += t[i];
+  } else {
+    double *o = (double *)output;
+    const double *t = (const double *)tmp.data();
+    for (uint64_t i = 0; i < 2 * output_len; ++i) o[i] += t[i];
+  }
+  return QIPB200_OK;
+}
+
+// ===================================================================================
+// measurement
+// ===================================================================================
+
+namespace {
+
+int check_indices(qipb200_state *s, const uint64_t *indices, uint32_t n_indices) {
+  if (!indices || n_indices == 0 || n_indices > s->n)
+    return set_err(s->ctx, QIPB200_ERR_INVALID_ARG, "measurement: bad index list");
+  uint64_t seen = 0;
+  for (uint32_t i = 0; i < n_indices; ++i) {
+    if (indices[i] >= s->n) return set_err(s->ctx, QIPB200_ERR_BAD_INDEX, "measurement: qubit index out of range");
+    if ((seen >> indices[i]) & 1) return set_err(s->ctx, QIPB200_ERR_BAD_INDEX, "measurement: repeated qubit index");
+    seen |= 1ull << indices[i];
+  }
+  return QIPB200_OK;
+}
+
+}  // namespace
+
+extern "C" int qipb200_state_measure_probs(qipb200_state *s, const uint64_t *indices, uint32_t n_indices, double *out) {
+  if (!s || !out) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "measure_probs: NULL argument");
+  qipb200_ctx *ctx = s->ctx;
+  int st = check_indices(s, indices, n_indices);
+  if (st != QIPB200_OK) return st;
+  if (n_indices > 26) return set_err(ctx, QIPB200_ERR_UNSUPPORTED, "measure_probs: more than 26 measured qubits");
+  CU(ctx, cudaSetDevice(ctx->device));
+  uint32_t bitpos[32];
+  for (uint32_t i = 0; i < n_indices; ++i) bitpos[i] = s->phys_of_logical[s->n - 1 - (uint32_t)indices[i]];
+  double *d_hist = nullptr;
+  CU(ctx, cudaMallocAsync((void **)&d_hist, sizeof(double) << n_indices, ctx->stream));
+  CU(ctx, launch_measure_probs(s->prec, s->buf, 1ull << s->n_local, (uint64_t)s->rank << s->n_local, bitpos,
+                               n_indices, d_hist, ctx->stream, &ctx->launches));
+  CU(ctx, cudaMemcpyAsync(out, d_hist, sizeof(double) << n_indices, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaFreeAsync(d_hist, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return QIPB200_OK;
+}
+
+extern "C" int qipb200_state_measure_prob(qipb200_state *s, uint64_t measured, const uint64_t *indices,
+                                          uint32_t n_indices, double *out) {
+  if (!s || !out) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "measure_prob: NULL argument");
+  int st = check_indices(s, indices, n_indices);
+  if (st != QIPB200_OK) return st;
+  if (n_indices > 26) return set_err(s->ctx, QIPB200_ERR_UNSUPPORTED, "measure_prob: more than 26 measured qubits");
+  std::vector<double> probs(1ull << n_indices);
+  st = qipb200_state_measure_probs(s, indices, n_indices, probs.data());
+  if (st != QIPB200_OK) return st;
+  *out = (measured >> n_indices) ? 0.0 : probs[measured];
+  return QIPB200_OK;
+}
+
+extern "C" int qipb200_state_soft_measure(qipb200_state *s, const uint64_t *indices, uint32_t n_indices, double r,
+                                          uint64_t *measured) {
+  if (!s || !measured) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "soft_measure: NULL argument");
+  qipb200_ctx *ctx = s->ctx;
+  int st = check_indices(s, indices, n_indices);
+  if (st != QIPB200_OK) return st;
+  if (s->world > 1) return set_err(ctx, QIPB200_ERR_UNSUPPORTED, "soft_measure on a sharded state: sample per rank via measure_probs");
+  CU(ctx, cudaSetDevice(ctx->device));
+  // Inverse-CDF sampling (measurement_ops.rs:153-176 is a serial scan): per-chunk sums on the
+  // device, chunk search on the host, then a scan of the one chunk that contains the crossing.
+  const uint64_t len = 1ull << s->n_local;
+  const uint32_t chunk_log2 = s->n_local > 12 ? 12 : s->n_local;
+  const uint64_t chunks = len >> chunk_log2;
+  double *d_sums = nullptr;
+  CU(ctx, cudaMallocAsync((void **)&d_sums, chunks * sizeof(double), ctx->stream));
+  CU(ctx, launch_chunk_sums(s->prec, s->buf, len, chunk_log2, d_sums, ctx->stream, &ctx->launches));
+  std::vector<double> sums(chunks);
+  CU(ctx, cudaMemcpyAsync(sums.data(), d_sums, chunks * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaFreeAsync(d_sums, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  double rem = r;  // full-length input: r * 1 (measurement_ops.rs:160-165)
+  uint64_t c = 0;
+  for (; c + 1 < chunks; ++c) {
+    if (rem - sums[c] <= 0.0) break;
+    rem -= sums[c];
+  }
+  const uint64_t clen = 1ull << chunk_log2;
+  const size_t ab = amp_bytes(s->prec);
+  std::vector<char> host(clen * ab);
+  CU(ctx, cudaMemcpyAsync(host.data(), (const char *)s->buf + c * clen * ab, clen * ab, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  uint64_t idx = 0;  // the reference leaves measured_indx = 0 when the scan never crosses
+  bool found = false;
+  for (uint64_t i = 0; i < clen; ++i) {
+    double re, im;
+    if (s->prec == QIP_F32) {
+      re = ((const float *)host.data())[2 * i];
+      im = ((const float *)host.data())[2 * i + 1];
+    } else {
+      re = ((const double *)host.data())[2 * i];
+      im = ((const double *)host.data())[2 * i + 1];
+    }
+    rem -= re * re + im * im;
+    if (rem <= 0.0) {
+      idx = c * clen + i;
+      found = true;
+      break;
+    }
+  }
+  (void)found;
+  uint64_t m = 0;  // extract_bits(measured_indx, [n-1-index]) (measurement_ops.rs:174-175)
+  for (uint32_t i = 0; i < n_indices; ++i) m |= ((idx >> (s->n - 1 - indices[i])) & 1ull) << i;
+  *measured = m;
+  return QIPB200_OK;
+}
+
+extern "C" int qipb200_state_collapse(qipb200_state *s, const uint64_t *indices, uint32_t n_indices,
+                                      uint64_t measured, double measured_prob) {
+  if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
+  qipb200_ctx *ctx = s->ctx;
+  int st = check_indices(s, indices, n_indices);
+  if (st != QIPB200_OK) return st;
+  if (measured_prob == 0.0) return QIPB200_OK;  // measurement_ops.rs:230: untouched
+  CU(ctx, cudaSetDevice(ctx->device));
+  uint64_t row_mask = 0, measured_mask = 0;
+  for (uint32_t i = 0; i < n_indices; ++i) {
+    const uint32_t bit = s->phys_of_logical[s->n - 1 - (uint32_t)indices[i]];
+    row_mask |= 1ull << bit;
+    measured_mask |= ((measured >> i) & 1ull) << bit;
+  }
+  // P::one() / measured_prob.sqrt() evaluated in the state's precision (measurement_ops.rs:231)
+  double p_mult;
+  if (s->prec == QIP_F32)
+    p_mult = (double)(1.0f / sqrtf((float)measured_prob));
+  else
+    p_mult = 1.0 / sqrt(measured_prob);
+  CU(ctx, launch_collapse(s->prec, s->buf, 1ull << s->n_local, (uint64_t)s->rank << s->n_local, row_mask,
+                          measured_mask, p_mult, ctx->stream, &ctx->launches));
+  return QIPB200_OK;
+}
+
+// ===================================================================================
+// multi-GPU plumbing
+// ===================================================================================
+
+extern "C" int qipb200_state_ipc_export(qipb200_state *s, void *amp_handle, void *flag_handle) {
+  if (!s || !amp_handle || !flag_handle) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "ipc_export: NULL argument");
+  qipb200_ctx *ctx = s->ctx;
+  if (s->world == 1) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "ipc_export: not a sharded state");
+  static_assert(sizeof(cudaIpcMemHandle_t) == QIPB200_IPC_HANDLE_BYTES, "IPC handle size");
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaIpcMemHandle_t h;
+  CU(ctx, cudaIpcGetMemHandle(&h, s->buf));
+  memcpy(amp_handle, &h, sizeof(h));
+  CU(ctx, cudaIpcGetMemHandle(&h, s->flags));
+  memcpy(flag_handle, &h, sizeof(h));
+  return QIPB200_OK;
+}
+
+extern "C" int qipb200_state_ipc_import(qipb200_state *s, const void *amp_handles, const void *flag_handles) {
+  if (!s || !amp_handles || !flag_handles) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "ipc_import: NULL argument");
+  qipb200_ctx *ctx = s->ctx;
+  if (s->world == 1) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "ipc_import: not a sharded state");
+  CU(ctx, cudaSetDevice(ctx->device));
+  s->peer_buf.assign(s->world, nullptr);
+  s->peer_flags.assign(s->world, nullptr);
+  for (int t = 0; t < s->world; ++t) {
+    if (t == s->rank) {
+      s->peer_buf[t] = s->buf;
+      s->peer_flags[t] = s->flags;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)amp_handles + (size_t)t * QIPB200_IPC_HANDLE_BYTES, sizeof(h));
+    cudaError_t e = cudaIpcOpenMemHandle(&s->peer_buf[t], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cuda_fail(ctx, e, "cudaIpcOpenMemHandle(amplitudes)");
+      return QIPB200_ERR_COMM;
+    }
+    memcpy(&h, (const char *)flag_handles + (size_t)t * QIPB200_IPC_HANDLE_BYTES, sizeof(h));
+    void *fp = nullptr;
+    e = cudaIpcOpenMemHandle(&fp, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cuda_fail(ctx, e, "cudaIpcOpenMemHandle(flags)");
+      return QIPB200_ERR_COMM;
+    }
+    s->peer_flags[t] = (uint32_t *)fp;
+  }
+  s->ipc_ready = true;
+  return QIPB200_OK;
+}
+
+extern "C" int qipb200_state_qubit_map(qipb200_state *s, uint32_t *bit_of_qubit) {
+  if (!s || !bit_of_qubit) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "qubit_map: NULL argument");
+  for (uint32_t q = 0; q < s->n; ++q) bit_of_qubit[q] = s->phys_of_logical[s->n - 1 - q];
+  return QIPB200_OK;
+}
+
+extern "C" int qipb200_state_exchange_bytes(qipb200_state *s, uint64_t *bytes) {
+  if (!s || !bytes) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "exchange_bytes: NULL argument");
+  *bytes = s->exchange_bytes;
+  return QIPB200_OK;
+}
+
+extern "C" int qipb200_plan_exchanges(qip_prec prec, uint32_t n_qubits, int world_size, const qip_op *ops,
+                                      size_t n_ops, uint32_t *needs_exchange) {
+  if (!is_pow2(world_size) || (!ops && n_ops) || !needs_exchange)
+    return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "plan_exchanges: bad argument");
+  const uint32_t n_local = n_qubits - (uint32_t)ilog2(world_size);
+  for (size_t i = 0; i < n_ops; ++i) {
+    FlatOp f;
+    std::string err;
+    int st = compile_op(&ops[i], prec, n_qubits, &f, &err);
+    if (st != QIPB200_OK) return set_err(nullptr, st, err);
+    std::vector<uint32_t> nd;
+    nondiag_bits(f, &nd);
+    uint32_t cnt = 0;
+    for (size_t j = 0; j < nd.size(); ++j) cnt += nd[j] >= n_local;
+    needs_exchange[i] = cnt;
+  }
+  return QIPB200_OK;
+}

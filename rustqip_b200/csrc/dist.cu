@@ -1,0 +1,111 @@
+// dist.cu -- multi-GPU pair exchange over NVLink peer memory.
+//
+// The 2^n state is sharded by its top log2(world) PHYSICAL index bits, one process
+// per GPU.  A gate that acts non-diagonally on a rank bit R is made local by
+// swapping R with a local bit l ("qubit migration"): rank r and its partner
+// r ^ (1 << (R - n_local)) trade the half-shards selected by bit l.  The kernel
+// below does the trade IN PLACE with direct loads/stores on the partner's
+// CUDA-IPC-mapped buffer (P2P over NVLink 5 / NVSwitch): every (mine[i], peer[j])
+// pair is owned by exactly one of the two ranks (split by a second local bit s),
+// which reads both sides and writes both sides -- no staging buffer, no
+// read-old/write-new hazard.  Per rank and direction 2^(n_local-1) amplitudes cross
+// the link (half pulled by me, half pushed by the partner).
+//
+// Cross-GPU ordering is a flag barrier in peer-visible memory (system-scope
+// release/acquire), launched on the same stream before and after the trade.
+#include "dist.cuh"
+
+namespace qipb200 {
+
+static const int kThreads = 256;
+
+struct ExArgs {
+  uint32_t pos_lo, pos_hi;  // the two removed bit positions (l and s), ascending
+  uint64_t fixed;           // bits to OR in: (!rb << l) | (rb << s)
+  uint64_t flip;            // 1 << l
+  uint64_t n_items;
+};
+
+template <typename V>
+__global__ void __launch_bounds__(kThreads)
+    k_pair_exchange(V *__restrict__ mine, V *__restrict__ peer, const ExArgs a) {
+  const uint64_t w = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (w >= a.n_items) return;
+  uint64_t idx = w;
+  idx = ((idx >> a.pos_lo) << (a.pos_lo + 1)) | (idx & ((1ull << a.pos_lo) - 1ull));
+  idx = ((idx >> a.pos_hi) << (a.pos_hi + 1)) | (idx & ((1ull << a.pos_hi) - 1ull));
+  const uint64_t i = idx | a.fixed;
+  const uint64_t j = i ^ a.flip;
+  const V x = mine[i];
+  const V y = peer[j];  // NVLink load
+  mine[i] = y;
+  peer[j] = x;          // NVLink store
+}
+
+cudaError_t launch_pair_exchange(qip_prec prec, void *mine, void *peer, uint32_t n_local, uint32_t l,
+                                 uint32_t s_bit, int rb, cudaStream_t s, uint64_t *launches) {
+  if (n_local < 2 || l == s_bit || l >= n_local || s_bit >= n_local) return cudaErrorInvalidValue;
+  ExArgs a;
+  a.pos_lo = l < s_bit ? l : s_bit;
+  a.pos_hi = l < s_bit ? s_bit : l;
+  a.fixed = ((uint64_t)(rb ? 0 : 1) << l) | ((uint64_t)(rb ? 1 : 0) << s_bit);
+  a.flip = 1ull << l;
+  a.n_items = 1ull << (n_local - 2);
+  const unsigned grid = (unsigned)((a.n_items + kThreads - 1) / kThreads);
+  if (prec == QIP_F32)
+    k_pair_exchange<float2><<<grid, kThreads, 0, s>>>((float2 *)mine, (float2 *)peer, a);
+  else
+    k_pair_exchange<double2><<<grid, kThreads, 0, s>>>((double2 *)mine, (double2 *)peer, a);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+// ---- flag barrier -----------------------------------------------------------------
+struct BarrierArgs {
+  uint32_t *peer_flags[kMaxWorld];  // peer_flags[t] = rank t's flag page (mapped), slot [rank] is ours
+  uint32_t *my_flags;
+  int rank, world;
+  uint32_t epoch;
+  uint32_t *error_word;  // set to 1 on timeout (pinned host or device memory)
+};
+
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void k_flag_barrier(const BarrierArgs a) {
+  const int t = threadIdx.x;
+  if (t >= a.world) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flags[t] + a.rank), "r"(a.epoch) : "memory");
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t v;
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.my_flags + t) : "memory");
+    if ((int32_t)(v - a.epoch) >= 0) break;
+    if (globaltimer_ns() - t0 > 20ull * 1000ull * 1000ull * 1000ull) {  // 20 s: a peer is gone
+      *a.error_word = 1u;
+      break;
+    }
+  }
+  __threadfence_system();
+}
+
+cudaError_t launch_flag_barrier(uint32_t *const *peer_flags, uint32_t *my_flags, int rank, int world,
+                                uint32_t epoch, uint32_t *error_word, cudaStream_t s, uint64_t *launches) {
+  if (world > kMaxWorld) return cudaErrorInvalidValue;
+  BarrierArgs a;
+  for (int t = 0; t < world; ++t) a.peer_flags[t] = peer_flags[t];
+  a.my_flags = my_flags;
+  a.rank = rank;
+  a.world = world;
+  a.epoch = epoch;
+  a.error_word = error_word;
+  k_flag_barrier<<<1, 32, 0, s>>>(a);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+}  // namespace qipb200

@@ -1,0 +1,25 @@
+// dist.cuh -- launch interface of the NVLink pair-exchange kernels (see dist.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/qipb200.h"
+
+namespace qipb200 {
+
+static const int kMaxWorld = 16;
+static const int kFlagErrorSlot = 32;   // flags[kFlagErrorSlot] != 0 => a barrier timed out
+static const int kFlagWords = 64;
+
+// Trade the half-shard selected by local bit `l` with the partner's (see dist.cu).
+// rb = this rank's value of the rank bit being migrated; s_bit = pair-ownership bit.
+cudaError_t launch_pair_exchange(qip_prec prec, void *mine, void *peer, uint32_t n_local, uint32_t l,
+                                 uint32_t s_bit, int rb, cudaStream_t s, uint64_t *launches);
+
+// All-rank barrier through peer-mapped flag pages; stream-ordered.
+cudaError_t launch_flag_barrier(uint32_t *const *peer_flags, uint32_t *my_flags, int rank, int world,
+                                uint32_t epoch, uint32_t *error_word, cudaStream_t s, uint64_t *launches);
+
+}  // namespace qipb200

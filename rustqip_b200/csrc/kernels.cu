@@ -1,0 +1,699 @@
+// kernels.cu -- per-gate sm_100a kernels of libqipb200.
+//
+// Data layout: the (local) state is one HBM buffer of 2^n amplitudes, interleaved
+// (re,im) of float or double == `&[Complex<P>]` of the reference.  Qubit q lives at
+// index bit n-1-q (qip-iterators/src/matrix_ops.rs:12-21).
+//
+// All gate kernels except k_gather work IN PLACE: a k-qubit gate only couples the
+// 2^k amplitudes that differ in its target bits, so one thread owns one such group
+// (times VEC neighbouring groups that share a 16-byte access), reads it once and
+// writes it once.  Algorithmic traffic per gate = 2 * 2^n * sizeof(amplitude)
+// (SURVEY.md section 8d); controlled / diagonal gates touch only the amplitudes the
+// reference would change (its identity rows multiply by exactly 1).
+//
+// Every kernel is HBM-bound (<= 2 flop/B for k<=2): the design rules are full
+// 32-byte-sector utilisation on both streams, 16-byte accesses per lane, and
+// enough independent loads in flight per SM.
+#include "kernels.cuh"
+
+#include <cstdio>
+
+namespace qipb200 {
+
+// ---------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------
+
+template <typename R>
+struct Vec2;
+template <>
+struct Vec2<float> {
+  typedef float2 type;
+};
+template <>
+struct Vec2<double> {
+  typedef double2 type;
+};
+
+// A lane's access: VEC consecutive amplitudes (16 bytes for <double,1> and <float,2>).
+template <typename R, int VEC>
+struct Pack {
+  R re[VEC], im[VEC];
+};
+
+template <typename R, int VEC>
+__device__ __forceinline__ Pack<R, VEC> ld_pack(const R *psi, uint64_t amp_index);
+template <typename R, int VEC>
+__device__ __forceinline__ void st_pack(R *psi, uint64_t amp_index, const Pack<R, VEC> &p);
+
+template <>
+__device__ __forceinline__ Pack<double, 1> ld_pack<double, 1>(const double *psi, uint64_t i) {
+  double2 v = *reinterpret_cast<const double2 *>(psi + 2 * i);
+  Pack<double, 1> p;
+  p.re[0] = v.x;
+  p.im[0] = v.y;
+  return p;
+}
+template <>
+__device__ __forceinline__ void st_pack<double, 1>(double *psi, uint64_t i, const Pack<double, 1> &p) {
+  *reinterpret_cast<double2 *>(psi + 2 * i) = make_double2(p.re[0], p.im[0]);
+}
+template <>
+__device__ __forceinline__ Pack<float, 1> ld_pack<float, 1>(const float *psi, uint64_t i) {
+  float2 v = *reinterpret_cast<const float2 *>(psi + 2 * i);
+  Pack<float, 1> p;
+  p.re[0] = v.x;
+  p.im[0] = v.y;
+  return p;
+}
+template <>
+__device__ __forceinline__ void st_pack<float, 1>(float *psi, uint64_t i, const Pack<float, 1> &p) {
+  *reinterpret_cast<float2 *>(psi + 2 * i) = make_float2(p.re[0], p.im[0]);
+}
+template <>
+__device__ __forceinline__ Pack<float, 2> ld_pack<float, 2>(const float *psi, uint64_t i) {
+  float4 v = *reinterpret_cast<const float4 *>(psi + 2 * i);
+  Pack<float, 2> p;
+  p.re[0] = v.x;
+  p.im[0] = v.y;
+  p.re[1] = v.z;
+  p.im[1] = v.w;
+  return p;
+}
+template <>
+__device__ __forceinline__ void st_pack<float, 2>(float *psi, uint64_t i, const Pack<float, 2> &p) {
+  *reinterpret_cast<float4 *>(psi + 2 * i) = make_float4(p.re[0], p.im[0], p.re[1], p.im[1]);
+}
+
+// Work-item index -> amplitude index: re-insert a zero bit at each (ascending) position.
+struct InsArgs {
+  uint32_t n_ins;
+  uint32_t pos[kMaxIns];
+};
+
+__device__ __forceinline__ uint64_t expand_index(uint64_t w, const InsArgs &ins) {
+  uint64_t idx = w;
+  for (uint32_t i = 0; i < ins.n_ins; ++i) {
+    const uint32_t p = ins.pos[i];
+    const uint64_t low = idx & ((1ull << p) - 1ull);
+    idx = ((idx >> p) << (p + 1)) | low;
+  }
+  return idx;
+}
+
+static const int kThreads = 256;
+
+static inline unsigned grid_for(uint64_t items) { return (unsigned)((items + kThreads - 1) / kThreads); }
+
+// Collect the sorted insertion positions of a control mask plus extra bits.
+static bool build_ins(uint64_t ctrl_mask, const uint32_t *extra, uint32_t n_extra, InsArgs *ins) {
+  uint64_t all = ctrl_mask;
+  for (uint32_t i = 0; i < n_extra; ++i) all |= 1ull << extra[i];
+  ins->n_ins = 0;
+  for (uint32_t b = 0; b < 64; ++b)
+    if ((all >> b) & 1) {
+      if (ins->n_ins >= (uint32_t)kMaxIns) return false;
+      ins->pos[ins->n_ins++] = b;
+    }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------
+// K1/K2 dense block in registers (k <= 4), optional controls.
+//   out_sub[u] = sum_v m[u][v] * in_sub[v]    (ops.rs:106 + qubit_iterators.rs:40-55)
+// with the block already re-indexed on the host so that bit i of u is the i-th
+// smallest target bit (opcompile.cpp: sort_block).
+// ---------------------------------------------------------------------------------
+template <typename R, int K>
+struct DenseArgs {
+  InsArgs ins;
+  uint64_t ctrl_mask;
+  uint64_t n_items;                 // work items (each VEC groups)
+  uint64_t off[1 << K];             // amplitude offset of sub-index u
+  R mre[1 << K][1 << K];
+  R mim[1 << K][1 << K];
+};
+
+template <typename R, int K, int VEC>
+__global__ void __launch_bounds__(kThreads)
+    k_dense(R *__restrict__ psi, const __grid_constant__ DenseArgs<R, K> a) {
+  const uint64_t w = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (w >= a.n_items) return;
+  const uint64_t base = expand_index(w * VEC, a.ins) | a.ctrl_mask;
+  constexpr int S = 1 << K;
+  Pack<R, VEC> in[S];
+#pragma unroll
+  for (int u = 0; u < S; ++u) in[u] = ld_pack<R, VEC>(psi, base + a.off[u]);
+#pragma unroll
+  for (int u = 0; u < S; ++u) {
+    Pack<R, VEC> o;
+#pragma unroll
+    for (int l = 0; l < VEC; ++l) {
+      R re = (R)0, im = (R)0;
+#pragma unroll
+      for (int v = 0; v < S; ++v) {
+        const R mr = a.mre[u][v], mi = a.mim[u][v];
+        re = fma(mr, in[v].re[l], re);
+        re = fma(-mi, in[v].im[l], re);
+        im = fma(mr, in[v].im[l], im);
+        im = fma(mi, in[v].re[l], im);
+      }
+      o.re[l] = re;
+      o.im[l] = im;
+    }
+    st_pack<R, VEC>(psi, base + a.off[u], o);
+  }
+}
+
+template <typename R, int K>
+static cudaError_t launch_dense_t(R *psi, uint32_t n_local, const FlatOp &f, cudaStream_t s,
+                                  uint64_t *launches) {
+  DenseArgs<R, K> a;
+  if (!build_ins(f.ctrl_mask, f.tgt_sorted.data(), K, &a.ins)) return cudaErrorInvalidValue;
+  a.ctrl_mask = f.ctrl_mask;
+  constexpr int S = 1 << K;
+  for (int u = 0; u < S; ++u) {
+    uint64_t off = 0;
+    for (int i = 0; i < K; ++i)
+      if ((u >> i) & 1) off |= 1ull << f.tgt_sorted[i];
+    a.off[u] = off;
+    for (int v = 0; v < S; ++v) {
+      a.mre[u][v] = (R)f.m_sorted[(size_t)u * S + v].real();
+      a.mim[u][v] = (R)f.m_sorted[(size_t)u * S + v].imag();
+    }
+  }
+  const uint64_t groups = 1ull << (n_local - a.ins.n_ins);
+  // 16-byte lane accesses: two f32 amplitudes per access when no involved bit is bit 0.
+  const bool vec2 = sizeof(R) == 4 && a.ins.pos[0] >= 1 && groups >= 2;
+  if (vec2) {
+    a.n_items = groups / 2;
+    k_dense<R, K, (sizeof(R) == 4 ? 2 : 1)><<<grid_for(a.n_items), kThreads, 0, s>>>(psi, a);
+  } else {
+    a.n_items = groups;
+    k_dense<R, K, 1><<<grid_for(a.n_items), kThreads, 0, s>>>(psi, a);
+  }
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dense(qip_prec prec, void *psi, uint32_t n_local, const FlatOp &f, cudaStream_t s,
+                         uint64_t *launches) {
+  const int K = (int)f.tgt_sorted.size();
+#define DISPATCH(KK)                                                                              \
+  case KK:                                                                                        \
+    return prec == QIP_F32 ? launch_dense_t<float, KK>((float *)psi, n_local, f, s, launches)     \
+                           : launch_dense_t<double, KK>((double *)psi, n_local, f, s, launches);
+  switch (K) {
+    DISPATCH(1)
+    DISPATCH(2)
+    DISPATCH(3)
+    DISPATCH(4)
+    default:
+      return cudaErrorInvalidValue;
+  }
+#undef DISPATCH
+}
+
+// ---------------------------------------------------------------------------------
+// K5 diagonal: a[i] *= d[sub(i)] on the amplitudes whose control bits are all 1.
+// After promotion (opcompile.cpp) T/S/Z/CZ/controlled-phase are a single scalar on
+// a bit mask: only 1/2 .. 1/4 of the state is touched.
+// ---------------------------------------------------------------------------------
+template <typename R>
+struct DiagArgs {
+  InsArgs ins;  // control positions only
+  uint64_t ctrl_mask;
+  uint64_t n_items;
+  uint32_t n_bits;
+  uint32_t bits[kMaxDiagParamK];
+  R dre[1 << kMaxDiagParamK];
+  R dim[1 << kMaxDiagParamK];
+};
+
+template <typename R, int VEC>
+__global__ void __launch_bounds__(kThreads)
+    k_diag(R *__restrict__ psi, const __grid_constant__ DiagArgs<R> a) {
+  const uint64_t w = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (w >= a.n_items) return;
+  const uint64_t base = expand_index(w * VEC, a.ins) | a.ctrl_mask;
+  Pack<R, VEC> p = ld_pack<R, VEC>(psi, base);
+#pragma unroll
+  for (int l = 0; l < VEC; ++l) {
+    const uint64_t i = base + l;
+    uint32_t u = 0;
+    for (uint32_t j = 0; j < a.n_bits; ++j) u |= (uint32_t)((i >> a.bits[j]) & 1ull) << j;
+    const R dr = a.dre[u], di = a.dim[u];
+    const R re = p.re[l], im = p.im[l];
+    p.re[l] = fma(dr, re, -di * im);
+    p.im[l] = fma(dr, im, di * re);
+  }
+  st_pack<R, VEC>(psi, base, p);
+}
+
+template <typename R>
+static cudaError_t launch_diag_t(R *psi, uint32_t n_local, uint64_t ctrl_mask,
+                                 const std::vector<uint32_t> &bits, const std::vector<cplx> &d,
+                                 cudaStream_t s, uint64_t *launches) {
+  DiagArgs<R> a;
+  if (bits.size() > (size_t)kMaxDiagParamK) return cudaErrorInvalidValue;
+  if (!build_ins(ctrl_mask, nullptr, 0, &a.ins)) return cudaErrorInvalidValue;
+  a.ctrl_mask = ctrl_mask;
+  a.n_bits = (uint32_t)bits.size();
+  for (size_t j = 0; j < bits.size(); ++j) a.bits[j] = bits[j];
+  for (size_t u = 0; u < d.size(); ++u) {
+    a.dre[u] = (R)d[u].real();
+    a.dim[u] = (R)d[u].imag();
+  }
+  const uint64_t groups = 1ull << (n_local - a.ins.n_ins);
+  const bool vec2 = sizeof(R) == 4 && (a.ins.n_ins == 0 || a.ins.pos[0] >= 1) && groups >= 2;
+  if (vec2) {
+    a.n_items = groups / 2;
+    k_diag<R, (sizeof(R) == 4 ? 2 : 1)><<<grid_for(a.n_items), kThreads, 0, s>>>(psi, a);
+  } else {
+    a.n_items = groups;
+    k_diag<R, 1><<<grid_for(a.n_items), kThreads, 0, s>>>(psi, a);
+  }
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_diag(qip_prec prec, void *psi, uint32_t n_local, uint64_t ctrl_mask,
+                        const std::vector<uint32_t> &bits, const std::vector<cplx> &d, cudaStream_t s,
+                        uint64_t *launches) {
+  return prec == QIP_F32 ? launch_diag_t<float>((float *)psi, n_local, ctrl_mask, bits, d, s, launches)
+                         : launch_diag_t<double>((double *)psi, n_local, ctrl_mask, bits, d, s, launches);
+}
+
+// ---------------------------------------------------------------------------------
+// K4 permutations: X / CNOT / Toffoli-X (pair exchange on one bit) and Swap (exchange
+// of two index bits), both under a control mask.  Pure moves: bit-exact.
+// ---------------------------------------------------------------------------------
+struct PermArgs {
+  InsArgs ins;
+  uint64_t ctrl_mask;
+  uint64_t n_items;
+  uint64_t off_a, off_b;  // the two amplitude offsets that trade places
+};
+
+template <typename R, int VEC>
+__global__ void __launch_bounds__(kThreads)
+    k_exchange(R *__restrict__ psi, const __grid_constant__ PermArgs a) {
+  const uint64_t w = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (w >= a.n_items) return;
+  const uint64_t base = expand_index(w * VEC, a.ins) | a.ctrl_mask;
+  const Pack<R, VEC> x = ld_pack<R, VEC>(psi, base + a.off_a);
+  const Pack<R, VEC> y = ld_pack<R, VEC>(psi, base + a.off_b);
+  st_pack<R, VEC>(psi, base + a.off_a, y);
+  st_pack<R, VEC>(psi, base + a.off_b, x);
+}
+
+template <typename R>
+static cudaError_t launch_exchange_t(R *psi, uint32_t n_local, PermArgs &a, cudaStream_t s,
+                                     uint64_t *launches) {
+  const uint64_t groups = 1ull << (n_local - a.ins.n_ins);
+  const bool vec2 = sizeof(R) == 4 && a.ins.pos[0] >= 1 && groups >= 2;
+  if (vec2) {
+    a.n_items = groups / 2;
+    k_exchange<R, (sizeof(R) == 4 ? 2 : 1)><<<grid_for(a.n_items), kThreads, 0, s>>>(psi, a);
+  } else {
+    a.n_items = groups;
+    k_exchange<R, 1><<<grid_for(a.n_items), kThreads, 0, s>>>(psi, a);
+  }
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_flip(qip_prec prec, void *psi, uint32_t n_local, uint64_t ctrl_mask, uint32_t tbit,
+                        cudaStream_t s, uint64_t *launches) {
+  PermArgs a;
+  if (!build_ins(ctrl_mask, &tbit, 1, &a.ins)) return cudaErrorInvalidValue;
+  a.ctrl_mask = ctrl_mask;
+  a.off_a = 0;
+  a.off_b = 1ull << tbit;
+  return prec == QIP_F32 ? launch_exchange_t<float>((float *)psi, n_local, a, s, launches)
+                         : launch_exchange_t<double>((double *)psi, n_local, a, s, launches);
+}
+
+cudaError_t launch_bitswap(qip_prec prec, void *psi, uint32_t n_local, uint64_t ctrl_mask, uint32_t p,
+                           uint32_t q, cudaStream_t s, uint64_t *launches) {
+  PermArgs a;
+  uint32_t both[2] = {p, q};
+  if (!build_ins(ctrl_mask, both, 2, &a.ins)) return cudaErrorInvalidValue;
+  a.ctrl_mask = ctrl_mask;
+  a.off_a = 1ull << p;  // (p=1,q=0) <-> (p=0,q=1); equal bits stay put
+  a.off_b = 1ull << q;
+  return prec == QIP_F32 ? launch_exchange_t<float>((float *)psi, n_local, a, s, launches)
+                         : launch_exchange_t<double>((double *)psi, n_local, a, s, launches);
+}
+
+// ---------------------------------------------------------------------------------
+// Universal row kernel: one thread == one evaluation of apply_op_row_indices
+// (qip-iterators/src/matrix_ops.rs:62-94) for any op kind, with input/output
+// offsets and the accumulate (`+=`, :110) / overwrite (`=`, :139) modes.
+// Arithmetic is issued with the never-contracted __*_rn intrinsics in the
+// reference's order (ascending non-zero columns from a zero accumulator,
+// 4-mul/2-add complex product), so results are bit-identical to the CPU path.
+// ---------------------------------------------------------------------------------
+template <typename R>
+struct Arith;
+template <>
+struct Arith<float> {
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+};
+template <>
+struct Arith<double> {
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+};
+
+struct GatherArgs {
+  uint32_t k, kop;
+  int base_kind;
+  uint64_t thr;
+  uint64_t all_mask;       // OR of all idx_bits
+  uint32_t idx_bits[24];   // reference order: idx_bits[j] <-> sub-index bit k-1-j
+  const void *dense;       // device, 4^kop complex<R>, reference order
+  const uint64_t *sp_rowptr, *sp_col;
+  const void *sp_val;
+  uint64_t in_len, in_off, out_len, out_off;
+  int accumulate;
+};
+
+template <typename R>
+__global__ void __launch_bounds__(kThreads)
+    k_gather(const R *__restrict__ in, R *__restrict__ out, const __grid_constant__ GatherArgs a) {
+  const uint64_t o = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (o >= a.out_len) return;
+  const uint64_t row = a.out_off + o;
+  uint64_t matrow = 0;  // full_to_sub, matrix_ops.rs:12-21
+  for (uint32_t j = 0; j < a.k; ++j) matrow |= ((row >> a.idx_bits[j]) & 1ull) << (a.k - 1 - j);
+  const uint64_t row_cleared = row & ~a.all_mask;
+  R ar = (R)0, ai = (R)0;
+
+  auto accum = [&](uint64_t col, R vr, R vi) {
+    uint64_t colbits = row_cleared;  // sub_to_full, matrix_ops.rs:24-30
+    for (uint32_t j = 0; j < a.k; ++j) colbits |= ((col >> (a.k - 1 - j)) & 1ull) << a.idx_bits[j];
+    R tr = (R)0, ti = (R)0;
+    if (colbits >= a.in_off) {
+      const uint64_t vecrow = colbits - a.in_off;
+      if (vecrow < a.in_len) {
+        const R pr = in[2 * vecrow], pi = in[2 * vecrow + 1];
+        tr = Arith<R>::sub(Arith<R>::mul(vr, pr), Arith<R>::mul(vi, pi));
+        ti = Arith<R>::add(Arith<R>::mul(vr, pi), Arith<R>::mul(vi, pr));
+      }
+    }
+    ar = Arith<R>::add(ar, tr);
+    ai = Arith<R>::add(ai, ti);
+  };
+
+  if (matrow < a.thr) {
+    accum(matrow, (R)1, (R)0);  // identity row of a control op, qubit_iterators.rs:160-169
+  } else {
+    const uint64_t r = matrow - a.thr;
+    if (a.base_kind == QIP_OP_MATRIX) {
+      const R *d = static_cast<const R *>(a.dense) + 2 * (r << a.kop);
+      const uint64_t side = 1ull << a.kop;
+      for (uint64_t c = 0; c < side; ++c) {
+        const R vr = d[2 * c], vi = d[2 * c + 1];
+        if (vr == (R)0 && vi == (R)0) continue;  // zero entries are skipped, qubit_iterators.rs:49
+        accum(c + a.thr, vr, vi);
+      }
+    } else if (a.base_kind == QIP_OP_SPARSE) {
+      const R *v = static_cast<const R *>(a.sp_val);
+      for (uint64_t e = a.sp_rowptr[r]; e < a.sp_rowptr[r + 1]; ++e)
+        accum(a.sp_col[e] + a.thr, v[2 * e], v[2 * e + 1]);
+    } else {  // swap, qubit_iterators.rs:208-218
+      const uint32_t half = a.kop >> 1;
+      const uint64_t lower_mask = ~(~0ull << half);
+      accum((((r & lower_mask) << half) + (r >> half)) + a.thr, (R)1, (R)0);
+    }
+  }
+  if (a.accumulate) {
+    out[2 * o] = Arith<R>::add(out[2 * o], ar);
+    out[2 * o + 1] = Arith<R>::add(out[2 * o + 1], ai);
+  } else {
+    out[2 * o] = ar;
+    out[2 * o + 1] = ai;
+  }
+}
+
+template <typename R>
+static cudaError_t launch_gather_t(const FlatOp &f, const R *in, uint64_t in_len, uint64_t in_off, R *out,
+                                   uint64_t out_len, uint64_t out_off, bool accumulate, cudaStream_t s,
+                                   uint64_t *launches) {
+  if (out_len == 0) return cudaSuccess;
+  GatherArgs a;
+  a.k = f.k;
+  a.kop = f.kop;
+  a.base_kind = f.base_kind;
+  a.thr = f.nc ? ((1ull << f.k) - (1ull << f.kop)) : 0;
+  a.all_mask = 0;
+  if (f.k > 24) return cudaErrorInvalidValue;
+  for (uint32_t j = 0; j < f.k; ++j) {
+    a.idx_bits[j] = f.idx_bits[j];
+    a.all_mask |= 1ull << f.idx_bits[j];
+  }
+  a.dense = nullptr;
+  a.sp_rowptr = a.sp_col = nullptr;
+  a.sp_val = nullptr;
+  a.in_len = in_len;
+  a.in_off = in_off;
+  a.out_len = out_len;
+  a.out_off = out_off;
+  a.accumulate = accumulate ? 1 : 0;
+
+  void *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;
+  cudaError_t e = cudaSuccess;
+  std::vector<R> tmp;
+  if (f.base_kind == QIP_OP_MATRIX || (f.base_kind == QIP_OP_SPARSE && f.has_dense)) {
+    // a densified sparse op is applied as a dense one (duplicates pre-summed)
+    a.base_kind = QIP_OP_MATRIX;
+    tmp.resize(2 * f.dense.size());
+    for (size_t i = 0; i < f.dense.size(); ++i) {
+      tmp[2 * i] = (R)f.dense[i].real();
+      tmp[2 * i + 1] = (R)f.dense[i].imag();
+    }
+    if ((e = cudaMallocAsync(&d_a, tmp.size() * sizeof(R), s)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(d_a, tmp.data(), tmp.size() * sizeof(R), cudaMemcpyHostToDevice, s)) != cudaSuccess)
+      return e;
+    a.dense = d_a;
+  } else if (f.base_kind == QIP_OP_SPARSE) {
+    tmp.resize(2 * f.sp_val.size());
+    for (size_t i = 0; i < f.sp_val.size(); ++i) {
+      tmp[2 * i] = (R)f.sp_val[i].real();
+      tmp[2 * i + 1] = (R)f.sp_val[i].imag();
+    }
+    if ((e = cudaMallocAsync(&d_a, tmp.size() * sizeof(R) + 16, s)) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(&d_b, f.sp_rowptr.size() * 8, s)) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(&d_c, f.sp_col.size() * 8 + 16, s)) != cudaSuccess) return e;
+    cudaMemcpyAsync(d_a, tmp.data(), tmp.size() * sizeof(R), cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_b, f.sp_rowptr.data(), f.sp_rowptr.size() * 8, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_c, f.sp_col.data(), f.sp_col.size() * 8, cudaMemcpyHostToDevice, s);
+    a.sp_val = d_a;
+    a.sp_rowptr = (const uint64_t *)d_b;
+    a.sp_col = (const uint64_t *)d_c;
+  }
+  // the staging vectors are pageable: the async copies above have completed their
+  // host read when they return, so `tmp` may go out of scope.
+  k_gather<R><<<grid_for(out_len), kThreads, 0, s>>>(in, out, a);
+  ++*launches;
+  e = cudaGetLastError();
+  if (d_a) cudaFreeAsync(d_a, s);
+  if (d_b) cudaFreeAsync(d_b, s);
+  if (d_c) cudaFreeAsync(d_c, s);
+  return e;
+}
+
+cudaError_t launch_gather(qip_prec prec, const FlatOp &f, uint32_t, const void *in, uint64_t in_len,
+                          uint64_t in_off, void *out, uint64_t out_len, uint64_t out_off, bool accumulate,
+                          cudaStream_t s, uint64_t *launches) {
+  return prec == QIP_F32
+             ? launch_gather_t<float>(f, (const float *)in, in_len, in_off, (float *)out, out_len, out_off,
+                                      accumulate, s, launches)
+             : launch_gather_t<double>(f, (const double *)in, in_len, in_off, (double *)out, out_len,
+                                       out_off, accumulate, s, launches);
+}
+
+// ---------------------------------------------------------------------------------
+// reductions / state set-up / measurement
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double sh[kThreads / 32];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = threadIdx.x < kThreads / 32 ? sh[threadIdx.x] : 0.0;
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  }
+  return v;  // valid in thread 0
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kThreads) k_norm2(const R *__restrict__ psi, uint64_t len, double *out) {
+  double acc = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < len; i += (uint64_t)gridDim.x * kThreads) {
+    typename Vec2<R>::type v = *reinterpret_cast<const typename Vec2<R>::type *>(psi + 2 * i);
+    acc += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+cudaError_t launch_norm2(qip_prec prec, const void *psi, uint64_t len, double *d_out, cudaStream_t s,
+                         uint64_t *launches) {
+  cudaError_t e = cudaMemsetAsync(d_out, 0, sizeof(double), s);
+  if (e != cudaSuccess) return e;
+  unsigned grid = (unsigned)std::min<uint64_t>((len + kThreads - 1) / kThreads, 148ull * 16);
+  if (grid == 0) grid = 1;
+  if (prec == QIP_F32)
+    k_norm2<float><<<grid, kThreads, 0, s>>>((const float *)psi, len, d_out);
+  else
+    k_norm2<double><<<grid, kThreads, 0, s>>>((const double *)psi, len, d_out);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+template <typename R>
+__global__ void k_set_one(R *psi, uint64_t index) {
+  psi[2 * index] = (R)1;
+  psi[2 * index + 1] = (R)0;
+}
+
+cudaError_t launch_set_basis(qip_prec prec, void *psi, uint64_t len, uint64_t index, bool owns_index,
+                             cudaStream_t s, uint64_t *launches) {
+  const size_t amp = prec == QIP_F32 ? 8 : 16;
+  cudaError_t e = cudaMemsetAsync(psi, 0, len * amp, s);
+  if (e != cudaSuccess || !owns_index) return e;
+  if (prec == QIP_F32)
+    k_set_one<float><<<1, 1, 0, s>>>((float *)psi, index);
+  else
+    k_set_one<double><<<1, 1, 0, s>>>((double *)psi, index);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+// measure_probs (measurement_ops.rs:115-127) as one histogram sweep: every amplitude
+// adds |a|^2 to the bin spelled by its measured bits.  Small histograms live in
+// shared memory per CTA and are flushed with one atomicAdd per bin.
+static const uint32_t kHistSmemBits = 10;
+
+struct HistArgs {
+  uint32_t n_bits;
+  uint32_t bitpos[32];
+  uint64_t len, index_base;
+};
+
+template <typename R>
+__global__ void __launch_bounds__(kThreads)
+    k_hist(const R *__restrict__ psi, double *hist, const __grid_constant__ HistArgs a) {
+  __shared__ double sh[1 << kHistSmemBits];
+  const bool use_smem = a.n_bits <= kHistSmemBits;
+  const uint32_t bins = 1u << a.n_bits;
+  if (use_smem) {
+    for (uint32_t b = threadIdx.x; b < bins; b += kThreads) sh[b] = 0.0;
+    __syncthreads();
+  }
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < a.len; i += (uint64_t)gridDim.x * kThreads) {
+    typename Vec2<R>::type v = *reinterpret_cast<const typename Vec2<R>::type *>(psi + 2 * i);
+    const double p = (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+    if (p == 0.0) continue;
+    const uint64_t g = a.index_base + i;
+    uint32_t m = 0;
+    for (uint32_t j = 0; j < a.n_bits; ++j) m |= (uint32_t)((g >> a.bitpos[j]) & 1ull) << j;
+    if (use_smem)
+      atomicAdd(&sh[m], p);
+    else
+      atomicAdd(&hist[m], p);
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < bins; b += kThreads)
+      if (sh[b] != 0.0) atomicAdd(&hist[b], sh[b]);
+  }
+}
+
+cudaError_t launch_measure_probs(qip_prec prec, const void *psi, uint64_t len, uint64_t index_base,
+                                 const uint32_t *bitpos, uint32_t n_bits, double *d_hist, cudaStream_t s,
+                                 uint64_t *launches) {
+  if (n_bits > 26) return cudaErrorInvalidValue;
+  HistArgs a;
+  a.n_bits = n_bits;
+  for (uint32_t j = 0; j < n_bits; ++j) a.bitpos[j] = bitpos[j];
+  a.len = len;
+  a.index_base = index_base;
+  cudaError_t e = cudaMemsetAsync(d_hist, 0, sizeof(double) << n_bits, s);
+  if (e != cudaSuccess) return e;
+  unsigned grid = (unsigned)std::min<uint64_t>((len + kThreads - 1) / kThreads, 148ull * 8);
+  if (grid == 0) grid = 1;
+  if (prec == QIP_F32)
+    k_hist<float><<<grid, kThreads, 0, s>>>((const float *)psi, d_hist, a);
+  else
+    k_hist<double><<<grid, kThreads, 0, s>>>((const double *)psi, d_hist, a);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kThreads)
+    k_chunk_sums(const R *__restrict__ psi, uint64_t len, uint32_t chunk_log2, double *sums) {
+  const uint64_t begin = (uint64_t)blockIdx.x << chunk_log2;
+  uint64_t end = begin + (1ull << chunk_log2);
+  if (end > len) end = len;
+  double acc = 0.0;
+  for (uint64_t i = begin + threadIdx.x; i < end; i += kThreads) {
+    typename Vec2<R>::type v = *reinterpret_cast<const typename Vec2<R>::type *>(psi + 2 * i);
+    acc += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) sums[blockIdx.x] = acc;
+}
+
+cudaError_t launch_chunk_sums(qip_prec prec, const void *psi, uint64_t len, uint32_t chunk_log2,
+                              double *d_sums, cudaStream_t s, uint64_t *launches) {
+  const uint64_t chunks = (len + (1ull << chunk_log2) - 1) >> chunk_log2;
+  if (prec == QIP_F32)
+    k_chunk_sums<float><<<(unsigned)chunks, kThreads, 0, s>>>((const float *)psi, len, chunk_log2, d_sums);
+  else
+    k_chunk_sums<double><<<(unsigned)chunks, kThreads, 0, s>>>((const double *)psi, len, chunk_log2, d_sums);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kThreads)
+    k_collapse(R *__restrict__ psi, uint64_t len, uint64_t index_base, uint64_t row_mask,
+               uint64_t measured_mask, R p_mult) {
+  const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= len) return;
+  typedef typename Vec2<R>::type V;
+  V *p = reinterpret_cast<V *>(psi + 2 * i);
+  if ((((index_base + i) & row_mask) ^ measured_mask) != 0) {
+    V z;
+    z.x = (R)0;
+    z.y = (R)0;
+    *p = z;  // measurement_ops.rs:255-257
+  } else {
+    V v = *p;
+    v.x *= p_mult;  // measurement_ops.rs:258-260
+    v.y *= p_mult;
+    *p = v;
+  }
+}
+
+cudaError_t launch_collapse(qip_prec prec, void *psi, uint64_t len, uint64_t index_base, uint64_t row_mask,
+                            uint64_t measured_mask, double p_mult, cudaStream_t s, uint64_t *launches) {
+  if (prec == QIP_F32)
+    k_collapse<float><<<grid_for(len), kThreads, 0, s>>>((float *)psi, len, index_base, row_mask,
+                                                         measured_mask, (float)p_mult);
+  else
+    k_collapse<double><<<grid_for(len), kThreads, 0, s>>>((double *)psi, len, index_base, row_mask,
+                                                          measured_mask, p_mult);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+}  // namespace qipb200

@@ -1,0 +1,19 @@
+// schedule.h -- the gate schedule executor (the fold of builder.rs:423-514).
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+
+#include "opcompile.h"
+#include "state.h"
+
+namespace qipb200 {
+
+// api.cu
+int apply_flat_local(qipb200_state *s, const FlatOp &f);
+int compile_and_localize(qipb200_state *s, const qip_op *op, FlatOp *f, const uint64_t *next_use);
+
+// schedule.cu: state <- ops[n-1] ... ops[0] state
+int run_schedule(qipb200_state *s, const qip_op *ops, size_t n_ops, uint32_t flags);
+
+}  // namespace qipb200
