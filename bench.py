@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- gate-applications/s and effective state GB/s of the RustQIP gate-application
+hot path on B200 (BASELINE.json metric), next to the reference CPU algorithm.
+
+  python bench.py --gpus N --steps K --warmup W            # this framework (one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+One "step" = one full pass of the synthetic circuit over the 2^n state, starting from |0..0>
+(set-basis + the whole gate schedule).  Workload at G GPUs (weak scaling): n = 30 + log2(G)
+qubits, f64, layer 0 = H on every qubit then depth-40 layers of random {H,T,CNOT}
+(generator G of SURVEY.md section 8d, seed 0x5EED0002): BASELINE.json's "N=30 random circuit"
+with configs[1]'s gate set; at 8 GPUs n = 33 = configs[4]'s size.
+Rank 0 prints ONE JSON line.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "gate_applications_per_second"
+UNIT = "gate-apps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-local", type=int, default=30, help="qubits per GPU (default 30: 16 GiB f64 shard)")
+    ap.add_argument("--depth", type=int, default=40)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--gate-set", default="H,T,CNOT")
+    ap.add_argument("--no-fusion", action="store_true", help="one kernel sweep per gate")
+    ap.add_argument("--no-extras", action="store_true", help="skip the unfused / per-kernel / CPU side measurements")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = sorted(sm)[len(sm) // 4:] if sm else []  # drop the idle tail of the samples
+        return {"sm_mhz": (float(np.median(busy)) if busy else None), "sm_max_mhz": mx,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_workload(args, world):
+    from rustqip_b200 import circuits
+    g = (world - 1).bit_length()
+    n = args.n_local + g
+    ops = circuits.random_circuit(n, args.depth, 0x5EED0002, args.gate_set)
+    name = "N=%d %s depth-%d random {%s} from |0>, layer 0 = H^n (SURVEY 8d generator, seed 0x5EED0002)" % (
+        n, args.dtype, args.depth, args.gate_set)
+    return n, ops, name
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm (oracle port, OpenMP over output rows)
+# ------------------------------------------------------------------------------------------
+def cpu_sample(n, ops, dtype, budget_s, max_gates=None):
+    """Run the first gates of the workload through the reference-faithful CPU port
+    (out-of-place apply_op_overwrite, all 2^n rows per gate) for about budget_s seconds."""
+    from oracle import qip_oracle as qo
+    avail = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_AVPHYS_PAGES")
+    amp = np.dtype(dtype).itemsize
+    n_run = n
+    while 2 * (amp << n_run) > 0.6 * avail and n_run > 20:
+        n_run -= 1
+    # index remap when the host cannot hold 2 x 2^n amplitudes: keep the low n_run qubits' gates
+    sample_ops = [op for op in ops if all(q >= n - n_run for q in op.indices())]
+    if n_run != n:
+        from rustqip_b200.ops import MatrixOp
+        shifted = []
+        for op in sample_ops:
+            def shift(o):
+                c = MatrixOp(o.kind, [q - (n - n_run) for q in o.indices()], data=o.data, rows=o.rows,
+                             n_control=o.n_control, inner=shift(o.inner) if o.inner is not None else None,
+                             swap_n=o.swap_n)
+                return c
+            shifted.append(shift(op))
+        sample_ops = shifted
+    state = np.zeros(1 << n_run, dtype=dtype)
+    arena = np.zeros_like(state)
+    state[0] = 1
+    # touch pages (first-touch cost is not part of the gate loop)
+    qo.apply_op_overwrite(n_run, sample_ops[0], state, arena)
+    state, arena = arena, state
+    done, t0 = 0, time.perf_counter()
+    for op in sample_ops[1:]:
+        qo.apply_op_overwrite(n_run, op, state, arena)
+        state, arena = arena, state
+        done += 1
+        if time.perf_counter() - t0 > budget_s or (max_gates and done >= max_gates):
+            break
+    dt = time.perf_counter() - t0
+    scale = float(1 << (n - n_run))  # cost per gate is linear in 2^n
+    gps = done / dt / scale
+    sample = "first %d gates of the workload after 1 warm-up gate, %.1f s, n=%d%s" % (
+        done, dt, n_run, "" if n_run == n else " (host RAM holds 2x2^%d only: scaled by 2^-%d, extrapolated)" % (n_run, n - n_run))
+    return gps, qo.max_threads(), sample, done
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    dtype = np.complex128 if args.dtype == "f64" else np.complex64
+    n, ops, name = build_workload(args, max(world, args.gpus))
+    vals = []
+    sample = ""
+    cores = 1
+    per_step = max(5.0, min(30.0, 120.0 / max(1, args.steps + args.warmup)))
+    for i in range(args.warmup + args.steps):
+        gps, cores, sample, done = cpu_sample(n, ops, dtype, per_step)
+        if i >= args.warmup:
+            vals.append(gps)
+    v = float(np.mean(vals))
+    amp = np.dtype(dtype).itemsize
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * len(ops) / v,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+        "data": "synthetic", "config": {"workload": name, "gates_per_step": len(ops)},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "each step: " + sample + "; oracle/qip_oracle.c = C restatement of "
+                                   "apply_op_overwrite (Rust reference cannot be built here), OpenMP static over rows"},
+        "effective_GBps": v * 2 * amp * (1 << n) / 1e9,
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# this framework
+# ------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from rustqip_b200 import _lib, gates
+    from rustqip_b200._abi import marshal_ops, prec_of
+    from rustqip_b200.state import Context, State
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun (one rank per GPU)" % args.gpus)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    dtype = np.complex128 if args.dtype == "f64" else np.complex64
+    amp = np.dtype(dtype).itemsize
+    n, ops, name = build_workload(args, world)
+    ctx = Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=torch.device("cuda", local_rank))
+    st = State(n, dtype, ctx, rank=rank, world_size=world)
+    if world > 1:
+        a, f = st.ipc_export()
+        ta = torch.tensor(list(a), dtype=torch.uint8, device="cuda")
+        tf = torch.tensor(list(f), dtype=torch.uint8, device="cuda")
+        ga = [torch.empty_like(ta) for _ in range(world)]
+        gf = [torch.empty_like(tf) for _ in range(world)]
+        dist.all_gather(ga, ta)
+        dist.all_gather(gf, tf)
+        st.ipc_import(b"".join(bytes(x.cpu().tolist()) for x in ga), b"".join(bytes(x.cpu().tolist()) for x in gf))
+    arr, keep = marshal_ops(ops, st.prec)
+    sched_bytes = sum(k.nbytes for k in keep if isinstance(k, np.ndarray)) + C.sizeof(arr)
+    fusion = not args.no_fusion
+
+    def step(fus=fusion):
+        st.set_basis(0)
+        st.apply_marshalled(arr, len(ops), fus)
+
+    def sync_all():
+        st.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, reps):
+        """device time of `reps` calls on the library's stream, max over ranks (ms)."""
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        st.sync()
+        e1.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        sync_all()
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.kernel_launches()
+    ms = timed(step, args.steps)
+    launches = ctx.kernel_launches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    gates_total = len(ops)
+    value = gates_total / (ms_per_step / 1e3)
+    bytes_alg_gate = 2.0 * amp * (1 << n)  # whole job: read + write every amplitude once per gate
+    peak, peak_src = peaks()
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": name, "gates_per_step": gates_total, "fusion": fusion,
+                   "state_bytes_per_gpu": amp << st.n if world == 1 else amp * st.local_len,
+                   "l2_policy": "state (>= 1 GiB per GPU) is far larger than the 126 MB L2; no flush needed",
+                   "parallelism": "state sharded by the top log2(G) index bits, NVLink P2P qubit migration" if world > 1 else "single GPU"},
+        "effective_state_GBps": value * bytes_alg_gate / 1e9,
+        "effective_frac_of_hbm_peak": value * bytes_alg_gate / 1e9 / (peak * world),
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+
+    if not args.no_extras:
+        extras = {}
+        # (a) unfused schedule: one sweep per gate, as the reference's per-entry loop
+        if fusion:
+            step(False)
+            ms_u = timed(lambda: step(False), 1)
+            extras["unfused"] = {"ms_per_step": ms_u, "gate_apps_per_s": gates_total / (ms_u / 1e3),
+                                 "effective_state_GBps": gates_total / (ms_u / 1e3) * bytes_alg_gate / 1e9}
+        # (b) dominant per-gate kernels, timed alone (CUDA events on the launch stream)
+        local_bytes = 2.0 * amp * st.local_len
+        kern = {}
+        g = (world - 1).bit_length()
+        probes = {"dense1_H_mid_bit": gates.h(g + (n - g) // 2), "dense1_H_bit0": gates.h(n - 1),
+                  "dense1_H_bit5": gates.h(n - 6), "dense1_H_top_local_bit": gates.h(g),
+                  "diag_T_mid_bit": gates.t(g + (n - g) // 2), "flip_CNOT": gates.cnot(g + 3, g + (n - g) // 2)}
+        for pname, op in probes.items():
+            parr, pkeep = marshal_ops([op], st.prec)
+            reps = 10
+            st.apply_marshalled(parr, 1, False)
+            pms = timed(lambda: st.apply_marshalled(parr, 1, False), reps) / reps
+            kern[pname] = {"ms": pms, "alg_GBps": local_bytes / (pms / 1e3) / 1e9,
+                           "frac_of_peak": local_bytes / (pms / 1e3) / 1e9 / peak}
+        extras["kernels_alone"] = kern
+        dom = kern["dense1_H_mid_bit"]
+        line["roofline"] = {"bound": "hbm", "kernel": "k_dense<double,1,1> (1-qubit dense gate, mid target bit)",
+                            "achieved": dom["alg_GBps"], "peak": peak, "unit": "GB/s", "frac": dom["frac_of_peak"],
+                            "peak_source": peak_src, "traffic": None,
+                            "algorithmic_bytes_per_launch": local_bytes, "avg_launch_ms": dom["ms"]}
+        line["extras"] = extras
+
+    # end to end through the reference-facing call: LocalBuilder::calculate_state_with_init
+    # == qipb200_calculate_state (alloc, |0>, schedule, D2H of all amplitudes into pinned host memory)
+    if world == 1:
+        st.free()
+        host = torch.empty((1 << n) * (2 if True else 1), dtype=torch.float64 if args.dtype == "f64" else torch.float32,
+                           pin_memory=True)
+        L = _lib.lib()
+        flags = _lib.SCHED_DEFAULT if fusion else _lib.SCHED_NO_FUSION
+
+        def e2e_once():
+            t0 = time.perf_counter()
+            rc = L.qipb200_calculate_state(ctx.handle, st.prec, n, 0, arr, len(ops), flags, C.c_void_p(host.data_ptr()))
+            _lib.check(rc, ctx.handle)
+            return time.perf_counter() - t0
+
+        e2e_once()
+        reps = max(1, min(args.steps, 3))
+        dt = sum(e2e_once() for _ in range(reps)) / reps
+        line["e2e"] = {"value": gates_total / dt, "unit": UNIT, "h2d_bytes_per_step": int(sched_bytes),
+                       "d2h_bytes_per_step": int(amp << n), "ms_per_step": dt * 1e3,
+                       "api": "qipb200_calculate_state (alloc + |0> + schedule + D2H of 2^n amplitudes to pinned host memory), host wall clock"}
+        nrm = float(torch.sum(host[: 1 << 20] ** 2).item())  # touch the result
+        line["e2e"]["checked_norm_prefix"] = nrm
+    else:
+        # sharded: each rank downloads its shard through the same C-ABI calls
+        host = torch.empty(st.local_len * 2, dtype=torch.float64 if args.dtype == "f64" else torch.float32, pin_memory=True)
+
+        def e2e_once():
+            sync_all()
+            t0 = time.perf_counter()
+            step()
+            st.download_ptr(host.data_ptr(), st.local_len)
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        e2e_once()
+        dt = e2e_once()
+        line["e2e"] = {"value": gates_total / dt, "unit": UNIT, "h2d_bytes_per_step": int(sched_bytes),
+                       "d2h_bytes_per_step": int(amp * st.local_len * world), "ms_per_step": dt * 1e3,
+                       "api": "state_set_basis + state_apply_schedule + state_download per rank (C ABI), host wall clock, max over ranks"}
+        line["exchange_bytes_per_rank_total"] = st.exchange_bytes()
+        st.free()
+
+    # CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            gps, cores, sample, done = cpu_sample(n, ops, dtype, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": gps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        except Exception as e:  # pragma: no cover
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

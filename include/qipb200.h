@@ -68,6 +68,10 @@ void qipb200_shutdown(qipb200_ctx *ctx);
  * failing call on this thread that had no ctx yet).  Never NULL. */
 const char *qipb200_last_error(const qipb200_ctx *ctx);
 
+/* The CUDA stream (a `cudaStream_t`) every kernel of `ctx` is launched on, so that a
+ * caller can bracket work with its own CUDA events. */
+int qipb200_stream_handle(const qipb200_ctx *ctx, void **stream);
+
 /* Number of this library's kernels launched through `ctx` so far. */
 uint64_t qipb200_kernel_launches(const qipb200_ctx *ctx);
 

@@ -129,6 +129,12 @@ extern "C" const char *qipb200_last_error(const qipb200_ctx *ctx) {
   return ctx ? ctx->err.c_str() : g_tls_err.c_str();
 }
 
+extern "C" int qipb200_stream_handle(const qipb200_ctx *ctx, void **stream) {
+  if (!ctx || !stream) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "stream_handle: NULL argument");
+  *stream = (void *)ctx->stream;
+  return QIPB200_OK;
+}
+
 extern "C" uint64_t qipb200_kernel_launches(const qipb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int qipb200_validate_op(const qipb200_ctx *ctx, qip_prec prec, uint32_t n_qubits, const qip_op *op) {

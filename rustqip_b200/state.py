@@ -33,6 +33,12 @@ class Context:
     def handle(self):
         return self._h
 
+    def stream_handle(self) -> int:
+        """Raw cudaStream_t of this context (for CUDA-event timing by the caller)."""
+        sp = C.c_void_p()
+        _lib.check(_lib.lib().qipb200_stream_handle(self._h, C.byref(sp)), self._h)
+        return int(sp.value or 0)
+
     def kernel_launches(self) -> int:
         return int(_lib.lib().qipb200_kernel_launches(self._h))
 
