@@ -335,58 +335,74 @@ static void nondiag_bits(const FlatOp &f, std::vector<uint32_t> *out) {
   }
 }
 
-// Apply a compiled op whose non-diagonal targets are all local.  Rank bits may
-// still appear as controls (a rank applies the inner op or nothing) or as diagonal
-// bits (a rank picks its slice of the diagonal): no communication.
-int apply_flat_local(qipb200_state *s, const FlatOp &f_in) {
-  qipb200_ctx *ctx = s->ctx;
+// Restrict a compiled op (physical bits, non-diagonal targets all local) to this rank:
+// controls held by the rank index either vanish or switch the op off; diagonal bits held
+// by the rank index select a slice of the diagonal.  No communication.  *skip = true when
+// the op is the identity on this rank.
+int restrict_to_rank(const qipb200_state *s, const FlatOp &f_in, FlatOp *out, bool *skip) {
   const uint32_t nl = s->n_local;
   const uint64_t lo_mask = (nl >= 64) ? ~0ull : ((1ull << nl) - 1ull);
   const uint64_t rank_val = (uint64_t)s->rank << nl;
+  *skip = false;
+  *out = f_in;
+  if (f_in.cls == CLASS_IDENTITY) {
+    *skip = true;
+    return QIPB200_OK;
+  }
   const uint64_t hc = f_in.ctrl_mask & ~lo_mask;
-  if ((rank_val & hc) != hc) return QIPB200_OK;  // a control held by the rank index is 0 here
-  const uint64_t cm = f_in.ctrl_mask & lo_mask;
-  switch (f_in.cls) {
-    case CLASS_IDENTITY:
-      return QIPB200_OK;
-    case CLASS_DIAGONAL: {
-      std::vector<uint32_t> bits;
-      std::vector<cplx> d = f_in.diag;
-      // fix the rank-held diagonal bits to this rank's values (highest first keeps indices valid)
-      std::vector<uint32_t> all = f_in.diag_bits;
-      for (int i = (int)all.size() - 1; i >= 0; --i) {
-        if (all[i] < nl) continue;
-        const int v = (int)((rank_val >> all[i]) & 1ull);
-        std::vector<cplx> nd;
-        for (uint64_t u = 0; u < d.size(); ++u)
-          if ((int)((u >> i) & 1) == v) nd.push_back(d[u]);
-        d.swap(nd);
-        all.erase(all.begin() + i);
-      }
-      bits = all;
-      if (bits.size() > (size_t)kMaxDiagParamK) {
-        // wide diagonal: run it as a dense-diagonal through the row kernel (single GPU only)
-        break;
-      }
-      bool all_one = true;
-      for (size_t u = 0; u < d.size(); ++u)
-        if (!(d[u].real() == 1.0 && d[u].imag() == 0.0)) all_one = false;
-      if (all_one) return QIPB200_OK;
-      CU(ctx, launch_diag(s->prec, s->buf, nl, cm, bits, d, ctx->stream, &ctx->launches));
+  if ((rank_val & hc) != hc) {  // a control held by the rank index is 0 here
+    *skip = true;
+    return QIPB200_OK;
+  }
+  out->ctrl_mask = f_in.ctrl_mask & lo_mask;
+  if (f_in.cls == CLASS_DIAGONAL) {
+    std::vector<cplx> d = f_in.diag;
+    std::vector<uint32_t> all = f_in.diag_bits;
+    for (int i = (int)all.size() - 1; i >= 0; --i) {  // highest first keeps indices valid
+      if (all[i] < nl) continue;
+      const int v = (int)((rank_val >> all[i]) & 1ull);
+      std::vector<cplx> nd;
+      for (uint64_t u = 0; u < d.size(); ++u)
+        if ((int)((u >> i) & 1) == v) nd.push_back(d[u]);
+      d.swap(nd);
+      all.erase(all.begin() + i);
+    }
+    bool all_one = true;
+    for (size_t u = 0; u < d.size(); ++u)
+      if (!(d[u].real() == 1.0 && d[u].imag() == 0.0)) all_one = false;
+    if (all_one) {
+      *skip = true;
       return QIPB200_OK;
     }
+    out->diag_bits = all;
+    out->diag = d;
+  }
+  return QIPB200_OK;
+}
+
+// Launch the per-gate kernel of an op whose bits are all local (after restrict_to_rank).
+int launch_local_op(qipb200_state *s, const FlatOp &f) {
+  qipb200_ctx *ctx = s->ctx;
+  const uint32_t nl = s->n_local;
+  const uint64_t cm = f.ctrl_mask;
+  switch (f.cls) {
+    case CLASS_IDENTITY:
+      return QIPB200_OK;
+    case CLASS_DIAGONAL:
+      if (f.diag_bits.size() > (size_t)kMaxDiagParamK || __builtin_popcountll(cm) > kMaxIns) break;
+      CU(ctx, launch_diag(s->prec, s->buf, nl, cm, f.diag_bits, f.diag, ctx->stream, &ctx->launches));
+      return QIPB200_OK;
     case CLASS_FLIP:
-      CU(ctx, launch_flip(s->prec, s->buf, nl, cm, f_in.tgt_sorted[0], ctx->stream, &ctx->launches));
+      CU(ctx, launch_flip(s->prec, s->buf, nl, cm, f.tgt_sorted[0], ctx->stream, &ctx->launches));
       return QIPB200_OK;
     case CLASS_BITSWAP:
-      for (size_t i = 0; i < f_in.swaps.size(); ++i)
-        CU(ctx, launch_bitswap(s->prec, s->buf, nl, cm, f_in.swaps[i].first, f_in.swaps[i].second, ctx->stream,
+      for (size_t i = 0; i < f.swaps.size(); ++i)
+        CU(ctx, launch_bitswap(s->prec, s->buf, nl, cm, f.swaps[i].first, f.swaps[i].second, ctx->stream,
                                &ctx->launches));
       return QIPB200_OK;
     case CLASS_DENSE:
-      if (f_in.tgt_sorted.size() <= (size_t)kMaxRegK && __builtin_popcountll(cm) + f_in.tgt_sorted.size() <= (size_t)kMaxIns) {
-        FlatOp f = f_in;
-        f.ctrl_mask = cm;
+      if (f.tgt_sorted.size() <= (size_t)kMaxRegK &&
+          __builtin_popcountll(cm) + f.tgt_sorted.size() <= (size_t)kMaxIns) {
         CU(ctx, launch_dense(s->prec, s->buf, nl, f, ctx->stream, &ctx->launches));
         return QIPB200_OK;
       }
@@ -403,10 +419,21 @@ int apply_flat_local(qipb200_state *s, const FlatOp &f_in) {
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(scratch arena)");
   }
   const uint64_t len = 1ull << nl;
-  CU(ctx, launch_gather(s->prec, f_in, s->n, s->buf, len, 0, s->scratch, len, 0, false, ctx->stream, &ctx->launches));
+  CU(ctx, launch_gather(s->prec, f, s->n, s->buf, len, 0, s->scratch, len, 0, false, ctx->stream, &ctx->launches));
   std::swap(s->buf, s->scratch);  // `Ok((arena, state, ..))`, builder.rs:514
   return QIPB200_OK;
 }
+
+int apply_flat_local(qipb200_state *s, const FlatOp &f_in) {
+  FlatOp f;
+  bool skip = false;
+  int st = restrict_to_rank(s, f_in, &f, &skip);
+  if (st != QIPB200_OK || skip) return st;
+  return launch_local_op(s, f);
+}
+
+int report_error(qipb200_state *s, int status, const std::string &msg) { return set_err(s->ctx, status, msg); }
+int report_cuda_error(qipb200_state *s, cudaError_t e, const char *what) { return cuda_fail(s->ctx, e, what); }
 
 // Compile `op` against the current layout and migrate rank-held target bits to
 // local bits if needed.  `next_use` (optional, n entries indexed by logical bit):

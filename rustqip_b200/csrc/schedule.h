@@ -2,7 +2,10 @@
 #pragma once
 
 #include <cstddef>
+#include <cuda_runtime.h>
+
 #include <cstdint>
+#include <string>
 
 #include "opcompile.h"
 #include "state.h"
@@ -11,6 +14,10 @@ namespace qipb200 {
 
 // api.cu
 int apply_flat_local(qipb200_state *s, const FlatOp &f);
+int restrict_to_rank(const qipb200_state *s, const FlatOp &f_in, FlatOp *out, bool *skip);
+int launch_local_op(qipb200_state *s, const FlatOp &f);
+int report_error(qipb200_state *s, int status, const std::string &msg);
+int report_cuda_error(qipb200_state *s, cudaError_t e, const char *what);
 int compile_and_localize(qipb200_state *s, const qip_op *op, FlatOp *f, const uint64_t *next_use);
 
 // schedule.cu: state <- ops[n-1] ... ops[0] state

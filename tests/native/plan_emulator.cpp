@@ -1,0 +1,195 @@
+// plan_emulator.cpp -- TEST INFRASTRUCTURE: executes the fusion planner's output on the CPU
+// exactly as the tile kernel would (same serialised blob, same micro-op semantics), so the
+// host logic (planner.cpp, opcompile.cpp, serialisation) is validated without a GPU.
+// Built by tests/test_planner_cpu.py into tests/native/_build/; never part of libqipb200.
+#include <complex>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../rustqip_b200/csrc/opcompile.h"
+#include "../../rustqip_b200/csrc/tile.cuh"
+
+using namespace qipb200;
+typedef std::complex<double> cd;
+
+// reference-semantics application of one compiled op on the full state (gather form)
+static void apply_single(const FlatOp &f, uint32_t n, std::vector<cd> &psi) {
+  const uint64_t N = 1ull << n;
+  std::vector<cd> out(N);
+  const uint64_t thr = f.nc ? ((1ull << f.k) - (1ull << f.kop)) : 0;
+  for (uint64_t row = 0; row < N; ++row) {
+    uint64_t matrow = 0;
+    for (uint32_t j = 0; j < f.k; ++j) matrow |= ((row >> f.idx_bits[j]) & 1ull) << (f.k - 1 - j);
+    auto full = [&](uint64_t col) {
+      uint64_t c = row;
+      for (uint32_t j = 0; j < f.k; ++j) {
+        c &= ~(1ull << f.idx_bits[j]);
+        c |= ((col >> (f.k - 1 - j)) & 1ull) << f.idx_bits[j];
+      }
+      return c;
+    };
+    cd acc(0, 0);
+    if (matrow < thr) {
+      acc = psi[row];
+    } else {
+      const uint64_t r = matrow - thr, side = 1ull << f.kop;
+      if (f.base_kind == QIP_OP_SWAP) {
+        const uint32_t half = f.kop >> 1;
+        const uint64_t lm = ~(~0ull << half);
+        acc = psi[full((((r & lm) << half) + (r >> half)) + thr)];
+      } else if (f.has_dense) {
+        for (uint64_t c = 0; c < side; ++c) acc += f.dense[r * side + c] * psi[full(c + thr)];
+      } else {
+        for (uint64_t e = f.sp_rowptr[r]; e < f.sp_rowptr[r + 1]; ++e) acc += f.sp_val[e] * psi[full(f.sp_col[e] + thr)];
+      }
+    }
+    out[row] = acc;
+  }
+  psi.swap(out);
+}
+
+template <typename R>
+static void run_pass_blob(const std::vector<unsigned char> &blob, uint32_t n, std::vector<cd> &psi) {
+  PassHeader h;
+  memcpy(&h, blob.data(), sizeof(h));
+  const uint32_t T = h.T, L = h.L, m = h.m;
+  const uint64_t tiles = 1ull << (n - T);
+  std::vector<cd> tile(1ull << T);
+  for (uint64_t tau = 0; tau < tiles; ++tau) {
+    uint64_t base = tau << L;  // expand: insert zeros at the high tile bits (ascending)
+    for (uint32_t i = 0; i < m; ++i) {
+      const uint32_t p = h.hi_pos[i];
+      base = ((base >> p) << (p + 1)) | (base & ((1ull << p) - 1));
+    }
+    for (uint64_t t = 0; t < (1ull << T); ++t) tile[t] = psi[base + h.chunk_off[t >> L] + (t & ((1ull << L) - 1))];
+    const unsigned char *rp = blob.data() + sizeof(PassHeader);
+    for (uint32_t oi = 0; oi < h.n_ops; ++oi) {
+      MicroOp mo;
+      memcpy(&mo, rp, sizeof(mo));
+      const unsigned char *data = rp + sizeof(mo);
+      rp += sizeof(mo) + mo.data_bytes;
+      if ((base & mo.gmask) != mo.gmask) continue;
+      if (mo.kind == MK_DIAG) {
+        const DiagTerm<R> *terms = reinterpret_cast<const DiagTerm<R> *>(data);
+        for (uint64_t t = 0; t < (1ull << T); ++t)
+          for (uint32_t k = 0; k < mo.nterms; ++k)
+            if ((base & terms[k].gmask) == terms[k].gval && ((uint32_t)t & terms[k].lmask) == terms[k].lval)
+              tile[t] *= cd(terms[k].re, terms[k].im);
+        continue;
+      }
+      const uint64_t groups = 1ull << mo.groups_log2;
+      for (uint64_t g = 0; g < groups; ++g) {
+        uint64_t t0 = g;
+        for (uint32_t i = 0; i < mo.ins_n; ++i) {
+          const uint32_t p = mo.ins_pos[i];
+          t0 = ((t0 >> p) << (p + 1)) | (t0 & ((1ull << p) - 1));
+        }
+        t0 |= mo.lor_mask;
+        if (mo.kind == MK_EXCH) {
+          std::swap(tile[t0 + mo.off[0]], tile[t0 + mo.off[1]]);
+        } else {
+          const uint32_t S = 1u << mo.k;
+          const R *mat = reinterpret_cast<const R *>(data);
+          cd in[8], out[8];
+          for (uint32_t u = 0; u < S; ++u) in[u] = tile[t0 + mo.off[u]];
+          for (uint32_t u = 0; u < S; ++u) {
+            cd a(0, 0);
+            for (uint32_t v = 0; v < S; ++v) a += cd(mat[2 * (u * S + v)], mat[2 * (u * S + v) + 1]) * in[v];
+            out[u] = a;
+          }
+          for (uint32_t u = 0; u < S; ++u) tile[t0 + mo.off[u]] = out[u];
+        }
+      }
+    }
+    for (uint64_t t = 0; t < (1ull << T); ++t) psi[base + h.chunk_off[t >> L] + (t & ((1ull << L) - 1))] = tile[t];
+  }
+}
+
+extern "C" int emul_schedule(int prec, uint32_t n, const qip_op *ops, size_t n_ops, double *state, uint32_t T,
+                             uint32_t L, int fuse_blocks, uint32_t max_k, uint64_t *stats, char *errbuf,
+                             size_t errlen) {
+  std::vector<FlatOp> flat(n_ops);
+  for (size_t i = 0; i < n_ops; ++i) {
+    std::string err;
+    int st = compile_op(&ops[i], (qip_prec)prec, n, &flat[i], &err);
+    if (st != QIPB200_OK) {
+      if (errbuf && errlen) snprintf(errbuf, errlen, "%s", err.c_str());
+      return st;
+    }
+  }
+  PlanConfig cfg = default_plan_config((qip_prec)prec, n);
+  if (T) cfg.T = T;
+  if (L) cfg.L = L;
+  cfg.fuse_blocks = fuse_blocks != 0;
+  if (max_k) cfg.max_block_k = max_k;
+  std::vector<PlanStep> steps;
+  plan_passes(flat, n, (qip_prec)prec, cfg, &steps);
+  std::vector<cd> psi(1ull << n);
+  for (uint64_t i = 0; i < (1ull << n); ++i) psi[i] = cd(state[2 * i], state[2 * i + 1]);
+  uint64_t n_pass = 0, n_single = 0, n_micro = 0, n_gates_in_pass = 0;
+  for (size_t s = 0; s < steps.size(); ++s) {
+    if (steps[s].is_pass) {
+      std::vector<unsigned char> blob;
+      serialise_pass(steps[s].pass, &blob);
+      if (prec == QIP_F32)
+        run_pass_blob<float>(blob, n, psi);
+      else
+        run_pass_blob<double>(blob, n, psi);
+      ++n_pass;
+      n_micro += steps[s].pass.ops.size();
+      n_gates_in_pass += steps[s].pass.n_gates;
+    } else {
+      apply_single(flat[steps[s].op_index], n, psi);
+      ++n_single;
+    }
+  }
+  for (uint64_t i = 0; i < (1ull << n); ++i) {
+    state[2 * i] = psi[i].real();
+    state[2 * i + 1] = psi[i].imag();
+  }
+  if (stats) {
+    stats[0] = n_pass;
+    stats[1] = n_single;
+    stats[2] = n_micro;
+    stats[3] = n_gates_in_pass;
+  }
+  return 0;
+}
+
+// plan only (no amplitudes): pass / single-step counts for big circuits
+extern "C" int emul_plan_stats(int prec, uint32_t n, const qip_op *ops, size_t n_ops, uint32_t T, uint32_t L,
+                               int fuse_blocks, uint32_t max_k, uint64_t *stats) {
+  std::vector<FlatOp> flat(n_ops);
+  for (size_t i = 0; i < n_ops; ++i) {
+    std::string err;
+    int st = compile_op(&ops[i], (qip_prec)prec, n, &flat[i], &err);
+    if (st != QIPB200_OK) return st;
+  }
+  PlanConfig cfg = default_plan_config((qip_prec)prec, n);
+  if (T) cfg.T = T;
+  if (L) cfg.L = L;
+  cfg.fuse_blocks = fuse_blocks != 0;
+  if (max_k) cfg.max_block_k = max_k;
+  std::vector<PlanStep> steps;
+  plan_passes(flat, n, (qip_prec)prec, cfg, &steps);
+  uint64_t n_pass = 0, n_single = 0, n_micro = 0, n_gates_in_pass = 0, dense_k[4] = {0, 0, 0, 0}, diag_terms = 0, exch = 0;
+  for (size_t s = 0; s < steps.size(); ++s) {
+    if (!steps[s].is_pass) {
+      ++n_single;
+      continue;
+    }
+    ++n_pass;
+    n_micro += steps[s].pass.ops.size();
+    n_gates_in_pass += steps[s].pass.n_gates;
+    for (size_t i = 0; i < steps[s].pass.ops.size(); ++i) {
+      const MicroOp &mo = steps[s].pass.ops[i].h;
+      if (mo.kind == MK_DENSE) dense_k[mo.k]++;
+      else if (mo.kind == MK_DIAG) diag_terms += mo.nterms;
+      else exch++;
+    }
+  }
+  stats[0] = n_pass; stats[1] = n_single; stats[2] = n_micro; stats[3] = n_gates_in_pass;
+  stats[4] = dense_k[1]; stats[5] = dense_k[2]; stats[6] = dense_k[3]; stats[7] = diag_terms; stats[8] = exch;
+  return 0;
+}

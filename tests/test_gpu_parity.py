@@ -380,3 +380,75 @@ def test_measure_state_reference_kat(ctx):
             assert np.allclose(st.download(), expect, atol=1e-10)
         st.upload(np.array([.5, .5, .5, .5], dtype=np.complex128))
         assert list(st.measure_probs([1])) == [0.5, 0.5]
+
+
+# ---------------------------------------------------------------------------------------
+# 5. fused tile passes with several tiles / high tile bits (n > T)
+# ---------------------------------------------------------------------------------------
+def _mixed_circuit(n, count, seed):
+    rng = np.random.default_rng(seed)
+    ops = []
+    for _ in range(count):
+        q = [int(x) for x in rng.choice(n, 4, replace=False)]
+        kind = int(rng.integers(14))
+        ops.append([
+            lambda: gates.h(q[0]), lambda: gates.t(q[0]), lambda: gates.x(q[0]), lambda: gates.cnot(q[0], q[1]),
+            lambda: gates.cz(q[0], q[1]), lambda: gates.cphase(q[0], q[1], 0.37), lambda: gates.rz(q[0], 1.1),
+            lambda: make_swap_op([q[0]], [q[1]]), lambda: gates.toffoli(q[0], q[1], q[2]),
+            lambda: make_matrix_op([q[0], q[1]], rand_unitary(2, rng).reshape(-1)),
+            lambda: make_matrix_op([q[2], q[0], q[1]], rand_unitary(3, rng).reshape(-1)),
+            lambda: make_control_op([q[0]], make_matrix_op([q[1]], rand_unitary(1, rng).reshape(-1))),
+            lambda: make_control_op([q[3]], make_swap_op([q[0]], [q[1]])),
+            lambda: make_matrix_op([q[1], q[3]], np.diag(np.exp(1j * rng.standard_normal(4))).reshape(-1)),
+        ][kind]())
+    return ops
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("n", [13, 15, 17])
+def test_fused_multi_tile(ctx, dtype, n):
+    ops = _mixed_circuit(n, 150, 4000 + n)
+    psi = rand_state(n, dtype, 12)
+    want = qo.run_pipeline(n, ops, state=psi, dtype=dtype)
+    l0 = ctx.kernel_launches()
+    got = gpu_state_apply(ctx, n, ops, psi, fusion=True)
+    fused_launches = ctx.kernel_launches() - l0
+    assert_close(got, want, dtype)
+    assert fused_launches < len(ops) // 2  # it really fused
+    got_unfused = gpu_state_apply(ctx, n, ops, psi, fusion=False)
+    assert_close(got_unfused, want, dtype)
+
+
+def test_fused_random_circuit_n20(ctx):
+    n = 20
+    ops = circuits.random_circuit(n, 12, 0x5EED0002, "H,T,CNOT") + circuits.random_circuit(n, 6, 0x5EED0005, "H,CZ,CNOT")
+    want = qo.run_pipeline(n, ops, 0, np.complex128)
+    with State(n, np.complex128, ctx) as st:
+        st.set_basis(0)
+        st.apply_schedule(ops, fusion=True)
+        got = st.download()
+        assert abs(st.norm2() - 1.0) < 1e-11
+    assert_close(got, want, np.complex128)
+
+
+def test_fused_qft_f32_n18(ctx):
+    n = 18
+    ops = circuits.qft(n)
+    psi = circuits.random_state(n, 0x5EED0003, np.complex64)
+    want = qo.run_pipeline(n, ops, state=psi, dtype=np.complex64)
+    got = gpu_state_apply(ctx, n, ops, psi, fusion=True)
+    assert_close(got, want, np.complex64)
+
+
+def test_fused_permutation_exact_multi_tile(ctx):
+    n = 16
+    rng = np.random.default_rng(17)
+    ops = []
+    for _ in range(200):
+        a, b, c = [int(x) for x in rng.choice(n, 3, replace=False)]
+        ops.append([gates.x(a), gates.cnot(a, b), gates.toffoli(a, b, c), make_swap_op([a], [b])][int(rng.integers(4))])
+    for dtype in (np.complex128, np.complex64):
+        psi = rand_state(n, dtype, 13)
+        want = qo.run_pipeline(n, ops, state=psi, dtype=dtype)
+        got = gpu_state_apply(ctx, n, ops, psi, fusion=True)
+        assert np.array_equal(got, want)

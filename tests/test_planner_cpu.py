@@ -1,0 +1,146 @@
+"""Host logic of the fusion planner (rustqip_b200/csrc/planner.cpp), validated without a GPU:
+the planner's serialised passes are executed by a CPU emulator of the tile kernel
+(tests/native/plan_emulator.cpp) and compared with the oracle's per-entry fold."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import qip_oracle as qo
+from rustqip_b200 import circuits, gates
+from rustqip_b200._abi import QipOp, marshal_ops, prec_of
+from rustqip_b200.ops import MatrixOp, make_control_op, make_matrix_op, make_swap_op
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SO = os.path.join(HERE, "native", "_build", "libplan_emul.so")
+SRCS = [os.path.join(HERE, "native", "plan_emulator.cpp"),
+        os.path.join(ROOT, "rustqip_b200", "csrc", "planner.cpp"),
+        os.path.join(ROOT, "rustqip_b200", "csrc", "opcompile.cpp")]
+HDRS = [os.path.join(ROOT, "rustqip_b200", "csrc", "tile.cuh"),
+        os.path.join(ROOT, "rustqip_b200", "csrc", "opcompile.h"),
+        os.path.join(ROOT, "include", "qip_op.h")]
+
+
+@pytest.fixture(scope="module")
+def emul():
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    stale = not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in SRCS + HDRS)
+    if stale:
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SO] + SRCS)
+    L = C.CDLL(SO)
+    L.emul_schedule.restype = C.c_int
+    L.emul_schedule.argtypes = [C.c_int, C.c_uint32, C.POINTER(QipOp), C.c_size_t, C.c_void_p, C.c_uint32,
+                                C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_char_p, C.c_size_t]
+    L.emul_plan_stats.restype = C.c_int
+    L.emul_plan_stats.argtypes = [C.c_int, C.c_uint32, C.POINTER(QipOp), C.c_size_t, C.c_uint32, C.c_uint32,
+                                  C.c_int, C.c_uint32, C.c_void_p]
+    return L
+
+
+def run_emul(L, n, ops, psi, dtype=np.complex128, T=0, Lo=0, fuse=True, max_k=3):
+    prec = prec_of(dtype)
+    arr, keep = marshal_ops(ops, prec)
+    st = np.ascontiguousarray(psi.astype(np.complex128))
+    stats = np.zeros(16, dtype=np.uint64)
+    err = C.create_string_buffer(256)
+    rc = L.emul_schedule(prec, n, arr, len(ops), st.ctypes.data, T, Lo, int(fuse), max_k, stats.ctypes.data, err, 256)
+    assert rc == 0, err.value
+    return st, stats
+
+
+def rand_state(n, seed):
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    return v / np.linalg.norm(v)
+
+
+def rand_unitary(k, rng):
+    a = rng.standard_normal((1 << k, 1 << k)) + 1j * rng.standard_normal((1 << k, 1 << k))
+    q, r = np.linalg.qr(a)
+    return q * (np.diag(r) / np.abs(np.diag(r)))
+
+
+def mixed_circuit(n, count, seed):
+    rng = np.random.default_rng(seed)
+    ops = []
+    for _ in range(count):
+        q = [int(x) for x in rng.choice(n, 4, replace=False)]
+        kind = int(rng.integers(14))
+        ops.append([
+            lambda: gates.h(q[0]), lambda: gates.t(q[0]), lambda: gates.x(q[0]), lambda: gates.cnot(q[0], q[1]),
+            lambda: gates.cz(q[0], q[1]), lambda: gates.cphase(q[0], q[1], 0.37), lambda: gates.rz(q[0], 1.1),
+            lambda: make_swap_op([q[0]], [q[1]]), lambda: gates.toffoli(q[0], q[1], q[2]),
+            lambda: make_matrix_op([q[0], q[1]], rand_unitary(2, rng).reshape(-1)),
+            lambda: make_matrix_op([q[2], q[0], q[1]], rand_unitary(3, rng).reshape(-1)),
+            lambda: make_control_op([q[0]], make_matrix_op([q[1]], rand_unitary(1, rng).reshape(-1))),
+            lambda: make_control_op([q[3]], make_swap_op([q[0]], [q[1]])),
+            lambda: make_matrix_op([q[1], q[3]], np.diag(np.exp(1j * rng.standard_normal(4))).reshape(-1)),
+        ][kind]())
+    return ops
+
+
+@pytest.mark.parametrize("n,T,Lo", [(8, 5, 2), (9, 6, 3), (10, 7, 2), (10, 10, 4), (7, 3, 1), (11, 8, 5)])
+@pytest.mark.parametrize("fuse", [True, False])
+def test_planner_matches_oracle_mixed(emul, n, T, Lo, fuse):
+    ops = mixed_circuit(n, 120, 1000 + n + T)
+    psi = rand_state(n, 5)
+    want = qo.run_pipeline(n, ops, state=psi)
+    got, stats = run_emul(emul, n, ops, psi, T=T, Lo=Lo, fuse=fuse)
+    assert np.max(np.abs(got - want)) < 1e-12
+    assert stats[0] > 0  # passes were actually produced
+
+
+def test_planner_random_and_qft(emul):
+    for n, T, Lo in [(10, 6, 3), (12, 8, 3)]:
+        ops = circuits.random_circuit(n, 8, 77, "H,T,CNOT") + circuits.random_circuit(n, 4, 78, "H,CZ,CNOT")
+        psi = rand_state(n, 6)
+        want = qo.run_pipeline(n, ops, state=psi)
+        got, stats = run_emul(emul, n, ops, psi, T=T, Lo=Lo)
+        assert np.max(np.abs(got - want)) < 1e-12
+        assert stats[0] + stats[1] < len(ops) / 3  # far fewer sweeps than gates
+    n = 10
+    ops = circuits.qft(n)
+    psi = rand_state(n, 7)
+    got, stats = run_emul(emul, n, ops, psi, T=7, Lo=3)
+    assert np.max(np.abs(got - qo.run_pipeline(n, ops, state=psi))) < 1e-12
+
+
+def test_planner_f32_data_path(emul):
+    n = 9
+    ops = mixed_circuit(n, 80, 99)
+    psi = rand_state(n, 8)
+    want = qo.run_pipeline(n, ops, state=psi)
+    got, _ = run_emul(emul, n, ops, psi, dtype=np.complex64, T=6, Lo=3)
+    assert np.max(np.abs(got - want)) < 5e-6  # matrices were rounded to f32
+
+
+def test_planner_permutations_exact(emul):
+    n = 10
+    rng = np.random.default_rng(3)
+    ops = []
+    for _ in range(150):
+        a, b, c = [int(x) for x in rng.choice(n, 3, replace=False)]
+        ops.append([gates.x(a), gates.cnot(a, b), gates.toffoli(a, b, c), make_swap_op([a], [b])][int(rng.integers(4))])
+    psi = rand_state(n, 9)
+    got, _ = run_emul(emul, n, ops, psi, T=6, Lo=2)
+    assert np.array_equal(got, qo.run_pipeline(n, ops, state=psi))
+
+
+def test_plan_stats_bench_circuits(emul):
+    """The bench workloads must fuse: report sweeps per circuit (also printed for DESIGN.md)."""
+    out = {}
+    for name, n, ops, dtype in [("n30_rand_HTCNOT_d40", 30, circuits.random_circuit(30, 40, 0x5EED0002), np.complex128),
+                                ("cfg2_n28", 28, circuits.config2(), np.complex128),
+                                ("cfg3_qft30_f32", 30, circuits.qft(30), np.complex64),
+                                ("cfg5_local_n30", 30, circuits.random_circuit(30, 30, 0x5EED0005, "H,CZ,CNOT"), np.complex128)]:
+        prec = prec_of(dtype)
+        arr, keep = marshal_ops(ops, prec)
+        stats = np.zeros(16, dtype=np.uint64)
+        assert emul.emul_plan_stats(prec, n, arr, len(ops), 0, 0, 1, 3, stats.ctypes.data) == 0
+        out[name] = (len(ops), [int(x) for x in stats[:9]])
+        sweeps = int(stats[0] + stats[1])
+        assert sweeps < len(ops) / 4, (name, sweeps)
+    print(out)
