@@ -10,6 +10,11 @@
 // block / X / Swap).  Two ops commute if on every shared bit both act diagonally.
 // A pass takes ops in program order, skipping an op only when it does not fit; an
 // op may overtake a skipped one only if the two commute by the rule above.
+//
+// Inside a pass, ops are grouped into SUPER-OPS: lists of elementary ops on <= 3
+// tile-local bits that one thread executes on 8 register-resident amplitudes.  Groups
+// on disjoint bit sets commute, so several stay open at once; an op whose bits span
+// groups merges them (if <= 3 bits in total) or closes them.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -21,6 +26,7 @@ namespace qipb200 {
 namespace {
 
 inline int popc(uint64_t x) { return __builtin_popcountll(x); }
+inline bool is_one(const cplx &c) { return c.real() == 1.0 && c.imag() == 0.0; }
 
 struct OpInfo {
   uint64_t nd = 0;        // bits acted on non-diagonally
@@ -28,9 +34,10 @@ struct OpInfo {
   uint64_t need_tile = 0; // bits that must be tile bits for the op to run in a pass
   bool tile_ok = false;
   double unfused_cost = 1.0;  // HBM sweeps of the per-gate kernel
+  uint32_t est_bytes = 0;     // upper bound of the descriptor bytes in a pass
 };
 
-OpInfo analyse(const FlatOp &f, const PlanConfig &cfg) {
+OpInfo analyse(const FlatOp &f) {
   OpInfo o;
   const int nctrl = popc(f.ctrl_mask);
   switch (f.cls) {
@@ -40,6 +47,7 @@ OpInfo analyse(const FlatOp &f, const PlanConfig &cfg) {
       o.need_tile = o.nd;
       o.tile_ok = f.tgt_sorted.size() <= 3 && f.tgt_sorted.size() + nctrl <= 6;
       o.unfused_cost = 1.0 / (1 << nctrl);
+      o.est_bytes = f.tgt_sorted.size() == 1 ? 256 : 128 + 128 + 1040;
       break;
     case CLASS_FLIP:
       o.nd = 1ull << f.tgt_sorted[0];
@@ -47,6 +55,7 @@ OpInfo analyse(const FlatOp &f, const PlanConfig &cfg) {
       o.need_tile = o.nd;
       o.tile_ok = nctrl + 1 <= 6;
       o.unfused_cost = 1.0 / (1 << nctrl);
+      o.est_bytes = 256;
       break;
     case CLASS_BITSWAP:
       for (size_t i = 0; i < f.swaps.size(); ++i) o.nd |= (1ull << f.swaps[i].first) | (1ull << f.swaps[i].second);
@@ -54,41 +63,37 @@ OpInfo analyse(const FlatOp &f, const PlanConfig &cfg) {
       o.need_tile = o.nd;
       o.tile_ok = nctrl + 2 <= 6 && f.swaps.size() <= 3;
       o.unfused_cost = 0.5 * f.swaps.size() / (1 << nctrl);
+      o.est_bytes = 256 * (uint32_t)f.swaps.size();
       break;
     case CLASS_DIAGONAL:
       o.dg = f.ctrl_mask;
       for (size_t i = 0; i < f.diag_bits.size(); ++i) o.dg |= 1ull << f.diag_bits[i];
       o.tile_ok = f.diag_bits.size() <= 3;  // expands to <= 8 masked-phase terms
       o.unfused_cost = 1.0 / (1 << nctrl);
+      o.est_bytes = 256 * (1u << f.diag_bits.size());
       break;
     default:  // CLASS_GENERAL (CLASS_IDENTITY never reaches here)
       for (uint32_t j = 0; j < f.k; ++j) o.nd |= 1ull << f.idx_bits[j];
       o.tile_ok = false;
       break;
   }
-  (void)cfg;
   return o;
 }
 
-// ---- small dense linear algebra on the host (block fusion) ----------------------------
-struct Block {
-  std::vector<uint32_t> bits;  // tile-local bit positions, ascending; sub-index bit i <-> bits[i]
-  std::vector<cplx> m;         // 2^k x 2^k row-major
-};
-
+// ---- small dense linear algebra on the host ------------------------------------------
 // Embed a matrix on `from` bits (ascending) into the sub-space of `to` bits (ascending, superset).
 std::vector<cplx> embed(const std::vector<cplx> &m, const std::vector<uint32_t> &from,
                         const std::vector<uint32_t> &to) {
   const size_t kf = from.size(), kt = to.size();
   std::vector<int> pos(kf);
   for (size_t i = 0; i < kf; ++i) pos[i] = (int)(std::find(to.begin(), to.end(), from[i]) - to.begin());
-  const size_t St = 1u << kt, Sf = 1u << kf;
+  const size_t St = (size_t)1 << kt, Sf = (size_t)1 << kf;
   std::vector<cplx> out(St * St, cplx(0, 0));
   uint32_t from_mask = 0;
   for (size_t i = 0; i < kf; ++i) from_mask |= 1u << pos[i];
   for (size_t r = 0; r < St; ++r)
     for (size_t c = 0; c < St; ++c) {
-      if ((r & ~from_mask) != (c & ~from_mask)) continue;  // identity on the other bits
+      if ((r & ~(size_t)from_mask) != (c & ~(size_t)from_mask)) continue;  // identity on the other bits
       size_t rs = 0, cs = 0;
       for (size_t i = 0; i < kf; ++i) {
         rs |= ((r >> pos[i]) & 1) << i;
@@ -110,352 +115,450 @@ std::vector<cplx> matmul(const std::vector<cplx> &a, const std::vector<cplx> &b,
   return out;
 }
 
-// Dense matrix (on the op's own target+local-control bits) of an op whose every bit is tile-local.
-// Returns false if the op cannot be expressed as a small host matrix (e.g. it has non-tile controls).
-struct LocalOp {
-  // a compiled op translated to tile-local coordinates
-  const FlatOp *f = nullptr;
-  uint64_t gmask = 0;                   // controls on non-tile bits
-  uint32_t lctrl = 0;                   // controls on tile-local bits
-  std::vector<uint32_t> ltgt;           // dense/flip targets (tile-local, ascending)
-  std::vector<std::pair<uint32_t, uint32_t>> lswaps;
+// ---- host-side elementary op (tile-local bit numbers) ----------------------------------
+struct HElem {
+  int type = E_DENSE1;
+  uint32_t lb_j = 0, lb_k = 0;   // target bit / swap pair (tile-local)
+  uint32_t lctrl = 0;            // tile-local control mask
+  uint32_t lmask = 0, lval = 0;  // PHASE condition (tile-local)
+  uint64_t gmask = 0, gval = 0;  // CTA-uniform condition
+  cplx m[4];                     // DENSE1 matrix / PHASE factor in m[0]
+  std::vector<uint32_t> mbits;   // DENSE3: the local bits the matrix acts on (ascending, <= 3)
+  std::vector<cplx> mk;          // DENSE3: 2^k x 2^k matrix on mbits
+  uint32_t bits() const {
+    uint32_t b = lctrl;
+    switch (type) {
+      case E_DENSE1:
+      case E_X:
+        b |= 1u << lb_j;
+        break;
+      case E_SWAP:
+        b |= (1u << lb_j) | (1u << lb_k);
+        break;
+      case E_PHASE:
+        b |= lmask;
+        break;
+      default:
+        for (size_t i = 0; i < mbits.size(); ++i) b |= 1u << mbits[i];
+    }
+    return b;
+  }
 };
 
-bool as_block(const LocalOp &lo, size_t max_k, Block *out) {
-  const FlatOp &f = *lo.f;
-  if (lo.gmask) return false;
-  if (f.cls == CLASS_DIAGONAL) return false;  // handled as phase terms (may involve non-tile bits)
-  std::vector<uint32_t> bits;
+struct Group {
+  uint32_t mask = 0;
+  std::vector<HElem> elems;
+};
+
+// 8x8 matrix of an elementary op over the 3 bits P (ascending tile-local bits).
+std::vector<cplx> elem_matrix(const HElem &e, const std::vector<uint32_t> &P) {
+  auto sub_of = [&](uint32_t lb) { return (uint32_t)(std::find(P.begin(), P.end(), lb) - P.begin()); };
+  uint32_t lc = 0;
   for (uint32_t b = 0; b < 32; ++b)
-    if ((lo.lctrl >> b) & 1) bits.push_back(b);
-  std::vector<uint32_t> tg;
-  if (f.cls == CLASS_BITSWAP) {
-    for (size_t i = 0; i < lo.lswaps.size(); ++i) {
-      tg.push_back(lo.lswaps[i].first);
-      tg.push_back(lo.lswaps[i].second);
+    if ((e.lctrl >> b) & 1) lc |= 1u << sub_of(b);
+  std::vector<cplx> M(64, cplx(0, 0));
+  for (uint32_t c = 0; c < 8; ++c) M[c * 8 + c] = cplx(1, 0);
+  if (e.type == E_DENSE1 || e.type == E_X) {
+    const uint32_t j = sub_of(e.lb_j);
+    cplx mm[4] = {e.m[0], e.m[1], e.m[2], e.m[3]};
+    if (e.type == E_X) {
+      mm[0] = mm[3] = cplx(0, 0);
+      mm[1] = mm[2] = cplx(1, 0);
     }
-  } else {
-    tg = lo.ltgt;
-  }
-  for (size_t i = 0; i < tg.size(); ++i) bits.push_back(tg[i]);
-  std::sort(bits.begin(), bits.end());
-  if (bits.size() > max_k) return false;
-  const size_t k = bits.size(), S = 1u << k;
-  // inner matrix on the target bits
-  std::vector<uint32_t> tsorted = tg;
-  std::sort(tsorted.begin(), tsorted.end());
-  const size_t kt = tsorted.size(), St = 1u << kt;
-  std::vector<cplx> inner(St * St, cplx(0, 0));
-  if (f.cls == CLASS_DENSE) {
-    inner = f.m_sorted;  // already in ascending-bit order
-  } else if (f.cls == CLASS_FLIP) {
-    inner = {cplx(0, 0), cplx(1, 0), cplx(1, 0), cplx(0, 0)};
-  } else {  // BITSWAP: permutation exchanging each pair of bits
-    for (size_t c = 0; c < St; ++c) {
-      size_t r = c;
-      for (size_t i = 0; i < lo.lswaps.size(); ++i) {
-        const int p = (int)(std::find(tsorted.begin(), tsorted.end(), lo.lswaps[i].first) - tsorted.begin());
-        const int q = (int)(std::find(tsorted.begin(), tsorted.end(), lo.lswaps[i].second) - tsorted.begin());
-        const size_t bp = (r >> p) & 1, bq = (r >> q) & 1;
-        r = (r & ~((size_t)1 << p) & ~((size_t)1 << q)) | (bq << p) | (bp << q);
+    for (uint32_t c = 0; c < 8; ++c) {
+      if ((c >> j) & 1) continue;
+      if ((c & lc) != lc) continue;
+      const uint32_t i0 = c, i1 = c | (1u << j);
+      M[i0 * 8 + i0] = mm[0];
+      M[i0 * 8 + i1] = mm[1];
+      M[i1 * 8 + i0] = mm[2];
+      M[i1 * 8 + i1] = mm[3];
+    }
+  } else if (e.type == E_PHASE) {
+    uint32_t lm = 0, lv = 0;
+    for (uint32_t b = 0; b < 32; ++b)
+      if ((e.lmask >> b) & 1) {
+        lm |= 1u << sub_of(b);
+        lv |= ((e.lval >> b) & 1u) << sub_of(b);
       }
-      inner[r * St + c] = cplx(1, 0);
+    for (uint32_t c = 0; c < 8; ++c)
+      if ((c & lm) == lv) M[c * 8 + c] = e.m[0];
+  } else if (e.type == E_SWAP) {
+    const uint32_t j = sub_of(e.lb_j), k = sub_of(e.lb_k);
+    for (uint32_t c = 0; c < 8; ++c) {
+      if ((c & lc) != lc) continue;
+      const uint32_t bj = (c >> j) & 1, bk = (c >> k) & 1;
+      if (bj == bk) continue;
+      const uint32_t d = c ^ (1u << j) ^ (1u << k);
+      M[c * 8 + c] = cplx(0, 0);
+      M[c * 8 + d] = cplx(1, 0);
     }
+  } else {  // DENSE3
+    M = embed(e.mk, e.mbits, P);
   }
-  std::vector<cplx> full = embed(inner, tsorted, bits);
-  // controls: identity rows/cols where any local control bit is 0
-  uint32_t cmask = 0;
-  for (size_t i = 0; i < k; ++i)
-    if ((lo.lctrl >> bits[i]) & 1) cmask |= 1u << i;
-  if (cmask) {
-    for (size_t r = 0; r < S; ++r)
-      for (size_t c = 0; c < S; ++c)
-        if ((r & cmask) != cmask || (c & cmask) != cmask) full[r * S + c] = (r == c) ? cplx(1, 0) : cplx(0, 0);
-  }
-  out->bits = bits;
-  out->m = full;
-  return true;
+  return M;
 }
 
 template <typename R>
-void push_dense(const Block &b, HostPass *pass, uint32_t T) {
-  HostMicroOp mo;
-  memset(&mo.h, 0, sizeof(mo.h));
-  mo.h.kind = MK_DENSE;
-  mo.h.k = (uint32_t)b.bits.size();
-  mo.h.ins_n = mo.h.k;
-  for (uint32_t i = 0; i < mo.h.k; ++i) mo.h.ins_pos[i] = b.bits[i];
-  const uint32_t S = 1u << mo.h.k;
-  for (uint32_t u = 0; u < S; ++u) {
-    uint32_t off = 0;
-    for (uint32_t i = 0; i < mo.h.k; ++i)
-      if ((u >> i) & 1) off |= 1u << b.bits[i];
-    mo.h.off[u] = off;
-  }
-  mo.h.groups_log2 = T - mo.h.ins_n;
-  mo.data.resize((size_t)S * S * 2 * sizeof(R));
-  R *d = reinterpret_cast<R *>(mo.data.data());
-  for (uint32_t i = 0; i < S * S; ++i) {
-    d[2 * i] = (R)b.m[i].real();
-    d[2 * i + 1] = (R)b.m[i].imag();
-  }
-  mo.h.data_bytes = (uint32_t)mo.data.size();
-  pass->ops.push_back(mo);
-}
+struct Emitter {
+  HostPass *pass;
+  uint32_t T;
+  const PlanConfig *cfg;
+  std::vector<Group> open;
+  std::vector<GlobalTerm<R>> gterms;
 
-// A dense / flip op that keeps its controls as predicates (non-tile controls and/or too many bits).
-template <typename R>
-void push_controlled_dense(const LocalOp &lo, HostPass *pass, uint32_t T) {
-  const FlatOp &f = *lo.f;
-  HostMicroOp mo;
-  memset(&mo.h, 0, sizeof(mo.h));
-  std::vector<uint32_t> ins = lo.ltgt;
-  for (uint32_t b = 0; b < 32; ++b)
-    if ((lo.lctrl >> b) & 1) ins.push_back(b);
-  std::sort(ins.begin(), ins.end());
-  mo.h.ins_n = (uint32_t)ins.size();
-  for (size_t i = 0; i < ins.size(); ++i) mo.h.ins_pos[i] = ins[i];
-  mo.h.lor_mask = lo.lctrl;
-  mo.h.gmask = lo.gmask;
-  mo.h.groups_log2 = T - mo.h.ins_n;
-  if (f.cls == CLASS_FLIP) {
-    mo.h.kind = MK_EXCH;
-    mo.h.off[0] = 0;
-    mo.h.off[1] = 1u << lo.ltgt[0];
-  } else {
-    mo.h.kind = MK_DENSE;
-    mo.h.k = (uint32_t)lo.ltgt.size();
-    const uint32_t S = 1u << mo.h.k;
-    for (uint32_t u = 0; u < S; ++u) {
-      uint32_t off = 0;
-      for (uint32_t i = 0; i < mo.h.k; ++i)
-        if ((u >> i) & 1) off |= 1u << lo.ltgt[i];
-      mo.h.off[u] = off;
+  void emit_group(const Group &g) {
+    // pad the bit set to 3 with the highest unused tile-local bits (keeps the low bits for the lanes)
+    std::vector<uint32_t> P;
+    uint32_t mask = g.mask;
+    for (int b = (int)T - 1; b >= 0 && popc(mask) < 3; --b)
+      if (!((mask >> b) & 1)) mask |= 1u << b;
+    for (uint32_t b = 0; b < 32; ++b)
+      if ((mask >> b) & 1) P.push_back(b);
+    auto sub_of = [&](uint32_t lb) { return (uint32_t)(std::find(P.begin(), P.end(), lb) - P.begin()); };
+
+    std::vector<HElem> elems = g.elems;
+    // many 2x2 gates and nothing conditional: one composed 8x8 is cheaper (32 vs 8 FMA-quads per gate)
+    size_t n_dense = 0;
+    bool conditional = false;
+    for (size_t i = 0; i < elems.size(); ++i) {
+      n_dense += elems[i].type == E_DENSE1 ? 1 : (elems[i].type == E_DENSE3 ? 4 : 0);
+      conditional |= elems[i].gmask != 0;
     }
-    mo.data.resize((size_t)S * S * 2 * sizeof(R));
-    R *d = reinterpret_cast<R *>(mo.data.data());
-    for (uint32_t i = 0; i < S * S; ++i) {
-      d[2 * i] = (R)f.m_sorted[i].real();
-      d[2 * i + 1] = (R)f.m_sorted[i].imag();
+    if (!conditional && elems.size() > 1 && n_dense >= cfg->compose_threshold) {
+      std::vector<cplx> acc(64, cplx(0, 0));
+      for (uint32_t c = 0; c < 8; ++c) acc[c * 8 + c] = cplx(1, 0);
+      for (size_t i = 0; i < elems.size(); ++i) acc = matmul(elem_matrix(elems[i], P), acc, 8);
+      HElem d;
+      d.type = E_DENSE3;
+      d.mbits = P;
+      d.mk = acc;
+      elems.clear();
+      elems.push_back(d);
     }
-  }
-  mo.h.data_bytes = (uint32_t)mo.data.size();
-  pass->ops.push_back(mo);
-}
 
-template <typename R>
-void push_exch(uint32_t a, uint32_t b, uint32_t lctrl, uint64_t gmask, HostPass *pass, uint32_t T) {
-  HostMicroOp mo;
-  memset(&mo.h, 0, sizeof(mo.h));
-  mo.h.kind = MK_EXCH;
-  std::vector<uint32_t> ins = {a, b};
-  for (uint32_t c = 0; c < 32; ++c)
-    if ((lctrl >> c) & 1) ins.push_back(c);
-  std::sort(ins.begin(), ins.end());
-  mo.h.ins_n = (uint32_t)ins.size();
-  for (size_t i = 0; i < ins.size(); ++i) mo.h.ins_pos[i] = ins[i];
-  mo.h.lor_mask = lctrl;
-  mo.h.gmask = gmask;
-  mo.h.groups_log2 = T - mo.h.ins_n;
-  mo.h.off[0] = 1u << a;
-  mo.h.off[1] = 1u << b;
-  pass->ops.push_back(mo);
-}
-
-template <typename R>
-struct DiagAccum {  // consecutive diagonal gates merge into one DIAG micro-op
-  std::vector<DiagTerm<R>> terms;
-  void flush(HostPass *pass) {
-    if (terms.empty()) return;
     HostMicroOp mo;
     memset(&mo.h, 0, sizeof(mo.h));
-    mo.h.kind = MK_DIAG;
-    mo.h.nterms = (uint32_t)terms.size();
-    mo.data.resize(terms.size() * sizeof(DiagTerm<R>));
-    memcpy(mo.data.data(), terms.data(), mo.data.size());
+    mo.h.kind = MK_SUPER;
+    mo.h.k = 3;
+    mo.h.ins_n = 3;
+    for (uint32_t i = 0; i < 3; ++i) mo.h.ins_pos[i] = P[i];
+    for (uint32_t u = 0; u < 8; ++u) {
+      uint32_t off = 0;
+      for (uint32_t i = 0; i < 3; ++i)
+        if ((u >> i) & 1) off |= 1u << P[i];
+      mo.h.off[u] = off;
+    }
+    mo.h.groups_log2 = T - 3;
+    mo.h.nterms = (uint32_t)elems.size();
+    for (size_t i = 0; i < elems.size(); ++i) {
+      const HElem &e = elems[i];
+      Elem<R> d;
+      memset(&d, 0, sizeof(d));
+      d.type = (uint32_t)e.type;
+      d.gmask = e.gmask;
+      d.gval = e.gval;
+      for (uint32_t b = 0; b < 32; ++b) {
+        if ((e.lctrl >> b) & 1) d.lc |= 1u << sub_of(b);
+        if ((e.lmask >> b) & 1) {
+          d.lmask |= 1u << sub_of(b);
+          d.lval |= ((e.lval >> b) & 1u) << sub_of(b);
+        }
+      }
+      if (e.type == E_DENSE1 || e.type == E_X) d.j = sub_of(e.lb_j);
+      if (e.type == E_SWAP) {
+        d.j = std::min(sub_of(e.lb_j), sub_of(e.lb_k));
+        d.k = std::max(sub_of(e.lb_j), sub_of(e.lb_k));
+      }
+      if (e.type == E_DENSE1) {
+        bool real = true;
+        for (int q = 0; q < 4; ++q) {
+          d.m[2 * q] = (R)e.m[q].real();
+          d.m[2 * q + 1] = (R)e.m[q].imag();
+          real &= e.m[q].imag() == 0.0;
+        }
+        if (real) d.flags |= EF_REAL;
+      } else if (e.type == E_PHASE) {
+        d.m[0] = (R)e.m[0].real();
+        d.m[1] = (R)e.m[0].imag();
+      }
+      const size_t at = mo.data.size();
+      mo.data.resize(at + sizeof(d));
+      memcpy(mo.data.data() + at, &d, sizeof(d));
+      if (e.type == E_DENSE3) {
+        const std::vector<cplx> M = embed(e.mk, e.mbits, P);
+        const size_t at2 = mo.data.size();
+        mo.data.resize(at2 + 128 * sizeof(R));
+        R *w = reinterpret_cast<R *>(mo.data.data() + at2);
+        for (int q = 0; q < 64; ++q) {
+          w[2 * q] = (R)M[q].real();
+          w[2 * q + 1] = (R)M[q].imag();
+        }
+      }
+    }
     mo.h.data_bytes = (uint32_t)mo.data.size();
     pass->ops.push_back(mo);
-    terms.clear();
   }
-};
 
-// Translate the taken ops of one pass into micro-ops, fusing runs of small all-local ops
-// into dense blocks of <= cfg.max_block_k bits.
-template <typename R>
-void emit_pass(const std::vector<FlatOp> &ops, const std::vector<size_t> &taken, const PassHeader &hdr,
-               const PlanConfig &cfg, HostPass *pass) {
-  const uint32_t T = hdr.T, L = hdr.L;
-  // physical bit -> tile-local bit (or -1)
-  int local_of[64];
-  for (int b = 0; b < 64; ++b) local_of[b] = -1;
-  for (uint32_t b = 0; b < L; ++b) local_of[b] = (int)b;
-  for (uint32_t i = 0; i < hdr.m; ++i) local_of[hdr.hi_pos[i]] = (int)(L + i);
-
-  std::vector<Block> open;  // open blocks with pairwise-disjoint bit sets
-  DiagAccum<R> diag;
-
-  auto flush_blocks_touching = [&](uint32_t lmask, bool all) {
+  void flush_touching(uint32_t lmask, bool all) {
     for (size_t i = 0; i < open.size();) {
-      uint32_t bm = 0;
-      for (size_t j = 0; j < open[i].bits.size(); ++j) bm |= 1u << open[i].bits[j];
-      if (all || (bm & lmask)) {
-        push_dense<R>(open[i], pass, T);
+      if (all || (open[i].mask & lmask)) {
+        emit_group(open[i]);
         open.erase(open.begin() + i);
       } else {
         ++i;
       }
     }
-  };
+  }
 
-  // Merge a new block with the open blocks it touches if the union stays within
-  // max_block_k bits; otherwise emit those and open the new one.
-  auto merge_block = [&](const Block &nb) {
-    uint32_t nbm = 0;
-    for (size_t j = 0; j < nb.bits.size(); ++j) nbm |= 1u << nb.bits[j];
-    std::vector<size_t> hit;
-    uint32_t um = nbm;
-    for (size_t i = 0; i < open.size(); ++i) {
-      uint32_t bm = 0;
-      for (size_t j = 0; j < open[i].bits.size(); ++j) bm |= 1u << open[i].bits[j];
-      if (bm & nbm) {
-        hit.push_back(i);
-        um |= bm;
-      }
-    }
-    if ((uint32_t)popc(um) > cfg.max_block_k) {
-      flush_blocks_touching(nbm, false);
-      open.push_back(nb);
+  // Append an elementary op: merge the groups it touches when the union has <= 3 bits.
+  void add(const HElem &e) {
+    const uint32_t bm = e.bits();
+    if (!cfg->fuse_blocks) {
+      Group g;
+      g.mask = bm;
+      g.elems.push_back(e);
+      emit_group(g);
       return;
     }
-    std::vector<uint32_t> ubits;
-    for (uint32_t b = 0; b < 32; ++b)
-      if ((um >> b) & 1) ubits.push_back(b);
-    const size_t S = (size_t)1 << ubits.size();
-    std::vector<cplx> acc(S * S, cplx(0, 0));
-    for (size_t r = 0; r < S; ++r) acc[r * S + r] = cplx(1, 0);
-    for (size_t h = 0; h < hit.size(); ++h)  // disjoint blocks commute: any order
-      acc = matmul(embed(open[hit[h]].m, open[hit[h]].bits, ubits), acc, S);
-    acc = matmul(embed(nb.m, nb.bits, ubits), acc, S);  // the new op acts last
+    uint32_t um = bm;
+    std::vector<size_t> hit;
+    for (size_t i = 0; i < open.size(); ++i)
+      if (open[i].mask & bm) {
+        hit.push_back(i);
+        um |= open[i].mask;
+      }
+    if (popc(um) > 3) {
+      flush_touching(bm, false);
+      Group g;
+      g.mask = bm;
+      g.elems.push_back(e);
+      open.push_back(g);
+      return;
+    }
+    Group merged;
+    merged.mask = um;
+    for (size_t h = 0; h < hit.size(); ++h)  // disjoint groups commute: any order
+      merged.elems.insert(merged.elems.end(), open[hit[h]].elems.begin(), open[hit[h]].elems.end());
+    merged.elems.push_back(e);
     for (size_t h = hit.size(); h-- > 0;) open.erase(open.begin() + hit[h]);
-    Block merged;
-    merged.bits = ubits;
-    merged.m = acc;
     open.push_back(merged);
-  };
+  }
+
+  // ---- wide micro-ops for what does not fit 3 bits ----------------------------------
+  void push_wide_dense(const FlatOp &f, const std::vector<uint32_t> &ltgt, uint32_t lctrl, uint64_t gmask) {
+    HostMicroOp mo;
+    memset(&mo.h, 0, sizeof(mo.h));
+    std::vector<uint32_t> ins = ltgt;
+    for (uint32_t b = 0; b < 32; ++b)
+      if ((lctrl >> b) & 1) ins.push_back(b);
+    std::sort(ins.begin(), ins.end());
+    mo.h.ins_n = (uint32_t)ins.size();
+    for (size_t i = 0; i < ins.size(); ++i) mo.h.ins_pos[i] = ins[i];
+    mo.h.lor_mask = lctrl;
+    mo.h.gmask = gmask;
+    mo.h.groups_log2 = T - mo.h.ins_n;
+    if (f.cls == CLASS_FLIP) {
+      mo.h.kind = MK_EXCH;
+      mo.h.off[0] = 0;
+      mo.h.off[1] = 1u << ltgt[0];
+    } else {
+      mo.h.kind = MK_DENSE;
+      mo.h.k = (uint32_t)ltgt.size();
+      const uint32_t S = 1u << mo.h.k;
+      for (uint32_t u = 0; u < S; ++u) {
+        uint32_t off = 0;
+        for (uint32_t i = 0; i < mo.h.k; ++i)
+          if ((u >> i) & 1) off |= 1u << ltgt[i];
+        mo.h.off[u] = off;
+      }
+      mo.data.resize((size_t)S * S * 2 * sizeof(R));
+      R *d = reinterpret_cast<R *>(mo.data.data());
+      for (uint32_t i = 0; i < S * S; ++i) {
+        d[2 * i] = (R)f.m_sorted[i].real();
+        d[2 * i + 1] = (R)f.m_sorted[i].imag();
+      }
+    }
+    mo.h.data_bytes = (uint32_t)mo.data.size();
+    pass->ops.push_back(mo);
+  }
+
+  void push_wide_exch(uint32_t a, uint32_t b, uint32_t lctrl, uint64_t gmask) {
+    HostMicroOp mo;
+    memset(&mo.h, 0, sizeof(mo.h));
+    mo.h.kind = MK_EXCH;
+    std::vector<uint32_t> ins = {a, b};
+    for (uint32_t c = 0; c < 32; ++c)
+      if ((lctrl >> c) & 1) ins.push_back(c);
+    std::sort(ins.begin(), ins.end());
+    mo.h.ins_n = (uint32_t)ins.size();
+    for (size_t i = 0; i < ins.size(); ++i) mo.h.ins_pos[i] = ins[i];
+    mo.h.lor_mask = lctrl;
+    mo.h.gmask = gmask;
+    mo.h.groups_log2 = T - mo.h.ins_n;
+    mo.h.off[0] = 1u << a;
+    mo.h.off[1] = 1u << b;
+    pass->ops.push_back(mo);
+  }
+
+  void push_wide_diag(const std::vector<DiagTerm<R>> &terms) {
+    for (size_t at = 0; at < terms.size(); at += kMaxDiagTerms) {
+      const size_t n = std::min<size_t>(kMaxDiagTerms, terms.size() - at);
+      HostMicroOp mo;
+      memset(&mo.h, 0, sizeof(mo.h));
+      mo.h.kind = MK_DIAG;
+      mo.h.nterms = (uint32_t)n;
+      mo.data.resize(n * sizeof(DiagTerm<R>));
+      memcpy(mo.data.data(), terms.data() + at, mo.data.size());
+      mo.h.data_bytes = (uint32_t)mo.data.size();
+      pass->ops.push_back(mo);
+    }
+  }
+};
+
+// Translate the taken ops of one pass into micro-ops.
+template <typename R>
+void emit_pass(const std::vector<FlatOp> &ops, const std::vector<size_t> &taken, const PassHeader &hdr,
+               const PlanConfig &cfg, HostPass *pass) {
+  const uint32_t T = hdr.T, L = hdr.L;
+  int local_of[64];  // physical bit -> tile-local bit (or -1)
+  for (int b = 0; b < 64; ++b) local_of[b] = -1;
+  for (uint32_t b = 0; b < L; ++b) local_of[b] = (int)b;
+  for (uint32_t i = 0; i < hdr.m; ++i) local_of[hdr.hi_pos[i]] = (int)(L + i);
+
+  Emitter<R> em;
+  em.pass = pass;
+  em.T = T;
+  em.cfg = &cfg;
 
   for (size_t ti = 0; ti < taken.size(); ++ti) {
     const FlatOp &f = ops[taken[ti]];
-    LocalOp lo;
-    lo.f = &f;
+    uint32_t lctrl = 0;
+    uint64_t gmask = 0;
     for (uint32_t b = 0; b < 64; ++b)
       if ((f.ctrl_mask >> b) & 1) {
         if (local_of[b] >= 0)
-          lo.lctrl |= 1u << local_of[b];
+          lctrl |= 1u << local_of[b];
         else
-          lo.gmask |= 1ull << b;
+          gmask |= 1ull << b;
       }
     if (f.cls == CLASS_DIAGONAL) {
-      uint32_t touch = lo.lctrl;
-      bool all_local = lo.gmask == 0;
-      for (size_t i = 0; i < f.diag_bits.size(); ++i) {
-        if (local_of[f.diag_bits[i]] >= 0)
-          touch |= 1u << local_of[f.diag_bits[i]];
-        else
-          all_local = false;
-      }
-      // A small all-local diagonal op that touches an open block is folded into it for free.
-      if (cfg.fuse_blocks && all_local && (uint32_t)popc(touch) <= cfg.max_block_k) {
-        uint32_t um = touch;
-        bool hits = false;
-        for (size_t i = 0; i < open.size(); ++i) {
-          uint32_t bm = 0;
-          for (size_t j = 0; j < open[i].bits.size(); ++j) bm |= 1u << open[i].bits[j];
-          if (bm & touch) {
-            hits = true;
-            um |= bm;
-          }
-        }
-        if (hits && (uint32_t)popc(um) <= cfg.max_block_k && diag.terms.empty()) {
-          Block db;
-          for (uint32_t b = 0; b < 32; ++b)
-            if ((touch >> b) & 1) db.bits.push_back(b);
-          const size_t S = (size_t)1 << db.bits.size();
-          db.m.assign(S * S, cplx(0, 0));
-          for (size_t sidx = 0; sidx < S; ++sidx) {
-            bool ctrl_ok = true;
-            size_t u = 0;
-            for (size_t j = 0; j < db.bits.size(); ++j) {
-              const uint32_t lb = db.bits[j];
-              const size_t v = (sidx >> j) & 1;
-              if (((lo.lctrl >> lb) & 1) && !v) ctrl_ok = false;
-              for (size_t i = 0; i < f.diag_bits.size(); ++i)
-                if ((uint32_t)local_of[f.diag_bits[i]] == lb) u |= v << i;
-            }
-            db.m[sidx * S + sidx] = ctrl_ok ? f.diag[u] : cplx(1, 0);
-          }
-          merge_block(db);
-          continue;
-        }
-      }
-      // masked-phase terms; diagonal ops commute with each other and with every block bit they
-      // touch only diagonally -- but not with open blocks acting NON-diagonally on shared bits.
-      flush_blocks_touching(touch, false);
       const size_t nd = f.diag_bits.size();
+      std::vector<DiagTerm<R>> wide;
       for (size_t u = 0; u < f.diag.size(); ++u) {
-        if (f.diag[u].real() == 1.0 && f.diag[u].imag() == 0.0) continue;
-        DiagTerm<R> t;
-        t.gmask = lo.gmask;
-        t.gval = lo.gmask;
-        t.lmask = lo.lctrl;
-        t.lval = lo.lctrl;
+        if (is_one(f.diag[u])) continue;
+        HElem e;
+        e.type = E_PHASE;
+        e.gmask = gmask;
+        e.gval = gmask;
+        e.lmask = lctrl;
+        e.lval = lctrl;
         for (size_t i = 0; i < nd; ++i) {
           const uint32_t b = f.diag_bits[i];
           const uint64_t v = (u >> i) & 1;
           if (local_of[b] >= 0) {
-            t.lmask |= 1u << local_of[b];
-            t.lval |= (uint32_t)v << local_of[b];
+            e.lmask |= 1u << local_of[b];
+            e.lval |= (uint32_t)v << local_of[b];
           } else {
-            t.gmask |= 1ull << b;
-            t.gval |= v << b;
+            e.gmask |= 1ull << b;
+            e.gval |= v << b;
           }
         }
-        t.re = (R)f.diag[u].real();
-        t.im = (R)f.diag[u].imag();
-        if (diag.terms.size() >= kMaxDiagTerms) diag.flush(pass);
-        diag.terms.push_back(t);
+        e.m[0] = f.diag[u];
+        if (e.lmask == 0 && em.gterms.size() < kMaxGlobalTerms) {
+          // a scalar for this CTA: commutes with everything, applied once at store time
+          GlobalTerm<R> g;
+          g.gmask = e.gmask;
+          g.gval = e.gval;
+          g.re = (R)e.m[0].real();
+          g.im = (R)e.m[0].imag();
+          em.gterms.push_back(g);
+        } else if (popc(e.lmask) <= 3) {
+          em.add(e);
+        } else {
+          DiagTerm<R> t;
+          t.gmask = e.gmask;
+          t.gval = e.gval;
+          t.lmask = e.lmask;
+          t.lval = e.lval;
+          t.re = (R)e.m[0].real();
+          t.im = (R)e.m[0].imag();
+          wide.push_back(t);
+        }
+      }
+      if (!wide.empty()) {
+        em.flush_touching(0, true);
+        em.push_wide_diag(wide);
       }
       continue;
     }
-    // non-diagonal op: pending diagonal terms must be emitted first if they share a bit
-    // (simple and safe: always flush them)
-    diag.flush(pass);
     if (f.cls == CLASS_BITSWAP) {
-      for (size_t i = 0; i < f.swaps.size(); ++i)
-        lo.lswaps.push_back(std::make_pair((uint32_t)local_of[f.swaps[i].first], (uint32_t)local_of[f.swaps[i].second]));
-    } else {
-      for (size_t i = 0; i < f.tgt_sorted.size(); ++i) lo.ltgt.push_back((uint32_t)local_of[f.tgt_sorted[i]]);
-      // local order equals physical order (low bits identity, high bits ascending), so m_sorted stays valid
-    }
-    Block nb;
-    const bool blockable = cfg.fuse_blocks && as_block(lo, cfg.max_block_k, &nb);
-    if (!blockable) {
-      uint32_t touch = lo.lctrl;
-      for (size_t i = 0; i < lo.ltgt.size(); ++i) touch |= 1u << lo.ltgt[i];
-      for (size_t i = 0; i < lo.lswaps.size(); ++i) touch |= (1u << lo.lswaps[i].first) | (1u << lo.lswaps[i].second);
-      flush_blocks_touching(touch, false);
-      if (f.cls == CLASS_BITSWAP) {
-        for (size_t i = 0; i < lo.lswaps.size(); ++i)
-          push_exch<R>(std::min(lo.lswaps[i].first, lo.lswaps[i].second),
-                       std::max(lo.lswaps[i].first, lo.lswaps[i].second), lo.lctrl, lo.gmask, pass, T);
-      } else {
-        push_controlled_dense<R>(lo, pass, T);
+      for (size_t i = 0; i < f.swaps.size(); ++i) {
+        const uint32_t a = (uint32_t)local_of[f.swaps[i].first], b = (uint32_t)local_of[f.swaps[i].second];
+        if (popc(lctrl) + 2 <= 3) {
+          HElem e;
+          e.type = E_SWAP;
+          e.lb_j = a;
+          e.lb_k = b;
+          e.lctrl = lctrl;
+          e.gmask = e.gval = gmask;
+          em.add(e);
+        } else {
+          em.flush_touching(0, true);
+          em.push_wide_exch(std::min(a, b), std::max(a, b), lctrl, gmask);
+        }
       }
       continue;
     }
-    merge_block(nb);
+    std::vector<uint32_t> ltgt;
+    for (size_t i = 0; i < f.tgt_sorted.size(); ++i) ltgt.push_back((uint32_t)local_of[f.tgt_sorted[i]]);
+    // local order equals physical order (low bits identity, high bits ascending), so m_sorted stays valid
+    if ((size_t)popc(lctrl) + ltgt.size() > 3) {
+      em.flush_touching(0, true);
+      em.push_wide_dense(f, ltgt, lctrl, gmask);
+      continue;
+    }
+    HElem e;
+    e.gmask = e.gval = gmask;
+    e.lctrl = lctrl;
+    if (f.cls == CLASS_FLIP) {
+      e.type = E_X;
+      e.lb_j = ltgt[0];
+    } else if (ltgt.size() == 1) {
+      e.type = E_DENSE1;
+      e.lb_j = ltgt[0];
+      for (int q = 0; q < 4; ++q) e.m[q] = f.m_sorted[q];
+    } else {
+      // dense 2- or 3-bit block: the controls (if any) are folded into the matrix
+      e.type = E_DENSE3;
+      e.lctrl = 0;
+      std::vector<uint32_t> bits = ltgt;
+      for (uint32_t b = 0; b < 32; ++b)
+        if ((lctrl >> b) & 1) bits.push_back(b);
+      std::sort(bits.begin(), bits.end());
+      std::vector<cplx> full = embed(f.m_sorted, ltgt, bits);
+      const size_t S = (size_t)1 << bits.size();
+      uint32_t cm = 0;
+      for (size_t i = 0; i < bits.size(); ++i)
+        if ((lctrl >> bits[i]) & 1) cm |= 1u << i;
+      if (cm)
+        for (size_t r = 0; r < S; ++r)
+          for (size_t c = 0; c < S; ++c)
+            if ((r & cm) != cm || (c & cm) != cm) full[r * S + c] = (r == c) ? cplx(1, 0) : cplx(0, 0);
+      e.mbits = bits;
+      e.mk = full;
+    }
+    em.add(e);
   }
-  diag.flush(pass);
-  flush_blocks_touching(0, true);
+  em.flush_touching(0, true);
+  pass->gterms.resize(em.gterms.size() * sizeof(GlobalTerm<R>));
+  if (!em.gterms.empty()) memcpy(pass->gterms.data(), em.gterms.data(), pass->gterms.size());
+}
+
+size_t pass_bytes(const HostPass &p) {
+  size_t bytes = 0;
+  for (size_t i = 0; i < p.ops.size(); ++i) bytes += sizeof(MicroOp) + ((p.ops[i].data.size() + 15) & ~(size_t)15);
+  return bytes + ((p.gterms.size() + 15) & ~(size_t)15);
 }
 
 }  // namespace
@@ -464,10 +567,10 @@ PlanConfig default_plan_config(qip_prec prec, uint32_t n_local) {
   PlanConfig c;
   c.T = prec == QIP_F32 ? 13 : 12;  // 64 KiB of amplitudes per tile
   c.L = prec == QIP_F32 ? 6 : 5;    // 512-byte contiguous runs in HBM
-  // test / tuning knobs (tile geometry only; results are unaffected)
+  // test / tuning knobs (tile geometry and grouping only; results are unaffected)
   if (const char *e = getenv("QIPB200_TILE_T")) c.T = std::min<uint32_t>((uint32_t)atoi(e), c.T);
   if (const char *e = getenv("QIPB200_TILE_L")) c.L = (uint32_t)atoi(e);
-  if (const char *e = getenv("QIPB200_BLOCK_K")) c.max_block_k = std::max(1, std::min(3, atoi(e)));
+  if (const char *e = getenv("QIPB200_COMPOSE")) c.compose_threshold = (uint32_t)std::max(1, atoi(e));
   if (const char *e = getenv("QIPB200_NO_BLOCK_FUSION")) c.fuse_blocks = atoi(e) == 0;
   if (n_local < c.T) c.T = n_local;
   if (c.L > c.T) c.L = c.T;
@@ -483,27 +586,31 @@ void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec
   if (cfg.L > cfg.T) cfg.L = cfg.T;
   const uint32_t m = cfg.T - cfg.L;
   const uint64_t low_mask = (1ull << cfg.L) - 1ull;
+  const bool can_tile = cfg.T >= 3;
   std::vector<OpInfo> info(ops.size());
   std::vector<size_t> remaining;
   for (size_t i = 0; i < ops.size(); ++i) {
     if (ops[i].cls == CLASS_IDENTITY) continue;
-    info[i] = analyse(ops[i], cfg);
+    info[i] = analyse(ops[i]);
     remaining.push_back(i);
   }
+  const uint32_t byte_budget = kMaxPassBytes - 2048;
   while (!remaining.empty()) {
     uint64_t S_high = 0, pend_d = 0, pend_nd = 0;
     std::vector<size_t> taken, left;
     double unfused = 0.0;
+    uint32_t bytes = 0;
     for (size_t r = 0; r < remaining.size(); ++r) {
       const size_t idx = remaining[r];
       const OpInfo &o = info[idx];
       const bool conflict = (o.nd & (pend_d | pend_nd)) || (o.dg & pend_nd);
-      if (!conflict && o.tile_ok) {
+      if (can_tile && !conflict && o.tile_ok && bytes + o.est_bytes <= byte_budget) {
         const uint64_t need = o.need_tile & ~low_mask & ~S_high;
         if ((uint32_t)popc(S_high | need) <= m) {
           S_high |= need;
           taken.push_back(idx);
           unfused += o.unfused_cost;
+          bytes += o.est_bytes;
           continue;
         }
       }
@@ -544,20 +651,18 @@ void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec
     else
       emit_pass<double>(ops, taken, h, cfg, &st.pass);
     h.n_ops = (uint32_t)st.pass.ops.size();
+    h.n_gterms = (uint32_t)(st.pass.gterms.size() / (prec == QIP_F32 ? sizeof(GlobalTerm<float>) : sizeof(GlobalTerm<double>)));
     st.pass.n_gates = (uint32_t)taken.size();
     steps->push_back(st);
     remaining.swap(left);
   }
 }
 
-void serialise_pass(const HostPass &p, std::vector<unsigned char> *blob) {
-  PassHeader h = p.hdr;
-  size_t bytes = 0;
-  for (size_t i = 0; i < p.ops.size(); ++i) bytes += sizeof(MicroOp) + ((p.ops[i].data.size() + 15) & ~(size_t)15);
-  h.blob_bytes = (uint32_t)bytes;
-  blob->resize(sizeof(PassHeader) + bytes);
-  memcpy(blob->data(), &h, sizeof(h));
-  unsigned char *w = blob->data() + sizeof(PassHeader);
+bool serialise_pass(const HostPass &p, PassParams *out) {
+  const size_t bytes = pass_bytes(p);
+  if (bytes > kMaxPassBytes) return false;
+  out->h = p.hdr;
+  unsigned char *w = out->recs;
   for (size_t i = 0; i < p.ops.size(); ++i) {
     MicroOp mh = p.ops[i].h;
     mh.data_bytes = (uint32_t)((p.ops[i].data.size() + 15) & ~(size_t)15);
@@ -566,6 +671,10 @@ void serialise_pass(const HostPass &p, std::vector<unsigned char> *blob) {
     if (!p.ops[i].data.empty()) memcpy(w, p.ops[i].data.data(), p.ops[i].data.size());
     w += mh.data_bytes;
   }
+  out->h.gterm_off = (uint32_t)(w - out->recs);
+  if (!p.gterms.empty()) memcpy(w, p.gterms.data(), p.gterms.size());
+  out->h.blob_bytes = (uint32_t)bytes;
+  return true;
 }
 
 }  // namespace qipb200

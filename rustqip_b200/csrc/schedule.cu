@@ -36,35 +36,21 @@ int flush_fused(qipb200_state *s, std::vector<FlatOp> *pending) {
   const PlanConfig cfg = default_plan_config(s->prec, s->n_local);
   std::vector<PlanStep> steps;
   plan_passes(*pending, s->n_local, s->prec, cfg, &steps);
-  // serialise every pass into one blob, upload once
-  std::vector<unsigned char> host;
-  std::vector<size_t> offs(steps.size(), 0);
-  for (size_t i = 0; i < steps.size(); ++i) {
-    if (!steps[i].is_pass) continue;
-    std::vector<unsigned char> b;
-    serialise_pass(steps[i].pass, &b);
-    const size_t at = (host.size() + 255) & ~(size_t)255;
-    host.resize(at + b.size());
-    memcpy(host.data() + at, b.data(), b.size());
-    offs[i] = at;
-  }
-  unsigned char *d_blob = nullptr;
-  if (!host.empty()) {
-    cudaError_t e = cudaMallocAsync((void **)&d_blob, host.size(), ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_blob, host.data(), host.size(), cudaMemcpyHostToDevice, ctx->stream);
-    if (e != cudaSuccess) return report_cuda_error(s, e, "upload of the fused pass descriptors");
-  }
   int st = QIPB200_OK;
+  PassParams *pp = new PassParams();
   for (size_t i = 0; i < steps.size() && st == QIPB200_OK; ++i) {
     if (steps[i].is_pass) {
-      cudaError_t e = launch_tile_pass(s->prec, s->buf, s->n_local, steps[i].pass.hdr.T, d_blob + offs[i],
-                                       ctx->stream, &ctx->launches);
+      if (!serialise_pass(steps[i].pass, pp)) {
+        st = report_error(s, QIPB200_ERR_UNSUPPORTED, "internal: fused pass exceeds the kernel parameter space");
+        break;
+      }
+      cudaError_t e = launch_tile_pass(s->prec, s->buf, s->n_local, *pp, ctx->stream, &ctx->launches);
       if (e != cudaSuccess) st = report_cuda_error(s, e, "launch_tile_pass");
     } else {
       st = launch_local_op(s, (*pending)[steps[i].op_index]);
     }
   }
-  if (d_blob) cudaFreeAsync(d_blob, ctx->stream);
+  delete pp;
   pending->clear();
   return st;
 }

@@ -8,6 +8,14 @@
 // control bits and diagonal gates may sit on ANY bit (a non-tile bit is a CTA-uniform
 // predicate).  Algorithmic HBM traffic of a pass = 2 * 2^n * sizeof(amplitude), the
 // same as ONE gate of the reference's per-entry loop (qip/src/builder.rs:423-514).
+//
+// The work-horse micro-op is MK_SUPER: a set of 3 tile-local bits and a LIST of
+// elementary ops on them.  A thread pulls the 8 amplitudes of one group into
+// registers, runs the whole list there (2x2 gates, X, phases, bit swaps, optional
+// CTA-uniform conditions for controls that live outside the tile) and writes the
+// group back: one shared-memory round trip for many gates.  All descriptors travel
+// as a __grid_constant__ kernel parameter, i.e. are read through the constant bank,
+// not through the shared-memory pipe that carries the amplitudes.
 #pragma once
 
 #include <cstdint>
@@ -17,25 +25,29 @@
 
 namespace qipb200 {
 
-static const uint32_t kTileMaxHigh = 8;    // m <= 8 -> 256 chunk offsets
-static const uint32_t kTileStageBytes = 1280;  // per staged micro-op: header + matrix / diag terms
-static const uint32_t kMaxDiagTerms = 24;  // per DIAG micro-op (24 * 48 B = 1152 B for f64)
+static const uint32_t kTileMaxHigh = 8;       // m <= 8 -> 256 chunk offsets
+static const uint32_t kMaxPassBytes = 27 * 1024;  // micro-op records per pass (kernel parameter space)
+static const uint32_t kMaxDiagTerms = 24;     // per MK_DIAG micro-op
+static const uint32_t kMaxGlobalTerms = 32;   // CTA-uniform phase terms applied at store time
 
-enum MicroKind { MK_DENSE = 0, MK_DIAG = 1, MK_EXCH = 2 };
+enum MicroKind { MK_DENSE = 0, MK_DIAG = 1, MK_EXCH = 2, MK_SUPER = 3 };
+enum ElemType { E_DENSE1 = 0, E_X = 1, E_PHASE = 2, E_SWAP = 3, E_DENSE3 = 4 };
+enum ElemFlags { EF_REAL = 1u };  // E_DENSE1 with a purely real matrix (H, Ry, X-like): half the FMAs
 
-// Device-visible micro-op header (fixed 128 bytes), followed in the blob by its data:
-//   MK_DENSE: 2^k x 2^k complex<R> (re,im interleaved), sub-index bit i <-> lbit[i]
+// Device-visible micro-op header (fixed 128 bytes), followed by its data:
+//   MK_DENSE: 2^k x 2^k complex<R> (re,im interleaved), sub-index bit i <-> ins_pos order of targets
 //   MK_DIAG : nterms x DiagTerm<R>
+//   MK_SUPER: nterms elementary records (Elem<R>, E_DENSE3 ones followed by 64 complex<R>)
 struct alignas(16) MicroOp {
   uint32_t kind;
-  uint32_t k;            // dense: number of target bits (1..3)
+  uint32_t k;            // dense: number of target bits (1..3); super: 3
   uint32_t ins_n;        // number of tile-local positions removed from the group counter
   uint32_t ins_pos[6];   // ascending tile-local positions (targets and local controls)
   uint32_t lor_mask;     // tile-local control bits (forced to 1)
-  uint32_t off[8];       // dense: tile-local offset of sub-index u; exch: off[0] <-> off[1]
+  uint32_t off[8];       // dense/super: tile-local offset of sub-index u; exch: off[0] <-> off[1]
   uint32_t groups_log2;  // T - ins_n
-  uint32_t nterms;       // diag
-  uint32_t data_bytes;   // bytes of data following the header in the blob
+  uint32_t nterms;       // diag terms / super elems
+  uint32_t data_bytes;   // bytes of data following the header
   uint32_t pad0;
   uint64_t gmask;        // control bits outside the tile: tested against the tile's base index
   uint64_t pad1[3];
@@ -49,13 +61,41 @@ struct alignas(16) DiagTerm {  // multiply by (re,im) where (global & gmask)==gv
   R re, im;
 };
 
+// Elementary op of a MK_SUPER group; j, k, lc, lmask, lval are in SUB-INDEX coordinates
+// (bit i of the sub-index <-> ins_pos[i] of the enclosing micro-op).
+template <typename R>
+struct alignas(16) Elem {
+  uint32_t type;         // ElemType
+  uint32_t j, k;         // target sub-bit (DENSE1/X), the two sub-bits of a SWAP
+  uint32_t lc;           // sub-index control mask (bits that must be 1)
+  uint32_t lmask, lval;  // PHASE: applies where (sub & lmask) == lval
+  uint32_t flags, pad;
+  uint64_t gmask, gval;  // CTA-uniform condition on the tile's base index
+  R m[8];                // DENSE1: m00,m01,m10,m11 (re,im); PHASE: w (re,im)
+};
+
+template <typename R>
+struct GlobalTerm {  // multiply the whole tile by (re,im) where (base & gmask) == gval
+  uint64_t gmask, gval;
+  R re, im;
+};
+
 struct PassHeader {
   uint32_t T, L, m, n_ops;
   uint32_t hi_pos[kTileMaxHigh];           // the m high tile bit positions, ascending
   uint64_t chunk_off[1u << kTileMaxHigh];  // amplitude offset of chunk c (bits of c spread over hi_pos)
-  uint32_t blob_bytes;                     // bytes of micro-op records after the header
-  uint32_t pad[3];
+  uint32_t blob_bytes;                     // bytes of micro-op records
+  uint32_t n_gterms;                       // GlobalTerm records at the very end of the blob
+  uint32_t gterm_off;                      // byte offset of the GlobalTerm array inside the blob
+  uint32_t pad;
 };
+
+// What the kernel receives by value (constant bank).
+struct PassParams {
+  PassHeader h;
+  unsigned char recs[kMaxPassBytes];
+};
+static_assert(sizeof(PassParams) <= 32000, "kernel parameter space");
 
 // ---- host side ---------------------------------------------------------------------
 struct HostMicroOp {
@@ -66,7 +106,8 @@ struct HostMicroOp {
 struct HostPass {
   PassHeader hdr;
   std::vector<HostMicroOp> ops;
-  uint32_t n_gates = 0;  // reference ops folded into this pass
+  std::vector<unsigned char> gterms;  // GlobalTerm<R> records
+  uint32_t n_gates = 0;               // reference ops folded into this pass
 };
 
 // One step of a planned schedule: either a fused pass or a single op run by the
@@ -80,8 +121,8 @@ struct PlanStep {
 struct PlanConfig {
   uint32_t T = 12;        // tile bits
   uint32_t L = 5;         // contiguous low bits
-  uint32_t max_block_k = 3;  // host-side gate fusion into dense blocks of <= this many bits
-  bool fuse_blocks = true;
+  bool fuse_blocks = true;      // group ops into 3-bit register-resident super-ops
+  uint32_t compose_threshold = 5;  // >= this many 2x2 gates in one group: compose them into one 8x8
 };
 
 // Plan `ops` (already compiled against the current layout and restricted to local bits;
@@ -89,8 +130,9 @@ struct PlanConfig {
 void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec, const PlanConfig &cfg,
                  std::vector<PlanStep> *steps);
 
-// Serialise a pass for the device (header + 128-byte micro-op records with data).
-void serialise_pass(const HostPass &p, std::vector<unsigned char> *blob);
+// Serialise a pass: header + micro-op records + global terms.  Returns false if the
+// records do not fit kMaxPassBytes (the planner bounds passes so that they do).
+bool serialise_pass(const HostPass &p, PassParams *out);
 
 // Tile geometry defaults per precision.
 PlanConfig default_plan_config(qip_prec prec, uint32_t n_local);

@@ -5,11 +5,15 @@
 //             16-byte cp.async (LDGSTS); the shared-memory image uses the 128-byte XOR
 //             swizzle (16-byte unit u lives at u ^ ((u >> 3) & 7)), so that groups of
 //             amplitudes at ANY power-of-two stride are at most 2-way bank conflicted.
-//   2. APPLY  the pass's micro-ops in shared memory, one __syncthreads() apiece; the
-//             next micro-op's matrix / phase terms are staged into a double buffer
-//             while the current one runs.
-//   3. STORE  shared memory -> HBM, 16 bytes per lane, same addresses as the load.
-// Three CTAs are resident per SM (3 x 66.5 KiB of shared memory), so one CTA's loads
+//   2. APPLY  the pass's micro-ops, one __syncthreads() apiece.  The work-horse is the
+//             SUPER-OP: a thread pulls the 8 amplitudes of a 3-bit group into registers
+//             and runs a whole list of elementary gates on them before writing back --
+//             one shared-memory round trip for many gates.  Gate descriptors arrive as
+//             a __grid_constant__ parameter: they are read through the constant bank and
+//             never compete with the amplitudes for shared-memory bandwidth.
+//   3. STORE  shared memory -> HBM, 16 bytes per lane, same addresses as the load; the
+//             product of the CTA-uniform phase terms is folded in here.
+// Three CTAs are resident per SM (3 x 64 KiB of shared memory), so one CTA's loads
 // and stores overlap the other CTAs' arithmetic.  HBM traffic per pass: every
 // amplitude read once and written once, no matter how many gates the pass folds in.
 #include <cuda_runtime.h>
@@ -53,69 +57,197 @@ __device__ __forceinline__ uint32_t expand_local(uint32_t g, const MicroOp *mo) 
   return t | mo->lor_mask;
 }
 
+// ---- elementary ops on 8 register-resident amplitudes -----------------------------------
+template <typename R>
+struct Amp8 {
+  R re[8], im[8];
+};
+
+template <typename R, int J>
+__device__ __forceinline__ void e_dense1(Amp8<R> &a, const Elem<R> *e) {
+  const uint32_t lc = e->lc;
+  const R m00r = e->m[0], m00i = e->m[1], m01r = e->m[2], m01i = e->m[3];
+  const R m10r = e->m[4], m10i = e->m[5], m11r = e->m[6], m11i = e->m[7];
+  const bool real = e->flags & EF_REAL;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if ((c >> J) & 1) continue;
+    if ((c & lc) != lc) continue;  // uniform across the CTA
+    const int i0 = c, i1 = c | (1 << J);
+    const R xr = a.re[i0], xi = a.im[i0], yr = a.re[i1], yi = a.im[i1];
+    if (real) {
+      a.re[i0] = fma(m00r, xr, m01r * yr);
+      a.im[i0] = fma(m00r, xi, m01r * yi);
+      a.re[i1] = fma(m10r, xr, m11r * yr);
+      a.im[i1] = fma(m10r, xi, m11r * yi);
+    } else {
+      a.re[i0] = fma(m00r, xr, fma(-m00i, xi, fma(m01r, yr, -m01i * yi)));
+      a.im[i0] = fma(m00r, xi, fma(m00i, xr, fma(m01r, yi, m01i * yr)));
+      a.re[i1] = fma(m10r, xr, fma(-m10i, xi, fma(m11r, yr, -m11i * yi)));
+      a.im[i1] = fma(m10r, xi, fma(m10i, xr, fma(m11r, yi, m11i * yr)));
+    }
+  }
+}
+
+template <typename R, int J>
+__device__ __forceinline__ void e_x(Amp8<R> &a, uint32_t lc) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if ((c >> J) & 1) continue;
+    if ((c & lc) != lc) continue;
+    const int i0 = c, i1 = c | (1 << J);
+    const R tr = a.re[i0], ti = a.im[i0];
+    a.re[i0] = a.re[i1];
+    a.im[i0] = a.im[i1];
+    a.re[i1] = tr;
+    a.im[i1] = ti;
+  }
+}
+
+template <typename R, int J, int K>
+__device__ __forceinline__ void e_swap(Amp8<R> &a, uint32_t lc) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if (!(((c >> J) & 1) == 1 && ((c >> K) & 1) == 0)) continue;
+    if ((c & lc) != lc) continue;
+    const int d = c ^ (1 << J) ^ (1 << K);
+    const R tr = a.re[c], ti = a.im[c];
+    a.re[c] = a.re[d];
+    a.im[c] = a.im[d];
+    a.re[d] = tr;
+    a.im[d] = ti;
+  }
+}
+
+template <typename R>
+__device__ __forceinline__ void e_phase(Amp8<R> &a, const Elem<R> *e) {
+  const uint32_t lm = e->lmask, lv = e->lval;
+  const R wr = e->m[0], wi = e->m[1];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if ((c & lm) != lv) continue;
+    const R xr = a.re[c], xi = a.im[c];
+    a.re[c] = fma(wr, xr, -wi * xi);
+    a.im[c] = fma(wr, xi, wi * xr);
+  }
+}
+
+template <typename R>
+__device__ __forceinline__ void e_dense3(Amp8<R> &a, const R *m) {
+  Amp8<R> o;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    R re = (R)0, im = (R)0;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      const R mr = m[2 * (u * 8 + v)], mi = m[2 * (u * 8 + v) + 1];
+      re = fma(mr, a.re[v], re);
+      re = fma(-mi, a.im[v], re);
+      im = fma(mr, a.im[v], im);
+      im = fma(mi, a.re[v], im);
+    }
+    o.re[u] = re;
+    o.im[u] = im;
+  }
+  a = o;
+}
+
+template <typename R>
+__device__ __forceinline__ void run_super(typename C2<R>::type *tile, const MicroOp *mo, const unsigned char *data,
+                                          uint64_t base) {
+  typedef typename C2<R>::type V;
+  const uint32_t groups = 1u << mo->groups_log2;
+  for (uint32_t g = threadIdx.x; g < groups; g += kTileThreads) {
+    const uint32_t t0 = expand_local(g, mo);
+    uint32_t addr[8];
+    Amp8<R> a;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      addr[u] = swz<R>(t0 + mo->off[u]);
+      const V v = tile[addr[u]];
+      a.re[u] = v.x;
+      a.im[u] = v.y;
+    }
+    const unsigned char *ep = data;
+    for (uint32_t ei = 0; ei < mo->nterms; ++ei) {
+      const Elem<R> *e = reinterpret_cast<const Elem<R> *>(ep);
+      ep += sizeof(Elem<R>);
+      const uint32_t type = e->type;
+      const R *m8 = reinterpret_cast<const R *>(ep);
+      if (type == E_DENSE3) ep += 128 * sizeof(R);
+      if ((base & e->gmask) != e->gval) continue;  // CTA-uniform: a control outside the tile is 0
+      switch (type) {
+        case E_DENSE1:
+          if (e->j == 0)
+            e_dense1<R, 0>(a, e);
+          else if (e->j == 1)
+            e_dense1<R, 1>(a, e);
+          else
+            e_dense1<R, 2>(a, e);
+          break;
+        case E_X:
+          if (e->j == 0)
+            e_x<R, 0>(a, e->lc);
+          else if (e->j == 1)
+            e_x<R, 1>(a, e->lc);
+          else
+            e_x<R, 2>(a, e->lc);
+          break;
+        case E_PHASE:
+          e_phase<R>(a, e);
+          break;
+        case E_SWAP:
+          if (e->j == 0 && e->k == 1)
+            e_swap<R, 0, 1>(a, e->lc);
+          else if (e->j == 0)
+            e_swap<R, 0, 2>(a, e->lc);
+          else
+            e_swap<R, 1, 2>(a, e->lc);
+          break;
+        default:
+          e_dense3<R>(a, m8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      V v;
+      v.x = a.re[u];
+      v.y = a.im[u];
+      tile[addr[u]] = v;
+    }
+  }
+}
+
+// ---- wide micro-ops (more than 3 involved bits): rare -----------------------------------
 template <typename R, int K>
 __device__ __forceinline__ void apply_dense(typename C2<R>::type *tile, const MicroOp *mo, const R *mat) {
   typedef typename C2<R>::type V;
   constexpr int S = 1 << K;
   const uint32_t groups = 1u << mo->groups_log2;
-  const V *m2 = reinterpret_cast<const V *>(mat);
-  if (K == 1 || (K == 2 && sizeof(R) == 4)) {
-    // small block: keep the matrix in registers for all groups of this thread
-    V mr[S * S];
+  for (uint32_t g = threadIdx.x; g < groups; g += kTileThreads) {
+    const uint32_t t0 = expand_local(g, mo);
+    V in[S];
+    uint32_t addr[S];
 #pragma unroll
-    for (int i = 0; i < S * S; ++i) mr[i] = m2[i];
-    for (uint32_t g = threadIdx.x; g < groups; g += kTileThreads) {
-      const uint32_t t0 = expand_local(g, mo);
-      V in[S];
-      uint32_t addr[S];
-#pragma unroll
-      for (int u = 0; u < S; ++u) {
-        addr[u] = swz<R>(t0 + mo->off[u]);
-        in[u] = tile[addr[u]];
-      }
-#pragma unroll
-      for (int u = 0; u < S; ++u) {
-        R re = (R)0, im = (R)0;
-#pragma unroll
-        for (int v = 0; v < S; ++v) {
-          const V mm = mr[u * S + v];
-          re = fma(mm.x, in[v].x, re);
-          re = fma(-mm.y, in[v].y, re);
-          im = fma(mm.x, in[v].y, im);
-          im = fma(mm.y, in[v].x, im);
-        }
-        V o;
-        o.x = re;
-        o.y = im;
-        tile[addr[u]] = o;
-      }
+    for (int u = 0; u < S; ++u) {
+      addr[u] = swz<R>(t0 + mo->off[u]);
+      in[u] = tile[addr[u]];
     }
-  } else {
-    for (uint32_t g = threadIdx.x; g < groups; g += kTileThreads) {
-      const uint32_t t0 = expand_local(g, mo);
-      V in[S];
-      uint32_t addr[S];
 #pragma unroll
-      for (int u = 0; u < S; ++u) {
-        addr[u] = swz<R>(t0 + mo->off[u]);
-        in[u] = tile[addr[u]];
+    for (int u = 0; u < S; ++u) {
+      R re = (R)0, im = (R)0;
+#pragma unroll
+      for (int v = 0; v < S; ++v) {
+        const R mr = mat[2 * (u * S + v)], mi = mat[2 * (u * S + v) + 1];
+        re = fma(mr, in[v].x, re);
+        re = fma(-mi, in[v].y, re);
+        im = fma(mr, in[v].y, im);
+        im = fma(mi, in[v].x, im);
       }
-#pragma unroll
-      for (int u = 0; u < S; ++u) {
-        R re = (R)0, im = (R)0;
-#pragma unroll
-        for (int v = 0; v < S; ++v) {
-          const V mm = m2[u * S + v];  // broadcast read from the staged matrix
-          re = fma(mm.x, in[v].x, re);
-          re = fma(-mm.y, in[v].y, re);
-          im = fma(mm.x, in[v].y, im);
-          im = fma(mm.y, in[v].x, im);
-        }
-        V o;
-        o.x = re;
-        o.y = im;
-        tile[addr[u]] = o;
-      }
+      V o;
+      o.x = re;
+      o.y = im;
+      tile[addr[u]] = o;
     }
   }
 }
@@ -161,22 +293,15 @@ __device__ __forceinline__ void apply_diag(typename C2<R>::type *tile, const Mic
   }
 }
 
-__device__ __forceinline__ void stage_record(unsigned char *dst, const unsigned char *src, uint32_t bytes) {
-  const uint32_t units = bytes >> 4;
-  for (uint32_t i = threadIdx.x; i < units; i += kTileThreads)
-    reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
-}
-
 template <typename R>
 __global__ void __launch_bounds__(kTileThreads, 3)
-    k_tile_pass(R *__restrict__ psi, const unsigned char *__restrict__ blob) {
+    k_tile_pass(R *__restrict__ psi, const __grid_constant__ PassParams pp) {
   typedef typename C2<R>::type V;
   extern __shared__ __align__(1024) unsigned char smem[];
-  const PassHeader *h = reinterpret_cast<const PassHeader *>(blob);
+  const PassHeader *h = &pp.h;
   const uint32_t T = h->T, L = h->L, m = h->m, n_ops = h->n_ops;
   const uint32_t tile_bytes = (uint32_t)(2 * sizeof(R)) << T;
   V *tile = reinterpret_cast<V *>(smem);
-  unsigned char *stage = smem + tile_bytes;
 
   uint64_t base = (uint64_t)blockIdx.x << L;
   for (uint32_t i = 0; i < m; ++i) {
@@ -196,28 +321,19 @@ __global__ void __launch_bounds__(kTileThreads, 3)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-
-  const unsigned char *rec = blob + sizeof(PassHeader);
-  uint32_t rec_bytes = 0;
-  if (n_ops) {
-    rec_bytes = (uint32_t)sizeof(MicroOp) + reinterpret_cast<const MicroOp *>(rec)->data_bytes;
-    stage_record(stage, rec, rec_bytes);
-  }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   // ---- 2. apply ----
+  const unsigned char *rec = pp.recs;
   for (uint32_t i = 0; i < n_ops; ++i) {
-    unsigned char *cur = stage + (i & 1u) * kTileStageBytes;
-    const MicroOp *mo = reinterpret_cast<const MicroOp *>(cur);
-    if (i + 1 < n_ops) {  // stage the next record while this one runs
-      rec += rec_bytes;
-      rec_bytes = (uint32_t)sizeof(MicroOp) + reinterpret_cast<const MicroOp *>(rec)->data_bytes;
-      stage_record(stage + ((i + 1) & 1u) * kTileStageBytes, rec, rec_bytes);
-    }
+    const MicroOp *mo = reinterpret_cast<const MicroOp *>(rec);
+    const unsigned char *data = rec + sizeof(MicroOp);
+    rec = data + mo->data_bytes;
     if ((base & mo->gmask) == mo->gmask) {
-      const unsigned char *data = cur + sizeof(MicroOp);
-      if (mo->kind == MK_DENSE) {
+      if (mo->kind == MK_SUPER) {
+        run_super<R>(tile, mo, data, base);
+      } else if (mo->kind == MK_DENSE) {
         const R *mat = reinterpret_cast<const R *>(data);
         if (mo->k == 1)
           apply_dense<R, 1>(tile, mo, mat);
@@ -234,12 +350,42 @@ __global__ void __launch_bounds__(kTileThreads, 3)
     __syncthreads();
   }
 
-  // ---- 3. store ----
+  // ---- 3. store (with the CTA-uniform phase product folded in) ----
+  R gr = (R)1, gi = (R)0;
+  bool has_g = false;
+  {
+    const GlobalTerm<R> *gt = reinterpret_cast<const GlobalTerm<R> *>(pp.recs + h->gterm_off);
+    for (uint32_t k = 0; k < h->n_gterms; ++k) {
+      if ((base & gt[k].gmask) != gt[k].gval) continue;
+      const R nr = gr * gt[k].re - gi * gt[k].im;
+      gi = gr * gt[k].im + gi * gt[k].re;
+      gr = nr;
+      has_g = true;
+    }
+  }
   for (uint32_t u = threadIdx.x; u < units; u += kTileThreads) {
     const uint32_t t = u * kAmpsPerUnit;
     R *g = psi + 2 * (base + h->chunk_off[t >> L] + (t & lmask));
-    const uint4 v = *reinterpret_cast<const uint4 *>(smem + 16u * (u ^ ((u >> 3) & 7u)));
-    *reinterpret_cast<uint4 *>(g) = v;
+    const unsigned char *sp = smem + 16u * (u ^ ((u >> 3) & 7u));
+    if (has_g) {
+      if (sizeof(R) == 8) {
+        double2 v = *reinterpret_cast<const double2 *>(sp);
+        double2 o;
+        o.x = fma((double)gr, v.x, -(double)gi * v.y);
+        o.y = fma((double)gr, v.y, (double)gi * v.x);
+        *reinterpret_cast<double2 *>(g) = o;
+      } else {
+        float4 v = *reinterpret_cast<const float4 *>(sp);
+        float4 o;
+        o.x = fmaf((float)gr, v.x, -(float)gi * v.y);
+        o.y = fmaf((float)gr, v.y, (float)gi * v.x);
+        o.z = fmaf((float)gr, v.z, -(float)gi * v.w);
+        o.w = fmaf((float)gr, v.w, (float)gi * v.z);
+        *reinterpret_cast<float4 *>(g) = o;
+      }
+    } else {
+      *reinterpret_cast<uint4 *>(g) = *reinterpret_cast<const uint4 *>(sp);
+    }
   }
 }
 
@@ -249,15 +395,15 @@ cudaError_t tile_pass_configure() {
   return cudaFuncSetAttribute(k_tile_pass<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
 }
 
-cudaError_t launch_tile_pass(qip_prec prec, void *psi, uint32_t n_local, uint32_t T, const unsigned char *d_blob,
-                             cudaStream_t s, uint64_t *launches) {
-  const size_t tile_bytes = (prec == QIP_F32 ? 8u : 16u) << T;
-  const size_t smem = tile_bytes + 2 * kTileStageBytes;
+cudaError_t launch_tile_pass(qip_prec prec, void *psi, uint32_t n_local, const PassParams &pp, cudaStream_t s,
+                             uint64_t *launches) {
+  const uint32_t T = pp.h.T;
+  const size_t smem = (prec == QIP_F32 ? 8u : 16u) << T;
   const unsigned grid = 1u << (n_local - T);
   if (prec == QIP_F32)
-    k_tile_pass<float><<<grid, kTileThreads, smem, s>>>((float *)psi, d_blob);
+    k_tile_pass<float><<<grid, kTileThreads, smem, s>>>((float *)psi, pp);
   else
-    k_tile_pass<double><<<grid, kTileThreads, smem, s>>>((double *)psi, d_blob);
+    k_tile_pass<double><<<grid, kTileThreads, smem, s>>>((double *)psi, pp);
   ++*launches;
   return cudaGetLastError();
 }

@@ -49,10 +49,53 @@ static void apply_single(const FlatOp &f, uint32_t n, std::vector<cd> &psi) {
   psi.swap(out);
 }
 
+// elementary op on the 8 register-resident amplitudes of one group (mirrors tile_kernel.cu)
 template <typename R>
-static void run_pass_blob(const std::vector<unsigned char> &blob, uint32_t n, std::vector<cd> &psi) {
-  PassHeader h;
-  memcpy(&h, blob.data(), sizeof(h));
+static void run_elem(const Elem<R> &e, const R *mat8, cd a[8], uint64_t base) {
+  if ((base & e.gmask) != e.gval) return;
+  switch (e.type) {
+    case E_DENSE1:
+      for (uint32_t c = 0; c < 8; ++c) {
+        if ((c >> e.j) & 1) continue;
+        if ((c & e.lc) != e.lc) continue;
+        const uint32_t i0 = c, i1 = c | (1u << e.j);
+        const cd x = a[i0], y = a[i1];
+        a[i0] = cd(e.m[0], e.m[1]) * x + cd(e.m[2], e.m[3]) * y;
+        a[i1] = cd(e.m[4], e.m[5]) * x + cd(e.m[6], e.m[7]) * y;
+      }
+      break;
+    case E_X:
+      for (uint32_t c = 0; c < 8; ++c) {
+        if ((c >> e.j) & 1) continue;
+        if ((c & e.lc) != e.lc) continue;
+        std::swap(a[c], a[c | (1u << e.j)]);
+      }
+      break;
+    case E_PHASE:
+      for (uint32_t c = 0; c < 8; ++c)
+        if ((c & e.lmask) == e.lval) a[c] *= cd(e.m[0], e.m[1]);
+      break;
+    case E_SWAP:
+      for (uint32_t c = 0; c < 8; ++c) {
+        if ((c & e.lc) != e.lc) continue;
+        if (((c >> e.j) & 1) == 1 && ((c >> e.k) & 1) == 0) std::swap(a[c], a[c ^ (1u << e.j) ^ (1u << e.k)]);
+      }
+      break;
+    default: {  // E_DENSE3
+      cd out[8];
+      for (uint32_t u = 0; u < 8; ++u) {
+        cd acc(0, 0);
+        for (uint32_t v = 0; v < 8; ++v) acc += cd(mat8[2 * (u * 8 + v)], mat8[2 * (u * 8 + v) + 1]) * a[v];
+        out[u] = acc;
+      }
+      for (uint32_t u = 0; u < 8; ++u) a[u] = out[u];
+    }
+  }
+}
+
+template <typename R>
+static void run_pass_params(const PassParams &pp, uint32_t n, std::vector<cd> &psi) {
+  const PassHeader &h = pp.h;
   const uint32_t T = h.T, L = h.L, m = h.m;
   const uint64_t tiles = 1ull << (n - T);
   std::vector<cd> tile(1ull << T);
@@ -63,7 +106,7 @@ static void run_pass_blob(const std::vector<unsigned char> &blob, uint32_t n, st
       base = ((base >> p) << (p + 1)) | (base & ((1ull << p) - 1));
     }
     for (uint64_t t = 0; t < (1ull << T); ++t) tile[t] = psi[base + h.chunk_off[t >> L] + (t & ((1ull << L) - 1))];
-    const unsigned char *rp = blob.data() + sizeof(PassHeader);
+    const unsigned char *rp = pp.recs;
     for (uint32_t oi = 0; oi < h.n_ops; ++oi) {
       MicroOp mo;
       memcpy(&mo, rp, sizeof(mo));
@@ -88,21 +131,39 @@ static void run_pass_blob(const std::vector<unsigned char> &blob, uint32_t n, st
         t0 |= mo.lor_mask;
         if (mo.kind == MK_EXCH) {
           std::swap(tile[t0 + mo.off[0]], tile[t0 + mo.off[1]]);
+        } else if (mo.kind == MK_SUPER) {
+          cd a[8];
+          for (uint32_t u = 0; u < 8; ++u) a[u] = tile[t0 + mo.off[u]];
+          const unsigned char *ep = data;
+          for (uint32_t ei = 0; ei < mo.nterms; ++ei) {
+            Elem<R> e;
+            memcpy(&e, ep, sizeof(e));
+            ep += sizeof(e);
+            const R *mat8 = reinterpret_cast<const R *>(ep);
+            if (e.type == E_DENSE3) ep += 128 * sizeof(R);
+            run_elem<R>(e, mat8, a, base);
+          }
+          for (uint32_t u = 0; u < 8; ++u) tile[t0 + mo.off[u]] = a[u];
         } else {
           const uint32_t S = 1u << mo.k;
           const R *mat = reinterpret_cast<const R *>(data);
           cd in[8], out[8];
           for (uint32_t u = 0; u < S; ++u) in[u] = tile[t0 + mo.off[u]];
           for (uint32_t u = 0; u < S; ++u) {
-            cd a(0, 0);
-            for (uint32_t v = 0; v < S; ++v) a += cd(mat[2 * (u * S + v)], mat[2 * (u * S + v) + 1]) * in[v];
-            out[u] = a;
+            cd acc(0, 0);
+            for (uint32_t v = 0; v < S; ++v) acc += cd(mat[2 * (u * S + v)], mat[2 * (u * S + v) + 1]) * in[v];
+            out[u] = acc;
           }
           for (uint32_t u = 0; u < S; ++u) tile[t0 + mo.off[u]] = out[u];
         }
       }
     }
-    for (uint64_t t = 0; t < (1ull << T); ++t) psi[base + h.chunk_off[t >> L] + (t & ((1ull << L) - 1))] = tile[t];
+    // CTA-uniform phase terms, applied once at store time
+    cd gp(1, 0);
+    const GlobalTerm<R> *gt = reinterpret_cast<const GlobalTerm<R> *>(pp.recs + h.gterm_off);
+    for (uint32_t k = 0; k < h.n_gterms; ++k)
+      if ((base & gt[k].gmask) == gt[k].gval) gp *= cd(gt[k].re, gt[k].im);
+    for (uint64_t t = 0; t < (1ull << T); ++t) psi[base + h.chunk_off[t >> L] + (t & ((1ull << L) - 1))] = tile[t] * gp;
   }
 }
 
@@ -122,7 +183,7 @@ extern "C" int emul_schedule(int prec, uint32_t n, const qip_op *ops, size_t n_o
   if (T) cfg.T = T;
   if (L) cfg.L = L;
   cfg.fuse_blocks = fuse_blocks != 0;
-  if (max_k) cfg.max_block_k = max_k;
+  if (max_k) cfg.compose_threshold = max_k;
   std::vector<PlanStep> steps;
   plan_passes(flat, n, (qip_prec)prec, cfg, &steps);
   std::vector<cd> psi(1ull << n);
@@ -130,12 +191,15 @@ extern "C" int emul_schedule(int prec, uint32_t n, const qip_op *ops, size_t n_o
   uint64_t n_pass = 0, n_single = 0, n_micro = 0, n_gates_in_pass = 0;
   for (size_t s = 0; s < steps.size(); ++s) {
     if (steps[s].is_pass) {
-      std::vector<unsigned char> blob;
-      serialise_pass(steps[s].pass, &blob);
+      PassParams pp;
+      if (!serialise_pass(steps[s].pass, &pp)) {
+        if (errbuf && errlen) snprintf(errbuf, errlen, "pass does not fit the parameter space");
+        return -2;
+      }
       if (prec == QIP_F32)
-        run_pass_blob<float>(blob, n, psi);
+        run_pass_params<float>(pp, n, psi);
       else
-        run_pass_blob<double>(blob, n, psi);
+        run_pass_params<double>(pp, n, psi);
       ++n_pass;
       n_micro += steps[s].pass.ops.size();
       n_gates_in_pass += steps[s].pass.n_gates;
@@ -170,7 +234,7 @@ extern "C" int emul_plan_stats(int prec, uint32_t n, const qip_op *ops, size_t n
   if (T) cfg.T = T;
   if (L) cfg.L = L;
   cfg.fuse_blocks = fuse_blocks != 0;
-  if (max_k) cfg.max_block_k = max_k;
+  if (max_k) cfg.compose_threshold = max_k;
   std::vector<PlanStep> steps;
   plan_passes(flat, n, (qip_prec)prec, cfg, &steps);
   uint64_t n_pass = 0, n_single = 0, n_micro = 0, n_gates_in_pass = 0, dense_k[4] = {0, 0, 0, 0}, diag_terms = 0, exch = 0;
@@ -186,10 +250,11 @@ extern "C" int emul_plan_stats(int prec, uint32_t n, const qip_op *ops, size_t n
       const MicroOp &mo = steps[s].pass.ops[i].h;
       if (mo.kind == MK_DENSE) dense_k[mo.k]++;
       else if (mo.kind == MK_DIAG) diag_terms += mo.nterms;
-      else exch++;
+      else if (mo.kind == MK_SUPER) { dense_k[0]++; exch += mo.nterms; }
+      else dense_k[1]++;
     }
   }
   stats[0] = n_pass; stats[1] = n_single; stats[2] = n_micro; stats[3] = n_gates_in_pass;
-  stats[4] = dense_k[1]; stats[5] = dense_k[2]; stats[6] = dense_k[3]; stats[7] = diag_terms; stats[8] = exch;
+  stats[4] = dense_k[0]; /* super-ops */ stats[5] = exch; /* elementary ops */ stats[6] = dense_k[2] + dense_k[3]; stats[7] = diag_terms; stats[8] = dense_k[1];
   return 0;
 }

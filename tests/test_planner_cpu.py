@@ -40,7 +40,7 @@ def emul():
     return L
 
 
-def run_emul(L, n, ops, psi, dtype=np.complex128, T=0, Lo=0, fuse=True, max_k=3):
+def run_emul(L, n, ops, psi, dtype=np.complex128, T=0, Lo=0, fuse=True, max_k=0):
     prec = prec_of(dtype)
     arr, keep = marshal_ops(ops, prec)
     st = np.ascontiguousarray(psi.astype(np.complex128))
@@ -139,7 +139,7 @@ def test_plan_stats_bench_circuits(emul):
         prec = prec_of(dtype)
         arr, keep = marshal_ops(ops, prec)
         stats = np.zeros(16, dtype=np.uint64)
-        assert emul.emul_plan_stats(prec, n, arr, len(ops), 0, 0, 1, 3, stats.ctypes.data) == 0
+        assert emul.emul_plan_stats(prec, n, arr, len(ops), 0, 0, 1, 0, stats.ctypes.data) == 0
         out[name] = (len(ops), [int(x) for x in stats[:9]])
         sweeps = int(stats[0] + stats[1])
         assert sweeps < len(ops) / 4, (name, sweeps)
