@@ -222,7 +222,7 @@ struct Emitter {
     size_t n_dense = 0;
     bool conditional = false;
     for (size_t i = 0; i < elems.size(); ++i) {
-      n_dense += elems[i].type == E_DENSE1 ? 1 : (elems[i].type == E_DENSE3 ? 4 : 0);
+      n_dense += elems[i].type == E_DENSE1 ? 1 : (elems[i].type == E_DENSE3 ? 4 : 0);  // host elems are never E_DENSE1R
       conditional |= elems[i].gmask != 0;
     }
     if (!conditional && elems.size() > 1 && n_dense >= cfg->compose_threshold) {
@@ -255,32 +255,58 @@ struct Emitter {
       const HElem &e = elems[i];
       Elem<R> d;
       memset(&d, 0, sizeof(d));
-      d.type = (uint32_t)e.type;
       d.gmask = e.gmask;
       d.gval = e.gval;
+      const bool cond = e.gmask != 0;
+      uint32_t lc = 0, lm = 0, lv = 0;
       for (uint32_t b = 0; b < 32; ++b) {
-        if ((e.lctrl >> b) & 1) d.lc |= 1u << sub_of(b);
+        if ((e.lctrl >> b) & 1) lc |= 1u << sub_of(b);
         if ((e.lmask >> b) & 1) {
-          d.lmask |= 1u << sub_of(b);
-          d.lval |= ((e.lval >> b) & 1u) << sub_of(b);
+          lm |= 1u << sub_of(b);
+          lv |= ((e.lval >> b) & 1u) << sub_of(b);
         }
       }
-      if (e.type == E_DENSE1 || e.type == E_X) d.j = sub_of(e.lb_j);
-      if (e.type == E_SWAP) {
-        d.j = std::min(sub_of(e.lb_j), sub_of(e.lb_k));
-        d.k = std::max(sub_of(e.lb_j), sub_of(e.lb_k));
-      }
-      if (e.type == E_DENSE1) {
-        bool real = true;
-        for (int q = 0; q < 4; ++q) {
-          d.m[2 * q] = (R)e.m[q].real();
-          d.m[2 * q + 1] = (R)e.m[q].imag();
-          real &= e.m[q].imag() == 0.0;
+      if (e.type == E_DENSE1 || e.type == E_X) {
+        const uint32_t j = sub_of(e.lb_j);
+        uint32_t pm = 0, p = 0;
+        for (uint32_t c = 0; c < 8; ++c) {
+          if ((c >> j) & 1) continue;
+          if ((c & lc) == lc) pm |= 1u << p;
+          ++p;
         }
-        if (real) d.flags |= EF_REAL;
+        if (e.type == E_X) {
+          d.op = elem_op(E_X, j, 0, pm, cond);
+        } else {
+          bool real = true;
+          for (int q = 0; q < 4; ++q) real &= e.m[q].imag() == 0.0;
+          d.op = elem_op(real ? E_DENSE1R : E_DENSE1, j, 0, pm, cond);
+          for (int q = 0; q < 4; ++q) {
+            if (real) {
+              d.m[q] = (R)e.m[q].real();
+            } else {
+              d.m[2 * q] = (R)e.m[q].real();
+              d.m[2 * q + 1] = (R)e.m[q].imag();
+            }
+          }
+        }
+      } else if (e.type == E_SWAP) {
+        const uint32_t j = std::min(sub_of(e.lb_j), sub_of(e.lb_k)), k = std::max(sub_of(e.lb_j), sub_of(e.lb_k));
+        uint32_t pm = 0, p = 0;
+        for (uint32_t c = 0; c < 8; ++c) {
+          if (!(((c >> j) & 1) == 1 && ((c >> k) & 1) == 0)) continue;
+          if ((c & lc) == lc) pm |= 1u << p;
+          ++p;
+        }
+        d.op = elem_op(E_SWAP, j, k, pm, cond);
       } else if (e.type == E_PHASE) {
+        uint32_t am = 0;
+        for (uint32_t c = 0; c < 8; ++c)
+          if ((c & lm) == lv) am |= 1u << c;
+        d.op = elem_op(E_PHASE, 0, 0, am, cond);
         d.m[0] = (R)e.m[0].real();
         d.m[1] = (R)e.m[0].imag();
+      } else {
+        d.op = elem_op(E_DENSE3, 0, 0, 0, cond);
       }
       const size_t at = mo.data.size();
       mo.data.resize(at + sizeof(d));

@@ -31,8 +31,19 @@ static const uint32_t kMaxDiagTerms = 24;     // per MK_DIAG micro-op
 static const uint32_t kMaxGlobalTerms = 32;   // CTA-uniform phase terms applied at store time
 
 enum MicroKind { MK_DENSE = 0, MK_DIAG = 1, MK_EXCH = 2, MK_SUPER = 3 };
-enum ElemType { E_DENSE1 = 0, E_X = 1, E_PHASE = 2, E_SWAP = 3, E_DENSE3 = 4 };
-enum ElemFlags { EF_REAL = 1u };  // E_DENSE1 with a purely real matrix (H, Ry, X-like): half the FMAs
+// Elementary-op kinds of a MK_SUPER group.  Real and complex 2x2 gates are separate kinds
+// (a real matrix -- H, Ry, X-like -- needs half the FMAs).
+enum ElemType { E_DENSE1 = 0, E_DENSE1R = 1, E_X = 2, E_PHASE = 3, E_SWAP = 4, E_DENSE3 = 5 };
+
+// Elem::op layout: bits 0-7 kind, 8-9 j, 10-11 k, 12-19 active mask, bit 31 "has a
+// CTA-uniform condition".  The active mask is precomputed on the host from the op's
+// controls: for DENSE1/X bit p <-> the p-th (ascending) sub-index with bit j clear;
+// for SWAP bit p <-> the p-th sub-index with bit j set and bit k clear; for PHASE bit c
+// <-> sub-index c.
+static const uint32_t kElemHasCond = 1u << 31;
+inline uint32_t elem_op(uint32_t kind, uint32_t j, uint32_t k, uint32_t mask, bool cond) {
+  return kind | (j << 8) | (k << 10) | (mask << 12) | (cond ? kElemHasCond : 0u);
+}
 
 // Device-visible micro-op header (fixed 128 bytes), followed by its data:
 //   MK_DENSE: 2^k x 2^k complex<R> (re,im interleaved), sub-index bit i <-> ins_pos order of targets
@@ -61,17 +72,15 @@ struct alignas(16) DiagTerm {  // multiply by (re,im) where (global & gmask)==gv
   R re, im;
 };
 
-// Elementary op of a MK_SUPER group; j, k, lc, lmask, lval are in SUB-INDEX coordinates
-// (bit i of the sub-index <-> ins_pos[i] of the enclosing micro-op).
+// Elementary op of a MK_SUPER group, in SUB-INDEX coordinates (bit i of the sub-index
+// <-> ins_pos[i] of the enclosing micro-op).  E_DENSE3 records are followed by 64 complex<R>.
 template <typename R>
 struct alignas(16) Elem {
-  uint32_t type;         // ElemType
-  uint32_t j, k;         // target sub-bit (DENSE1/X), the two sub-bits of a SWAP
-  uint32_t lc;           // sub-index control mask (bits that must be 1)
-  uint32_t lmask, lval;  // PHASE: applies where (sub & lmask) == lval
-  uint32_t flags, pad;
-  uint64_t gmask, gval;  // CTA-uniform condition on the tile's base index
-  R m[8];                // DENSE1: m00,m01,m10,m11 (re,im); PHASE: w (re,im)
+  uint32_t op;           // see elem_op()
+  uint32_t pad;
+  uint64_t gmask, gval;  // CTA-uniform condition on the tile's base index (read only if kElemHasCond)
+  uint64_t pad2;
+  R m[8];                // DENSE1: m00,m01,m10,m11 (re,im); DENSE1R: m00,m01,m10,m11 (re); PHASE: w (re,im)
 };
 
 template <typename R>

@@ -63,39 +63,49 @@ struct Amp8 {
   R re[8], im[8];
 };
 
+// The p-th (ascending) sub-index with bit J clear.
+template <int J>
+__device__ __forceinline__ constexpr int pair_base(int p) {
+  return ((p >> J) << (J + 1)) | (p & ((1 << J) - 1));
+}
+
 template <typename R, int J>
-__device__ __forceinline__ void e_dense1(Amp8<R> &a, const Elem<R> *e) {
-  const uint32_t lc = e->lc;
+__device__ __forceinline__ void e_dense1c(Amp8<R> &a, const Elem<R> *e, uint32_t pm) {
   const R m00r = e->m[0], m00i = e->m[1], m01r = e->m[2], m01i = e->m[3];
   const R m10r = e->m[4], m10i = e->m[5], m11r = e->m[6], m11i = e->m[7];
-  const bool real = e->flags & EF_REAL;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    if ((c >> J) & 1) continue;
-    if ((c & lc) != lc) continue;  // uniform across the CTA
-    const int i0 = c, i1 = c | (1 << J);
+  for (int p = 0; p < 4; ++p) {
+    if (!((pm >> p) & 1u)) continue;  // CTA-uniform (a control inside the group)
+    const int i0 = pair_base<J>(p), i1 = i0 | (1 << J);
     const R xr = a.re[i0], xi = a.im[i0], yr = a.re[i1], yi = a.im[i1];
-    if (real) {
-      a.re[i0] = fma(m00r, xr, m01r * yr);
-      a.im[i0] = fma(m00r, xi, m01r * yi);
-      a.re[i1] = fma(m10r, xr, m11r * yr);
-      a.im[i1] = fma(m10r, xi, m11r * yi);
-    } else {
-      a.re[i0] = fma(m00r, xr, fma(-m00i, xi, fma(m01r, yr, -m01i * yi)));
-      a.im[i0] = fma(m00r, xi, fma(m00i, xr, fma(m01r, yi, m01i * yr)));
-      a.re[i1] = fma(m10r, xr, fma(-m10i, xi, fma(m11r, yr, -m11i * yi)));
-      a.im[i1] = fma(m10r, xi, fma(m10i, xr, fma(m11r, yi, m11i * yr)));
-    }
+    a.re[i0] = fma(m00r, xr, fma(-m00i, xi, fma(m01r, yr, -m01i * yi)));
+    a.im[i0] = fma(m00r, xi, fma(m00i, xr, fma(m01r, yi, m01i * yr)));
+    a.re[i1] = fma(m10r, xr, fma(-m10i, xi, fma(m11r, yr, -m11i * yi)));
+    a.im[i1] = fma(m10r, xi, fma(m10i, xr, fma(m11r, yi, m11i * yr)));
   }
 }
 
 template <typename R, int J>
-__device__ __forceinline__ void e_x(Amp8<R> &a, uint32_t lc) {
+__device__ __forceinline__ void e_dense1r(Amp8<R> &a, const Elem<R> *e, uint32_t pm) {
+  const R m00 = e->m[0], m01 = e->m[1], m10 = e->m[2], m11 = e->m[3];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    if ((c >> J) & 1) continue;
-    if ((c & lc) != lc) continue;
-    const int i0 = c, i1 = c | (1 << J);
+  for (int p = 0; p < 4; ++p) {
+    if (!((pm >> p) & 1u)) continue;
+    const int i0 = pair_base<J>(p), i1 = i0 | (1 << J);
+    const R xr = a.re[i0], xi = a.im[i0], yr = a.re[i1], yi = a.im[i1];
+    a.re[i0] = fma(m00, xr, m01 * yr);
+    a.im[i0] = fma(m00, xi, m01 * yi);
+    a.re[i1] = fma(m10, xr, m11 * yr);
+    a.im[i1] = fma(m10, xi, m11 * yi);
+  }
+}
+
+template <typename R, int J>
+__device__ __forceinline__ void e_x(Amp8<R> &a, uint32_t pm) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    if (!((pm >> p) & 1u)) continue;
+    const int i0 = pair_base<J>(p), i1 = i0 | (1 << J);
     const R tr = a.re[i0], ti = a.im[i0];
     a.re[i0] = a.re[i1];
     a.im[i0] = a.im[i1];
@@ -105,11 +115,14 @@ __device__ __forceinline__ void e_x(Amp8<R> &a, uint32_t lc) {
 }
 
 template <typename R, int J, int K>
-__device__ __forceinline__ void e_swap(Amp8<R> &a, uint32_t lc) {
+__device__ __forceinline__ void e_swap(Amp8<R> &a, uint32_t pm) {
+  int p = 0;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     if (!(((c >> J) & 1) == 1 && ((c >> K) & 1) == 0)) continue;
-    if ((c & lc) != lc) continue;
+    const bool on = (pm >> p) & 1u;
+    ++p;
+    if (!on) continue;
     const int d = c ^ (1 << J) ^ (1 << K);
     const R tr = a.re[c], ti = a.im[c];
     a.re[c] = a.re[d];
@@ -120,12 +133,11 @@ __device__ __forceinline__ void e_swap(Amp8<R> &a, uint32_t lc) {
 }
 
 template <typename R>
-__device__ __forceinline__ void e_phase(Amp8<R> &a, const Elem<R> *e) {
-  const uint32_t lm = e->lmask, lv = e->lval;
+__device__ __forceinline__ void e_phase(Amp8<R> &a, const Elem<R> *e, uint32_t am) {
   const R wr = e->m[0], wi = e->m[1];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    if ((c & lm) != lv) continue;
+    if (!((am >> c) & 1u)) continue;
     const R xr = a.re[c], xi = a.im[c];
     a.re[c] = fma(wr, xr, -wi * xi);
     a.im[c] = fma(wr, xi, wi * xr);
@@ -172,38 +184,49 @@ __device__ __forceinline__ void run_super(typename C2<R>::type *tile, const Micr
     for (uint32_t ei = 0; ei < mo->nterms; ++ei) {
       const Elem<R> *e = reinterpret_cast<const Elem<R> *>(ep);
       ep += sizeof(Elem<R>);
-      const uint32_t type = e->type;
+      const uint32_t op = e->op;
+      const uint32_t kind = op & 0xffu, j = (op >> 8) & 3u, mask = (op >> 12) & 0xffu;
       const R *m8 = reinterpret_cast<const R *>(ep);
-      if (type == E_DENSE3) ep += 128 * sizeof(R);
-      if ((base & e->gmask) != e->gval) continue;  // CTA-uniform: a control outside the tile is 0
-      switch (type) {
-        case E_DENSE1:
-          if (e->j == 0)
-            e_dense1<R, 0>(a, e);
-          else if (e->j == 1)
-            e_dense1<R, 1>(a, e);
+      if (kind == E_DENSE3) ep += 128 * sizeof(R);
+      if ((op & kElemHasCond) && (base & e->gmask) != e->gval) continue;  // a control outside the tile is 0
+      switch (kind) {
+        case E_DENSE1R:
+          if (j == 0)
+            e_dense1r<R, 0>(a, e, mask);
+          else if (j == 1)
+            e_dense1r<R, 1>(a, e, mask);
           else
-            e_dense1<R, 2>(a, e);
+            e_dense1r<R, 2>(a, e, mask);
+          break;
+        case E_DENSE1:
+          if (j == 0)
+            e_dense1c<R, 0>(a, e, mask);
+          else if (j == 1)
+            e_dense1c<R, 1>(a, e, mask);
+          else
+            e_dense1c<R, 2>(a, e, mask);
           break;
         case E_X:
-          if (e->j == 0)
-            e_x<R, 0>(a, e->lc);
-          else if (e->j == 1)
-            e_x<R, 1>(a, e->lc);
+          if (j == 0)
+            e_x<R, 0>(a, mask);
+          else if (j == 1)
+            e_x<R, 1>(a, mask);
           else
-            e_x<R, 2>(a, e->lc);
+            e_x<R, 2>(a, mask);
           break;
         case E_PHASE:
-          e_phase<R>(a, e);
+          e_phase<R>(a, e, mask);
           break;
-        case E_SWAP:
-          if (e->j == 0 && e->k == 1)
-            e_swap<R, 0, 1>(a, e->lc);
-          else if (e->j == 0)
-            e_swap<R, 0, 2>(a, e->lc);
+        case E_SWAP: {
+          const uint32_t k = (op >> 10) & 3u;
+          if (j == 0 && k == 1)
+            e_swap<R, 0, 1>(a, mask);
+          else if (j == 0)
+            e_swap<R, 0, 2>(a, mask);
           else
-            e_swap<R, 1, 2>(a, e->lc);
+            e_swap<R, 1, 2>(a, mask);
           break;
+        }
         default:
           e_dense3<R>(a, m8);
       }

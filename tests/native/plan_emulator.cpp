@@ -52,33 +52,46 @@ static void apply_single(const FlatOp &f, uint32_t n, std::vector<cd> &psi) {
 // elementary op on the 8 register-resident amplitudes of one group (mirrors tile_kernel.cu)
 template <typename R>
 static void run_elem(const Elem<R> &e, const R *mat8, cd a[8], uint64_t base) {
-  if ((base & e.gmask) != e.gval) return;
-  switch (e.type) {
+  if ((e.op & kElemHasCond) && (base & e.gmask) != e.gval) return;
+  const uint32_t kind = e.op & 0xff, j = (e.op >> 8) & 3, k = (e.op >> 10) & 3, mask = (e.op >> 12) & 0xff;
+  uint32_t p = 0;
+  switch (kind) {
     case E_DENSE1:
+    case E_DENSE1R:
       for (uint32_t c = 0; c < 8; ++c) {
-        if ((c >> e.j) & 1) continue;
-        if ((c & e.lc) != e.lc) continue;
-        const uint32_t i0 = c, i1 = c | (1u << e.j);
+        if ((c >> j) & 1) continue;
+        const bool on = (mask >> p) & 1;
+        ++p;
+        if (!on) continue;
+        const uint32_t i0 = c, i1 = c | (1u << j);
         const cd x = a[i0], y = a[i1];
-        a[i0] = cd(e.m[0], e.m[1]) * x + cd(e.m[2], e.m[3]) * y;
-        a[i1] = cd(e.m[4], e.m[5]) * x + cd(e.m[6], e.m[7]) * y;
+        if (kind == E_DENSE1R) {
+          a[i0] = (double)e.m[0] * x + (double)e.m[1] * y;
+          a[i1] = (double)e.m[2] * x + (double)e.m[3] * y;
+        } else {
+          a[i0] = cd(e.m[0], e.m[1]) * x + cd(e.m[2], e.m[3]) * y;
+          a[i1] = cd(e.m[4], e.m[5]) * x + cd(e.m[6], e.m[7]) * y;
+        }
       }
       break;
     case E_X:
       for (uint32_t c = 0; c < 8; ++c) {
-        if ((c >> e.j) & 1) continue;
-        if ((c & e.lc) != e.lc) continue;
-        std::swap(a[c], a[c | (1u << e.j)]);
+        if ((c >> j) & 1) continue;
+        const bool on = (mask >> p) & 1;
+        ++p;
+        if (on) std::swap(a[c], a[c | (1u << j)]);
       }
       break;
     case E_PHASE:
       for (uint32_t c = 0; c < 8; ++c)
-        if ((c & e.lmask) == e.lval) a[c] *= cd(e.m[0], e.m[1]);
+        if ((mask >> c) & 1) a[c] *= cd(e.m[0], e.m[1]);
       break;
     case E_SWAP:
       for (uint32_t c = 0; c < 8; ++c) {
-        if ((c & e.lc) != e.lc) continue;
-        if (((c >> e.j) & 1) == 1 && ((c >> e.k) & 1) == 0) std::swap(a[c], a[c ^ (1u << e.j) ^ (1u << e.k)]);
+        if (!(((c >> j) & 1) == 1 && ((c >> k) & 1) == 0)) continue;
+        const bool on = (mask >> p) & 1;
+        ++p;
+        if (on) std::swap(a[c], a[c ^ (1u << j) ^ (1u << k)]);
       }
       break;
     default: {  // E_DENSE3
@@ -140,7 +153,7 @@ static void run_pass_params(const PassParams &pp, uint32_t n, std::vector<cd> &p
             memcpy(&e, ep, sizeof(e));
             ep += sizeof(e);
             const R *mat8 = reinterpret_cast<const R *>(ep);
-            if (e.type == E_DENSE3) ep += 128 * sizeof(R);
+            if ((e.op & 0xff) == E_DENSE3) ep += 128 * sizeof(R);
             run_elem<R>(e, mat8, a, base);
           }
           for (uint32_t u = 0; u < 8; ++u) tile[t0 + mo.off[u]] = a[u];
