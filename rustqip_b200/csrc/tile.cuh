@@ -35,15 +35,25 @@ enum MicroKind { MK_DENSE = 0, MK_DIAG = 1, MK_EXCH = 2, MK_SUPER = 3 };
 // (a real matrix -- H, Ry, X-like -- needs half the FMAs).
 enum ElemType { E_DENSE1 = 0, E_DENSE1R = 1, E_X = 2, E_PHASE = 3, E_SWAP = 4, E_DENSE3 = 5 };
 
-// Elem::op layout: bits 0-7 kind, 8-9 j, 10-11 k, 12-19 active mask, bit 31 "has a
-// CTA-uniform condition".  The active mask is precomputed on the host from the op's
-// controls: for DENSE1/X bit p <-> the p-th (ascending) sub-index with bit j clear;
-// for SWAP bit p <-> the p-th sub-index with bit j set and bit k clear; for PHASE bit c
-// <-> sub-index c.
+// Elem::op layout: bits 0-7 interpreter opcode, bits 12-19 active mask, bit 31 "has a
+// CTA-uniform condition".  opcode = kind*4 + j (DENSE1/DENSE1R/X: target sub-bit j;
+// SWAP: 0,1,2 <-> sub-bit pairs (0,1),(0,2),(1,2)), plus 32 for a 2x2 gate whose pairs are
+// all active (no mask tests in the kernel).  The active mask is precomputed on the host
+// from the op's controls: for DENSE1/X bit p <-> the p-th (ascending) sub-index with bit j
+// clear; for SWAP bit p <-> the p-th sub-index with bit j set and bit k clear; for PHASE
+// bit c <-> sub-index c.
 static const uint32_t kElemHasCond = 1u << 31;
 inline uint32_t elem_op(uint32_t kind, uint32_t j, uint32_t k, uint32_t mask, bool cond) {
-  return kind | (j << 8) | (k << 10) | (mask << 12) | (cond ? kElemHasCond : 0u);
+  uint32_t code = kind * 4;
+  if (kind == E_SWAP)
+    code += (j == 0 && k == 1) ? 0u : (j == 0 ? 1u : 2u);
+  else if (kind == E_DENSE1 || kind == E_DENSE1R || kind == E_X)
+    code += j;
+  if ((kind == E_DENSE1 || kind == E_DENSE1R) && mask == 0xfu) code += 32;
+  return code | (mask << 12) | (cond ? kElemHasCond : 0u);
 }
+inline uint32_t elem_kind(uint32_t op) { return ((op & 0xffu) & 31u) / 4; }
+inline uint32_t elem_j(uint32_t op) { return (op & 0xffu) & 3u; }
 
 // Device-visible micro-op header (fixed 128 bytes), followed by its data:
 //   MK_DENSE: 2^k x 2^k complex<R> (re,im interleaved), sub-index bit i <-> ins_pos order of targets
@@ -131,7 +141,7 @@ struct PlanConfig {
   uint32_t T = 12;        // tile bits
   uint32_t L = 5;         // contiguous low bits
   bool fuse_blocks = true;      // group ops into 3-bit register-resident super-ops
-  uint32_t compose_threshold = 5;  // >= this many 2x2 gates in one group: compose them into one 8x8
+  uint32_t compose_threshold = 8;  // >= this many 2x2 gates in one group: compose them into one 8x8
 };
 
 // Plan `ops` (already compiled against the current layout and restricted to local bits;

@@ -13,8 +13,9 @@
 //             never compete with the amplitudes for shared-memory bandwidth.
 //   3. STORE  shared memory -> HBM, 16 bytes per lane, same addresses as the load; the
 //             product of the CTA-uniform phase terms is folded in here.
-// Three CTAs are resident per SM (3 x 64 KiB of shared memory), so one CTA's loads
-// and stores overlap the other CTAs' arithmetic.  HBM traffic per pass: every
+// Two CTAs are resident per SM (2 x 64 KiB of shared memory, 128 registers per thread for
+// the two register-resident groups), so one CTA's loads and stores overlap the other's
+// arithmetic.  HBM traffic per pass: every
 // amplitude read once and written once, no matter how many gates the pass folds in.
 #include <cuda_runtime.h>
 
@@ -69,53 +70,67 @@ __device__ __forceinline__ constexpr int pair_base(int p) {
   return ((p >> J) << (J + 1)) | (p & ((1 << J) - 1));
 }
 
-template <typename R, int J>
-__device__ __forceinline__ void e_dense1c(Amp8<R> &a, const Elem<R> *e, uint32_t pm) {
+// Every elementary op is applied to TWO register-resident groups at once (a0, a1): the
+// descriptor is decoded and its matrix fetched once per pair of groups.
+template <typename R, int J, bool FULL>
+__device__ __forceinline__ void e_dense1c(Amp8<R> &a0, Amp8<R> &a1, const Elem<R> *e, uint32_t pm) {
   const R m00r = e->m[0], m00i = e->m[1], m01r = e->m[2], m01i = e->m[3];
   const R m10r = e->m[4], m10i = e->m[5], m11r = e->m[6], m11i = e->m[7];
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
-    if (!((pm >> p) & 1u)) continue;  // CTA-uniform (a control inside the group)
+    if (!FULL && !((pm >> p) & 1u)) continue;  // CTA-uniform (a control inside the group)
     const int i0 = pair_base<J>(p), i1 = i0 | (1 << J);
-    const R xr = a.re[i0], xi = a.im[i0], yr = a.re[i1], yi = a.im[i1];
-    a.re[i0] = fma(m00r, xr, fma(-m00i, xi, fma(m01r, yr, -m01i * yi)));
-    a.im[i0] = fma(m00r, xi, fma(m00i, xr, fma(m01r, yi, m01i * yr)));
-    a.re[i1] = fma(m10r, xr, fma(-m10i, xi, fma(m11r, yr, -m11i * yi)));
-    a.im[i1] = fma(m10r, xi, fma(m10i, xr, fma(m11r, yi, m11i * yr)));
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      Amp8<R> &a = q ? a1 : a0;
+      const R xr = a.re[i0], xi = a.im[i0], yr = a.re[i1], yi = a.im[i1];
+      a.re[i0] = fma(m00r, xr, fma(-m00i, xi, fma(m01r, yr, -m01i * yi)));
+      a.im[i0] = fma(m00r, xi, fma(m00i, xr, fma(m01r, yi, m01i * yr)));
+      a.re[i1] = fma(m10r, xr, fma(-m10i, xi, fma(m11r, yr, -m11i * yi)));
+      a.im[i1] = fma(m10r, xi, fma(m10i, xr, fma(m11r, yi, m11i * yr)));
+    }
   }
 }
 
-template <typename R, int J>
-__device__ __forceinline__ void e_dense1r(Amp8<R> &a, const Elem<R> *e, uint32_t pm) {
+template <typename R, int J, bool FULL>
+__device__ __forceinline__ void e_dense1r(Amp8<R> &a0, Amp8<R> &a1, const Elem<R> *e, uint32_t pm) {
   const R m00 = e->m[0], m01 = e->m[1], m10 = e->m[2], m11 = e->m[3];
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
-    if (!((pm >> p) & 1u)) continue;
+    if (!FULL && !((pm >> p) & 1u)) continue;
     const int i0 = pair_base<J>(p), i1 = i0 | (1 << J);
-    const R xr = a.re[i0], xi = a.im[i0], yr = a.re[i1], yi = a.im[i1];
-    a.re[i0] = fma(m00, xr, m01 * yr);
-    a.im[i0] = fma(m00, xi, m01 * yi);
-    a.re[i1] = fma(m10, xr, m11 * yr);
-    a.im[i1] = fma(m10, xi, m11 * yi);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      Amp8<R> &a = q ? a1 : a0;
+      const R xr = a.re[i0], xi = a.im[i0], yr = a.re[i1], yi = a.im[i1];
+      a.re[i0] = fma(m00, xr, m01 * yr);
+      a.im[i0] = fma(m00, xi, m01 * yi);
+      a.re[i1] = fma(m10, xr, m11 * yr);
+      a.im[i1] = fma(m10, xi, m11 * yi);
+    }
   }
 }
 
 template <typename R, int J>
-__device__ __forceinline__ void e_x(Amp8<R> &a, uint32_t pm) {
+__device__ __forceinline__ void e_x(Amp8<R> &a0, Amp8<R> &a1, uint32_t pm) {
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     if (!((pm >> p) & 1u)) continue;
     const int i0 = pair_base<J>(p), i1 = i0 | (1 << J);
-    const R tr = a.re[i0], ti = a.im[i0];
-    a.re[i0] = a.re[i1];
-    a.im[i0] = a.im[i1];
-    a.re[i1] = tr;
-    a.im[i1] = ti;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      Amp8<R> &a = q ? a1 : a0;
+      const R tr = a.re[i0], ti = a.im[i0];
+      a.re[i0] = a.re[i1];
+      a.im[i0] = a.im[i1];
+      a.re[i1] = tr;
+      a.im[i1] = ti;
+    }
   }
 }
 
 template <typename R, int J, int K>
-__device__ __forceinline__ void e_swap(Amp8<R> &a, uint32_t pm) {
+__device__ __forceinline__ void e_swap(Amp8<R> &a0, Amp8<R> &a1, uint32_t pm) {
   int p = 0;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
@@ -124,23 +139,31 @@ __device__ __forceinline__ void e_swap(Amp8<R> &a, uint32_t pm) {
     ++p;
     if (!on) continue;
     const int d = c ^ (1 << J) ^ (1 << K);
-    const R tr = a.re[c], ti = a.im[c];
-    a.re[c] = a.re[d];
-    a.im[c] = a.im[d];
-    a.re[d] = tr;
-    a.im[d] = ti;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      Amp8<R> &a = q ? a1 : a0;
+      const R tr = a.re[c], ti = a.im[c];
+      a.re[c] = a.re[d];
+      a.im[c] = a.im[d];
+      a.re[d] = tr;
+      a.im[d] = ti;
+    }
   }
 }
 
 template <typename R>
-__device__ __forceinline__ void e_phase(Amp8<R> &a, const Elem<R> *e, uint32_t am) {
+__device__ __forceinline__ void e_phase(Amp8<R> &a0, Amp8<R> &a1, const Elem<R> *e, uint32_t am) {
   const R wr = e->m[0], wi = e->m[1];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     if (!((am >> c) & 1u)) continue;
-    const R xr = a.re[c], xi = a.im[c];
-    a.re[c] = fma(wr, xr, -wi * xi);
-    a.im[c] = fma(wr, xi, wi * xr);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      Amp8<R> &a = q ? a1 : a0;
+      const R xr = a.re[c], xi = a.im[c];
+      a.re[c] = fma(wr, xr, -wi * xi);
+      a.im[c] = fma(wr, xi, wi * xr);
+    }
   }
 }
 
@@ -164,79 +187,82 @@ __device__ __forceinline__ void e_dense3(Amp8<R> &a, const R *m) {
   a = o;
 }
 
+// Interpreter opcode = kind * 4 + j (SWAP: kind * 4 + pair index), + 32 when every pair is
+// active (the common case: no mask tests, no selects).
 template <typename R>
 __device__ __forceinline__ void run_super(typename C2<R>::type *tile, const MicroOp *mo, const unsigned char *data,
                                           uint64_t base) {
   typedef typename C2<R>::type V;
   const uint32_t groups = 1u << mo->groups_log2;
-  for (uint32_t g = threadIdx.x; g < groups; g += kTileThreads) {
+  for (uint32_t g = threadIdx.x; g < groups; g += 2 * kTileThreads) {
+    const bool two = g + kTileThreads < groups;  // warp-uniform (groups is a power of two)
     const uint32_t t0 = expand_local(g, mo);
-    uint32_t addr[8];
-    Amp8<R> a;
+    const uint32_t t1 = expand_local(two ? g + kTileThreads : g, mo);
+    uint32_t addr0[8], addr1[8];
+    Amp8<R> a0, a1;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      addr[u] = swz<R>(t0 + mo->off[u]);
-      const V v = tile[addr[u]];
-      a.re[u] = v.x;
-      a.im[u] = v.y;
+      const uint32_t off = mo->off[u];
+      addr0[u] = swz<R>(t0 + off);
+      addr1[u] = swz<R>(t1 + off);
+      const V v0 = tile[addr0[u]];
+      const V v1 = tile[addr1[u]];
+      a0.re[u] = v0.x;
+      a0.im[u] = v0.y;
+      a1.re[u] = v1.x;
+      a1.im[u] = v1.y;
     }
     const unsigned char *ep = data;
     for (uint32_t ei = 0; ei < mo->nterms; ++ei) {
       const Elem<R> *e = reinterpret_cast<const Elem<R> *>(ep);
       ep += sizeof(Elem<R>);
       const uint32_t op = e->op;
-      const uint32_t kind = op & 0xffu, j = (op >> 8) & 3u, mask = (op >> 12) & 0xffu;
-      const R *m8 = reinterpret_cast<const R *>(ep);
-      if (kind == E_DENSE3) ep += 128 * sizeof(R);
-      if ((op & kElemHasCond) && (base & e->gmask) != e->gval) continue;  // a control outside the tile is 0
-      switch (kind) {
-        case E_DENSE1R:
-          if (j == 0)
-            e_dense1r<R, 0>(a, e, mask);
-          else if (j == 1)
-            e_dense1r<R, 1>(a, e, mask);
-          else
-            e_dense1r<R, 2>(a, e, mask);
-          break;
-        case E_DENSE1:
-          if (j == 0)
-            e_dense1c<R, 0>(a, e, mask);
-          else if (j == 1)
-            e_dense1c<R, 1>(a, e, mask);
-          else
-            e_dense1c<R, 2>(a, e, mask);
-          break;
-        case E_X:
-          if (j == 0)
-            e_x<R, 0>(a, mask);
-          else if (j == 1)
-            e_x<R, 1>(a, mask);
-          else
-            e_x<R, 2>(a, mask);
-          break;
-        case E_PHASE:
-          e_phase<R>(a, e, mask);
-          break;
-        case E_SWAP: {
-          const uint32_t k = (op >> 10) & 3u;
-          if (j == 0 && k == 1)
-            e_swap<R, 0, 1>(a, mask);
-          else if (j == 0)
-            e_swap<R, 0, 2>(a, mask);
-          else
-            e_swap<R, 1, 2>(a, mask);
-          break;
-        }
+      const uint32_t code = op & 0xffu, mask = (op >> 12) & 0xffu;
+      if ((op & kElemHasCond) && (base & e->gmask) != e->gval) {  // a control outside the tile is 0
+        if (code == E_DENSE3 * 4) ep += 128 * sizeof(R);
+        continue;
+      }
+      switch (code) {
+        case 32 + E_DENSE1R * 4 + 0: e_dense1r<R, 0, true>(a0, a1, e, 0xfu); break;
+        case 32 + E_DENSE1R * 4 + 1: e_dense1r<R, 1, true>(a0, a1, e, 0xfu); break;
+        case 32 + E_DENSE1R * 4 + 2: e_dense1r<R, 2, true>(a0, a1, e, 0xfu); break;
+        case 32 + E_DENSE1 * 4 + 0: e_dense1c<R, 0, true>(a0, a1, e, 0xfu); break;
+        case 32 + E_DENSE1 * 4 + 1: e_dense1c<R, 1, true>(a0, a1, e, 0xfu); break;
+        case 32 + E_DENSE1 * 4 + 2: e_dense1c<R, 2, true>(a0, a1, e, 0xfu); break;
+        case E_DENSE1R * 4 + 0: e_dense1r<R, 0, false>(a0, a1, e, mask); break;
+        case E_DENSE1R * 4 + 1: e_dense1r<R, 1, false>(a0, a1, e, mask); break;
+        case E_DENSE1R * 4 + 2: e_dense1r<R, 2, false>(a0, a1, e, mask); break;
+        case E_DENSE1 * 4 + 0: e_dense1c<R, 0, false>(a0, a1, e, mask); break;
+        case E_DENSE1 * 4 + 1: e_dense1c<R, 1, false>(a0, a1, e, mask); break;
+        case E_DENSE1 * 4 + 2: e_dense1c<R, 2, false>(a0, a1, e, mask); break;
+        case E_X * 4 + 0: e_x<R, 0>(a0, a1, mask); break;
+        case E_X * 4 + 1: e_x<R, 1>(a0, a1, mask); break;
+        case E_X * 4 + 2: e_x<R, 2>(a0, a1, mask); break;
+        case E_PHASE * 4: e_phase<R>(a0, a1, e, mask); break;
+        case E_SWAP * 4 + 0: e_swap<R, 0, 1>(a0, a1, mask); break;
+        case E_SWAP * 4 + 1: e_swap<R, 0, 2>(a0, a1, mask); break;
+        case E_SWAP * 4 + 2: e_swap<R, 1, 2>(a0, a1, mask); break;
         default:
-          e_dense3<R>(a, m8);
+          e_dense3<R>(a0, reinterpret_cast<const R *>(ep));
+          e_dense3<R>(a1, reinterpret_cast<const R *>(ep));
+          ep += 128 * sizeof(R);
       }
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       V v;
-      v.x = a.re[u];
-      v.y = a.im[u];
-      tile[addr[u]] = v;
+      v.x = a0.re[u];
+      v.y = a0.im[u];
+      tile[addr0[u]] = v;
+    }
+    if (two) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        V v;
+        v.x = a1.re[u];
+        v.y = a1.im[u];
+        tile[addr1[u]] = v;
+      }
     }
   }
 }
@@ -317,7 +343,7 @@ __device__ __forceinline__ void apply_diag(typename C2<R>::type *tile, const Mic
 }
 
 template <typename R>
-__global__ void __launch_bounds__(kTileThreads, 3)
+__global__ void __launch_bounds__(kTileThreads, 2)
     k_tile_pass(R *__restrict__ psi, const __grid_constant__ PassParams pp) {
   typedef typename C2<R>::type V;
   extern __shared__ __align__(1024) unsigned char smem[];

@@ -53,7 +53,13 @@ static void apply_single(const FlatOp &f, uint32_t n, std::vector<cd> &psi) {
 template <typename R>
 static void run_elem(const Elem<R> &e, const R *mat8, cd a[8], uint64_t base) {
   if ((e.op & kElemHasCond) && (base & e.gmask) != e.gval) return;
-  const uint32_t kind = e.op & 0xff, j = (e.op >> 8) & 3, k = (e.op >> 10) & 3, mask = (e.op >> 12) & 0xff;
+  const uint32_t kind = elem_kind(e.op), mask = (e.op >> 12) & 0xff;
+  uint32_t j = elem_j(e.op), k = 0;
+  if (kind == E_SWAP) {
+    const uint32_t pr = elem_j(e.op);
+    j = pr == 2 ? 1 : 0;
+    k = pr == 0 ? 1 : 2;
+  }
   uint32_t p = 0;
   switch (kind) {
     case E_DENSE1:
@@ -153,7 +159,7 @@ static void run_pass_params(const PassParams &pp, uint32_t n, std::vector<cd> &p
             memcpy(&e, ep, sizeof(e));
             ep += sizeof(e);
             const R *mat8 = reinterpret_cast<const R *>(ep);
-            if ((e.op & 0xff) == E_DENSE3) ep += 128 * sizeof(R);
+            if (elem_kind(e.op) == E_DENSE3) ep += 128 * sizeof(R);
             run_elem<R>(e, mat8, a, base);
           }
           for (uint32_t u = 0; u < 8; ++u) tile[t0 + mo.off[u]] = a[u];
