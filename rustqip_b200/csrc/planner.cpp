@@ -251,6 +251,35 @@ struct Emitter {
     }
     mo.h.groups_log2 = T - 3;
     mo.h.nterms = (uint32_t)elems.size();
+    // Lower the register-permuting ops to in-place arithmetic (exact: 0*x + 1*y == y for finite
+    // amplitudes): X -> real 2x2 [0 1; 1 0]; SWAP(j,k) -> CX(j->k) CX(k->j) CX(j->k).
+    {
+      std::vector<HElem> low;
+      for (size_t i = 0; i < elems.size(); ++i) {
+        const HElem &e = elems[i];
+        if (e.type == E_X) {
+          HElem d = e;
+          d.type = E_DENSE1;
+          d.m[0] = d.m[3] = cplx(0, 0);
+          d.m[1] = d.m[2] = cplx(1, 0);
+          low.push_back(d);
+        } else if (e.type == E_SWAP) {
+          for (int step = 0; step < 3; ++step) {
+            HElem d = e;
+            d.type = E_DENSE1;
+            d.lb_j = (step == 1) ? e.lb_j : e.lb_k;
+            d.lctrl = e.lctrl | (1u << ((step == 1) ? e.lb_k : e.lb_j));
+            d.m[0] = d.m[3] = cplx(0, 0);
+            d.m[1] = d.m[2] = cplx(1, 0);
+            low.push_back(d);
+          }
+        } else {
+          low.push_back(e);
+        }
+      }
+      elems.swap(low);
+    }
+    mo.h.nterms = (uint32_t)elems.size();
     for (size_t i = 0; i < elems.size(); ++i) {
       const HElem &e = elems[i];
       Elem<R> d;
@@ -597,6 +626,7 @@ PlanConfig default_plan_config(qip_prec prec, uint32_t n_local) {
   if (const char *e = getenv("QIPB200_TILE_T")) c.T = std::min<uint32_t>((uint32_t)atoi(e), c.T);
   if (const char *e = getenv("QIPB200_TILE_L")) c.L = (uint32_t)atoi(e);
   if (const char *e = getenv("QIPB200_COMPOSE")) c.compose_threshold = (uint32_t)std::max(1, atoi(e));
+  if (const char *e = getenv("QIPB200_TILE_G")) c.groups_per_thread = atoi(e) == 1 ? 1 : 2;
   if (const char *e = getenv("QIPB200_NO_BLOCK_FUSION")) c.fuse_blocks = atoi(e) == 0;
   if (n_local < c.T) c.T = n_local;
   if (c.L > c.T) c.L = c.T;

@@ -44,7 +44,7 @@ int flush_fused(qipb200_state *s, std::vector<FlatOp> *pending) {
         st = report_error(s, QIPB200_ERR_UNSUPPORTED, "internal: fused pass exceeds the kernel parameter space");
         break;
       }
-      cudaError_t e = launch_tile_pass(s->prec, s->buf, s->n_local, *pp, ctx->stream, &ctx->launches);
+      cudaError_t e = launch_tile_pass(s->prec, s->buf, s->n_local, *pp, cfg.groups_per_thread, ctx->stream, &ctx->launches);
       if (e != cudaSuccess) st = report_cuda_error(s, e, "launch_tile_pass");
     } else {
       st = launch_local_op(s, (*pending)[steps[i].op_index]);

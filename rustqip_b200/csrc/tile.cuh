@@ -33,6 +33,8 @@ static const uint32_t kMaxGlobalTerms = 32;   // CTA-uniform phase terms applied
 enum MicroKind { MK_DENSE = 0, MK_DIAG = 1, MK_EXCH = 2, MK_SUPER = 3 };
 // Elementary-op kinds of a MK_SUPER group.  Real and complex 2x2 gates are separate kinds
 // (a real matrix -- H, Ry, X-like -- needs half the FMAs).
+// Device kinds are all IN-PLACE updates: the planner lowers X to the exact real gate [0 1; 1 0]
+// and SWAP to three controlled such gates (E_X / E_SWAP exist on the host side only).
 enum ElemType { E_DENSE1 = 0, E_DENSE1R = 1, E_X = 2, E_PHASE = 3, E_SWAP = 4, E_DENSE3 = 5 };
 
 // Elem::op layout: bits 0-7 interpreter opcode, bits 12-19 active mask, bit 31 "has a
@@ -141,6 +143,7 @@ struct PlanConfig {
   uint32_t T = 12;        // tile bits
   uint32_t L = 5;         // contiguous low bits
   bool fuse_blocks = true;      // group ops into 3-bit register-resident super-ops
+  int groups_per_thread = 2;       // register-resident groups per interpreter decode (1 or 2)
   uint32_t compose_threshold = 8;  // >= this many 2x2 gates in one group: compose them into one 8x8
 };
 

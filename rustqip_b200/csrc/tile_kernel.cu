@@ -70,10 +70,14 @@ __device__ __forceinline__ constexpr int pair_base(int p) {
   return ((p >> J) << (J + 1)) | (p & ((1 << J) - 1));
 }
 
-// Every elementary op is applied to TWO register-resident groups at once (a0, a1): the
-// descriptor is decoded and its matrix fetched once per pair of groups.
-template <typename R, int J, bool FULL>
-__device__ __forceinline__ void e_dense1c(Amp8<R> &a0, Amp8<R> &a1, const Elem<R> *e, uint32_t pm) {
+// Every elementary op is an IN-PLACE update of register-resident amplitudes -- no op moves
+// a value from one register to another (X and SWAP are issued by the planner as exact
+// 0/1 real 2x2 gates), so the register assignment of the G groups is identical on every
+// path through the interpreter and no copies are needed at the loop back-edge.
+// Each op is applied to G groups at once: the descriptor is decoded and its matrix
+// fetched once per G groups.
+template <typename R, int G, int J, bool FULL>
+__device__ __forceinline__ void e_dense1c(Amp8<R> (&a)[G], const Elem<R> *e, uint32_t pm) {
   const R m00r = e->m[0], m00i = e->m[1], m01r = e->m[2], m01i = e->m[3];
   const R m10r = e->m[4], m10i = e->m[5], m11r = e->m[6], m11i = e->m[7];
 #pragma unroll
@@ -81,88 +85,45 @@ __device__ __forceinline__ void e_dense1c(Amp8<R> &a0, Amp8<R> &a1, const Elem<R
     if (!FULL && !((pm >> p) & 1u)) continue;  // CTA-uniform (a control inside the group)
     const int i0 = pair_base<J>(p), i1 = i0 | (1 << J);
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      Amp8<R> &a = q ? a1 : a0;
-      const R xr = a.re[i0], xi = a.im[i0], yr = a.re[i1], yi = a.im[i1];
-      a.re[i0] = fma(m00r, xr, fma(-m00i, xi, fma(m01r, yr, -m01i * yi)));
-      a.im[i0] = fma(m00r, xi, fma(m00i, xr, fma(m01r, yi, m01i * yr)));
-      a.re[i1] = fma(m10r, xr, fma(-m10i, xi, fma(m11r, yr, -m11i * yi)));
-      a.im[i1] = fma(m10r, xi, fma(m10i, xr, fma(m11r, yi, m11i * yr)));
+    for (int q = 0; q < G; ++q) {
+      const R xr = a[q].re[i0], xi = a[q].im[i0], yr = a[q].re[i1], yi = a[q].im[i1];
+      a[q].re[i0] = fma(m00r, xr, fma(-m00i, xi, fma(m01r, yr, -m01i * yi)));
+      a[q].im[i0] = fma(m00r, xi, fma(m00i, xr, fma(m01r, yi, m01i * yr)));
+      a[q].re[i1] = fma(m10r, xr, fma(-m10i, xi, fma(m11r, yr, -m11i * yi)));
+      a[q].im[i1] = fma(m10r, xi, fma(m10i, xr, fma(m11r, yi, m11i * yr)));
     }
   }
 }
 
-template <typename R, int J, bool FULL>
-__device__ __forceinline__ void e_dense1r(Amp8<R> &a0, Amp8<R> &a1, const Elem<R> *e, uint32_t pm) {
+template <typename R, int G, int J, bool FULL>
+__device__ __forceinline__ void e_dense1r(Amp8<R> (&a)[G], const Elem<R> *e, uint32_t pm) {
   const R m00 = e->m[0], m01 = e->m[1], m10 = e->m[2], m11 = e->m[3];
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     if (!FULL && !((pm >> p) & 1u)) continue;
     const int i0 = pair_base<J>(p), i1 = i0 | (1 << J);
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      Amp8<R> &a = q ? a1 : a0;
-      const R xr = a.re[i0], xi = a.im[i0], yr = a.re[i1], yi = a.im[i1];
-      a.re[i0] = fma(m00, xr, m01 * yr);
-      a.im[i0] = fma(m00, xi, m01 * yi);
-      a.re[i1] = fma(m10, xr, m11 * yr);
-      a.im[i1] = fma(m10, xi, m11 * yi);
+    for (int q = 0; q < G; ++q) {
+      const R xr = a[q].re[i0], xi = a[q].im[i0], yr = a[q].re[i1], yi = a[q].im[i1];
+      a[q].re[i0] = fma(m00, xr, m01 * yr);
+      a[q].im[i0] = fma(m00, xi, m01 * yi);
+      a[q].re[i1] = fma(m10, xr, m11 * yr);
+      a[q].im[i1] = fma(m10, xi, m11 * yi);
     }
   }
 }
 
-template <typename R, int J>
-__device__ __forceinline__ void e_x(Amp8<R> &a0, Amp8<R> &a1, uint32_t pm) {
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    if (!((pm >> p) & 1u)) continue;
-    const int i0 = pair_base<J>(p), i1 = i0 | (1 << J);
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      Amp8<R> &a = q ? a1 : a0;
-      const R tr = a.re[i0], ti = a.im[i0];
-      a.re[i0] = a.re[i1];
-      a.im[i0] = a.im[i1];
-      a.re[i1] = tr;
-      a.im[i1] = ti;
-    }
-  }
-}
-
-template <typename R, int J, int K>
-__device__ __forceinline__ void e_swap(Amp8<R> &a0, Amp8<R> &a1, uint32_t pm) {
-  int p = 0;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    if (!(((c >> J) & 1) == 1 && ((c >> K) & 1) == 0)) continue;
-    const bool on = (pm >> p) & 1u;
-    ++p;
-    if (!on) continue;
-    const int d = c ^ (1 << J) ^ (1 << K);
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      Amp8<R> &a = q ? a1 : a0;
-      const R tr = a.re[c], ti = a.im[c];
-      a.re[c] = a.re[d];
-      a.im[c] = a.im[d];
-      a.re[d] = tr;
-      a.im[d] = ti;
-    }
-  }
-}
-
-template <typename R>
-__device__ __forceinline__ void e_phase(Amp8<R> &a0, Amp8<R> &a1, const Elem<R> *e, uint32_t am) {
+template <typename R, int G>
+__device__ __forceinline__ void e_phase(Amp8<R> (&a)[G], const Elem<R> *e, uint32_t am) {
   const R wr = e->m[0], wi = e->m[1];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     if (!((am >> c) & 1u)) continue;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      Amp8<R> &a = q ? a1 : a0;
-      const R xr = a.re[c], xi = a.im[c];
-      a.re[c] = fma(wr, xr, -wi * xi);
-      a.im[c] = fma(wr, xi, wi * xr);
+    for (int q = 0; q < G; ++q) {
+      const R xr = a[q].re[c], xi = a[q].im[c];
+      a[q].re[c] = fma(wr, xr, -wi * xi);
+      a[q].im[c] = fma(wr, xi, wi * xr);
     }
   }
 }
@@ -184,84 +145,76 @@ __device__ __forceinline__ void e_dense3(Amp8<R> &a, const R *m) {
     o.re[u] = re;
     o.im[u] = im;
   }
-  a = o;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    a.re[u] = o.re[u];
+    a.im[u] = o.im[u];
+  }
 }
 
-// Interpreter opcode = kind * 4 + j (SWAP: kind * 4 + pair index), + 32 when every pair is
-// active (the common case: no mask tests, no selects).
-template <typename R>
+// Interpreter opcode = kind * 4 + j, + 32 when every pair is active (the common case: no
+// mask tests, no selects).
+template <typename R, int G>
 __device__ __forceinline__ void run_super(typename C2<R>::type *tile, const MicroOp *mo, const unsigned char *data,
                                           uint64_t base) {
   typedef typename C2<R>::type V;
   const uint32_t groups = 1u << mo->groups_log2;
-  for (uint32_t g = threadIdx.x; g < groups; g += 2 * kTileThreads) {
-    const bool two = g + kTileThreads < groups;  // warp-uniform (groups is a power of two)
-    const uint32_t t0 = expand_local(g, mo);
-    const uint32_t t1 = expand_local(two ? g + kTileThreads : g, mo);
-    uint32_t addr0[8], addr1[8];
-    Amp8<R> a0, a1;
+  for (uint32_t g = threadIdx.x; g < groups; g += G * kTileThreads) {
+    uint32_t addr[G][8];
+    Amp8<R> a[G];
+    bool valid[G];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const uint32_t off = mo->off[u];
-      addr0[u] = swz<R>(t0 + off);
-      addr1[u] = swz<R>(t1 + off);
-      const V v0 = tile[addr0[u]];
-      const V v1 = tile[addr1[u]];
-      a0.re[u] = v0.x;
-      a0.im[u] = v0.y;
-      a1.re[u] = v1.x;
-      a1.im[u] = v1.y;
+    for (int q = 0; q < G; ++q) {
+      valid[q] = g + q * kTileThreads < groups;  // warp-uniform (groups is a power of two)
+      const uint32_t t0 = expand_local(valid[q] ? g + q * kTileThreads : g, mo);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        addr[q][u] = swz<R>(t0 + mo->off[u]);
+        const V v = tile[addr[q][u]];
+        a[q].re[u] = v.x;
+        a[q].im[u] = v.y;
+      }
     }
     const unsigned char *ep = data;
     for (uint32_t ei = 0; ei < mo->nterms; ++ei) {
       const Elem<R> *e = reinterpret_cast<const Elem<R> *>(ep);
-      ep += sizeof(Elem<R>);
       const uint32_t op = e->op;
       const uint32_t code = op & 0xffu, mask = (op >> 12) & 0xffu;
-      if ((op & kElemHasCond) && (base & e->gmask) != e->gval) {  // a control outside the tile is 0
-        if (code == E_DENSE3 * 4) ep += 128 * sizeof(R);
-        continue;
-      }
-      switch (code) {
-        case 32 + E_DENSE1R * 4 + 0: e_dense1r<R, 0, true>(a0, a1, e, 0xfu); break;
-        case 32 + E_DENSE1R * 4 + 1: e_dense1r<R, 1, true>(a0, a1, e, 0xfu); break;
-        case 32 + E_DENSE1R * 4 + 2: e_dense1r<R, 2, true>(a0, a1, e, 0xfu); break;
-        case 32 + E_DENSE1 * 4 + 0: e_dense1c<R, 0, true>(a0, a1, e, 0xfu); break;
-        case 32 + E_DENSE1 * 4 + 1: e_dense1c<R, 1, true>(a0, a1, e, 0xfu); break;
-        case 32 + E_DENSE1 * 4 + 2: e_dense1c<R, 2, true>(a0, a1, e, 0xfu); break;
-        case E_DENSE1R * 4 + 0: e_dense1r<R, 0, false>(a0, a1, e, mask); break;
-        case E_DENSE1R * 4 + 1: e_dense1r<R, 1, false>(a0, a1, e, mask); break;
-        case E_DENSE1R * 4 + 2: e_dense1r<R, 2, false>(a0, a1, e, mask); break;
-        case E_DENSE1 * 4 + 0: e_dense1c<R, 0, false>(a0, a1, e, mask); break;
-        case E_DENSE1 * 4 + 1: e_dense1c<R, 1, false>(a0, a1, e, mask); break;
-        case E_DENSE1 * 4 + 2: e_dense1c<R, 2, false>(a0, a1, e, mask); break;
-        case E_X * 4 + 0: e_x<R, 0>(a0, a1, mask); break;
-        case E_X * 4 + 1: e_x<R, 1>(a0, a1, mask); break;
-        case E_X * 4 + 2: e_x<R, 2>(a0, a1, mask); break;
-        case E_PHASE * 4: e_phase<R>(a0, a1, e, mask); break;
-        case E_SWAP * 4 + 0: e_swap<R, 0, 1>(a0, a1, mask); break;
-        case E_SWAP * 4 + 1: e_swap<R, 0, 2>(a0, a1, mask); break;
-        case E_SWAP * 4 + 2: e_swap<R, 1, 2>(a0, a1, mask); break;
-        default:
-          e_dense3<R>(a0, reinterpret_cast<const R *>(ep));
-          e_dense3<R>(a1, reinterpret_cast<const R *>(ep));
-          ep += 128 * sizeof(R);
+      const bool is_d3 = code == E_DENSE3 * 4;
+      ep += sizeof(Elem<R>) + (is_d3 ? 128 * sizeof(R) : 0);
+      const bool on = !(op & kElemHasCond) || (base & e->gmask) == e->gval;  // a control outside the tile
+      if (on) {
+        switch (code) {
+          case 32 + E_DENSE1R * 4 + 0: e_dense1r<R, G, 0, true>(a, e, 0xfu); break;
+          case 32 + E_DENSE1R * 4 + 1: e_dense1r<R, G, 1, true>(a, e, 0xfu); break;
+          case 32 + E_DENSE1R * 4 + 2: e_dense1r<R, G, 2, true>(a, e, 0xfu); break;
+          case 32 + E_DENSE1 * 4 + 0: e_dense1c<R, G, 0, true>(a, e, 0xfu); break;
+          case 32 + E_DENSE1 * 4 + 1: e_dense1c<R, G, 1, true>(a, e, 0xfu); break;
+          case 32 + E_DENSE1 * 4 + 2: e_dense1c<R, G, 2, true>(a, e, 0xfu); break;
+          case E_DENSE1R * 4 + 0: e_dense1r<R, G, 0, false>(a, e, mask); break;
+          case E_DENSE1R * 4 + 1: e_dense1r<R, G, 1, false>(a, e, mask); break;
+          case E_DENSE1R * 4 + 2: e_dense1r<R, G, 2, false>(a, e, mask); break;
+          case E_DENSE1 * 4 + 0: e_dense1c<R, G, 0, false>(a, e, mask); break;
+          case E_DENSE1 * 4 + 1: e_dense1c<R, G, 1, false>(a, e, mask); break;
+          case E_DENSE1 * 4 + 2: e_dense1c<R, G, 2, false>(a, e, mask); break;
+          case E_PHASE * 4: e_phase<R, G>(a, e, mask); break;
+          default: {
+            const R *m8 = reinterpret_cast<const R *>(e + 1);
+#pragma unroll
+            for (int q = 0; q < G; ++q) e_dense3<R>(a[q], m8);
+          }
+        }
       }
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      V v;
-      v.x = a0.re[u];
-      v.y = a0.im[u];
-      tile[addr0[u]] = v;
-    }
-    if (two) {
+    for (int q = 0; q < G; ++q) {
+      if (!valid[q]) continue;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         V v;
-        v.x = a1.re[u];
-        v.y = a1.im[u];
-        tile[addr1[u]] = v;
+        v.x = a[q].re[u];
+        v.y = a[q].im[u];
+        tile[addr[q][u]] = v;
       }
     }
   }
@@ -342,8 +295,8 @@ __device__ __forceinline__ void apply_diag(typename C2<R>::type *tile, const Mic
   }
 }
 
-template <typename R>
-__global__ void __launch_bounds__(kTileThreads, 2)
+template <typename R, int G>
+__global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
     k_tile_pass(R *__restrict__ psi, const __grid_constant__ PassParams pp) {
   typedef typename C2<R>::type V;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -381,7 +334,7 @@ __global__ void __launch_bounds__(kTileThreads, 2)
     rec = data + mo->data_bytes;
     if ((base & mo->gmask) == mo->gmask) {
       if (mo->kind == MK_SUPER) {
-        run_super<R>(tile, mo, data, base);
+        run_super<R, G>(tile, mo, data, base);
       } else if (mo->kind == MK_DENSE) {
         const R *mat = reinterpret_cast<const R *>(data);
         if (mo->k == 1)
@@ -439,20 +392,29 @@ __global__ void __launch_bounds__(kTileThreads, 2)
 }
 
 cudaError_t tile_pass_configure() {
-  cudaError_t e = cudaFuncSetAttribute(k_tile_pass<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_tile_pass<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(k_tile_pass<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_tile_pass<double, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_tile_pass<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_tile_pass<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
 }
 
-cudaError_t launch_tile_pass(qip_prec prec, void *psi, uint32_t n_local, const PassParams &pp, cudaStream_t s,
-                             uint64_t *launches) {
+cudaError_t launch_tile_pass(qip_prec prec, void *psi, uint32_t n_local, const PassParams &pp, int groups_per_thread,
+                             cudaStream_t s, uint64_t *launches) {
   const uint32_t T = pp.h.T;
   const size_t smem = (prec == QIP_F32 ? 8u : 16u) << T;
   const unsigned grid = 1u << (n_local - T);
-  if (prec == QIP_F32)
-    k_tile_pass<float><<<grid, kTileThreads, smem, s>>>((float *)psi, pp);
-  else
-    k_tile_pass<double><<<grid, kTileThreads, smem, s>>>((double *)psi, pp);
+  if (prec == QIP_F32) {
+    if (groups_per_thread == 1)
+      k_tile_pass<float, 1><<<grid, kTileThreads, smem, s>>>((float *)psi, pp);
+    else
+      k_tile_pass<float, 2><<<grid, kTileThreads, smem, s>>>((float *)psi, pp);
+  } else {
+    if (groups_per_thread == 1)
+      k_tile_pass<double, 1><<<grid, kTileThreads, smem, s>>>((double *)psi, pp);
+    else
+      k_tile_pass<double, 2><<<grid, kTileThreads, smem, s>>>((double *)psi, pp);
+  }
   ++*launches;
   return cudaGetLastError();
 }

@@ -14,7 +14,8 @@ namespace qipb200 {
 cudaError_t tile_pass_configure();
 
 // Run one serialised pass (passed by value as a kernel parameter) over the local state.
-cudaError_t launch_tile_pass(qip_prec prec, void *psi, uint32_t n_local, const PassParams &pp, cudaStream_t s,
-                             uint64_t *launches);
+// groups_per_thread: 1 (3 CTAs/SM) or 2 (2 CTAs/SM, descriptors decoded once per two groups).
+cudaError_t launch_tile_pass(qip_prec prec, void *psi, uint32_t n_local, const PassParams &pp, int groups_per_thread,
+                             cudaStream_t s, uint64_t *launches);
 
 }  // namespace qipb200
