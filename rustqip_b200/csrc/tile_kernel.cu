@@ -21,10 +21,13 @@
 
 #include "tile.cuh"
 #include "tile_launch.cuh"
+#include "tile_interp.cuh"
 
 namespace qipb200 {
 
 static const int kTileThreads = 256;
+
+__device__ __forceinline__ uint32_t expand_local(uint32_t g, const MicroOp *mo);
 
 template <typename R>
 struct C2;
@@ -58,167 +61,12 @@ __device__ __forceinline__ uint32_t expand_local(uint32_t g, const MicroOp *mo) 
   return t | mo->lor_mask;
 }
 
-// ---- elementary ops on 8 register-resident amplitudes -----------------------------------
-template <typename R>
-struct Amp8 {
-  R re[8], im[8];
-};
+// ---- MK_SUPER interpreter: inline PTX on named registers (tile_interp.cuh) ------------------
+__device__ __forceinline__ uint32_t swz_d(uint32_t t) { return t ^ ((t >> 3) & 7u); }
+__device__ __forceinline__ uint32_t swz_f(uint32_t t) { return t ^ (((t >> 4) & 7u) << 1); }
 
-// The p-th (ascending) sub-index with bit J clear.
-template <int J>
-__device__ __forceinline__ constexpr int pair_base(int p) {
-  return ((p >> J) << (J + 1)) | (p & ((1 << J) - 1));
-}
-
-// Every elementary op is an IN-PLACE update of register-resident amplitudes -- no op moves
-// a value from one register to another (X and SWAP are issued by the planner as exact
-// 0/1 real 2x2 gates), so the register assignment of the G groups is identical on every
-// path through the interpreter and no copies are needed at the loop back-edge.
-// Each op is applied to G groups at once: the descriptor is decoded and its matrix
-// fetched once per G groups.
-template <typename R, int G, int J, bool FULL>
-__device__ __forceinline__ void e_dense1c(Amp8<R> (&a)[G], const Elem<R> *e, uint32_t pm) {
-  const R m00r = e->m[0], m00i = e->m[1], m01r = e->m[2], m01i = e->m[3];
-  const R m10r = e->m[4], m10i = e->m[5], m11r = e->m[6], m11i = e->m[7];
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    if (!FULL && !((pm >> p) & 1u)) continue;  // CTA-uniform (a control inside the group)
-    const int i0 = pair_base<J>(p), i1 = i0 | (1 << J);
-#pragma unroll
-    for (int q = 0; q < G; ++q) {
-      const R xr = a[q].re[i0], xi = a[q].im[i0], yr = a[q].re[i1], yi = a[q].im[i1];
-      a[q].re[i0] = fma(m00r, xr, fma(-m00i, xi, fma(m01r, yr, -m01i * yi)));
-      a[q].im[i0] = fma(m00r, xi, fma(m00i, xr, fma(m01r, yi, m01i * yr)));
-      a[q].re[i1] = fma(m10r, xr, fma(-m10i, xi, fma(m11r, yr, -m11i * yi)));
-      a[q].im[i1] = fma(m10r, xi, fma(m10i, xr, fma(m11r, yi, m11i * yr)));
-    }
-  }
-}
-
-template <typename R, int G, int J, bool FULL>
-__device__ __forceinline__ void e_dense1r(Amp8<R> (&a)[G], const Elem<R> *e, uint32_t pm) {
-  const R m00 = e->m[0], m01 = e->m[1], m10 = e->m[2], m11 = e->m[3];
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    if (!FULL && !((pm >> p) & 1u)) continue;
-    const int i0 = pair_base<J>(p), i1 = i0 | (1 << J);
-#pragma unroll
-    for (int q = 0; q < G; ++q) {
-      const R xr = a[q].re[i0], xi = a[q].im[i0], yr = a[q].re[i1], yi = a[q].im[i1];
-      a[q].re[i0] = fma(m00, xr, m01 * yr);
-      a[q].im[i0] = fma(m00, xi, m01 * yi);
-      a[q].re[i1] = fma(m10, xr, m11 * yr);
-      a[q].im[i1] = fma(m10, xi, m11 * yi);
-    }
-  }
-}
-
-template <typename R, int G>
-__device__ __forceinline__ void e_phase(Amp8<R> (&a)[G], const Elem<R> *e, uint32_t am) {
-  const R wr = e->m[0], wi = e->m[1];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    if (!((am >> c) & 1u)) continue;
-#pragma unroll
-    for (int q = 0; q < G; ++q) {
-      const R xr = a[q].re[c], xi = a[q].im[c];
-      a[q].re[c] = fma(wr, xr, -wi * xi);
-      a[q].im[c] = fma(wr, xi, wi * xr);
-    }
-  }
-}
-
-template <typename R>
-__device__ __forceinline__ void e_dense3(Amp8<R> &a, const R *m) {
-  Amp8<R> o;
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    R re = (R)0, im = (R)0;
-#pragma unroll
-    for (int v = 0; v < 8; ++v) {
-      const R mr = m[2 * (u * 8 + v)], mi = m[2 * (u * 8 + v) + 1];
-      re = fma(mr, a.re[v], re);
-      re = fma(-mi, a.im[v], re);
-      im = fma(mr, a.im[v], im);
-      im = fma(mi, a.re[v], im);
-    }
-    o.re[u] = re;
-    o.im[u] = im;
-  }
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    a.re[u] = o.re[u];
-    a.im[u] = o.im[u];
-  }
-}
-
-// Interpreter opcode = kind * 4 + j, + 32 when every pair is active (the common case: no
-// mask tests, no selects).
-template <typename R, int G>
-__device__ __forceinline__ void run_super(typename C2<R>::type *tile, const MicroOp *mo, const unsigned char *data,
-                                          uint64_t base) {
-  typedef typename C2<R>::type V;
-  const uint32_t groups = 1u << mo->groups_log2;
-  for (uint32_t g = threadIdx.x; g < groups; g += G * kTileThreads) {
-    uint32_t addr[G][8];
-    Amp8<R> a[G];
-    bool valid[G];
-#pragma unroll
-    for (int q = 0; q < G; ++q) {
-      valid[q] = g + q * kTileThreads < groups;  // warp-uniform (groups is a power of two)
-      const uint32_t t0 = expand_local(valid[q] ? g + q * kTileThreads : g, mo);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        addr[q][u] = swz<R>(t0 + mo->off[u]);
-        const V v = tile[addr[q][u]];
-        a[q].re[u] = v.x;
-        a[q].im[u] = v.y;
-      }
-    }
-    const unsigned char *ep = data;
-    for (uint32_t ei = 0; ei < mo->nterms; ++ei) {
-      const Elem<R> *e = reinterpret_cast<const Elem<R> *>(ep);
-      const uint32_t op = e->op;
-      const uint32_t code = op & 0xffu, mask = (op >> 12) & 0xffu;
-      const bool is_d3 = code == E_DENSE3 * 4;
-      ep += sizeof(Elem<R>) + (is_d3 ? 128 * sizeof(R) : 0);
-      const bool on = !(op & kElemHasCond) || (base & e->gmask) == e->gval;  // a control outside the tile
-      if (on) {
-        switch (code) {
-          case 32 + E_DENSE1R * 4 + 0: e_dense1r<R, G, 0, true>(a, e, 0xfu); break;
-          case 32 + E_DENSE1R * 4 + 1: e_dense1r<R, G, 1, true>(a, e, 0xfu); break;
-          case 32 + E_DENSE1R * 4 + 2: e_dense1r<R, G, 2, true>(a, e, 0xfu); break;
-          case 32 + E_DENSE1 * 4 + 0: e_dense1c<R, G, 0, true>(a, e, 0xfu); break;
-          case 32 + E_DENSE1 * 4 + 1: e_dense1c<R, G, 1, true>(a, e, 0xfu); break;
-          case 32 + E_DENSE1 * 4 + 2: e_dense1c<R, G, 2, true>(a, e, 0xfu); break;
-          case E_DENSE1R * 4 + 0: e_dense1r<R, G, 0, false>(a, e, mask); break;
-          case E_DENSE1R * 4 + 1: e_dense1r<R, G, 1, false>(a, e, mask); break;
-          case E_DENSE1R * 4 + 2: e_dense1r<R, G, 2, false>(a, e, mask); break;
-          case E_DENSE1 * 4 + 0: e_dense1c<R, G, 0, false>(a, e, mask); break;
-          case E_DENSE1 * 4 + 1: e_dense1c<R, G, 1, false>(a, e, mask); break;
-          case E_DENSE1 * 4 + 2: e_dense1c<R, G, 2, false>(a, e, mask); break;
-          case E_PHASE * 4: e_phase<R, G>(a, e, mask); break;
-          default: {
-            const R *m8 = reinterpret_cast<const R *>(e + 1);
-#pragma unroll
-            for (int q = 0; q < G; ++q) e_dense3<R>(a[q], m8);
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < G; ++q) {
-      if (!valid[q]) continue;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        V v;
-        v.x = a[q].re[u];
-        v.y = a[q].im[u];
-        tile[addr[q][u]] = v;
-      }
-    }
-  }
-}
+QIP_DEFINE_RUN_SUPER(run_super_f64, double, "f64", QIP_CD, QIP_COD, swz_d, 4)
+QIP_DEFINE_RUN_SUPER(run_super_f32, float, "f32", QIP_CF, QIP_COF, swz_f, 3)
 
 // ---- wide micro-ops (more than 3 involved bits): rare -----------------------------------
 template <typename R, int K>
@@ -299,6 +147,14 @@ template <typename R, int G>
 __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
     k_tile_pass(R *__restrict__ psi, const __grid_constant__ PassParams pp) {
   typedef typename C2<R>::type V;
+  // the named PTX registers that hold the register-resident groups (tile_interp.cuh)
+  if (sizeof(R) == 8) {
+    QIP_DECL_GROUP("f64", "a");
+    if (G == 2) QIP_DECL_GROUP("f64", "b");
+  } else {
+    QIP_DECL_GROUP("f32", "a");
+    if (G == 2) QIP_DECL_GROUP("f32", "b");
+  }
   extern __shared__ __align__(1024) unsigned char smem[];
   const PassHeader *h = &pp.h;
   const uint32_t T = h->T, L = h->L, m = h->m, n_ops = h->n_ops;
@@ -334,7 +190,10 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
     rec = data + mo->data_bytes;
     if ((base & mo->gmask) == mo->gmask) {
       if (mo->kind == MK_SUPER) {
-        run_super<R, G>(tile, mo, data, base);
+        if constexpr (sizeof(R) == 8)
+          run_super_f64<G>(smem_base, mo, data, base);
+        else
+          run_super_f32<G>(smem_base, mo, data, base);
       } else if (mo->kind == MK_DENSE) {
         const R *mat = reinterpret_cast<const R *>(data);
         if (mo->k == 1)
