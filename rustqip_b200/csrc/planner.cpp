@@ -626,7 +626,7 @@ PlanConfig default_plan_config(qip_prec prec, uint32_t n_local) {
   if (const char *e = getenv("QIPB200_TILE_T")) c.T = std::min<uint32_t>((uint32_t)atoi(e), c.T);
   if (const char *e = getenv("QIPB200_TILE_L")) c.L = (uint32_t)atoi(e);
   if (const char *e = getenv("QIPB200_COMPOSE")) c.compose_threshold = (uint32_t)std::max(1, atoi(e));
-  if (const char *e = getenv("QIPB200_TILE_G")) c.groups_per_thread = atoi(e) == 1 ? 1 : 2;
+  if (const char *e = getenv("QIPB200_TILE_G")) c.groups_per_thread = atoi(e) == 2 ? 2 : 1;
   if (const char *e = getenv("QIPB200_NO_BLOCK_FUSION")) c.fuse_blocks = atoi(e) == 0;
   if (n_local < c.T) c.T = n_local;
   if (c.L > c.T) c.L = c.T;

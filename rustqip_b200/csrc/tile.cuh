@@ -143,7 +143,7 @@ struct PlanConfig {
   uint32_t T = 12;        // tile bits
   uint32_t L = 5;         // contiguous low bits
   bool fuse_blocks = true;      // group ops into 3-bit register-resident super-ops
-  int groups_per_thread = 2;       // register-resident groups per interpreter decode (1 or 2)
+  int groups_per_thread = 1;       // register-resident groups per interpreter decode (1: 3 CTAs/SM, 2: 2 CTAs/SM)
   uint32_t compose_threshold = 8;  // >= this many 2x2 gates in one group: compose them into one 8x8
 };
 

@@ -142,13 +142,23 @@
   }
 
 // --- bodies (use the local names of QIP_DEFINE_RUN_SUPER) ---
-#define _QIP_D1R_STEP(T, C, p, i0, i1)                                  \
-  if (full || ((pm >> p) & 1u)) {                                       \
-    QIP_D1R(T, C, "a", i0, i1, m00, m01, m10, m11);                     \
-    if (G == 2) QIP_D1R(T, C, "b", i0, i1, m00, m01, m10, m11);         \
-  }
+// "full" ops (every pair active) are straight-line: 4 pairs x G groups of independent
+// arithmetic for the scheduler to interleave; masked ops test one mask bit per pair.
+#define _QIP_D1R_U(T, C, i0, i1)                                        \
+  QIP_D1R(T, C, "a", i0, i1, m00, m01, m10, m11);                       \
+  if (G == 2) QIP_D1R(T, C, "b", i0, i1, m00, m01, m10, m11);
+#define _QIP_D1R_STEP(T, C, p, i0, i1) \
+  if ((pm >> p) & 1u) { _QIP_D1R_U(T, C, i0, i1) }
 #define _QIP_D1R_BODY(T, C)                                             \
-  if (j == 0) {                                                         \
+  if (full) {                                                           \
+    if (j == 0) {                                                       \
+      _QIP_D1R_U(T, C, 0, 1) _QIP_D1R_U(T, C, 2, 3) _QIP_D1R_U(T, C, 4, 5) _QIP_D1R_U(T, C, 6, 7) \
+    } else if (j == 1) {                                                \
+      _QIP_D1R_U(T, C, 0, 2) _QIP_D1R_U(T, C, 1, 3) _QIP_D1R_U(T, C, 4, 6) _QIP_D1R_U(T, C, 5, 7) \
+    } else {                                                            \
+      _QIP_D1R_U(T, C, 0, 4) _QIP_D1R_U(T, C, 1, 5) _QIP_D1R_U(T, C, 2, 6) _QIP_D1R_U(T, C, 3, 7) \
+    }                                                                   \
+  } else if (j == 0) {                                                  \
     _QIP_D1R_STEP(T, C, 0, 0, 1) _QIP_D1R_STEP(T, C, 1, 2, 3) _QIP_D1R_STEP(T, C, 2, 4, 5) _QIP_D1R_STEP(T, C, 3, 6, 7) \
   } else if (j == 1) {                                                  \
     _QIP_D1R_STEP(T, C, 0, 0, 2) _QIP_D1R_STEP(T, C, 1, 1, 3) _QIP_D1R_STEP(T, C, 2, 4, 6) _QIP_D1R_STEP(T, C, 3, 5, 7) \
@@ -156,13 +166,21 @@
     _QIP_D1R_STEP(T, C, 0, 0, 4) _QIP_D1R_STEP(T, C, 1, 1, 5) _QIP_D1R_STEP(T, C, 2, 2, 6) _QIP_D1R_STEP(T, C, 3, 3, 7) \
   }
 
-#define _QIP_D1C_STEP(T, C, p, i0, i1)                                                          \
-  if (full || ((pm >> p) & 1u)) {                                                               \
-    QIP_D1C(T, C, "a", i0, i1, m0, m1, m2, m3, m4, m5, m6, m7, n1, n3, n5, n7);                 \
-    if (G == 2) QIP_D1C(T, C, "b", i0, i1, m0, m1, m2, m3, m4, m5, m6, m7, n1, n3, n5, n7);     \
-  }
+#define _QIP_D1C_U(T, C, i0, i1)                                                                \
+  QIP_D1C(T, C, "a", i0, i1, m0, m1, m2, m3, m4, m5, m6, m7, n1, n3, n5, n7);                   \
+  if (G == 2) QIP_D1C(T, C, "b", i0, i1, m0, m1, m2, m3, m4, m5, m6, m7, n1, n3, n5, n7);
+#define _QIP_D1C_STEP(T, C, p, i0, i1) \
+  if ((pm >> p) & 1u) { _QIP_D1C_U(T, C, i0, i1) }
 #define _QIP_D1C_BODY(T, C)                                             \
-  if (j == 0) {                                                         \
+  if (full) {                                                           \
+    if (j == 0) {                                                       \
+      _QIP_D1C_U(T, C, 0, 1) _QIP_D1C_U(T, C, 2, 3) _QIP_D1C_U(T, C, 4, 5) _QIP_D1C_U(T, C, 6, 7) \
+    } else if (j == 1) {                                                \
+      _QIP_D1C_U(T, C, 0, 2) _QIP_D1C_U(T, C, 1, 3) _QIP_D1C_U(T, C, 4, 6) _QIP_D1C_U(T, C, 5, 7) \
+    } else {                                                            \
+      _QIP_D1C_U(T, C, 0, 4) _QIP_D1C_U(T, C, 1, 5) _QIP_D1C_U(T, C, 2, 6) _QIP_D1C_U(T, C, 3, 7) \
+    }                                                                   \
+  } else if (j == 0) {                                                  \
     _QIP_D1C_STEP(T, C, 0, 0, 1) _QIP_D1C_STEP(T, C, 1, 2, 3) _QIP_D1C_STEP(T, C, 2, 4, 5) _QIP_D1C_STEP(T, C, 3, 6, 7) \
   } else if (j == 1) {                                                  \
     _QIP_D1C_STEP(T, C, 0, 0, 2) _QIP_D1C_STEP(T, C, 1, 1, 3) _QIP_D1C_STEP(T, C, 2, 4, 6) _QIP_D1C_STEP(T, C, 3, 5, 7) \
