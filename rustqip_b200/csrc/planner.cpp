@@ -47,7 +47,7 @@ OpInfo analyse(const FlatOp &f) {
       o.need_tile = o.nd;
       o.tile_ok = f.tgt_sorted.size() <= 3 && f.tgt_sorted.size() + nctrl <= 6;
       o.unfused_cost = 1.0 / (1 << nctrl);
-      o.est_bytes = f.tgt_sorted.size() == 1 ? 256 : 128 + 128 + 1040;
+      o.est_bytes = f.tgt_sorted.size() == 1 ? 352 : 128 + 2 * 112 + 1040;
       break;
     case CLASS_FLIP:
       o.nd = 1ull << f.tgt_sorted[0];
@@ -55,7 +55,7 @@ OpInfo analyse(const FlatOp &f) {
       o.need_tile = o.nd;
       o.tile_ok = nctrl + 1 <= 6;
       o.unfused_cost = 1.0 / (1 << nctrl);
-      o.est_bytes = 256;
+      o.est_bytes = 352;
       break;
     case CLASS_BITSWAP:
       for (size_t i = 0; i < f.swaps.size(); ++i) o.nd |= (1ull << f.swaps[i].first) | (1ull << f.swaps[i].second);
@@ -63,14 +63,14 @@ OpInfo analyse(const FlatOp &f) {
       o.need_tile = o.nd;
       o.tile_ok = nctrl + 2 <= 6 && f.swaps.size() <= 3;
       o.unfused_cost = 0.5 * f.swaps.size() / (1 << nctrl);
-      o.est_bytes = 256 * (uint32_t)f.swaps.size();
+      o.est_bytes = 576 * (uint32_t)f.swaps.size();
       break;
     case CLASS_DIAGONAL:
       o.dg = f.ctrl_mask;
       for (size_t i = 0; i < f.diag_bits.size(); ++i) o.dg |= 1ull << f.diag_bits[i];
       o.tile_ok = f.diag_bits.size() <= 3;  // expands to <= 8 masked-phase terms
       o.unfused_cost = 1.0 / (1 << nctrl);
-      o.est_bytes = 256 * (1u << f.diag_bits.size());
+      o.est_bytes = 352 * (1u << f.diag_bits.size());
       break;
     default:  // CLASS_GENERAL (CLASS_IDENTITY never reaches here)
       for (uint32_t j = 0; j < f.k; ++j) o.nd |= 1ull << f.idx_bits[j];
@@ -251,34 +251,6 @@ struct Emitter {
     }
     mo.h.groups_log2 = T - 3;
     mo.h.nterms = (uint32_t)elems.size();
-    // Lower the register-permuting ops to in-place arithmetic (exact: 0*x + 1*y == y for finite
-    // amplitudes): X -> real 2x2 [0 1; 1 0]; SWAP(j,k) -> CX(j->k) CX(k->j) CX(j->k).
-    {
-      std::vector<HElem> low;
-      for (size_t i = 0; i < elems.size(); ++i) {
-        const HElem &e = elems[i];
-        if (e.type == E_X) {
-          HElem d = e;
-          d.type = E_DENSE1;
-          d.m[0] = d.m[3] = cplx(0, 0);
-          d.m[1] = d.m[2] = cplx(1, 0);
-          low.push_back(d);
-        } else if (e.type == E_SWAP) {
-          for (int step = 0; step < 3; ++step) {
-            HElem d = e;
-            d.type = E_DENSE1;
-            d.lb_j = (step == 1) ? e.lb_j : e.lb_k;
-            d.lctrl = e.lctrl | (1u << ((step == 1) ? e.lb_k : e.lb_j));
-            d.m[0] = d.m[3] = cplx(0, 0);
-            d.m[1] = d.m[2] = cplx(1, 0);
-            low.push_back(d);
-          }
-        } else {
-          low.push_back(e);
-        }
-      }
-      elems.swap(low);
-    }
     mo.h.nterms = (uint32_t)elems.size();
     for (size_t i = 0; i < elems.size(); ++i) {
       const HElem &e = elems[i];
@@ -295,7 +267,8 @@ struct Emitter {
           lv |= ((e.lval >> b) & 1u) << sub_of(b);
         }
       }
-      if (e.type == E_DENSE1 || e.type == E_X) {
+      const uint32_t rec_bytes = (uint32_t)sizeof(d) + (e.type == E_DENSE3 ? (uint32_t)(128 * sizeof(R)) : 0u);
+      if (e.type == E_DENSE1) {
         const uint32_t j = sub_of(e.lb_j);
         uint32_t pm = 0, p = 0;
         for (uint32_t c = 0; c < 8; ++c) {
@@ -303,39 +276,26 @@ struct Emitter {
           if ((c & lc) == lc) pm |= 1u << p;
           ++p;
         }
-        if (e.type == E_X) {
-          d.op = elem_op(E_X, j, 0, pm, cond);
-        } else {
-          bool real = true;
-          for (int q = 0; q < 4; ++q) real &= e.m[q].imag() == 0.0;
-          d.op = elem_op(real ? E_DENSE1R : E_DENSE1, j, 0, pm, cond);
-          for (int q = 0; q < 4; ++q) {
-            if (real) {
-              d.m[q] = (R)e.m[q].real();
-            } else {
-              d.m[2 * q] = (R)e.m[q].real();
-              d.m[2 * q + 1] = (R)e.m[q].imag();
-            }
+        bool real = true;
+        for (int q = 0; q < 4; ++q) real &= e.m[q].imag() == 0.0;
+        d.op = elem_op(real ? E_DENSE1R : E_DENSE1, j, pm, cond, rec_bytes);
+        for (int q = 0; q < 4; ++q) {
+          if (real) {
+            d.m[q] = (R)e.m[q].real();
+          } else {
+            d.m[2 * q] = (R)e.m[q].real();
+            d.m[2 * q + 1] = (R)e.m[q].imag();
           }
         }
-      } else if (e.type == E_SWAP) {
-        const uint32_t j = std::min(sub_of(e.lb_j), sub_of(e.lb_k)), k = std::max(sub_of(e.lb_j), sub_of(e.lb_k));
-        uint32_t pm = 0, p = 0;
-        for (uint32_t c = 0; c < 8; ++c) {
-          if (!(((c >> j) & 1) == 1 && ((c >> k) & 1) == 0)) continue;
-          if ((c & lc) == lc) pm |= 1u << p;
-          ++p;
-        }
-        d.op = elem_op(E_SWAP, j, k, pm, cond);
       } else if (e.type == E_PHASE) {
         uint32_t am = 0;
         for (uint32_t c = 0; c < 8; ++c)
           if ((c & lm) == lv) am |= 1u << c;
-        d.op = elem_op(E_PHASE, 0, 0, am, cond);
+        d.op = elem_op(E_PHASE, 0, am, cond, rec_bytes);
         d.m[0] = (R)e.m[0].real();
         d.m[1] = (R)e.m[0].imag();
-      } else {
-        d.op = elem_op(E_DENSE3, 0, 0, 0, cond);
+      } else {  // E_DENSE3 (E_X / E_SWAP were lowered above)
+        d.op = elem_op(E_DENSE3, 0, 0, cond, rec_bytes);
       }
       const size_t at = mo.data.size();
       mo.data.resize(at + sizeof(d));
@@ -350,6 +310,13 @@ struct Emitter {
           w[2 * q + 1] = (R)M[q].imag();
         }
       }
+    }
+    {  // END sentinel: the interpreter loops until it reads case id 0
+      Elem<R> endrec;
+      memset(&endrec, 0, sizeof(endrec));
+      const size_t at = mo.data.size();
+      mo.data.resize(at + sizeof(endrec));
+      memcpy(mo.data.data() + at, &endrec, sizeof(endrec));
     }
     mo.h.data_bytes = (uint32_t)mo.data.size();
     pass->ops.push_back(mo);
@@ -366,8 +333,67 @@ struct Emitter {
     }
   }
 
+  // Peephole: fold `e` into the last elementary op of a group when both act on the same
+  // target bit under the same controls/condition (H.T.H -> one complex 2x2, T after a 2x2 ->
+  // a scaled row, two phases on the same mask -> one phase).  Returns true when folded.
+  static bool fold_into(HElem &b, const HElem &e) {
+    if (b.gmask != e.gmask || b.gval != e.gval) return false;
+    auto phase_target_ok = [](const HElem &ph, const HElem &d1) {
+      // ph == diag(1, w) on d1's target bit under exactly d1's controls
+      const uint32_t tb = 1u << d1.lb_j;
+      return ph.lval == ph.lmask && (ph.lmask & tb) && (ph.lmask & ~tb) == d1.lctrl;
+    };
+    if (b.type == E_DENSE1 && e.type == E_DENSE1) {
+      if (b.lb_j != e.lb_j || b.lctrl != e.lctrl) return false;
+      const cplx a0 = b.m[0], a1 = b.m[1], a2 = b.m[2], a3 = b.m[3];
+      b.m[0] = e.m[0] * a0 + e.m[1] * a2;  // e.m * b.m
+      b.m[1] = e.m[0] * a1 + e.m[1] * a3;
+      b.m[2] = e.m[2] * a0 + e.m[3] * a2;
+      b.m[3] = e.m[2] * a1 + e.m[3] * a3;
+      return true;
+    }
+    if (b.type == E_DENSE1 && e.type == E_PHASE) {
+      if (!phase_target_ok(e, b)) return false;
+      b.m[2] *= e.m[0];  // diag(1,w) * M: scales the row of the |1> output
+      b.m[3] *= e.m[0];
+      return true;
+    }
+    if (b.type == E_PHASE && e.type == E_DENSE1) {
+      if (!phase_target_ok(b, e)) return false;
+      HElem d = e;
+      d.m[1] *= b.m[0];  // M * diag(1,w): scales the column of the |1> input
+      d.m[3] *= b.m[0];
+      b = d;
+      return true;
+    }
+    if (b.type == E_PHASE && e.type == E_PHASE) {
+      if (b.lmask != e.lmask || b.lval != e.lval) return false;
+      b.m[0] *= e.m[0];
+      return true;
+    }
+    return false;
+  }
+
   // Append an elementary op: merge the groups it touches when the union has <= 3 bits.
-  void add(const HElem &e) {
+  void add(const HElem &e_in) {
+    // Register-permuting ops are lowered to exact in-place arithmetic (0*x + 1*y == y for
+    // finite amplitudes): X -> real 2x2 [0 1; 1 0]; SWAP(j,k) -> CX(j->k) CX(k->j) CX(j->k).
+    if (e_in.type == E_SWAP) {
+      for (int step = 0; step < 3; ++step) {
+        HElem d = e_in;
+        d.type = E_X;
+        d.lb_j = (step == 1) ? e_in.lb_j : e_in.lb_k;
+        d.lctrl = e_in.lctrl | (1u << ((step == 1) ? e_in.lb_k : e_in.lb_j));
+        add(d);
+      }
+      return;
+    }
+    HElem e = e_in;
+    if (e.type == E_X) {
+      e.type = E_DENSE1;
+      e.m[0] = e.m[3] = cplx(0, 0);
+      e.m[1] = e.m[2] = cplx(1, 0);
+    }
     const uint32_t bm = e.bits();
     if (!cfg->fuse_blocks) {
       Group g;
@@ -389,6 +415,10 @@ struct Emitter {
       g.mask = bm;
       g.elems.push_back(e);
       open.push_back(g);
+      return;
+    }
+    if (hit.size() == 1 && cfg->peephole && fold_into(open[hit[0]].elems.back(), e)) {
+      open[hit[0]].mask = um;  // a folded phase may have brought no new bit; keep the union anyway
       return;
     }
     Group merged;
@@ -628,6 +658,7 @@ PlanConfig default_plan_config(qip_prec prec, uint32_t n_local) {
   if (const char *e = getenv("QIPB200_COMPOSE")) c.compose_threshold = (uint32_t)std::max(1, atoi(e));
   if (const char *e = getenv("QIPB200_TILE_G")) c.groups_per_thread = atoi(e) == 2 ? 2 : 1;
   if (const char *e = getenv("QIPB200_NO_BLOCK_FUSION")) c.fuse_blocks = atoi(e) == 0;
+  if (const char *e = getenv("QIPB200_NO_PEEPHOLE")) c.peephole = atoi(e) == 0;
   if (n_local < c.T) c.T = n_local;
   if (c.L > c.T) c.L = c.T;
   if (c.T - c.L > kTileMaxHigh) c.L = c.T - kTileMaxHigh;

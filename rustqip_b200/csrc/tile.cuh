@@ -37,30 +37,35 @@ enum MicroKind { MK_DENSE = 0, MK_DIAG = 1, MK_EXCH = 2, MK_SUPER = 3 };
 // and SWAP to three controlled such gates (E_X / E_SWAP exist on the host side only).
 enum ElemType { E_DENSE1 = 0, E_DENSE1R = 1, E_X = 2, E_PHASE = 3, E_SWAP = 4, E_DENSE3 = 5 };
 
-// Elem::op layout: bits 0-7 interpreter opcode, bits 12-19 active mask, bit 31 "has a
-// CTA-uniform condition".  opcode = kind*4 + j (DENSE1/DENSE1R/X: target sub-bit j;
-// SWAP: 0,1,2 <-> sub-bit pairs (0,1),(0,2),(1,2)), plus 32 for a 2x2 gate whose pairs are
-// all active (no mask tests in the kernel).  The active mask is precomputed on the host
-// from the op's controls: for DENSE1/X bit p <-> the p-th (ascending) sub-index with bit j
-// clear; for SWAP bit p <-> the p-th sub-index with bit j set and bit k clear; for PHASE
-// bit c <-> sub-index c.
+// Elem::op layout (host-precomputed so the kernel's dispatch is a handful of compares):
+//   bits 0-3   interpreter case id: 0 END (sentinel after the last op of a super-op),
+//              1-3 real 2x2 on sub-bit 0/1/2 with every pair active, 4-6 complex ditto,
+//              7-9 real 2x2 masked, 10-12 complex 2x2 masked, 13 PHASE, 14 dense 8x8
+//   bits 12-19 active mask: 2x2 kinds: bit p <-> the p-th (ascending) sub-index with bit j
+//              clear; PHASE: bit c <-> sub-index c
+//   bits 20-30 record size in 16-byte units (the dense 8x8 matrix follows its record)
+//   bit 31     the op has a CTA-uniform condition (gmask/gval must be tested)
 static const uint32_t kElemHasCond = 1u << 31;
-inline uint32_t elem_op(uint32_t kind, uint32_t j, uint32_t k, uint32_t mask, bool cond) {
-  uint32_t code = kind * 4;
-  if (kind == E_SWAP)
-    code += (j == 0 && k == 1) ? 0u : (j == 0 ? 1u : 2u);
-  else if (kind == E_DENSE1 || kind == E_DENSE1R || kind == E_X)
-    code += j;
-  if ((kind == E_DENSE1 || kind == E_DENSE1R) && mask == 0xfu) code += 32;
-  return code | (mask << 12) | (cond ? kElemHasCond : 0u);
+enum ElemCase { EC_END = 0, EC_D1R_FULL = 1, EC_D1C_FULL = 4, EC_D1R_MASK = 7, EC_D1C_MASK = 10, EC_PHASE = 13, EC_DENSE3 = 14 };
+inline uint32_t elem_op(uint32_t kind, uint32_t j, uint32_t mask, bool cond, uint32_t size_bytes) {
+  uint32_t id;
+  if (kind == E_DENSE1R)
+    id = (mask == 0xfu ? EC_D1R_FULL : EC_D1R_MASK) + j;
+  else if (kind == E_DENSE1)
+    id = (mask == 0xfu ? EC_D1C_FULL : EC_D1C_MASK) + j;
+  else if (kind == E_PHASE)
+    id = EC_PHASE;
+  else
+    id = EC_DENSE3;
+  return id | (mask << 12) | ((size_bytes >> 4) << 20) | (cond ? kElemHasCond : 0u);
 }
-inline uint32_t elem_kind(uint32_t op) { return ((op & 0xffu) & 31u) / 4; }
-inline uint32_t elem_j(uint32_t op) { return (op & 0xffu) & 3u; }
+inline uint32_t elem_case(uint32_t op) { return op & 0xfu; }
+inline uint32_t elem_size_bytes(uint32_t op) { return ((op >> 20) & 0x7ffu) << 4; }
 
 // Device-visible micro-op header (fixed 128 bytes), followed by its data:
 //   MK_DENSE: 2^k x 2^k complex<R> (re,im interleaved), sub-index bit i <-> ins_pos order of targets
 //   MK_DIAG : nterms x DiagTerm<R>
-//   MK_SUPER: nterms elementary records (Elem<R>, E_DENSE3 ones followed by 64 complex<R>)
+//   MK_SUPER: nterms elementary records (Elem<R>, dense 8x8 ones followed by 64 complex<R>) + END record
 struct alignas(16) MicroOp {
   uint32_t kind;
   uint32_t k;            // dense: number of target bits (1..3); super: 3
@@ -143,6 +148,7 @@ struct PlanConfig {
   uint32_t T = 12;        // tile bits
   uint32_t L = 5;         // contiguous low bits
   bool fuse_blocks = true;      // group ops into 3-bit register-resident super-ops
+  bool peephole = true;         // fold consecutive ops on the same target bit into one 2x2
   int groups_per_thread = 1;       // register-resident groups per interpreter decode (1: 3 CTAs/SM, 2: 2 CTAs/SM)
   uint32_t compose_threshold = 8;  // >= this many 2x2 gates in one group: compose them into one 8x8
 };

@@ -106,26 +106,37 @@
         QIP_LD(T, "b", 4, ab[4]); QIP_LD(T, "b", 5, ab[5]); QIP_LD(T, "b", 6, ab[6]); QIP_LD(T, "b", 7, ab[7]); \
       }                                                                                                         \
       const unsigned char *ep = data;                                                                           \
-      for (uint32_t ei = 0; ei < mo->nterms; ++ei) {                                                            \
+      for (;;) {                                                                                                \
         const Elem<R> *e = reinterpret_cast<const Elem<R> *>(ep);                                               \
         const uint32_t op = e->op;                                                                              \
-        const uint32_t code = op & 0xffu, pm = (op >> 12) & 0xffu;                                              \
-        const bool is_d3 = code == E_DENSE3 * 4;                                                                \
-        ep += sizeof(Elem<R>) + (is_d3 ? 128 * sizeof(R) : 0);                                                  \
-        if ((op & kElemHasCond) && (base & e->gmask) != e->gval) continue; /* control outside the tile is 0 */ \
-        const uint32_t kind = (code & 31u) >> 2, j = code & 3u;                                                 \
-        const bool full = code >= 32u;                                                                          \
-        if (kind == E_DENSE1R) {                                                                                \
+        const uint32_t id = op & 0xfu;                                                                          \
+        if (id == EC_END) break;                                                                                \
+        ep += ((op >> 20) & 0x7ffu) << 4;                                                                       \
+        if ((int32_t)op < 0 && (base & e->gmask) != e->gval) continue; /* control outside the tile is 0 */      \
+        const uint32_t pm = (op >> 12) & 0xffu;                                                                 \
+        if (id < EC_D1C_FULL) { /* real 2x2, every pair active: H, X, ... */                                    \
           const R m00 = e->m[0], m01 = e->m[1], m10 = e->m[2], m11 = e->m[3];                                   \
-          _QIP_D1R_BODY(T, C)                                                                                   \
-        } else if (kind == E_DENSE1) {                                                                          \
+          const uint32_t j = id - EC_D1R_FULL;                                                                  \
+          _QIP_D1R_FULL(T, C)                                                                                   \
+        } else if (id < EC_D1R_MASK) { /* complex 2x2, every pair active */                                     \
           const R m0 = e->m[0], m1 = e->m[1], m2 = e->m[2], m3 = e->m[3];                                       \
           const R m4 = e->m[4], m5 = e->m[5], m6 = e->m[6], m7 = e->m[7];                                       \
           const R n1 = -m1, n3 = -m3, n5 = -m5, n7 = -m7;                                                       \
-          _QIP_D1C_BODY(T, C)                                                                                   \
-        } else if (kind == E_PHASE) {                                                                           \
+          const uint32_t j = id - EC_D1C_FULL;                                                                  \
+          _QIP_D1C_FULL(T, C)                                                                                   \
+        } else if (id == EC_PHASE) {                                                                            \
           const R wr = e->m[0], wi = e->m[1];                                                                   \
           _QIP_PH_BODY(T, C)                                                                                    \
+        } else if (id < EC_D1C_MASK) { /* real 2x2 under controls inside the group: CNOT, Toffoli */            \
+          const R m00 = e->m[0], m01 = e->m[1], m10 = e->m[2], m11 = e->m[3];                                   \
+          const uint32_t j = id - EC_D1R_MASK;                                                                  \
+          _QIP_D1R_MASKED(T, C)                                                                                 \
+        } else if (id < EC_PHASE) {                                                                             \
+          const R m0 = e->m[0], m1 = e->m[1], m2 = e->m[2], m3 = e->m[3];                                       \
+          const R m4 = e->m[4], m5 = e->m[5], m6 = e->m[6], m7 = e->m[7];                                       \
+          const R n1 = -m1, n3 = -m3, n5 = -m5, n7 = -m7;                                                       \
+          const uint32_t j = id - EC_D1C_MASK;                                                                  \
+          _QIP_D1C_MASKED(T, C)                                                                                 \
         } else {                                                                                                \
           const R *m8 = reinterpret_cast<const R *>(e + 1);                                                     \
           _QIP_D3_BODY(T, C, CO, R, "a")                                                                        \
@@ -149,16 +160,16 @@
   if (G == 2) QIP_D1R(T, C, "b", i0, i1, m00, m01, m10, m11);
 #define _QIP_D1R_STEP(T, C, p, i0, i1) \
   if ((pm >> p) & 1u) { _QIP_D1R_U(T, C, i0, i1) }
-#define _QIP_D1R_BODY(T, C)                                             \
-  if (full) {                                                           \
-    if (j == 0) {                                                       \
-      _QIP_D1R_U(T, C, 0, 1) _QIP_D1R_U(T, C, 2, 3) _QIP_D1R_U(T, C, 4, 5) _QIP_D1R_U(T, C, 6, 7) \
-    } else if (j == 1) {                                                \
-      _QIP_D1R_U(T, C, 0, 2) _QIP_D1R_U(T, C, 1, 3) _QIP_D1R_U(T, C, 4, 6) _QIP_D1R_U(T, C, 5, 7) \
-    } else {                                                            \
-      _QIP_D1R_U(T, C, 0, 4) _QIP_D1R_U(T, C, 1, 5) _QIP_D1R_U(T, C, 2, 6) _QIP_D1R_U(T, C, 3, 7) \
-    }                                                                   \
-  } else if (j == 0) {                                                  \
+#define _QIP_D1R_FULL(T, C)                                             \
+  if (j == 0) {                                                         \
+    _QIP_D1R_U(T, C, 0, 1) _QIP_D1R_U(T, C, 2, 3) _QIP_D1R_U(T, C, 4, 5) _QIP_D1R_U(T, C, 6, 7) \
+  } else if (j == 1) {                                                  \
+    _QIP_D1R_U(T, C, 0, 2) _QIP_D1R_U(T, C, 1, 3) _QIP_D1R_U(T, C, 4, 6) _QIP_D1R_U(T, C, 5, 7) \
+  } else {                                                              \
+    _QIP_D1R_U(T, C, 0, 4) _QIP_D1R_U(T, C, 1, 5) _QIP_D1R_U(T, C, 2, 6) _QIP_D1R_U(T, C, 3, 7) \
+  }
+#define _QIP_D1R_MASKED(T, C)                                           \
+  if (j == 0) {                                                         \
     _QIP_D1R_STEP(T, C, 0, 0, 1) _QIP_D1R_STEP(T, C, 1, 2, 3) _QIP_D1R_STEP(T, C, 2, 4, 5) _QIP_D1R_STEP(T, C, 3, 6, 7) \
   } else if (j == 1) {                                                  \
     _QIP_D1R_STEP(T, C, 0, 0, 2) _QIP_D1R_STEP(T, C, 1, 1, 3) _QIP_D1R_STEP(T, C, 2, 4, 6) _QIP_D1R_STEP(T, C, 3, 5, 7) \
@@ -171,16 +182,16 @@
   if (G == 2) QIP_D1C(T, C, "b", i0, i1, m0, m1, m2, m3, m4, m5, m6, m7, n1, n3, n5, n7);
 #define _QIP_D1C_STEP(T, C, p, i0, i1) \
   if ((pm >> p) & 1u) { _QIP_D1C_U(T, C, i0, i1) }
-#define _QIP_D1C_BODY(T, C)                                             \
-  if (full) {                                                           \
-    if (j == 0) {                                                       \
-      _QIP_D1C_U(T, C, 0, 1) _QIP_D1C_U(T, C, 2, 3) _QIP_D1C_U(T, C, 4, 5) _QIP_D1C_U(T, C, 6, 7) \
-    } else if (j == 1) {                                                \
-      _QIP_D1C_U(T, C, 0, 2) _QIP_D1C_U(T, C, 1, 3) _QIP_D1C_U(T, C, 4, 6) _QIP_D1C_U(T, C, 5, 7) \
-    } else {                                                            \
-      _QIP_D1C_U(T, C, 0, 4) _QIP_D1C_U(T, C, 1, 5) _QIP_D1C_U(T, C, 2, 6) _QIP_D1C_U(T, C, 3, 7) \
-    }                                                                   \
-  } else if (j == 0) {                                                  \
+#define _QIP_D1C_FULL(T, C)                                             \
+  if (j == 0) {                                                         \
+    _QIP_D1C_U(T, C, 0, 1) _QIP_D1C_U(T, C, 2, 3) _QIP_D1C_U(T, C, 4, 5) _QIP_D1C_U(T, C, 6, 7) \
+  } else if (j == 1) {                                                  \
+    _QIP_D1C_U(T, C, 0, 2) _QIP_D1C_U(T, C, 1, 3) _QIP_D1C_U(T, C, 4, 6) _QIP_D1C_U(T, C, 5, 7) \
+  } else {                                                              \
+    _QIP_D1C_U(T, C, 0, 4) _QIP_D1C_U(T, C, 1, 5) _QIP_D1C_U(T, C, 2, 6) _QIP_D1C_U(T, C, 3, 7) \
+  }
+#define _QIP_D1C_MASKED(T, C)                                           \
+  if (j == 0) {                                                         \
     _QIP_D1C_STEP(T, C, 0, 0, 1) _QIP_D1C_STEP(T, C, 1, 2, 3) _QIP_D1C_STEP(T, C, 2, 4, 5) _QIP_D1C_STEP(T, C, 3, 6, 7) \
   } else if (j == 1) {                                                  \
     _QIP_D1C_STEP(T, C, 0, 0, 2) _QIP_D1C_STEP(T, C, 1, 1, 3) _QIP_D1C_STEP(T, C, 2, 4, 6) _QIP_D1C_STEP(T, C, 3, 5, 7) \

@@ -53,62 +53,37 @@ static void apply_single(const FlatOp &f, uint32_t n, std::vector<cd> &psi) {
 template <typename R>
 static void run_elem(const Elem<R> &e, const R *mat8, cd a[8], uint64_t base) {
   if ((e.op & kElemHasCond) && (base & e.gmask) != e.gval) return;
-  const uint32_t kind = elem_kind(e.op), mask = (e.op >> 12) & 0xff;
-  uint32_t j = elem_j(e.op), k = 0;
-  if (kind == E_SWAP) {
-    const uint32_t pr = elem_j(e.op);
-    j = pr == 2 ? 1 : 0;
-    k = pr == 0 ? 1 : 2;
-  }
-  uint32_t p = 0;
-  switch (kind) {
-    case E_DENSE1:
-    case E_DENSE1R:
-      for (uint32_t c = 0; c < 8; ++c) {
-        if ((c >> j) & 1) continue;
-        const bool on = (mask >> p) & 1;
-        ++p;
-        if (!on) continue;
-        const uint32_t i0 = c, i1 = c | (1u << j);
-        const cd x = a[i0], y = a[i1];
-        if (kind == E_DENSE1R) {
-          a[i0] = (double)e.m[0] * x + (double)e.m[1] * y;
-          a[i1] = (double)e.m[2] * x + (double)e.m[3] * y;
-        } else {
-          a[i0] = cd(e.m[0], e.m[1]) * x + cd(e.m[2], e.m[3]) * y;
-          a[i1] = cd(e.m[4], e.m[5]) * x + cd(e.m[6], e.m[7]) * y;
-        }
+  const uint32_t id = elem_case(e.op), mask = (e.op >> 12) & 0xff;
+  if (id >= EC_D1R_FULL && id < EC_PHASE) {
+    const bool real = (id >= EC_D1R_FULL && id < EC_D1C_FULL) || (id >= EC_D1R_MASK && id < EC_D1C_MASK);
+    const uint32_t j = (id - 1) % 3;
+    uint32_t p = 0;
+    for (uint32_t c = 0; c < 8; ++c) {
+      if ((c >> j) & 1) continue;
+      const bool on = (mask >> p) & 1;
+      ++p;
+      if (!on) continue;
+      const uint32_t i0 = c, i1 = c | (1u << j);
+      const cd x = a[i0], y = a[i1];
+      if (real) {
+        a[i0] = (double)e.m[0] * x + (double)e.m[1] * y;
+        a[i1] = (double)e.m[2] * x + (double)e.m[3] * y;
+      } else {
+        a[i0] = cd(e.m[0], e.m[1]) * x + cd(e.m[2], e.m[3]) * y;
+        a[i1] = cd(e.m[4], e.m[5]) * x + cd(e.m[6], e.m[7]) * y;
       }
-      break;
-    case E_X:
-      for (uint32_t c = 0; c < 8; ++c) {
-        if ((c >> j) & 1) continue;
-        const bool on = (mask >> p) & 1;
-        ++p;
-        if (on) std::swap(a[c], a[c | (1u << j)]);
-      }
-      break;
-    case E_PHASE:
-      for (uint32_t c = 0; c < 8; ++c)
-        if ((mask >> c) & 1) a[c] *= cd(e.m[0], e.m[1]);
-      break;
-    case E_SWAP:
-      for (uint32_t c = 0; c < 8; ++c) {
-        if (!(((c >> j) & 1) == 1 && ((c >> k) & 1) == 0)) continue;
-        const bool on = (mask >> p) & 1;
-        ++p;
-        if (on) std::swap(a[c], a[c ^ (1u << j) ^ (1u << k)]);
-      }
-      break;
-    default: {  // E_DENSE3
-      cd out[8];
-      for (uint32_t u = 0; u < 8; ++u) {
-        cd acc(0, 0);
-        for (uint32_t v = 0; v < 8; ++v) acc += cd(mat8[2 * (u * 8 + v)], mat8[2 * (u * 8 + v) + 1]) * a[v];
-        out[u] = acc;
-      }
-      for (uint32_t u = 0; u < 8; ++u) a[u] = out[u];
     }
+  } else if (id == EC_PHASE) {
+    for (uint32_t c = 0; c < 8; ++c)
+      if ((mask >> c) & 1) a[c] *= cd(e.m[0], e.m[1]);
+  } else {  // EC_DENSE3
+    cd out[8];
+    for (uint32_t u = 0; u < 8; ++u) {
+      cd acc(0, 0);
+      for (uint32_t v = 0; v < 8; ++v) acc += cd(mat8[2 * (u * 8 + v)], mat8[2 * (u * 8 + v) + 1]) * a[v];
+      out[u] = acc;
+    }
+    for (uint32_t u = 0; u < 8; ++u) a[u] = out[u];
   }
 }
 
@@ -154,12 +129,12 @@ static void run_pass_params(const PassParams &pp, uint32_t n, std::vector<cd> &p
           cd a[8];
           for (uint32_t u = 0; u < 8; ++u) a[u] = tile[t0 + mo.off[u]];
           const unsigned char *ep = data;
-          for (uint32_t ei = 0; ei < mo.nterms; ++ei) {
+          for (;;) {
             Elem<R> e;
             memcpy(&e, ep, sizeof(e));
-            ep += sizeof(e);
-            const R *mat8 = reinterpret_cast<const R *>(ep);
-            if (elem_kind(e.op) == E_DENSE3) ep += 128 * sizeof(R);
+            if (elem_case(e.op) == EC_END) break;
+            const R *mat8 = reinterpret_cast<const R *>(ep + sizeof(e));
+            ep += elem_size_bytes(e.op);
             run_elem<R>(e, mat8, a, base);
           }
           for (uint32_t u = 0; u < 8; ++u) tile[t0 + mo.off[u]] = a[u];
