@@ -1,0 +1,64 @@
+"""Worker for the multi-GPU parity test: launched by torchrun, one rank per GPU.
+Compares the sharded GPU result with the CPU oracle on rank 0 and exits non-zero on mismatch."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from oracle import qip_oracle as qo
+    from rustqip_b200 import circuits, gates
+    from rustqip_b200.dist import gather_state, init_sharded_state
+    from rustqip_b200.ops import make_matrix_op, make_swap_op
+    from rustqip_b200.state import Context
+
+    local_rank = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    g = (world - 1).bit_length()
+    ctx = Context(local_rank)
+    failures = 0
+    rng = np.random.default_rng(5)
+    u2 = np.linalg.qr(rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4)))[0]
+    for n, dtype, fusion in [(12, np.complex128, False), (14, np.complex128, True), (15, np.complex64, True),
+                             (17, np.complex128, True)]:
+        # gates on rank-held qubits (0..g-1) of every kind + a random circuit touching them repeatedly
+        ops = [gates.h(0), gates.cnot(0, n - 1), gates.cnot(n - 1, 0), gates.t(0), gates.cz(0, 3),
+               gates.cphase(2, 0, 0.3), gates.h(g - 1), gates.x(0), gates.toffoli(0, 1, 2), gates.toffoli(3, 4, 0),
+               make_swap_op([0], [n - 2]), gates.rz(0, 0.4), make_matrix_op([0, 5], u2.reshape(-1)),
+               make_matrix_op([4, g - 1], u2.reshape(-1)), make_swap_op([0], [g - 1]) if g > 1 else gates.h(1)]
+        ops += circuits.random_circuit(n, 6, 1234 + n, "H,T,CNOT") + circuits.random_circuit(n, 4, 99 + n, "H,CZ,CNOT")
+        ops += circuits.qft(n)[: 3 * n]
+        st = init_sharded_state(n, dtype, ctx)
+        st.set_basis(5)
+        st.apply_schedule(ops, fusion=fusion)
+        norm_local = st.norm2()
+        exch = st.exchange_bytes()
+        got = gather_state(st)
+        norms = [None] * world
+        dist.all_gather_object(norms, norm_local)
+        st.free()
+        if rank == 0:
+            want = qo.run_pipeline(n, ops, 5, dtype)
+            tol = 1e-10 if dtype == np.complex128 else 1e-5
+            err = float(np.max(np.abs(got.astype(np.complex128) - want.astype(np.complex128))))
+            ok = err <= tol and abs(sum(norms) - 1.0) < 1e-4
+            print("n=%d %s fusion=%s world=%d: max err %.3e, norm %.12f, exchanged %.1f MiB/rank -> %s" % (
+                n, np.dtype(dtype).name, fusion, world, err, sum(norms), exch / 2 ** 20, "OK" if ok else "FAIL"), flush=True)
+            failures += 0 if ok else 1
+    flag = [failures]
+    dist.broadcast_object_list(flag, src=0)
+    ctx.close()
+    dist.destroy_process_group()
+    sys.exit(1 if flag[0] else 0)
+
+
+if __name__ == "__main__":
+    main()
