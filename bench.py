@@ -122,47 +122,64 @@ def build_workload(args, world):
 # ------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU algorithm (oracle port, OpenMP over output rows)
 # ------------------------------------------------------------------------------------------
-def cpu_sample(n, ops, dtype, budget_s, max_gates=None):
-    """Run the first gates of the workload through the reference-faithful CPU port
-    (out-of-place apply_op_overwrite, all 2^n rows per gate) for about budget_s seconds."""
-    from oracle import qip_oracle as qo
-    avail = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_AVPHYS_PAGES")
-    amp = np.dtype(dtype).itemsize
-    n_run = n
-    while 2 * (amp << n_run) > 0.6 * avail and n_run > 20:
-        n_run -= 1
-    # index remap when the host cannot hold 2 x 2^n amplitudes: keep the low n_run qubits' gates
-    sample_ops = [op for op in ops if all(q >= n - n_run for q in op.indices())]
-    if n_run != n:
-        from rustqip_b200.ops import MatrixOp
-        shifted = []
-        for op in sample_ops:
+class CpuRunner:
+    """The reference's CPU algorithm on a bounded sample of the workload: out-of-place
+    apply_op_overwrite + buffer swap per gate (qip/src/builder.rs:499,514), all 2^n rows per
+    gate, OpenMP over rows on every host core (oracle/qip_oracle.c, a C port: the Rust
+    reference cannot be built in this image)."""
+
+    MAX_BYTES = 80 << 30  # two buffers; keeps first-touch time of a step within seconds
+
+    def __init__(self, n, ops, dtype):
+        from oracle import qip_oracle as qo
+        self.qo = qo
+        self.n = n
+        amp = np.dtype(dtype).itemsize
+        avail = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_AVPHYS_PAGES")
+        n_run = n
+        while 2 * (amp << n_run) > min(0.6 * avail, self.MAX_BYTES) and n_run > 20:
+            n_run -= 1
+        self.n_run = n_run
+        sample_ops = [op for op in ops if all(q >= n - n_run for q in op.indices())]
+        if n_run != n:  # gates on the low n_run qubits, renumbered; cost per gate is linear in 2^n
+            from rustqip_b200.ops import MatrixOp
+
             def shift(o):
-                c = MatrixOp(o.kind, [q - (n - n_run) for q in o.indices()], data=o.data, rows=o.rows,
-                             n_control=o.n_control, inner=shift(o.inner) if o.inner is not None else None,
-                             swap_n=o.swap_n)
-                return c
-            shifted.append(shift(op))
-        sample_ops = shifted
-    state = np.zeros(1 << n_run, dtype=dtype)
-    arena = np.zeros_like(state)
-    state[0] = 1
-    # touch pages (first-touch cost is not part of the gate loop)
-    qo.apply_op_overwrite(n_run, sample_ops[0], state, arena)
-    state, arena = arena, state
-    done, t0 = 0, time.perf_counter()
-    for op in sample_ops[1:]:
-        qo.apply_op_overwrite(n_run, op, state, arena)
-        state, arena = arena, state
-        done += 1
-        if time.perf_counter() - t0 > budget_s or (max_gates and done >= max_gates):
-            break
-    dt = time.perf_counter() - t0
-    scale = float(1 << (n - n_run))  # cost per gate is linear in 2^n
-    gps = done / dt / scale
-    sample = "first %d gates of the workload after 1 warm-up gate, %.1f s, n=%d%s" % (
-        done, dt, n_run, "" if n_run == n else " (host RAM holds 2x2^%d only: scaled by 2^-%d, extrapolated)" % (n_run, n - n_run))
-    return gps, qo.max_threads(), sample, done
+                return MatrixOp(o.kind, [q - (n - n_run) for q in o.indices()], data=o.data, rows=o.rows,
+                                n_control=o.n_control, inner=shift(o.inner) if o.inner is not None else None,
+                                swap_n=o.swap_n)
+            sample_ops = [shift(op) for op in sample_ops]
+        self.ops = sample_ops
+        self.state = np.zeros(1 << n_run, dtype=dtype)
+        self.arena = np.zeros_like(self.state)
+        self.state[0] = 1
+        self.pos = 0
+        self.cores = qo.max_threads()
+        self._gate()  # touch every page once: first-touch cost is not part of the gate loop
+        self._gate()
+
+    def _gate(self):
+        op = self.ops[self.pos % len(self.ops)]
+        self.pos += 1
+        self.qo.apply_op_overwrite(self.n_run, op, self.state, self.arena)
+        self.state, self.arena = self.arena, self.state
+
+    def run(self, budget_s, max_gates=None):
+        """-> (gate-apps/s at the full n, gates done, seconds)"""
+        done, t0 = 0, time.perf_counter()
+        while True:
+            self._gate()
+            done += 1
+            if time.perf_counter() - t0 > budget_s or (max_gates and done >= max_gates):
+                break
+        dt = time.perf_counter() - t0
+        return done / dt / float(1 << (self.n - self.n_run)), done, dt
+
+    def describe(self, done, dt):
+        return "%d consecutive gates of the workload after 2 untimed page-touch gates, %.1f s, n=%d%s" % (
+            done, dt, self.n_run,
+            "" if self.n_run == self.n else " (2 x 2^%d amplitudes exceed the sample's memory cap: per-gate cost is "
+            "linear in 2^n, value scaled by 2^-%d, EXTRAPOLATED)" % (self.n, self.n - self.n_run))
 
 
 def run_reference(args):
@@ -172,12 +189,11 @@ def run_reference(args):
         return
     dtype = np.complex128 if args.dtype == "f64" else np.complex64
     n, ops, name = build_workload(args, max(world, args.gpus))
-    vals = []
-    sample = ""
-    cores = 1
-    per_step = max(5.0, min(30.0, 120.0 / max(1, args.steps + args.warmup)))
+    runner = CpuRunner(n, ops, dtype)
+    per_step = max(4.0, min(20.0, 100.0 / max(1, args.steps + args.warmup)))
+    vals, done, dt = [], 0, 0.0
     for i in range(args.warmup + args.steps):
-        gps, cores, sample, done = cpu_sample(n, ops, dtype, per_step)
+        gps, done, dt = runner.run(per_step)
         if i >= args.warmup:
             vals.append(gps)
     v = float(np.mean(vals))
@@ -187,10 +203,11 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * len(ops) / v,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
         "data": "synthetic", "config": {"workload": name, "gates_per_step": len(ops)},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "each step: " + sample + "; oracle/qip_oracle.c = C restatement of "
-                                   "apply_op_overwrite (Rust reference cannot be built here), OpenMP static over rows"},
-        "effective_GBps": v * 2 * amp * (1 << n) / 1e9,
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": runner.cores, "kind": "port",
+                         "sample": "each step: " + runner.describe(done, dt) + "; oracle/qip_oracle.c = C restatement of "
+                                   "apply_op_overwrite (the Rust reference cannot be built here), OpenMP static over rows; "
+                                   "ms_per_step is the whole circuit at this rate"},
+        "effective_state_GBps": v * 2 * amp * (1 << n) / 1e9,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -267,9 +284,13 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = ctx.kernel_launches()
+    s0 = ctx.launch_stats()
     ms = timed(step, args.steps)
-    launches = ctx.kernel_launches() - l0
+    s1 = ctx.launch_stats()
+    launches = s1["all"] - s0["all"]
+    tile_passes = (s1["tile_passes"] - s0["tile_passes"]) / args.steps
+    exchanges = (s1["exchanges"] - s0["exchanges"]) / args.steps
+    fused_gates = (s1["fused_gates"] - s0["fused_gates"]) / args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     gates_total = len(ops)
@@ -288,8 +309,23 @@ def run_b200(args):
         "effective_state_GBps": value * bytes_alg_gate / 1e9,
         "effective_frac_of_hbm_peak": value * bytes_alg_gate / 1e9 / (peak * world),
         "gpu_launches": int(launches),
+        "launches_per_step": {"all": launches / args.steps, "fused_tile_passes": tile_passes,
+                              "nvlink_exchanges": exchanges, "gates_in_fused_passes": fused_gates},
         "clocks": clocks,
     }
+    local_bytes = 2.0 * amp * st.local_len  # one sweep of this rank's shard: read + write every amplitude
+    if fusion and tile_passes > 0:
+        # dominant kernel of the step = the fused tile pass; its average launch duration is taken
+        # from the CUDA-event time of the whole step (set-basis memset and the few per-gate
+        # kernels included, so `achieved` is a slight under-estimate)
+        avg_ms = ms_per_step / (launches / args.steps - 1)
+        line["roofline"] = {"bound": "hbm", "kernel": "k_tile_pass<%s> (fused shared-memory tile pass, %.1f gates per launch)" % (
+                                "double" if args.dtype == "f64" else "float", fused_gates / tile_passes),
+                            "achieved": local_bytes / (avg_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": local_bytes / (avg_ms / 1e3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                            "algorithmic_bytes_per_launch": local_bytes, "avg_launch_ms": avg_ms,
+                            "note": "per launch: every amplitude of the shard read once and written once (SURVEY 8d: 2*2^N*16 B), "
+                                    "independent of the number of gates folded into the pass"}
 
     if not args.no_extras:
         extras = {}
@@ -300,7 +336,6 @@ def run_b200(args):
             extras["unfused"] = {"ms_per_step": ms_u, "gate_apps_per_s": gates_total / (ms_u / 1e3),
                                  "effective_state_GBps": gates_total / (ms_u / 1e3) * bytes_alg_gate / 1e9}
         # (b) dominant per-gate kernels, timed alone (CUDA events on the launch stream)
-        local_bytes = 2.0 * amp * st.local_len
         kern = {}
         g = (world - 1).bit_length()
         probes = {"dense1_H_mid_bit": gates.h(g + (n - g) // 2), "dense1_H_bit0": gates.h(n - 1),
@@ -315,10 +350,15 @@ def run_b200(args):
                            "frac_of_peak": local_bytes / (pms / 1e3) / 1e9 / peak}
         extras["kernels_alone"] = kern
         dom = kern["dense1_H_mid_bit"]
-        line["roofline"] = {"bound": "hbm", "kernel": "k_dense<double,1,1> (1-qubit dense gate, mid target bit)",
-                            "achieved": dom["alg_GBps"], "peak": peak, "unit": "GB/s", "frac": dom["frac_of_peak"],
-                            "peak_source": peak_src, "traffic": None,
-                            "algorithmic_bytes_per_launch": local_bytes, "avg_launch_ms": dom["ms"]}
+        pergate = {"bound": "hbm", "kernel": "k_dense<%s,1,1> (1-qubit dense gate, mid target bit; the unfused per-gate sweep)" % (
+                       "double" if args.dtype == "f64" else "float"),
+                   "achieved": dom["alg_GBps"], "peak": peak, "unit": "GB/s", "frac": dom["frac_of_peak"],
+                   "peak_source": peak_src, "traffic": None,
+                   "algorithmic_bytes_per_launch": local_bytes, "avg_launch_ms": dom["ms"]}
+        if "roofline" in line:
+            extras["roofline_per_gate_kernel"] = pergate
+        else:
+            line["roofline"] = pergate
         line["extras"] = extras
 
     # end to end through the reference-facing call: LocalBuilder::calculate_state_with_init
@@ -368,8 +408,10 @@ def run_b200(args):
     # CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     if rank == 0 and world == 1 and not args.no_extras:
         try:
-            gps, cores, sample, done = cpu_sample(n, ops, dtype, args.cpu_seconds)
-            line["cpu_baseline"] = {"value": gps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            runner = CpuRunner(n, ops, dtype)
+            gps, done, dt = runner.run(args.cpu_seconds)
+            line["cpu_baseline"] = {"value": gps, "unit": UNIT, "cores": runner.cores, "kind": "port",
+                                    "sample": runner.describe(done, dt)}
         except Exception as e:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
 

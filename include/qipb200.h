@@ -74,6 +74,8 @@ int qipb200_stream_handle(const qipb200_ctx *ctx, void **stream);
 
 /* Number of this library's kernels launched through `ctx` so far. */
 uint64_t qipb200_kernel_launches(const qipb200_ctx *ctx);
+/* out4 = { all kernels, fused tile passes, NVLink exchange kernels, reference ops folded into tile passes }. */
+int qipb200_launch_stats(const qipb200_ctx *ctx, uint64_t *out4);
 
 /* Validate an op exactly as the reference's constructors do
  * (qip/src/state_ops/matrix_ops.rs:12-122: non-empty indices, len(dense)==4^k,

@@ -23,7 +23,7 @@ _lib = None
 # every symbol include/qipb200.h declares
 EXPORTS = [
     "qipb200_abi_version", "qipb200_init", "qipb200_shutdown", "qipb200_last_error",
-    "qipb200_kernel_launches", "qipb200_stream_handle", "qipb200_validate_op", "qipb200_apply_op",
+    "qipb200_kernel_launches", "qipb200_launch_stats", "qipb200_stream_handle", "qipb200_validate_op", "qipb200_apply_op",
     "qipb200_apply_op_overwrite", "qipb200_apply_ops", "qipb200_state_new", "qipb200_state_free",
     "qipb200_state_set_basis", "qipb200_state_upload", "qipb200_state_download",
     "qipb200_state_apply_op", "qipb200_state_apply_schedule", "qipb200_state_norm2",
@@ -51,6 +51,7 @@ def lib():
     L.qipb200_shutdown.restype, L.qipb200_shutdown.argtypes = None, [vp]
     L.qipb200_last_error.restype, L.qipb200_last_error.argtypes = C.c_char_p, [vp]
     L.qipb200_stream_handle.restype, L.qipb200_stream_handle.argtypes = i32, [vp, C.POINTER(vp)]
+    L.qipb200_launch_stats.restype, L.qipb200_launch_stats.argtypes = i32, [vp, vp]
     L.qipb200_kernel_launches.restype, L.qipb200_kernel_launches.argtypes = u64, [vp]
     L.qipb200_validate_op.restype, L.qipb200_validate_op.argtypes = i32, [vp, i32, u32, opp]
     for name in ("qipb200_apply_op", "qipb200_apply_op_overwrite"):

@@ -137,6 +137,15 @@ extern "C" int qipb200_stream_handle(const qipb200_ctx *ctx, void **stream) {
 
 extern "C" uint64_t qipb200_kernel_launches(const qipb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int qipb200_launch_stats(const qipb200_ctx *ctx, uint64_t *out4) {
+  if (!ctx || !out4) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "launch_stats: NULL argument");
+  out4[0] = ctx->launches;
+  out4[1] = ctx->tile_launches;
+  out4[2] = ctx->exchange_launches;
+  out4[3] = ctx->fused_gates;
+  return QIPB200_OK;
+}
+
 extern "C" int qipb200_validate_op(const qipb200_ctx *ctx, qip_prec prec, uint32_t n_qubits, const qip_op *op) {
   std::string err;
   int st = validate_op(op, prec, n_qubits, &err);
@@ -261,6 +270,7 @@ int exchange_bits(qipb200_state *s, uint32_t R, uint32_t l) {
                               s->flags + kFlagErrorSlot, ctx->stream, &ctx->launches));
   CU(ctx, launch_pair_exchange(s->prec, s->buf, s->peer_buf[partner], s->n_local, l, s_bit, rb, ctx->stream,
                                &ctx->launches));
+  ++ctx->exchange_launches;
   CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch,
                               s->flags + kFlagErrorSlot, ctx->stream, &ctx->launches));
   s->exchange_bytes += (uint64_t)amp_bytes(s->prec) << (s->n_local - 1);

@@ -46,6 +46,8 @@ int flush_fused(qipb200_state *s, std::vector<FlatOp> *pending) {
       }
       cudaError_t e = launch_tile_pass(s->prec, s->buf, s->n_local, *pp, cfg.groups_per_thread, ctx->stream, &ctx->launches);
       if (e != cudaSuccess) st = report_cuda_error(s, e, "launch_tile_pass");
+      ++ctx->tile_launches;
+      ctx->fused_gates += steps[i].pass.n_gates;
     } else {
       st = launch_local_op(s, (*pending)[steps[i].op_index]);
     }

@@ -15,6 +15,9 @@ struct qipb200_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   uint64_t launches = 0;
+  uint64_t tile_launches = 0;      // fused tile passes among `launches`
+  uint64_t exchange_launches = 0;  // NVLink pair-exchange kernels among `launches`
+  uint64_t fused_gates = 0;        // reference ops folded into tile passes
   // staging buffers of the host-buffer drop-ins (qipb200_apply_op*)
   void *d_in = nullptr, *d_out = nullptr;
   size_t d_in_bytes = 0, d_out_bytes = 0;

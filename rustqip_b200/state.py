@@ -39,6 +39,12 @@ class Context:
         _lib.check(_lib.lib().qipb200_stream_handle(self._h, C.byref(sp)), self._h)
         return int(sp.value or 0)
 
+    def launch_stats(self):
+        """dict(all, tile_passes, exchanges, fused_gates) -- cumulative counters of this context."""
+        out = (C.c_uint64 * 4)()
+        _lib.check(_lib.lib().qipb200_launch_stats(self._h, out), self._h)
+        return {"all": int(out[0]), "tile_passes": int(out[1]), "exchanges": int(out[2]), "fused_gates": int(out[3])}
+
     def kernel_launches(self) -> int:
         return int(_lib.lib().qipb200_kernel_launches(self._h))
 
