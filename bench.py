@@ -27,8 +27,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "gate_applications_per_second"
-UNIT = "gate-apps/s"
+# BASELINE.json metric: "gate-apps/sec & state GB/s".  `value` is the state GB/s half --
+# effective_state_GBps = gate-apps/s * 2 * 2^N * sizeof(amplitude), the
+# whole-job aggregate that grows with the GPU count under weak scaling -- and the gate-apps/s
+# half travels beside it in "gate_apps_per_s".
+METRIC = "effective_state_GBps (= gate_apps_per_s * 2 * 2^N * sizeof(amplitude))"
+UNIT = "GB/s"
 
 
 def parse_args():
@@ -199,16 +203,18 @@ def run_reference(args):
     v = float(np.mean(vals))
     amp = np.dtype(dtype).itemsize
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC, "value": v * 2 * amp * (1 << n) / 1e9, "unit": UNIT,
+        "gate_apps_per_s": v, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * len(ops) / v,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
         "data": "synthetic", "config": {"workload": name, "gates_per_step": len(ops)},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": runner.cores, "kind": "port",
+        "cpu_baseline": {"value": v * 2 * amp * (1 << n) / 1e9, "unit": UNIT, "gate_apps_per_s": v,
+                         "cores": runner.cores, "kind": "port",
                          "sample": "each step: " + runner.describe(done, dt) + "; oracle/qip_oracle.c = C restatement of "
                                    "apply_op_overwrite (the Rust reference cannot be built here), OpenMP static over rows; "
                                    "ms_per_step is the whole circuit at this rate"},
-        "effective_state_GBps": v * 2 * amp * (1 << n) / 1e9,
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": v * 2 * amp * (1 << n) / 1e9, "unit": UNIT, "gate_apps_per_s": v,
+                "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
@@ -294,20 +300,20 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     gates_total = len(ops)
-    value = gates_total / (ms_per_step / 1e3)
+    gps = gates_total / (ms_per_step / 1e3)
     bytes_alg_gate = 2.0 * amp * (1 << n)  # whole job: read + write every amplitude once per gate
+    value = gps * bytes_alg_gate / 1e9
     peak, peak_src = peaks()
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": value, "unit": UNIT, "gate_apps_per_s": gps, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": name, "gates_per_step": gates_total, "fusion": fusion,
                    "state_bytes_per_gpu": amp << st.n if world == 1 else amp * st.local_len,
                    "l2_policy": "state (>= 1 GiB per GPU) is far larger than the 126 MB L2; no flush needed",
                    "parallelism": "state sharded by the top log2(G) index bits, NVLink P2P qubit migration" if world > 1 else "single GPU"},
-        "effective_state_GBps": value * bytes_alg_gate / 1e9,
-        "effective_frac_of_hbm_peak": value * bytes_alg_gate / 1e9 / (peak * world),
+        "effective_frac_of_hbm_peak": value / (peak * world),
         "gpu_launches": int(launches),
         "launches_per_step": {"all": launches / args.steps, "fused_tile_passes": tile_passes,
                               "nvlink_exchanges": exchanges, "gates_in_fused_passes": fused_gates},
@@ -334,7 +340,8 @@ def run_b200(args):
             step(False)
             ms_u = timed(lambda: step(False), 1)
             extras["unfused"] = {"ms_per_step": ms_u, "gate_apps_per_s": gates_total / (ms_u / 1e3),
-                                 "effective_state_GBps": gates_total / (ms_u / 1e3) * bytes_alg_gate / 1e9}
+                                 "effective_state_GBps": gates_total / (ms_u / 1e3) * bytes_alg_gate / 1e9,
+                                 "note": "QIPB200_SCHED_NO_FUSION: one in-place kernel sweep per gate, as the reference's per-entry loop"}
         # (b) dominant per-gate kernels, timed alone (CUDA events on the launch stream)
         kern = {}
         g = (world - 1).bit_length()
@@ -379,7 +386,8 @@ def run_b200(args):
         e2e_once()
         reps = max(1, min(args.steps, 3))
         dt = sum(e2e_once() for _ in range(reps)) / reps
-        line["e2e"] = {"value": gates_total / dt, "unit": UNIT, "h2d_bytes_per_step": int(sched_bytes),
+        line["e2e"] = {"value": gates_total / dt * bytes_alg_gate / 1e9, "unit": UNIT, "gate_apps_per_s": gates_total / dt,
+                       "h2d_bytes_per_step": int(sched_bytes),
                        "d2h_bytes_per_step": int(amp << n), "ms_per_step": dt * 1e3,
                        "api": "qipb200_calculate_state (alloc + |0> + schedule + D2H of 2^n amplitudes to pinned host memory), host wall clock"}
         nrm = float(torch.sum(host[: 1 << 20] ** 2).item())  # touch the result
@@ -399,7 +407,8 @@ def run_b200(args):
 
         e2e_once()
         dt = e2e_once()
-        line["e2e"] = {"value": gates_total / dt, "unit": UNIT, "h2d_bytes_per_step": int(sched_bytes),
+        line["e2e"] = {"value": gates_total / dt * bytes_alg_gate / 1e9, "unit": UNIT, "gate_apps_per_s": gates_total / dt,
+                       "h2d_bytes_per_step": int(sched_bytes),
                        "d2h_bytes_per_step": int(amp * st.local_len * world), "ms_per_step": dt * 1e3,
                        "api": "state_set_basis + state_apply_schedule + state_download per rank (C ABI), host wall clock, max over ranks"}
         line["exchange_bytes_per_rank_total"] = st.exchange_bytes()
@@ -409,9 +418,9 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_extras:
         try:
             runner = CpuRunner(n, ops, dtype)
-            gps, done, dt = runner.run(args.cpu_seconds)
-            line["cpu_baseline"] = {"value": gps, "unit": UNIT, "cores": runner.cores, "kind": "port",
-                                    "sample": runner.describe(done, dt)}
+            cgps, done, dt = runner.run(args.cpu_seconds)
+            line["cpu_baseline"] = {"value": cgps * bytes_alg_gate / 1e9, "unit": UNIT, "gate_apps_per_s": cgps,
+                                    "cores": runner.cores, "kind": "port", "sample": runner.describe(done, dt)}
         except Exception as e:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
 
