@@ -78,3 +78,16 @@ def test_oracle_vectors_on_device(ctx):
                 st.apply_schedule(ops, fusion=fusion)
                 got = st.download()
             assert np.max(np.abs(got.astype(np.complex128) - want.astype(np.complex128))) <= tol * max(1.0, np.max(np.abs(want))), name
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_example():
+    """examples/cswap_host.cpp (include/qipb200.hpp over the C ABI) runs the CSWAP on the device."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "cswap_host")
+    if not os.path.exists(exe):
+        pytest.skip("examples/cswap_host not built (run __graft_entry__.build())")
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "P(q=0)=0.500" in p.stdout and "amp[4] = +0.500" in p.stdout and "amp[96] = -0.500" in p.stdout
