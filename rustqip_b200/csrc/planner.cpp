@@ -268,7 +268,7 @@ struct Emitter {
         }
       }
       const uint32_t rec_bytes = (uint32_t)sizeof(d) + (e.type == E_DENSE3 ? (uint32_t)(128 * sizeof(R)) : 0u);
-      if (e.type == E_DENSE1) {
+      if (e.type == E_DENSE1 || e.type == E_X) {
         const uint32_t j = sub_of(e.lb_j);
         uint32_t pm = 0, p = 0;
         for (uint32_t c = 0; c < 8; ++c) {
@@ -276,6 +276,9 @@ struct Emitter {
           if ((c & lc) == lc) pm |= 1u << p;
           ++p;
         }
+        if (e.type == E_X) {
+          d.op = elem_op(E_X, j, pm, cond, rec_bytes);
+        } else {
         bool real = true;
         for (int q = 0; q < 4; ++q) real &= e.m[q].imag() == 0.0;
         d.op = elem_op(real ? E_DENSE1R : E_DENSE1, j, pm, cond, rec_bytes);
@@ -286,6 +289,7 @@ struct Emitter {
             d.m[2 * q] = (R)e.m[q].real();
             d.m[2 * q + 1] = (R)e.m[q].imag();
           }
+        }
         }
       } else if (e.type == E_PHASE) {
         uint32_t am = 0;
@@ -343,8 +347,10 @@ struct Emitter {
       const uint32_t tb = 1u << d1.lb_j;
       return ph.lval == ph.lmask && (ph.lmask & tb) && (ph.lmask & ~tb) == d1.lctrl;
     };
-    if (b.type == E_DENSE1 && e.type == E_DENSE1) {
+    const bool b_mat = b.type == E_DENSE1 || b.type == E_X, e_mat = e.type == E_DENSE1 || e.type == E_X;
+    if (b_mat && e_mat && !(b.type == E_X && e.type == E_X)) {
       if (b.lb_j != e.lb_j || b.lctrl != e.lctrl) return false;
+      b.type = E_DENSE1;
       const cplx a0 = b.m[0], a1 = b.m[1], a2 = b.m[2], a3 = b.m[3];
       b.m[0] = e.m[0] * a0 + e.m[1] * a2;  // e.m * b.m
       b.m[1] = e.m[0] * a1 + e.m[1] * a3;
@@ -389,8 +395,7 @@ struct Emitter {
       return;
     }
     HElem e = e_in;
-    if (e.type == E_X) {
-      e.type = E_DENSE1;
+    if (e.type == E_X) {  // matrix kept for host-side composition / folding
       e.m[0] = e.m[3] = cplx(0, 0);
       e.m[1] = e.m[2] = cplx(1, 0);
     }

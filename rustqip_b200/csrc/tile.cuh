@@ -33,33 +33,37 @@ static const uint32_t kMaxGlobalTerms = 32;   // CTA-uniform phase terms applied
 enum MicroKind { MK_DENSE = 0, MK_DIAG = 1, MK_EXCH = 2, MK_SUPER = 3 };
 // Elementary-op kinds of a MK_SUPER group.  Real and complex 2x2 gates are separate kinds
 // (a real matrix -- H, Ry, X-like -- needs half the FMAs).
-// Device kinds are all IN-PLACE updates: the planner lowers X to the exact real gate [0 1; 1 0]
-// and SWAP to three controlled such gates (E_X / E_SWAP exist on the host side only).
+// SWAP exists on the host side only: the planner lowers it to three controlled X.  X is a pair
+// exchange done with register moves (bit-exact, no FP64 work).
 enum ElemType { E_DENSE1 = 0, E_DENSE1R = 1, E_X = 2, E_PHASE = 3, E_SWAP = 4, E_DENSE3 = 5 };
 
 // Elem::op layout (host-precomputed so the kernel's dispatch is a handful of compares):
-//   bits 0-3   interpreter case id: 0 END (sentinel after the last op of a super-op),
+//   bits 0-4   interpreter case id: 0 END (sentinel after the last op of a super-op),
 //              1-3 real 2x2 on sub-bit 0/1/2 with every pair active, 4-6 complex ditto,
-//              7-9 real 2x2 masked, 10-12 complex 2x2 masked, 13 PHASE, 14 dense 8x8
+//              7-9 real 2x2 masked, 10-12 complex 2x2 masked, 13 PHASE, 14 dense 8x8,
+//              15-17 X (pair exchange by register moves) every pair active, 18-20 X masked
 //   bits 12-19 active mask: 2x2 kinds: bit p <-> the p-th (ascending) sub-index with bit j
 //              clear; PHASE: bit c <-> sub-index c
 //   bits 20-30 record size in 16-byte units (the dense 8x8 matrix follows its record)
 //   bit 31     the op has a CTA-uniform condition (gmask/gval must be tested)
 static const uint32_t kElemHasCond = 1u << 31;
-enum ElemCase { EC_END = 0, EC_D1R_FULL = 1, EC_D1C_FULL = 4, EC_D1R_MASK = 7, EC_D1C_MASK = 10, EC_PHASE = 13, EC_DENSE3 = 14 };
+enum ElemCase { EC_END = 0, EC_D1R_FULL = 1, EC_D1C_FULL = 4, EC_D1R_MASK = 7, EC_D1C_MASK = 10, EC_PHASE = 13, EC_DENSE3 = 14,
+                EC_X_FULL = 15, EC_X_MASK = 18 };
 inline uint32_t elem_op(uint32_t kind, uint32_t j, uint32_t mask, bool cond, uint32_t size_bytes) {
   uint32_t id;
   if (kind == E_DENSE1R)
     id = (mask == 0xfu ? EC_D1R_FULL : EC_D1R_MASK) + j;
   else if (kind == E_DENSE1)
     id = (mask == 0xfu ? EC_D1C_FULL : EC_D1C_MASK) + j;
+  else if (kind == E_X)
+    id = (mask == 0xfu ? EC_X_FULL : EC_X_MASK) + j;
   else if (kind == E_PHASE)
     id = EC_PHASE;
   else
     id = EC_DENSE3;
   return id | (mask << 12) | ((size_bytes >> 4) << 20) | (cond ? kElemHasCond : 0u);
 }
-inline uint32_t elem_case(uint32_t op) { return op & 0xfu; }
+inline uint32_t elem_case(uint32_t op) { return op & 0x1fu; }
 inline uint32_t elem_size_bytes(uint32_t op) { return ((op >> 20) & 0x7ffu) << 4; }
 
 // Device-visible micro-op header (fixed 128 bytes), followed by its data:

@@ -56,6 +56,16 @@
                "fma.rn." T " q" P "i" #I0 ", %1, tx, q" P "i" #I0 ";\n\t}"             /*       + m00i*xr(old) */ \
                ::C(A), C(B), C(Cc), C(D), C(E), C(F), C(G), C(H), C(NB), C(ND), C(NF), C(NH))
 
+// exchange amplitudes I0 <-> I1 (X on the pair): register moves only, bit-exact
+#define QIP_XCH(T, P, I0, I1)                                               \
+  asm volatile("{\n\t.reg ." T " t1, t2;\n\t"                              \
+               "mov." T " t1, q" P "r" #I0 ";\n\t"                          \
+               "mov." T " t2, q" P "i" #I0 ";\n\t"                          \
+               "mov." T " q" P "r" #I0 ", q" P "r" #I1 ";\n\t"              \
+               "mov." T " q" P "i" #I0 ", q" P "i" #I1 ";\n\t"              \
+               "mov." T " q" P "r" #I1 ", t1;\n\t"                          \
+               "mov." T " q" P "i" #I1 ", t2;\n\t}" ::)
+
 // amplitude I *= (wr + i wi)
 #define QIP_PH(T, C, P, I, WR, WI)                                                   \
   asm volatile("{\n\t.reg ." T " t1, t2;\n\t"                                        \
@@ -106,12 +116,14 @@
         QIP_LD(T, "b", 4, ab[4]); QIP_LD(T, "b", 5, ab[5]); QIP_LD(T, "b", 6, ab[6]); QIP_LD(T, "b", 7, ab[7]); \
       }                                                                                                         \
       const unsigned char *ep = data;                                                                           \
+      uint32_t op_next = reinterpret_cast<const Elem<R> *>(ep)->op;                                             \
       for (;;) {                                                                                                \
-        const Elem<R> *e = reinterpret_cast<const Elem<R> *>(ep);                                               \
-        const uint32_t op = e->op;                                                                              \
-        const uint32_t id = op & 0xfu;                                                                          \
+        const uint32_t op = op_next;                                                                            \
+        const uint32_t id = op & 0x1fu;                                                                         \
         if (id == EC_END) break;                                                                                \
+        const Elem<R> *e = reinterpret_cast<const Elem<R> *>(ep);                                               \
         ep += ((op >> 20) & 0x7ffu) << 4;                                                                       \
+        op_next = reinterpret_cast<const Elem<R> *>(ep)->op; /* next descriptor in flight during this op */     \
         if ((int32_t)op < 0 && (base & e->gmask) != e->gval) continue; /* control outside the tile is 0 */      \
         const uint32_t pm = (op >> 12) & 0xffu;                                                                 \
         if (id < EC_D1C_FULL) { /* real 2x2, every pair active: H, X, ... */                                    \
@@ -127,6 +139,10 @@
         } else if (id == EC_PHASE) {                                                                            \
           const R wr = e->m[0], wi = e->m[1];                                                                   \
           _QIP_PH_BODY(T, C)                                                                                    \
+        } else if (id >= EC_X_FULL) { /* X / CNOT / Toffoli-X: pair exchange by register moves */               \
+          const uint32_t xm = id >= EC_X_MASK ? pm : 0xfu;                                                      \
+          const uint32_t j = id >= EC_X_MASK ? id - EC_X_MASK : id - EC_X_FULL;                                 \
+          _QIP_X_BODY(T)                                                                                        \
         } else if (id < EC_D1C_MASK) { /* real 2x2 under controls inside the group: CNOT, Toffoli */            \
           const R m00 = e->m[0], m01 = e->m[1], m10 = e->m[2], m11 = e->m[3];                                   \
           const uint32_t j = id - EC_D1R_MASK;                                                                  \
@@ -197,6 +213,20 @@
     _QIP_D1C_STEP(T, C, 0, 0, 2) _QIP_D1C_STEP(T, C, 1, 1, 3) _QIP_D1C_STEP(T, C, 2, 4, 6) _QIP_D1C_STEP(T, C, 3, 5, 7) \
   } else {                                                              \
     _QIP_D1C_STEP(T, C, 0, 0, 4) _QIP_D1C_STEP(T, C, 1, 1, 5) _QIP_D1C_STEP(T, C, 2, 2, 6) _QIP_D1C_STEP(T, C, 3, 3, 7) \
+  }
+
+#define _QIP_X_STEP(T, p, i0, i1)                 \
+  if ((xm >> p) & 1u) {                           \
+    QIP_XCH(T, "a", i0, i1);                      \
+    if (G == 2) QIP_XCH(T, "b", i0, i1);          \
+  }
+#define _QIP_X_BODY(T)                                                  \
+  if (j == 0) {                                                         \
+    _QIP_X_STEP(T, 0, 0, 1) _QIP_X_STEP(T, 1, 2, 3) _QIP_X_STEP(T, 2, 4, 5) _QIP_X_STEP(T, 3, 6, 7) \
+  } else if (j == 1) {                                                  \
+    _QIP_X_STEP(T, 0, 0, 2) _QIP_X_STEP(T, 1, 1, 3) _QIP_X_STEP(T, 2, 4, 6) _QIP_X_STEP(T, 3, 5, 7) \
+  } else {                                                              \
+    _QIP_X_STEP(T, 0, 0, 4) _QIP_X_STEP(T, 1, 1, 5) _QIP_X_STEP(T, 2, 2, 6) _QIP_X_STEP(T, 3, 3, 7) \
   }
 
 #define _QIP_PH_STEP(T, C, c)                       \

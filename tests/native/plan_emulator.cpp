@@ -73,6 +73,15 @@ static void run_elem(const Elem<R> &e, const R *mat8, cd a[8], uint64_t base) {
         a[i1] = cd(e.m[4], e.m[5]) * x + cd(e.m[6], e.m[7]) * y;
       }
     }
+  } else if (id >= EC_X_FULL) {
+    const uint32_t j = (id - EC_X_FULL) % 3;
+    uint32_t p = 0;
+    for (uint32_t c = 0; c < 8; ++c) {
+      if ((c >> j) & 1) continue;
+      const bool on = (mask >> p) & 1;
+      ++p;
+      if (on) std::swap(a[c], a[c | (1u << j)]);
+    }
   } else if (id == EC_PHASE) {
     for (uint32_t c = 0; c < 8; ++c)
       if ((mask >> c) & 1) a[c] *= cd(e.m[0], e.m[1]);
@@ -244,7 +253,19 @@ extern "C" int emul_plan_stats(int prec, uint32_t n, const qip_op *ops, size_t n
       const MicroOp &mo = steps[s].pass.ops[i].h;
       if (mo.kind == MK_DENSE) dense_k[mo.k]++;
       else if (mo.kind == MK_DIAG) diag_terms += mo.nterms;
-      else if (mo.kind == MK_SUPER) { dense_k[0]++; exch += mo.nterms; }
+      else if (mo.kind == MK_SUPER) {
+        dense_k[0]++;
+        exch += mo.nterms;
+        const unsigned char *ep = steps[s].pass.ops[i].data.data();
+        for (;;) {
+          uint32_t op;
+          memcpy(&op, ep, 4);
+          if (elem_case(op) == EC_END) break;
+          stats[16 + elem_case(op)]++;
+          if (op & kElemHasCond) stats[15]++;
+          ep += elem_size_bytes(op);
+        }
+      }
       else dense_k[1]++;
     }
   }

@@ -44,7 +44,7 @@ def run_emul(L, n, ops, psi, dtype=np.complex128, T=0, Lo=0, fuse=True, max_k=0)
     prec = prec_of(dtype)
     arr, keep = marshal_ops(ops, prec)
     st = np.ascontiguousarray(psi.astype(np.complex128))
-    stats = np.zeros(16, dtype=np.uint64)
+    stats = np.zeros(64, dtype=np.uint64)
     err = C.create_string_buffer(256)
     rc = L.emul_schedule(prec, n, arr, len(ops), st.ctypes.data, T, Lo, int(fuse), max_k, stats.ctypes.data, err, 256)
     assert rc == 0, err.value
@@ -138,7 +138,7 @@ def test_plan_stats_bench_circuits(emul):
                                 ("cfg5_local_n30", 30, circuits.random_circuit(30, 30, 0x5EED0005, "H,CZ,CNOT"), np.complex128)]:
         prec = prec_of(dtype)
         arr, keep = marshal_ops(ops, prec)
-        stats = np.zeros(16, dtype=np.uint64)
+        stats = np.zeros(64, dtype=np.uint64)
         assert emul.emul_plan_stats(prec, n, arr, len(ops), 0, 0, 1, 0, stats.ctypes.data) == 0
         out[name] = (len(ops), [int(x) for x in stats[:9]])
         sweeps = int(stats[0] + stats[1])
