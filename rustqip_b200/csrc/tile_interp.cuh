@@ -103,11 +103,14 @@
       const bool two = (G == 2) && (g + kTileThreads < groups); /* warp-uniform */                              \
       const uint32_t ta = expand_local(g, mo);                                                                  \
       const uint32_t tb = expand_local(two ? g + kTileThreads : g, mo);                                         \
+      /* the XOR swizzle is GF(2)-linear and ta/tb have zeros at the group's bit positions, so        \
+         swz(t + off[u]) == swz(t) ^ swz(off[u]): one XOR + one ADD per amplitude */                       \
+      const uint32_t sa = SWZ(ta) << ESHIFT, sb = SWZ(tb) << ESHIFT;                                        \
       uint32_t aa[8], ab[8];                                                                                    \
       _Pragma("unroll") for (int u = 0; u < 8; ++u) {                                                           \
-        const uint32_t off = mo->off[u];                                                                        \
-        aa[u] = tile_saddr + (SWZ(ta + off) << ESHIFT);                                                         \
-        ab[u] = tile_saddr + (SWZ(tb + off) << ESHIFT);                                                         \
+        const uint32_t so = SWZ(mo->off[u]) << ESHIFT;                                                          \
+        aa[u] = tile_saddr + (sa ^ so);                                                                         \
+        ab[u] = tile_saddr + (sb ^ so);                                                                         \
       }                                                                                                         \
       QIP_LD(T, "a", 0, aa[0]); QIP_LD(T, "a", 1, aa[1]); QIP_LD(T, "a", 2, aa[2]); QIP_LD(T, "a", 3, aa[3]);   \
       QIP_LD(T, "a", 4, aa[4]); QIP_LD(T, "a", 5, aa[5]); QIP_LD(T, "a", 6, aa[6]); QIP_LD(T, "a", 7, aa[7]);   \
