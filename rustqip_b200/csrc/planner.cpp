@@ -671,8 +671,15 @@ PlanConfig default_plan_config(qip_prec prec, uint32_t n_local) {
   return c;
 }
 
+void op_dependency_masks(const FlatOp &f, DepMasks *out) {
+  const OpInfo o = analyse(f);
+  out->nd = o.nd;
+  out->dg = o.dg;
+}
+
 void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec, const PlanConfig &cfg_in,
-                 std::vector<PlanStep> *steps) {
+                 std::vector<PlanStep> *steps, const std::vector<char> *blocked, std::vector<size_t> *leftover,
+                 const std::vector<DepMasks> *dep) {
   PlanConfig cfg = cfg_in;
   if (cfg.T > n_local) cfg.T = n_local;
   if (cfg.L > cfg.T) cfg.L = cfg.T;
@@ -682,8 +689,14 @@ void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec
   std::vector<OpInfo> info(ops.size());
   std::vector<size_t> remaining;
   for (size_t i = 0; i < ops.size(); ++i) {
-    if (ops[i].cls == CLASS_IDENTITY) continue;
+    const bool is_blocked = blocked && (*blocked)[i];
+    if (ops[i].cls == CLASS_IDENTITY && !is_blocked) continue;
     info[i] = analyse(ops[i]);
+    if (dep) {
+      info[i].nd = (*dep)[i].nd;
+      info[i].dg = (*dep)[i].dg;
+    }
+    if (is_blocked) info[i].tile_ok = false;
     remaining.push_back(i);
   }
   const uint32_t byte_budget = kMaxPassBytes - 2048;
@@ -692,10 +705,16 @@ void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec
     std::vector<size_t> taken, left;
     double unfused = 0.0;
     uint32_t bytes = 0;
+    long single = -1;  // first op that may run alone right now: not blocked, commutes past EVERY earlier op
+    uint64_t seen_d = 0, seen_nd = 0;
     for (size_t r = 0; r < remaining.size(); ++r) {
       const size_t idx = remaining[r];
       const OpInfo &o = info[idx];
+      const bool is_blocked = blocked && (*blocked)[idx];
       const bool conflict = (o.nd & (pend_d | pend_nd)) || (o.dg & pend_nd);
+      if (single < 0 && !is_blocked && !((o.nd & (seen_d | seen_nd)) || (o.dg & seen_nd))) single = (long)r;
+      seen_d |= o.dg;
+      seen_nd |= o.nd;
       if (can_tile && !conflict && o.tile_ok && bytes + o.est_bytes <= byte_budget) {
         const uint64_t need = o.need_tile & ~low_mask & ~S_high;
         if ((uint32_t)popc(S_high | need) <= m) {
@@ -711,12 +730,13 @@ void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec
       left.push_back(idx);
     }
     if (taken.empty() || unfused <= 1.05) {
-      // not worth a full sweep: run the first remaining op with its per-gate kernel
+      if (single < 0) break;  // everything left is blocked or stuck behind a blocked op
+      // not worth a full sweep: run one op with its per-gate kernel
       PlanStep st;
       st.is_pass = false;
-      st.op_index = remaining[0];
+      st.op_index = remaining[(size_t)single];
       steps->push_back(st);
-      remaining.erase(remaining.begin());
+      remaining.erase(remaining.begin() + single);
       continue;
     }
     PlanStep st;
@@ -748,6 +768,7 @@ void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec
     steps->push_back(st);
     remaining.swap(left);
   }
+  if (leftover) *leftover = remaining;
 }
 
 bool serialise_pass(const HostPass &p, PassParams *out) {

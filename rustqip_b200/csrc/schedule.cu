@@ -23,19 +23,25 @@ static const uint64_t kNever = ~0ull >> 1;
 
 namespace {
 
-// Plan and run a batch of ops that are all local under the current layout.
-int flush_fused(qipb200_state *s, std::vector<FlatOp> *pending) {
-  if (pending->empty()) return QIPB200_OK;
-  qipb200_ctx *ctx = s->ctx;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = tile_pass_configure();
-    if (e != cudaSuccess) return report_cuda_error(s, e, "cudaFuncSetAttribute(tile pass)");
-    configured = true;
+bool needs_exchange(const qipb200_state *s, const FlatOp &f) {
+  if (s->world == 1) return false;
+  const uint32_t nl = s->n_local;
+  if (f.cls == CLASS_DENSE || f.cls == CLASS_FLIP) {
+    for (size_t j = 0; j < f.tgt_sorted.size(); ++j)
+      if (f.tgt_sorted[j] >= nl) return true;
+  } else if (f.cls == CLASS_BITSWAP) {
+    for (size_t j = 0; j < f.swaps.size(); ++j)
+      if (f.swaps[j].first >= nl || f.swaps[j].second >= nl) return true;
+  } else if (f.cls == CLASS_GENERAL) {
+    for (uint32_t j = f.nc; j < f.k; ++j)
+      if (f.idx_bits[j] >= nl) return true;
   }
-  const PlanConfig cfg = default_plan_config(s->prec, s->n_local);
-  std::vector<PlanStep> steps;
-  plan_passes(*pending, s->n_local, s->prec, cfg, &steps);
+  return false;
+}
+
+int execute_steps(qipb200_state *s, const std::vector<PlanStep> &steps, const std::vector<FlatOp> &local,
+                  const PlanConfig &cfg) {
+  qipb200_ctx *ctx = s->ctx;
   int st = QIPB200_OK;
   PassParams *pp = new PassParams();
   for (size_t i = 0; i < steps.size() && st == QIPB200_OK; ++i) {
@@ -49,29 +55,89 @@ int flush_fused(qipb200_state *s, std::vector<FlatOp> *pending) {
       ++ctx->tile_launches;
       ctx->fused_gates += steps[i].pass.n_gates;
     } else {
-      st = launch_local_op(s, (*pending)[steps[i].op_index]);
+      st = launch_local_op(s, local[steps[i].op_index]);
     }
   }
   delete pp;
-  pending->clear();
   return st;
 }
 
-bool needs_exchange(const qipb200_state *s, const FlatOp &f) {
-  if (s->world == 1) return false;
-  if (f.cls == CLASS_BITSWAP && f.ctrl_mask == 0) return true;  // handled as a relabelling by compile_and_localize
-  const uint32_t nl = s->n_local;
-  if (f.cls == CLASS_DENSE || f.cls == CLASS_FLIP) {
-    for (size_t j = 0; j < f.tgt_sorted.size(); ++j)
-      if (f.tgt_sorted[j] >= nl) return true;
-  } else if (f.cls == CLASS_BITSWAP) {
-    for (size_t j = 0; j < f.swaps.size(); ++j)
-      if (f.swaps[j].first >= nl || f.swaps[j].second >= nl) return true;
-  } else if (f.cls == CLASS_GENERAL) {
-    for (uint32_t j = f.nc; j < f.k; ++j)
-      if (f.idx_bits[j] >= nl) return true;
+// Fused execution.  The schedule is consumed in EPOCHS: under the current layout every op whose
+// non-diagonal targets are local is planned into tile passes (ops needing a rank-held qubit are
+// "blocked"; later ops may overtake them only when they commute); when nothing more can run, the
+// first blocked op's qubit is migrated over NVLink (one exchange) and the next epoch starts.
+int run_fused(qipb200_state *s, const qip_op *ops, size_t n_ops, const std::vector<uint64_t> &next_use) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = tile_pass_configure();
+    if (e != cudaSuccess) return report_cuda_error(s, e, "cudaFuncSetAttribute(tile pass)");
+    configured = true;
   }
-  return false;
+  const PlanConfig cfg = default_plan_config(s->prec, s->n_local);
+  std::vector<size_t> remaining(n_ops);
+  for (size_t i = 0; i < n_ops; ++i) remaining[i] = i;
+  while (!remaining.empty()) {
+    // compile what is left under the current layout
+    std::vector<FlatOp> local(remaining.size());
+    std::vector<char> blocked(remaining.size(), 0);
+    std::vector<DepMasks> dep(remaining.size());
+    std::vector<char> drop(remaining.size(), 0);
+    for (size_t r = 0; r < remaining.size(); ++r) {
+      FlatOp f;
+      std::string err;
+      int st = compile_op(&ops[remaining[r]], s->prec, s->n, &f, &err, s->phys_of_logical.data());
+      if (st != QIPB200_OK) {
+        // run everything before the bad op, then report (sequential semantics)
+        local.resize(r);
+        blocked.resize(r);
+        dep.resize(r);
+        std::vector<PlanStep> steps;
+        std::vector<size_t> left;
+        plan_passes(local, s->n_local, s->prec, cfg, &steps, &blocked, &left, &dep);
+        execute_steps(s, steps, local, cfg);
+        return report_error(s, st, err);
+      }
+      op_dependency_masks(f, &dep[r]);
+      if (needs_exchange(s, f)) {
+        blocked[r] = 1;
+        local[r] = f;
+        continue;
+      }
+      bool skip = false;
+      if ((st = restrict_to_rank(s, f, &local[r], &skip)) != QIPB200_OK) return st;
+      if (skip) {
+        local[r] = FlatOp();
+        local[r].cls = CLASS_IDENTITY;
+        drop[r] = 1;
+      }
+    }
+    std::vector<PlanStep> steps;
+    std::vector<size_t> left;  // indices into `local`
+    plan_passes(local, s->n_local, s->prec, cfg, &steps, &blocked, &left, &dep);
+    int st = execute_steps(s, steps, local, cfg);
+    if (st != QIPB200_OK) return st;
+    if (left.empty()) break;
+    // the first blocked op (program order) decides the migration; identical on every rank
+    size_t first_blocked = left.size();
+    for (size_t i = 0; i < left.size(); ++i)
+      if (blocked[left[i]]) {
+        first_blocked = i;
+        break;
+      }
+    if (first_blocked == left.size())
+      return report_error(s, QIPB200_ERR_UNSUPPORTED, "internal: schedule made no progress");
+    const size_t op_idx = remaining[left[first_blocked]];
+    FlatOp f;
+    const uint64_t *nu = next_use.empty() ? nullptr : &next_use[(op_idx + 1) * s->n];
+    if ((st = compile_and_localize(s, &ops[op_idx], &f, nu)) != QIPB200_OK) return st;  // exchange(s) happen here
+    // an uncontrolled Swap on a rank-held qubit was consumed as a relabelling of the bit map
+    const bool consumed = f.cls == CLASS_IDENTITY;
+    std::vector<size_t> next;
+    for (size_t i = 0; i < left.size(); ++i)
+      if (!(consumed && i == first_blocked)) next.push_back(remaining[left[i]]);
+    remaining.swap(next);
+  }
+  return QIPB200_OK;
 }
 
 }  // namespace
@@ -93,34 +159,16 @@ int run_schedule(qipb200_state *s, const qip_op *ops, size_t n_ops, uint32_t fla
     }
   }
   const bool fuse = !(flags & QIPB200_SCHED_NO_FUSION) && s->n_local >= 6;
-  std::vector<FlatOp> pending;
+  if (fuse) return run_fused(s, ops, n_ops, next_use);
   for (size_t i = 0; i < n_ops; ++i) {
     FlatOp f;
     const uint64_t *nu = next_use.empty() ? nullptr : &next_use[(i + 1) * s->n];
-    if (fuse) {
-      // peek: compile under the current layout; an op that needs an exchange is a barrier
-      std::string err;
-      int st = compile_op(&ops[i], s->prec, s->n, &f, &err, s->phys_of_logical.data());
-      if (st != QIPB200_OK) {
-        flush_fused(s, &pending);
-        return report_error(s, st, err);
-      }
-      if (needs_exchange(s, f)) {
-        if ((st = flush_fused(s, &pending)) != QIPB200_OK) return st;
-        if ((st = compile_and_localize(s, &ops[i], &f, nu)) != QIPB200_OK) return st;
-      }
-      FlatOp local;
-      bool skip = false;
-      if ((st = restrict_to_rank(s, f, &local, &skip)) != QIPB200_OK) return st;
-      if (!skip) pending.push_back(local);
-    } else {
-      int st = compile_and_localize(s, &ops[i], &f, nu);
-      if (st != QIPB200_OK) return st;
-      st = apply_flat_local(s, f);
-      if (st != QIPB200_OK) return st;
-    }
+    int st = compile_and_localize(s, &ops[i], &f, nu);
+    if (st != QIPB200_OK) return st;
+    st = apply_flat_local(s, f);
+    if (st != QIPB200_OK) return st;
   }
-  return flush_fused(s, &pending);
+  return QIPB200_OK;
 }
 
 }  // namespace qipb200

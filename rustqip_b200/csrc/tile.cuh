@@ -159,8 +159,19 @@ struct PlanConfig {
 
 // Plan `ops` (already compiled against the current layout and restricted to local bits;
 // ops[i].cls == CLASS_IDENTITY entries are dropped) for a local state of n_local bits.
+// `blocked` (optional, same length as ops): ops that cannot run under the current layout (their
+// non-diagonal targets are held by the rank index of a sharded state).  They are never emitted;
+// they and everything that does not commute past them are returned in `leftover` (program order).
+// `dep` (optional): per-op (non-diagonal, diagonal) bit masks to use for the commutation analysis
+// instead of the ones derived from `ops` -- on a sharded state `ops` are restricted to the rank
+// (rank-held controls dropped) but the ordering must respect the unrestricted bits.
+struct DepMasks {
+  uint64_t nd = 0, dg = 0;
+};
+void op_dependency_masks(const FlatOp &f, DepMasks *out);
 void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec, const PlanConfig &cfg,
-                 std::vector<PlanStep> *steps);
+                 std::vector<PlanStep> *steps, const std::vector<char> *blocked = nullptr,
+                 std::vector<size_t> *leftover = nullptr, const std::vector<DepMasks> *dep = nullptr);
 
 // Serialise a pass: header + micro-op records + global terms.  Returns false if the
 // records do not fit kMaxPassBytes (the planner bounds passes so that they do).
