@@ -523,6 +523,7 @@ void emit_pass(const std::vector<FlatOp> &ops, const std::vector<size_t> &taken,
 
   for (size_t ti = 0; ti < taken.size(); ++ti) {
     const FlatOp &f = ops[taken[ti]];
+    if (f.cls == CLASS_IDENTITY) continue;  // retired without emitting anything
     uint32_t lctrl = 0;
     uint64_t gmask = 0;
     for (uint32_t b = 0; b < 64; ++b)
@@ -690,7 +691,19 @@ void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec
   std::vector<size_t> remaining;
   for (size_t i = 0; i < ops.size(); ++i) {
     const bool is_blocked = blocked && (*blocked)[i];
-    if (ops[i].cls == CLASS_IDENTITY && !is_blocked) continue;
+    if (ops[i].cls == CLASS_IDENTITY && !is_blocked) {
+      if (!dep) continue;  // a plain identity gate: nothing to do, nothing to order
+      // identity ON THIS RANK under the current layout (e.g. a rank-held control is 0): it emits
+      // nothing, but it may only be retired once everything it depends on has run -- if it stays
+      // behind a blocked op it must be re-examined under the next layout.
+      info[i] = OpInfo();
+      info[i].nd = (*dep)[i].nd;
+      info[i].dg = (*dep)[i].dg;
+      info[i].tile_ok = true;
+      info[i].unfused_cost = 0.0;
+      remaining.push_back(i);
+      continue;
+    }
     info[i] = analyse(ops[i]);
     if (dep) {
       info[i].nd = (*dep)[i].nd;
