@@ -398,6 +398,7 @@ struct Emitter {
     if (e.type == E_X) {  // matrix kept for host-side composition / folding
       e.m[0] = e.m[3] = cplx(0, 0);
       e.m[1] = e.m[2] = cplx(1, 0);
+      if (!cfg->x_as_moves) e.type = E_DENSE1;  // 0*x + 1*y == y exactly for finite amplitudes
     }
     const uint32_t bm = e.bits();
     if (!cfg->fuse_blocks) {
@@ -665,6 +666,7 @@ PlanConfig default_plan_config(qip_prec prec, uint32_t n_local) {
   if (const char *e = getenv("QIPB200_TILE_G")) c.groups_per_thread = atoi(e) == 2 ? 2 : 1;
   if (const char *e = getenv("QIPB200_NO_BLOCK_FUSION")) c.fuse_blocks = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_NO_PEEPHOLE")) c.peephole = atoi(e) == 0;
+  if (const char *e = getenv("QIPB200_X_MOVES")) c.x_as_moves = atoi(e) != 0;
   if (n_local < c.T) c.T = n_local;
   if (c.L > c.T) c.L = c.T;
   if (c.T - c.L > kTileMaxHigh) c.L = c.T - kTileMaxHigh;

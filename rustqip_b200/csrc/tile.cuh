@@ -153,6 +153,8 @@ struct PlanConfig {
   uint32_t L = 5;         // contiguous low bits
   bool fuse_blocks = true;      // group ops into 3-bit register-resident super-ops
   bool peephole = true;         // fold consecutive ops on the same target bit into one 2x2
+  bool x_as_moves = false;      // X inside a tile as register moves (exact for non-finite amplitudes too) instead of the
+                                // exact-for-finite 0/1 real 2x2; moves cost more issue slots, the FP64 pipe has slack
   int groups_per_thread = 1;       // register-resident groups per interpreter decode (1: 3 CTAs/SM, 2: 2 CTAs/SM)
   uint32_t compose_threshold = 8;  // >= this many 2x2 gates in one group: compose them into one 8x8
 };
