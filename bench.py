@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--depth", type=int, default=40)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--gate-set", default="H,T,CNOT")
+    ap.add_argument("--workload", default="random", choices=["random", "qft", "dense4"],
+                    help="random: depth-D random layers (BASELINE metric / configs[1], [4]); qft: configs[2]; dense4: configs[3]")
     ap.add_argument("--no-fusion", action="store_true", help="one kernel sweep per gate")
     ap.add_argument("--no-extras", action="store_true", help="skip the unfused / per-kernel / CPU side measurements")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
@@ -117,9 +119,16 @@ def build_workload(args, world):
     from rustqip_b200 import circuits
     g = (world - 1).bit_length()
     n = args.n_local + g
-    ops = circuits.random_circuit(n, args.depth, 0x5EED0002, args.gate_set)
-    name = "N=%d %s depth-%d random {%s} from |0>, layer 0 = H^n (SURVEY 8d generator, seed 0x5EED0002)" % (
-        n, args.dtype, args.depth, args.gate_set)
+    if args.workload == "qft":
+        ops = circuits.qft(n)
+        name = "N=%d %s textbook QFT at MatrixOp level (H, controlled phases, final swaps; BASELINE configs[2]) from |0>" % (n, args.dtype)
+    elif args.workload == "dense4":
+        ops = circuits.config4(n, blocks=args.depth)
+        name = "N=%d %s H^n then %d dense 4-qubit Haar blocks on seeded random qubits (BASELINE configs[3])" % (n, args.dtype, args.depth)
+    else:
+        ops = circuits.random_circuit(n, args.depth, 0x5EED0002, args.gate_set)
+        name = "N=%d %s depth-%d random {%s} from |0>, layer 0 = H^n (SURVEY 8d generator, seed 0x5EED0002)" % (
+            n, args.dtype, args.depth, args.gate_set)
     return n, ops, name
 
 
@@ -366,6 +375,38 @@ def run_b200(args):
             extras["roofline_per_gate_kernel"] = pergate
         else:
             line["roofline"] = pergate
+        # the other single-GPU BASELINE configs, one timed pass each after one warm-up pass
+        if world == 1:
+            from rustqip_b200 import circuits as _c
+            other = {}
+            st.free()
+            for cname, cn, cdtype, cops in [("configs[1] N=28 f64 depth-40 {H,T,CNOT}", 28, np.complex128, _c.config2()),
+                                            ("configs[2] N=30 f32 QFT", 30, np.complex64, _c.qft(30)),
+                                            ("configs[3] N=26 f64 200 dense 4-qubit blocks", 26, np.complex128, _c.config4(26, 200))]:
+                cst = State(cn, cdtype, ctx)
+                carr, ckeep = marshal_ops(cops, cst.prec)
+                camp = np.dtype(cdtype).itemsize
+                res = {}
+                for label, fus in (("fused", True), ("unfused", False)):
+                    def cstep():
+                        cst.set_basis(0)
+                        cst.apply_marshalled(carr, len(cops), fus)
+                    cstep()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    cst.sync()
+                    e0.record(stream)
+                    cstep()
+                    e1.record(stream)
+                    cst.sync()
+                    e1.synchronize()
+                    cms = e0.elapsed_time(e1)
+                    res[label] = {"ms": cms, "gate_apps_per_s": len(cops) / (cms / 1e3),
+                                  "effective_state_GBps": len(cops) / (cms / 1e3) * 2 * camp * (1 << cn) / 1e9}
+                res["gates"] = len(cops)
+                other[cname] = res
+                cst.free()
+            extras["other_configs"] = other
+            st = State(n, dtype, ctx)  # re-create for the sections below
         line["extras"] = extras
 
     # end to end through the reference-facing call: LocalBuilder::calculate_state_with_init

@@ -470,7 +470,6 @@ int compile_and_localize(qipb200_state *s, const qip_op *op, FlatOp *f, const ui
   }
   std::vector<uint32_t> nd;
   nondiag_bits(*f, &nd);
-  bool moved = false;
   for (size_t i = 0; i < nd.size(); ++i) {
     if (nd[i] < s->n_local) continue;
     // choose the local bit to evict: not used by this op, next non-diagonal use furthest away
@@ -495,14 +494,12 @@ int compile_and_localize(qipb200_state *s, const qip_op *op, FlatOp *f, const ui
     }
     if (best < 0) return set_err(ctx, QIPB200_ERR_UNSUPPORTED, "op touches every local bit: cannot migrate a rank bit");
     if ((st = exchange_bits(s, nd[i], (uint32_t)best)) != QIPB200_OK) return st;
-    moved = true;
     // recompile after every move so later decisions see the new layout
     st = compile_op(op, s->prec, s->n, f, &err, s->phys_of_logical.data());
     if (st != QIPB200_OK) return set_err(ctx, st, err);
     nondiag_bits(*f, &nd);
     i = (size_t)-1;  // restart scan
   }
-  (void)moved;
   return QIPB200_OK;
 }
 
@@ -754,7 +751,6 @@ extern "C" int qipb200_state_soft_measure(qipb200_state *s, const uint64_t *indi
   CU(ctx, cudaMemcpyAsync(host.data(), (const char *)s->buf + c * clen * ab, clen * ab, cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   uint64_t idx = 0;  // the reference leaves measured_indx = 0 when the scan never crosses
-  bool found = false;
   for (uint64_t i = 0; i < clen; ++i) {
     double re, im;
     if (s->prec == QIP_F32) {
@@ -767,11 +763,9 @@ extern "C" int qipb200_state_soft_measure(qipb200_state *s, const uint64_t *indi
     rem -= re * re + im * im;
     if (rem <= 0.0) {
       idx = c * clen + i;
-      found = true;
       break;
     }
   }
-  (void)found;
   uint64_t m = 0;  // extract_bits(measured_indx, [n-1-index]) (measurement_ops.rs:174-175)
   for (uint32_t i = 0; i < n_indices; ++i) m |= ((idx >> (s->n - 1 - indices[i])) & 1ull) << i;
   *measured = m;

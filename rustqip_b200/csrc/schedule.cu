@@ -81,7 +81,6 @@ int run_fused(qipb200_state *s, const qip_op *ops, size_t n_ops, const std::vect
     std::vector<FlatOp> local(remaining.size());
     std::vector<char> blocked(remaining.size(), 0);
     std::vector<DepMasks> dep(remaining.size());
-    std::vector<char> drop(remaining.size(), 0);
     for (size_t r = 0; r < remaining.size(); ++r) {
       FlatOp f;
       std::string err;
@@ -108,7 +107,6 @@ int run_fused(qipb200_state *s, const qip_op *ops, size_t n_ops, const std::vect
       if (skip) {
         local[r] = FlatOp();
         local[r].cls = CLASS_IDENTITY;
-        drop[r] = 1;
       }
     }
     std::vector<PlanStep> steps;

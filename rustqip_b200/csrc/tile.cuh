@@ -134,7 +134,7 @@ struct HostMicroOp {
 };
 
 struct HostPass {
-  PassHeader hdr;
+  PassHeader hdr{};
   std::vector<HostMicroOp> ops;
   std::vector<unsigned char> gterms;  // GlobalTerm<R> records
   uint32_t n_gates = 0;               // reference ops folded into this pass
