@@ -123,6 +123,11 @@ struct HElem {
   uint32_t lmask = 0, lval = 0;  // PHASE condition (tile-local)
   uint64_t gmask = 0, gval = 0;  // CTA-uniform condition
   cplx m[4];                     // DENSE1 matrix / PHASE factor in m[0]
+  struct CondPhase {
+    uint64_t gmask, gval;
+    cplx w;
+  };
+  std::vector<CondPhase> terms;   // PHASE: extra CTA-conditional factors on the same local mask (-> EC_PHASEN)
   std::vector<uint32_t> mbits;   // DENSE3: the local bits the matrix acts on (ascending, <= 3)
   std::vector<cplx> mk;          // DENSE3: 2^k x 2^k matrix on mbits
   uint32_t bits() const {
@@ -223,7 +228,7 @@ struct Emitter {
     bool conditional = false;
     for (size_t i = 0; i < elems.size(); ++i) {
       n_dense += elems[i].type == E_DENSE1 ? 1 : (elems[i].type == E_DENSE3 ? 4 : 0);  // host elems are never E_DENSE1R
-      conditional |= elems[i].gmask != 0;
+      conditional |= elems[i].gmask != 0 || !elems[i].terms.empty();
     }
     if (!conditional && elems.size() > 1 && n_dense >= cfg->compose_threshold) {
       std::vector<cplx> acc(64, cplx(0, 0));
@@ -267,7 +272,8 @@ struct Emitter {
           lv |= ((e.lval >> b) & 1u) << sub_of(b);
         }
       }
-      const uint32_t rec_bytes = (uint32_t)sizeof(d) + (e.type == E_DENSE3 ? (uint32_t)(128 * sizeof(R)) : 0u);
+      const uint32_t rec_bytes = (uint32_t)sizeof(d) + (e.type == E_DENSE3 ? (uint32_t)(128 * sizeof(R)) : 0u) +
+                                 (uint32_t)(e.terms.size() * sizeof(PhaseTerm<R>));
       if (e.type == E_DENSE1 || e.type == E_X) {
         const uint32_t j = sub_of(e.lb_j);
         uint32_t pm = 0, p = 0;
@@ -295,7 +301,8 @@ struct Emitter {
         uint32_t am = 0;
         for (uint32_t c = 0; c < 8; ++c)
           if ((c & lm) == lv) am |= 1u << c;
-        d.op = elem_op(E_PHASE, 0, am, cond, rec_bytes);
+        d.op = e.terms.empty() ? elem_op(E_PHASE, 0, am, cond, rec_bytes) : elem_op_phasen(am, rec_bytes);
+        d.pad = (uint32_t)e.terms.size();
         d.m[0] = (R)e.m[0].real();
         d.m[1] = (R)e.m[0].imag();
       } else {  // E_DENSE3 (E_X / E_SWAP were lowered above)
@@ -304,6 +311,17 @@ struct Emitter {
       const size_t at = mo.data.size();
       mo.data.resize(at + sizeof(d));
       memcpy(mo.data.data() + at, &d, sizeof(d));
+      for (size_t k = 0; k < e.terms.size(); ++k) {
+        PhaseTerm<R> pt;
+        memset(&pt, 0, sizeof(pt));
+        pt.gmask = e.terms[k].gmask;
+        pt.gval = e.terms[k].gval;
+        pt.re = (R)e.terms[k].w.real();
+        pt.im = (R)e.terms[k].w.imag();
+        const size_t at3 = mo.data.size();
+        mo.data.resize(at3 + sizeof(pt));
+        memcpy(mo.data.data() + at3, &pt, sizeof(pt));
+      }
       if (e.type == E_DENSE3) {
         const std::vector<cplx> M = embed(e.mk, e.mbits, P);
         const size_t at2 = mo.data.size();
@@ -341,6 +359,24 @@ struct Emitter {
   // target bit under the same controls/condition (H.T.H -> one complex 2x2, T after a 2x2 ->
   // a scaled row, two phases on the same mask -> one phase).  Returns true when folded.
   static bool fold_into(HElem &b, const HElem &e) {
+    if (b.type == E_PHASE && e.type == E_PHASE && b.lmask == e.lmask && b.lval == e.lval &&
+        (b.gmask != e.gmask || b.gval != e.gval || !b.terms.empty() || !e.terms.empty())) {
+      // same amplitudes, different CTA-uniform conditions: keep one op with a list of conditional factors
+      if (b.gmask) {
+        HElem::CondPhase t = {b.gmask, b.gval, b.m[0]};
+        b.terms.push_back(t);
+        b.m[0] = cplx(1, 0);
+        b.gmask = b.gval = 0;
+      }
+      if (e.gmask) {
+        HElem::CondPhase t = {e.gmask, e.gval, e.m[0]};
+        b.terms.push_back(t);
+      } else {
+        b.m[0] *= e.m[0];
+      }
+      b.terms.insert(b.terms.end(), e.terms.begin(), e.terms.end());
+      return true;
+    }
     if (b.gmask != e.gmask || b.gval != e.gval) return false;
     auto phase_target_ok = [](const HElem &ph, const HElem &d1) {
       // ph == diag(1, w) on d1's target bit under exactly d1's controls
@@ -359,13 +395,13 @@ struct Emitter {
       return true;
     }
     if (b.type == E_DENSE1 && e.type == E_PHASE) {
-      if (!phase_target_ok(e, b)) return false;
+      if (!e.terms.empty() || !phase_target_ok(e, b)) return false;
       b.m[2] *= e.m[0];  // diag(1,w) * M: scales the row of the |1> output
       b.m[3] *= e.m[0];
       return true;
     }
     if (b.type == E_PHASE && e.type == E_DENSE1) {
-      if (!phase_target_ok(b, e)) return false;
+      if (!b.terms.empty() || !phase_target_ok(b, e)) return false;
       HElem d = e;
       d.m[1] *= b.m[0];  // M * diag(1,w): scales the column of the |1> input
       d.m[3] *= b.m[0];
@@ -423,9 +459,20 @@ struct Emitter {
       open.push_back(g);
       return;
     }
-    if (hit.size() == 1 && cfg->peephole && fold_into(open[hit[0]].elems.back(), e)) {
-      open[hit[0]].mask = um;  // a folded phase may have brought no new bit; keep the union anyway
-      return;
+    if (hit.size() == 1 && cfg->peephole) {
+      std::vector<HElem> &el = open[hit[0]].elems;
+      if (fold_into(el.back(), e)) {
+        open[hit[0]].mask = um;
+        return;
+      }
+      if (e.type == E_PHASE && e.terms.size() < 48) {
+        // phases commute with each other: look further back through the run of phases for the same mask
+        for (size_t k = el.size(); k-- > 0 && el[k].type == E_PHASE;)
+          if (el[k].lmask == e.lmask && el[k].lval == e.lval && el[k].terms.size() < 48 && fold_into(el[k], e)) {
+            open[hit[0]].mask = um;
+            return;
+          }
+      }
     }
     Group merged;
     merged.mask = um;

@@ -41,14 +41,17 @@ enum ElemType { E_DENSE1 = 0, E_DENSE1R = 1, E_X = 2, E_PHASE = 3, E_SWAP = 4, E
 //   bits 0-4   interpreter case id: 0 END (sentinel after the last op of a super-op),
 //              1-3 real 2x2 on sub-bit 0/1/2 with every pair active, 4-6 complex ditto,
 //              7-9 real 2x2 masked, 10-12 complex 2x2 masked, 13 PHASE, 14 dense 8x8,
-//              15-17 X (pair exchange by register moves) every pair active, 18-20 X masked
+//              15-17 X (pair exchange by register moves) every pair active, 18-20 X masked,
+//              21 PHASEN: one phase mask, base factor m[0..1] times the product of the CTA-uniform
+//                 conditional factors listed after the record (count in Elem::pad) -- a run of
+//                 controlled phases whose controls lie outside the tile costs one application
 //   bits 12-19 active mask: 2x2 kinds: bit p <-> the p-th (ascending) sub-index with bit j
 //              clear; PHASE: bit c <-> sub-index c
 //   bits 20-30 record size in 16-byte units (the dense 8x8 matrix follows its record)
 //   bit 31     the op has a CTA-uniform condition (gmask/gval must be tested)
 static const uint32_t kElemHasCond = 1u << 31;
 enum ElemCase { EC_END = 0, EC_D1R_FULL = 1, EC_D1C_FULL = 4, EC_D1R_MASK = 7, EC_D1C_MASK = 10, EC_PHASE = 13, EC_DENSE3 = 14,
-                EC_X_FULL = 15, EC_X_MASK = 18 };
+                EC_X_FULL = 15, EC_X_MASK = 18, EC_PHASEN = 21 };
 inline uint32_t elem_op(uint32_t kind, uint32_t j, uint32_t mask, bool cond, uint32_t size_bytes) {
   uint32_t id;
   if (kind == E_DENSE1R)
@@ -64,6 +67,7 @@ inline uint32_t elem_op(uint32_t kind, uint32_t j, uint32_t mask, bool cond, uin
   return id | (mask << 12) | ((size_bytes >> 4) << 20) | (cond ? kElemHasCond : 0u);
 }
 inline uint32_t elem_case(uint32_t op) { return op & 0x1fu; }
+inline uint32_t elem_op_phasen(uint32_t mask, uint32_t size_bytes) { return EC_PHASEN | (mask << 12) | ((size_bytes >> 4) << 20); }
 inline uint32_t elem_size_bytes(uint32_t op) { return ((op >> 20) & 0x7ffu) << 4; }
 
 // Device-visible micro-op header (fixed 128 bytes), followed by its data:
@@ -98,10 +102,16 @@ struct alignas(16) DiagTerm {  // multiply by (re,im) where (global & gmask)==gv
 template <typename R>
 struct alignas(16) Elem {
   uint32_t op;           // see elem_op()
-  uint32_t pad;
+  uint32_t pad;          // EC_PHASEN: number of PhaseTerm records that follow
   uint64_t gmask, gval;  // CTA-uniform condition on the tile's base index (read only if kElemHasCond)
   uint64_t pad2;
   R m[8];                // DENSE1: m00,m01,m10,m11 (re,im); DENSE1R: m00,m01,m10,m11 (re); PHASE: w (re,im)
+};
+
+template <typename R>
+struct alignas(16) PhaseTerm {  // conditional factor of an EC_PHASEN record
+  uint64_t gmask, gval;
+  R re, im;
 };
 
 template <typename R>

@@ -142,6 +142,17 @@
         } else if (id == EC_PHASE) {                                                                            \
           const R wr = e->m[0], wi = e->m[1];                                                                   \
           _QIP_PH_BODY(T, C)                                                                                    \
+        } else if (id == EC_PHASEN) { /* a run of controlled phases with controls outside the tile */            \
+          R wr = e->m[0], wi = e->m[1];                                                                         \
+          const PhaseTerm<R> *pt = reinterpret_cast<const PhaseTerm<R> *>(e + 1);                               \
+          const uint32_t nt = e->pad;                                                                           \
+          for (uint32_t k = 0; k < nt; ++k) {                                                                   \
+            if ((base & pt[k].gmask) != pt[k].gval) continue;                                                   \
+            const R nr = wr * pt[k].re - wi * pt[k].im;                                                         \
+            wi = wr * pt[k].im + wi * pt[k].re;                                                                 \
+            wr = nr;                                                                                            \
+          }                                                                                                     \
+          _QIP_PH_BODY(T, C)                                                                                    \
         } else if (id >= EC_X_FULL) { /* X / CNOT / Toffoli-X: pair exchange by register moves */               \
           const uint32_t xm = id >= EC_X_MASK ? pm : 0xfu;                                                      \
           const uint32_t j = id >= EC_X_MASK ? id - EC_X_MASK : id - EC_X_FULL;                                 \

@@ -73,7 +73,7 @@ static void run_elem(const Elem<R> &e, const R *mat8, cd a[8], uint64_t base) {
         a[i1] = cd(e.m[4], e.m[5]) * x + cd(e.m[6], e.m[7]) * y;
       }
     }
-  } else if (id >= EC_X_FULL) {
+  } else if (id >= EC_X_FULL && id < EC_PHASEN) {
     const uint32_t j = (id - EC_X_FULL) % 3;
     uint32_t p = 0;
     for (uint32_t c = 0; c < 8; ++c) {
@@ -82,6 +82,13 @@ static void run_elem(const Elem<R> &e, const R *mat8, cd a[8], uint64_t base) {
       ++p;
       if (on) std::swap(a[c], a[c | (1u << j)]);
     }
+  } else if (id == EC_PHASEN) {
+    cd w(e.m[0], e.m[1]);
+    const PhaseTerm<R> *t = reinterpret_cast<const PhaseTerm<R> *>(mat8);
+    for (uint32_t k = 0; k < e.pad; ++k)
+      if ((base & t[k].gmask) == t[k].gval) w *= cd(t[k].re, t[k].im);
+    for (uint32_t c = 0; c < 8; ++c)
+      if ((mask >> c) & 1) a[c] *= w;
   } else if (id == EC_PHASE) {
     for (uint32_t c = 0; c < 8; ++c)
       if ((mask >> c) & 1) a[c] *= cd(e.m[0], e.m[1]);
