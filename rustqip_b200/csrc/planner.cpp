@@ -358,8 +358,8 @@ struct Emitter {
   // Peephole: fold `e` into the last elementary op of a group when both act on the same
   // target bit under the same controls/condition (H.T.H -> one complex 2x2, T after a 2x2 ->
   // a scaled row, two phases on the same mask -> one phase).  Returns true when folded.
-  static bool fold_into(HElem &b, const HElem &e) {
-    if (b.type == E_PHASE && e.type == E_PHASE && b.lmask == e.lmask && b.lval == e.lval &&
+  static bool fold_into(HElem &b, const HElem &e, bool fold_cond) {
+    if (fold_cond && b.type == E_PHASE && e.type == E_PHASE && b.lmask == e.lmask && b.lval == e.lval &&
         (b.gmask != e.gmask || b.gval != e.gval || !b.terms.empty() || !e.terms.empty())) {
       // same amplitudes, different CTA-uniform conditions: keep one op with a list of conditional factors
       if (b.gmask) {
@@ -461,14 +461,14 @@ struct Emitter {
     }
     if (hit.size() == 1 && cfg->peephole) {
       std::vector<HElem> &el = open[hit[0]].elems;
-      if (fold_into(el.back(), e)) {
+      if (fold_into(el.back(), e, cfg->fold_cond_phases)) {
         open[hit[0]].mask = um;
         return;
       }
-      if (e.type == E_PHASE && e.terms.size() < 48) {
+      if (cfg->fold_cond_phases && e.type == E_PHASE && e.terms.size() < 48) {
         // phases commute with each other: look further back through the run of phases for the same mask
         for (size_t k = el.size(); k-- > 0 && el[k].type == E_PHASE;)
-          if (el[k].lmask == e.lmask && el[k].lval == e.lval && el[k].terms.size() < 48 && fold_into(el[k], e)) {
+          if (el[k].lmask == e.lmask && el[k].lval == e.lval && el[k].terms.size() < 48 && fold_into(el[k], e, true)) {
             open[hit[0]].mask = um;
             return;
           }
@@ -714,6 +714,7 @@ PlanConfig default_plan_config(qip_prec prec, uint32_t n_local) {
   if (const char *e = getenv("QIPB200_NO_BLOCK_FUSION")) c.fuse_blocks = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_NO_PEEPHOLE")) c.peephole = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_X_MOVES")) c.x_as_moves = atoi(e) != 0;
+  if (const char *e = getenv("QIPB200_NO_PHASEN")) c.fold_cond_phases = atoi(e) == 0;
   if (n_local < c.T) c.T = n_local;
   if (c.L > c.T) c.L = c.T;
   if (c.T - c.L > kTileMaxHigh) c.L = c.T - kTileMaxHigh;

@@ -163,6 +163,7 @@ struct PlanConfig {
   uint32_t L = 5;         // contiguous low bits
   bool fuse_blocks = true;      // group ops into 3-bit register-resident super-ops
   bool peephole = true;         // fold consecutive ops on the same target bit into one 2x2
+  bool fold_cond_phases = true; // fold phases that differ only in their CTA-uniform condition into one EC_PHASEN op
   bool x_as_moves = false;      // X inside a tile as register moves (exact for non-finite amplitudes too) instead of the
                                 // exact-for-finite 0/1 real 2x2; moves cost more issue slots, the FP64 pipe has slack
   int groups_per_thread = 1;       // register-resident groups per interpreter decode (1: 3 CTAs/SM, 2: 2 CTAs/SM)
