@@ -242,6 +242,29 @@ struct Emitter {
       elems.push_back(d);
     }
 
+    {  // the per-CTA factor table has kMaxPhasen slots: beyond that, unfold into plain conditional phases
+      std::vector<HElem> flat;
+      uint32_t slots = pass->hdr.n_phasen;
+      for (size_t i = 0; i < elems.size(); ++i) {
+        if (elems[i].type != E_PHASE || elems[i].terms.empty() || slots < kMaxPhasen) {
+          slots += (elems[i].type == E_PHASE && !elems[i].terms.empty()) ? 1u : 0u;
+          flat.push_back(elems[i]);
+          continue;
+        }
+        HElem base = elems[i];
+        base.terms.clear();
+        if (!is_one(base.m[0])) flat.push_back(base);
+        for (size_t k = 0; k < elems[i].terms.size(); ++k) {
+          HElem c = base;
+          c.gmask = elems[i].terms[k].gmask;
+          c.gval = elems[i].terms[k].gval;
+          c.m[0] = elems[i].terms[k].w;
+          flat.push_back(c);
+        }
+      }
+      elems.swap(flat);
+    }
+
     HostMicroOp mo;
     memset(&mo.h, 0, sizeof(mo.h));
     mo.h.kind = MK_SUPER;
@@ -302,7 +325,7 @@ struct Emitter {
         for (uint32_t c = 0; c < 8; ++c)
           if ((c & lm) == lv) am |= 1u << c;
         d.op = e.terms.empty() ? elem_op(E_PHASE, 0, am, cond, rec_bytes) : elem_op_phasen(am, rec_bytes);
-        d.pad = (uint32_t)e.terms.size();
+        d.pad = e.terms.empty() ? 0u : pass->hdr.n_phasen++;
         d.m[0] = (R)e.m[0].real();
         d.m[1] = (R)e.m[0].imag();
       } else {  // E_DENSE3 (E_X / E_SWAP were lowered above)

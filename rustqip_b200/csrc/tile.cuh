@@ -29,6 +29,7 @@ static const uint32_t kTileMaxHigh = 8;       // m <= 8 -> 256 chunk offsets
 static const uint32_t kMaxPassBytes = 27 * 1024;  // micro-op records per pass (kernel parameter space)
 static const uint32_t kMaxDiagTerms = 24;     // per MK_DIAG micro-op
 static const uint32_t kMaxGlobalTerms = 32;   // CTA-uniform phase terms applied at store time
+static const uint32_t kMaxPhasen = 256;       // EC_PHASEN ops per pass (4 KiB factor table in shared memory)
 
 enum MicroKind { MK_DENSE = 0, MK_DIAG = 1, MK_EXCH = 2, MK_SUPER = 3 };
 // Elementary-op kinds of a MK_SUPER group.  Real and complex 2x2 gates are separate kinds
@@ -102,7 +103,7 @@ struct alignas(16) DiagTerm {  // multiply by (re,im) where (global & gmask)==gv
 template <typename R>
 struct alignas(16) Elem {
   uint32_t op;           // see elem_op()
-  uint32_t pad;          // EC_PHASEN: number of PhaseTerm records that follow
+  uint32_t pad;          // EC_PHASEN: slot of this op in the per-CTA factor table (terms follow the record)
   uint64_t gmask, gval;  // CTA-uniform condition on the tile's base index (read only if kElemHasCond)
   uint64_t pad2;
   R m[8];                // DENSE1: m00,m01,m10,m11 (re,im); DENSE1R: m00,m01,m10,m11 (re); PHASE: w (re,im)
@@ -127,7 +128,7 @@ struct PassHeader {
   uint32_t blob_bytes;                     // bytes of micro-op records
   uint32_t n_gterms;                       // GlobalTerm records at the very end of the blob
   uint32_t gterm_off;                      // byte offset of the GlobalTerm array inside the blob
-  uint32_t pad;
+  uint32_t n_phasen;                       // EC_PHASEN ops in this pass (slots of the per-CTA factor table)
 };
 
 // What the kernel receives by value (constant bank).

@@ -92,12 +92,12 @@
 #define QIP_COD(x) "=d"(x)
 #define QIP_COF(x) "=f"(x)
 
-// Defines  template <int G> void NAME(uint32_t tile_saddr, const MicroOp *mo, const unsigned char *data, uint64_t base)
+// Defines  template <int G> void NAME(uint32_t tile_saddr, const MicroOp *mo, const unsigned char *data, uint64_t base, const R *tbl)
 // for one precision.  tile_saddr = shared-memory byte address of the tile.
 #define QIP_DEFINE_RUN_SUPER(NAME, R, T, C, CO, SWZ, ESHIFT)                                                     \
   template <int G>                                                                                              \
   __device__ __forceinline__ void NAME(uint32_t tile_saddr, const MicroOp *mo, const unsigned char *data,      \
-                                       uint64_t base) {                                                         \
+                                       uint64_t base, const R *tbl) {                                           \
     const uint32_t groups = 1u << mo->groups_log2;                                                              \
     for (uint32_t g = threadIdx.x; g < groups; g += G * kTileThreads) {                                         \
       const bool two = (G == 2) && (g + kTileThreads < groups); /* warp-uniform */                              \
@@ -142,16 +142,8 @@
         } else if (id == EC_PHASE) {                                                                            \
           const R wr = e->m[0], wi = e->m[1];                                                                   \
           _QIP_PH_BODY(T, C)                                                                                    \
-        } else if (id == EC_PHASEN) { /* a run of controlled phases with controls outside the tile */            \
-          R wr = e->m[0], wi = e->m[1];                                                                         \
-          const PhaseTerm<R> *pt = reinterpret_cast<const PhaseTerm<R> *>(e + 1);                               \
-          const uint32_t nt = e->pad;                                                                           \
-          for (uint32_t k = 0; k < nt; ++k) {                                                                   \
-            if ((base & pt[k].gmask) != pt[k].gval) continue;                                                   \
-            const R nr = wr * pt[k].re - wi * pt[k].im;                                                         \
-            wi = wr * pt[k].im + wi * pt[k].re;                                                                 \
-            wr = nr;                                                                                            \
-          }                                                                                                     \
+        } else if (id == EC_PHASEN) { /* run of controlled phases, controls outside the tile: the product */    \
+          const R wr = tbl[2 * e->pad], wi = tbl[2 * e->pad + 1]; /* was formed once per CTA (factor table) */  \
           _QIP_PH_BODY(T, C)                                                                                    \
         } else if (id >= EC_X_FULL) { /* X / CNOT / Toffoli-X: pair exchange by register moves */               \
           const uint32_t xm = id >= EC_X_MASK ? pm : 0xfu;                                                      \

@@ -179,6 +179,39 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+
+  // While the tile streams in: the per-CTA factor table of the EC_PHASEN ops (product of the
+  // conditional factors whose condition this tile's base index satisfies).  Thread t walks
+  // micro-op t; the table sits behind the tile in shared memory.
+  R *tbl = reinterpret_cast<R *>(smem + tile_bytes);
+  if (h->n_phasen && threadIdx.x < n_ops) {
+    const unsigned char *rec = pp.recs;
+    for (uint32_t i = 0; i < threadIdx.x; ++i) rec += sizeof(MicroOp) + reinterpret_cast<const MicroOp *>(rec)->data_bytes;
+    const MicroOp *mo = reinterpret_cast<const MicroOp *>(rec);
+    if (mo->kind == MK_SUPER) {
+      const unsigned char *ep = rec + sizeof(MicroOp);
+      for (;;) {
+        const Elem<R> *e = reinterpret_cast<const Elem<R> *>(ep);
+        const uint32_t op = e->op;
+        if ((op & 0x1fu) == EC_END) break;
+        const uint32_t size = ((op >> 20) & 0x7ffu) << 4;
+        if ((op & 0x1fu) == EC_PHASEN) {
+          R wr = e->m[0], wi = e->m[1];
+          const PhaseTerm<R> *pt = reinterpret_cast<const PhaseTerm<R> *>(e + 1);
+          const uint32_t nt = (size - (uint32_t)sizeof(Elem<R>)) / (uint32_t)sizeof(PhaseTerm<R>);
+          for (uint32_t k = 0; k < nt; ++k) {
+            if ((base & pt[k].gmask) != pt[k].gval) continue;
+            const R nr = wr * pt[k].re - wi * pt[k].im;
+            wi = wr * pt[k].im + wi * pt[k].re;
+            wr = nr;
+          }
+          tbl[2 * e->pad] = wr;
+          tbl[2 * e->pad + 1] = wi;
+        }
+        ep += size;
+      }
+    }
+  }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
@@ -191,9 +224,9 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
     if ((base & mo->gmask) == mo->gmask) {
       if (mo->kind == MK_SUPER) {
         if constexpr (sizeof(R) == 8)
-          run_super_f64<G>(smem_base, mo, data, base);
+          run_super_f64<G>(smem_base, mo, data, base, reinterpret_cast<const double *>(tbl));
         else
-          run_super_f32<G>(smem_base, mo, data, base);
+          run_super_f32<G>(smem_base, mo, data, base, reinterpret_cast<const float *>(tbl));
       } else if (mo->kind == MK_DENSE) {
         const R *mat = reinterpret_cast<const R *>(data);
         if (mo->k == 1)
@@ -261,7 +294,7 @@ cudaError_t tile_pass_configure() {
 cudaError_t launch_tile_pass(qip_prec prec, void *psi, uint32_t n_local, const PassParams &pp, int groups_per_thread,
                              cudaStream_t s, uint64_t *launches) {
   const uint32_t T = pp.h.T;
-  const size_t smem = (prec == QIP_F32 ? 8u : 16u) << T;
+  const size_t smem = ((size_t)(prec == QIP_F32 ? 8u : 16u) << T) + (pp.h.n_phasen ? kMaxPhasen * 16 : 0);
   const unsigned grid = 1u << (n_local - T);
   if (prec == QIP_F32) {
     if (groups_per_thread == 1)

@@ -85,7 +85,8 @@ static void run_elem(const Elem<R> &e, const R *mat8, cd a[8], uint64_t base) {
   } else if (id == EC_PHASEN) {
     cd w(e.m[0], e.m[1]);
     const PhaseTerm<R> *t = reinterpret_cast<const PhaseTerm<R> *>(mat8);
-    for (uint32_t k = 0; k < e.pad; ++k)
+    const uint32_t nt = (elem_size_bytes(e.op) - (uint32_t)sizeof(Elem<R>)) / (uint32_t)sizeof(PhaseTerm<R>);
+    for (uint32_t k = 0; k < nt; ++k)
       if ((base & t[k].gmask) == t[k].gval) w *= cd(t[k].re, t[k].im);
     for (uint32_t c = 0; c < 8; ++c)
       if ((mask >> c) & 1) a[c] *= w;
