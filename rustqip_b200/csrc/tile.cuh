@@ -131,12 +131,14 @@ struct PassHeader {
   uint32_t n_phasen;                       // EC_PHASEN ops in this pass (slots of the per-CTA factor table)
 };
 
-// What the kernel receives by value (constant bank).
-struct PassParams {
+// What the kernel receives by value (constant bank).  16-byte aligned so that the records
+// (16-byte aligned relative to `recs`) keep their alignment in parameter space.
+struct alignas(16) PassParams {
   PassHeader h;
   unsigned char recs[kMaxPassBytes];
 };
 static_assert(sizeof(PassParams) <= 32000, "kernel parameter space");
+static_assert(sizeof(PassHeader) % 16 == 0, "records must start 16-byte aligned");
 
 // ---- host side ---------------------------------------------------------------------
 struct HostMicroOp {
