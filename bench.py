@@ -53,6 +53,15 @@ def parse_args():
     return ap.parse_args()
 
 
+def ncu_traffic(kernel, algorithmic_bytes):
+    """DRAM traffic per launch from the committed ncu capture (profiles/traffic.json), scaled to this size."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
+        return {"bytes": t["ratio"] * algorithmic_bytes, "source": t["capture"]}
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -333,11 +342,13 @@ def run_b200(args):
         # dominant kernel of the step = the fused tile pass; its average launch duration is taken
         # from the CUDA-event time of the whole step (set-basis memset and the few per-gate
         # kernels included, so `achieved` is a slight under-estimate)
-        avg_ms = ms_per_step / (launches / args.steps - 1)
+        avg_ms = ms_per_step / max(1.0, tile_passes + exchanges)
         line["roofline"] = {"bound": "hbm", "kernel": "k_tile_pass<%s> (fused shared-memory tile pass, %.1f gates per launch)" % (
                                 "double" if args.dtype == "f64" else "float", fused_gates / tile_passes),
                             "achieved": local_bytes / (avg_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                            "frac": local_bytes / (avg_ms / 1e3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+                            "frac": local_bytes / (avg_ms / 1e3) / 1e9 / peak, "peak_source": peak_src,
+                            "traffic": (ncu_traffic("k_tile_pass", local_bytes) or {}).get("bytes"),
+                            "traffic_source": (ncu_traffic("k_tile_pass", local_bytes) or {}).get("source"),
                             "algorithmic_bytes_per_launch": local_bytes, "avg_launch_ms": avg_ms,
                             "note": "per launch: every amplitude of the shard read once and written once (SURVEY 8d: 2*2^N*16 B), "
                                     "independent of the number of gates folded into the pass"}
@@ -369,7 +380,8 @@ def run_b200(args):
         pergate = {"bound": "hbm", "kernel": "k_dense<%s,1,1> (1-qubit dense gate, mid target bit; the unfused per-gate sweep)" % (
                        "double" if args.dtype == "f64" else "float"),
                    "achieved": dom["alg_GBps"], "peak": peak, "unit": "GB/s", "frac": dom["frac_of_peak"],
-                   "peak_source": peak_src, "traffic": None,
+                   "peak_source": peak_src, "traffic": (ncu_traffic("k_dense", local_bytes) or {}).get("bytes"),
+                   "traffic_source": (ncu_traffic("k_dense", local_bytes) or {}).get("source"),
                    "algorithmic_bytes_per_launch": local_bytes, "avg_launch_ms": dom["ms"]}
         if "roofline" in line:
             extras["roofline_per_gate_kernel"] = pergate
