@@ -738,6 +738,7 @@ PlanConfig default_plan_config(qip_prec prec, uint32_t n_local) {
   if (const char *e = getenv("QIPB200_NO_PEEPHOLE")) c.peephole = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_X_MOVES")) c.x_as_moves = atoi(e) != 0;
   if (const char *e = getenv("QIPB200_NO_PHASEN")) c.fold_cond_phases = atoi(e) == 0;
+  if (const char *e = getenv("QIPB200_NO_TMA")) c.use_tma = atoi(e) == 0;
   if (n_local < c.T) c.T = n_local;
   if (c.L > c.T) c.L = c.T;
   if (c.T - c.L > kTileMaxHigh) c.L = c.T - kTileMaxHigh;

@@ -129,6 +129,8 @@ struct PassHeader {
   uint32_t n_gterms;                       // GlobalTerm records at the very end of the blob
   uint32_t gterm_off;                      // byte offset of the GlobalTerm array inside the blob
   uint32_t n_phasen;                       // EC_PHASEN ops in this pass (slots of the per-CTA factor table)
+  uint32_t use_tma;                        // set by the launcher: tile moved by TMA tensor copies
+  uint32_t pad_[3];
 };
 
 // What the kernel receives by value (constant bank).  16-byte aligned so that the records
@@ -167,6 +169,7 @@ struct PlanConfig {
   bool fuse_blocks = true;      // group ops into 3-bit register-resident super-ops
   bool peephole = true;         // fold consecutive ops on the same target bit into one 2x2
   bool fold_cond_phases = true; // fold phases that differ only in their CTA-uniform condition into one EC_PHASEN op
+  bool use_tma = true;          // move tiles with TMA (cp.async.bulk.tensor, 128B-swizzle tensor map) when the geometry allows
   bool x_as_moves = false;      // X inside a tile as register moves (exact for non-finite amplitudes too) instead of the
                                 // exact-for-finite 0/1 real 2x2; moves cost more issue slots, the FP64 pipe has slack
   int groups_per_thread = 1;       // register-resident groups per interpreter decode (1: 3 CTAs/SM, 2: 2 CTAs/SM)

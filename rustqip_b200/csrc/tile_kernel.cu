@@ -17,11 +17,14 @@
 // the two register-resident groups), so one CTA's loads and stores overlap the other's
 // arithmetic.  HBM traffic per pass: every
 // amplitude read once and written once, no matter how many gates the pass folds in.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "tile.cuh"
 #include "tile_launch.cuh"
 #include "tile_interp.cuh"
+
+#include <cstring>
 
 namespace qipb200 {
 
@@ -143,9 +146,46 @@ __device__ __forceinline__ void apply_diag(typename C2<R>::type *tile, const Mic
   }
 }
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers -----------------------------------------
+// The state is viewed as a 5-D tensor [bits >= h3][h2..h3)[h1..h2)[low3..h1)[128 bytes] (a plain
+// reshape of the contiguous buffer, h1 < h2 < h3 = the three lowest high tile bits); one box =
+// {128 B, 2^(L-low3), 2, 2, 2} = 2^(L+3) amplitudes lands in shared memory in exactly the
+// tile-local index order, and CU_TENSOR_MAP_SWIZZLE_128B is the same XOR swizzle the
+// interpreter addresses with.  The remaining m-3 tile bits select 2^(m-3) boxes.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(mbar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *map, uint32_t mbar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+
 template <typename R, int G>
 __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
-    k_tile_pass(R *__restrict__ psi, const __grid_constant__ PassParams pp) {
+    k_tile_pass(R *__restrict__ psi, const __grid_constant__ PassParams pp, const __grid_constant__ CUtensorMap tmap) {
   typedef typename C2<R>::type V;
   // the named PTX registers that hold the register-resident groups (tile_interp.cuh)
   if (sizeof(R) == 8) {
@@ -169,16 +209,36 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
 
   // ---- 1. load ----
   constexpr uint32_t kAmpsPerUnit = 16 / (2 * sizeof(R));
+  constexpr uint32_t kLow3 = sizeof(R) == 8 ? 3 : 4;  // index bits covered by one 128-byte row
   const uint32_t units = tile_bytes >> 4;
   const uint32_t lmask = (1u << L) - 1u;
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
-  for (uint32_t u = threadIdx.x; u < units; u += kTileThreads) {
-    const uint32_t t = u * kAmpsPerUnit;
-    const R *g = psi + 2 * (base + h->chunk_off[t >> L] + (t & lmask));
-    const uint32_t sa = smem_base + 16u * (u ^ ((u >> 3) & 7u));
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
+  const bool use_tma = h->use_tma != 0;
+  const uint32_t mbar = smem_base + tile_bytes + kMaxPhasen * 16;
+  const uint32_t n_boxes = 1u << (m - 3);           // only meaningful with use_tma (m >= 3)
+  const uint32_t box_bytes = (uint32_t)(2 * sizeof(R)) << (L + 3);
+  if (use_tma) {
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(mbar, tile_bytes);
+      const uint32_t h1 = h->hi_pos[0], h2 = h->hi_pos[1], h3 = h->hi_pos[2];
+      for (uint32_t b = 0; b < n_boxes; ++b) {
+        const uint64_t idx = base + h->chunk_off[b << 3];  // chunk index bits 3.. <-> tile bits hi_pos[3..]
+        tma_load_5d(smem_base + b * box_bytes, &tmap, mbar, 0, (int)((idx >> kLow3) & ((1ull << (h1 - kLow3)) - 1ull)),
+                    (int)((idx >> h1) & ((1ull << (h2 - h1)) - 1ull)), (int)((idx >> h2) & ((1ull << (h3 - h2)) - 1ull)),
+                    (int)(idx >> h3));
+      }
+    }
+  } else {
+    for (uint32_t u = threadIdx.x; u < units; u += kTileThreads) {
+      const uint32_t t = u * kAmpsPerUnit;
+      const R *g = psi + 2 * (base + h->chunk_off[t >> L] + (t & lmask));
+      const uint32_t sa = smem_base + 16u * (u ^ ((u >> 3) & 7u));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
 
   // While the tile streams in: the per-CTA factor table of the EC_PHASEN ops (product of the
   // conditional factors whose condition this tile's base index satisfies).  Thread t walks
@@ -212,7 +272,10 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
       }
     }
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (use_tma)
+    mbar_wait(mbar, 0);
+  else
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   // ---- 2. apply ----
@@ -257,6 +320,23 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
       has_g = true;
     }
   }
+  if (use_tma && !has_g) {
+    // shared memory -> HBM with TMA tensor stores (same boxes, same swizzle)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t h1 = h->hi_pos[0], h2 = h->hi_pos[1], h3 = h->hi_pos[2];
+      for (uint32_t b = 0; b < n_boxes; ++b) {
+        const uint64_t idx = base + h->chunk_off[b << 3];
+        tma_store_5d(&tmap, smem_base + b * box_bytes, 0, (int)((idx >> kLow3) & ((1ull << (h1 - kLow3)) - 1ull)),
+                     (int)((idx >> h1) & ((1ull << (h2 - h1)) - 1ull)), (int)((idx >> h2) & ((1ull << (h3 - h2)) - 1ull)),
+                     (int)(idx >> h3));
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    return;
+  }
   for (uint32_t u = threadIdx.x; u < units; u += kTileThreads) {
     const uint32_t t = u * kAmpsPerUnit;
     R *g = psi + 2 * (base + h->chunk_off[t >> L] + (t & lmask));
@@ -291,21 +371,63 @@ cudaError_t tile_pass_configure() {
   return cudaFuncSetAttribute(k_tile_pass<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
 }
 
-cudaError_t launch_tile_pass(qip_prec prec, void *psi, uint32_t n_local, const PassParams &pp, int groups_per_thread,
-                             cudaStream_t s, uint64_t *launches) {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// Tensor map of the local state for one pass (see the comment above mbar_init).  Returns false
+// when the geometry does not fit (then the pass runs with the cp.async path).
+static bool make_tile_map(CUtensorMap *map, qip_prec prec, void *psi, uint32_t n_local, const PassHeader &h) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  const uint32_t low3 = prec == QIP_F64 ? 3 : 4;
+  if (!enc || h.m < 3 || h.L < low3 || h.T > n_local) return false;
+  const uint32_t h1 = h.hi_pos[0], h2 = h.hi_pos[1], h3 = h.hi_pos[2];
+  const uint64_t amp = prec == QIP_F64 ? 16 : 8;
+  const uint64_t esz = prec == QIP_F64 ? 8 : 4;
+  cuuint64_t dims[5] = {128 / esz, 1ull << (h1 - low3), 1ull << (h2 - h1), 1ull << (h3 - h2), 1ull << (n_local - h3)};
+  cuuint64_t strides[4] = {128, amp << h1, amp << h2, amp << h3};
+  cuuint32_t box[5] = {(cuuint32_t)(128 / esz), 1u << (h.L - low3), 2, 2, 2};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (box[1] > 256 || dims[4] > (1ull << 32)) return false;
+  const CUresult r = enc(map, prec == QIP_F64 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 5, psi, dims,
+                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+cudaError_t launch_tile_pass(qip_prec prec, void *psi, uint32_t n_local, PassParams &pp, int groups_per_thread,
+                             bool use_tma, cudaStream_t s, uint64_t *launches) {
   const uint32_t T = pp.h.T;
-  const size_t smem = ((size_t)(prec == QIP_F32 ? 8u : 16u) << T) + (pp.h.n_phasen ? kMaxPhasen * 16 : 0);
+  alignas(64) CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  pp.h.use_tma = (use_tma && make_tile_map(&tmap, prec, psi, n_local, pp.h)) ? 1u : 0u;
+  // tile | EC_PHASEN factor table | mbarrier
+  const size_t smem = ((size_t)(prec == QIP_F32 ? 8u : 16u) << T) + kMaxPhasen * 16 + 16;
   const unsigned grid = 1u << (n_local - T);
   if (prec == QIP_F32) {
     if (groups_per_thread == 1)
-      k_tile_pass<float, 1><<<grid, kTileThreads, smem, s>>>((float *)psi, pp);
+      k_tile_pass<float, 1><<<grid, kTileThreads, smem, s>>>((float *)psi, pp, tmap);
     else
-      k_tile_pass<float, 2><<<grid, kTileThreads, smem, s>>>((float *)psi, pp);
+      k_tile_pass<float, 2><<<grid, kTileThreads, smem, s>>>((float *)psi, pp, tmap);
   } else {
     if (groups_per_thread == 1)
-      k_tile_pass<double, 1><<<grid, kTileThreads, smem, s>>>((double *)psi, pp);
+      k_tile_pass<double, 1><<<grid, kTileThreads, smem, s>>>((double *)psi, pp, tmap);
     else
-      k_tile_pass<double, 2><<<grid, kTileThreads, smem, s>>>((double *)psi, pp);
+      k_tile_pass<double, 2><<<grid, kTileThreads, smem, s>>>((double *)psi, pp, tmap);
   }
   ++*launches;
   return cudaGetLastError();
