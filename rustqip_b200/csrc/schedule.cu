@@ -125,32 +125,18 @@ int run_fused(qipb200_state *s, const qip_op *ops, size_t n_ops, const std::vect
       }
     if (first_blocked == left.size())
       return report_error(s, QIPB200_ERR_UNSUPPORTED, "internal: schedule made no progress");
-    // Migrate the first blocked op's qubit, then -- while rank bits are being reshuffled anyway --
-    // the qubits of the other blocked ops that are waiting (at most one exchange per rank bit per
-    // boundary): fewer epochs, fuller passes.  Every rank takes the same decisions.
-    const int g = (int)(s->n - s->n_local);
-    int exchanges_done = 0;
+    // Migrate the first blocked op's qubit only.  (Migrating the qubits of the other waiting
+    // blocked ops at the same boundary was measured at 8 GPUs: 24 exchanges instead of 12 for the
+    // same 36 passes -- eager migrations evict qubits that are needed again soon.)
     std::vector<char> consumed(left.size(), 0);
-    for (size_t i = first_blocked; i < left.size() && exchanges_done < g; ++i) {
-      if (!blocked[left[i]]) continue;
-      const size_t op_idx = remaining[left[i]];
+    {
+      const size_t op_idx = remaining[left[first_blocked]];
       FlatOp f;
-      std::string err;
-      if (i != first_blocked) {  // still blocked under the layout as it is now?
-        if (compile_op(&ops[op_idx], s->prec, s->n, &f, &err, s->phys_of_logical.data()) != QIPB200_OK) break;
-        if (!needs_exchange(s, f)) continue;
-        if (f.cls == CLASS_BITSWAP && f.ctrl_mask == 0) continue;  // a relabelling is only legal for the first op
-      }
-      const uint64_t before = s->ctx->exchange_launches;
       const uint64_t *nu = next_use.empty() ? nullptr : &next_use[(op_idx + 1) * s->n];
       if ((st = compile_and_localize(s, &ops[op_idx], &f, nu)) != QIPB200_OK) return st;  // exchange(s) happen here
-      exchanges_done += (int)(s->ctx->exchange_launches - before);
-      // an uncontrolled Swap on a rank-held qubit is consumed as a relabelling of the bit map; it may only
-      // be consumed when it is the FIRST leftover op (nothing earlier may still depend on the old labels)
-      if (f.cls == CLASS_IDENTITY) {
-        consumed[i] = 1;
-        break;
-      }
+      // an uncontrolled Swap on a rank-held qubit is consumed as a relabelling of the bit map (it is
+      // the first leftover op: nothing earlier can still depend on the old labels)
+      if (f.cls == CLASS_IDENTITY) consumed[first_blocked] = 1;
     }
     std::vector<size_t> next;
     for (size_t i = 0; i < left.size(); ++i)
