@@ -1,0 +1,69 @@
+"""Schedule wire format + state dump/load."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import qip_oracle as qo
+from rustqip_b200 import circuits, gates, wire
+from rustqip_b200.errors import CircuitError
+from rustqip_b200.ops import MatrixOp, make_control_op, make_matrix_op, make_swap_op
+
+
+def _zoo(n):
+    rng = np.random.default_rng(2)
+    u = np.linalg.qr(rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4)))[0]
+    return circuits.random_circuit(n, 3, 5) + circuits.qft(n)[:20] + [
+        make_matrix_op([2, 0], u.reshape(-1)), make_swap_op([0, 1], [3, 4]), gates.toffoli(0, 4, 2),
+        make_control_op([1], make_swap_op([0], [3])),
+        MatrixOp.new_sparse([0, n - 1], [[(0, 0.6), (3, 0.8j)], [(1, 1.0)], [(2, -1.0)], [(0, 0.8j), (3, 0.6)]]),
+        MatrixOp.new_control([0], [1, 2], MatrixOp.new_control([1], [2], gates.x(2)))]
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_schedule_round_trip(tmp_path, dtype):
+    n = 6
+    ops = _zoo(n)
+    path = os.path.join(tmp_path, "circuit.qips")
+    wire.dump_schedule(path, n, ops, dtype)
+    n2, dt2, ops2 = wire.load_schedule(path)
+    assert n2 == n and dt2 == dtype and len(ops2) == len(ops)
+    assert [repr(a) for a in ops] == [repr(b) for b in ops2]
+    psi = np.ascontiguousarray((np.arange(1, 65) / 100.0).astype(dtype))
+    assert np.array_equal(qo.run_pipeline(n, ops, state=psi, dtype=dtype), qo.run_pipeline(n, ops2, state=psi, dtype=dtype))
+
+
+def test_bad_files_are_rejected(tmp_path):
+    p = os.path.join(tmp_path, "x.qips")
+    open(p, "wb").write(b"nonsense-nonsense-nonsense")
+    with pytest.raises(CircuitError):
+        wire.load_schedule(p)
+    wire.dump_schedule(p, 3, [gates.h(0)])
+    data = open(p, "rb").read()
+    open(p, "wb").write(data[:-5])
+    with pytest.raises(CircuitError, match="truncated"):
+        wire.load_schedule(p)
+
+
+@pytest.mark.gpu
+def test_schedule_and_state_files_on_device(ctx, tmp_path):
+    from rustqip_b200.state import State
+    n = 11
+    ops = _zoo(n)
+    sched = os.path.join(tmp_path, "c.qips")
+    snap = os.path.join(tmp_path, "s.qipa")
+    wire.dump_schedule(sched, n, ops)
+    _, _, loaded = wire.load_schedule(sched)
+    want = qo.run_pipeline(n, ops, 3)
+    with State(n, np.complex128, ctx) as st:
+        st.set_basis(3)
+        st.apply_schedule(loaded[:40])
+        wire.dump_state(snap, st)          # checkpoint mid-circuit ...
+    with State(n, np.complex128, ctx) as st2:
+        wire.load_state(snap, st2)         # ... resume in a fresh state
+        st2.apply_schedule(loaded[40:])
+        got = st2.download()
+    assert np.max(np.abs(got - want)) < 1e-10
+    with State(n, np.complex64, ctx) as st3:
+        with pytest.raises(CircuitError, match="does not match"):
+            wire.load_state(snap, st3)
