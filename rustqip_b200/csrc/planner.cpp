@@ -367,15 +367,35 @@ struct Emitter {
     pass->ops.push_back(mo);
   }
 
+  // Emit the open groups that touch `lmask` (or all of them).  Groups on disjoint bits commute,
+  // so the ones leaving together are first packed into as few 3-bit super-ops as possible
+  // (three 1-bit groups, or a 2-bit and a 1-bit group, share one shared-memory round trip).
   void flush_touching(uint32_t lmask, bool all) {
+    std::vector<Group> out;
     for (size_t i = 0; i < open.size();) {
       if (all || (open[i].mask & lmask)) {
-        emit_group(open[i]);
+        out.push_back(open[i]);
         open.erase(open.begin() + i);
       } else {
         ++i;
       }
     }
+    if (cfg->fuse_blocks) {
+      std::stable_sort(out.begin(), out.end(), [](const Group &a, const Group &b) { return popc(a.mask) > popc(b.mask); });
+      std::vector<Group> packed;
+      for (size_t i = 0; i < out.size(); ++i) {
+        bool placed = false;
+        for (size_t j = 0; j < packed.size() && !placed; ++j)
+          if (popc(packed[j].mask | out[i].mask) <= 3) {
+            packed[j].mask |= out[i].mask;
+            packed[j].elems.insert(packed[j].elems.end(), out[i].elems.begin(), out[i].elems.end());
+            placed = true;
+          }
+        if (!placed) packed.push_back(out[i]);
+      }
+      out.swap(packed);
+    }
+    for (size_t i = 0; i < out.size(); ++i) emit_group(out[i]);
   }
 
   // Peephole: fold `e` into the last elementary op of a group when both act on the same
