@@ -47,7 +47,7 @@ OpInfo analyse(const FlatOp &f) {
       o.need_tile = o.nd;
       o.tile_ok = f.tgt_sorted.size() <= 3 && f.tgt_sorted.size() + nctrl <= 6;
       o.unfused_cost = 1.0 / (1 << nctrl);
-      o.est_bytes = f.tgt_sorted.size() == 1 ? 352 : 128 + 2 * 112 + 1040;
+      o.est_bytes = f.tgt_sorted.size() == 1 ? 368 : (uint32_t)sizeof(MicroOp) + 2 * 112 + 1040;
       break;
     case CLASS_FLIP:
       o.nd = 1ull << f.tgt_sorted[0];
@@ -55,7 +55,7 @@ OpInfo analyse(const FlatOp &f) {
       o.need_tile = o.nd;
       o.tile_ok = nctrl + 1 <= 6;
       o.unfused_cost = 1.0 / (1 << nctrl);
-      o.est_bytes = 352;
+      o.est_bytes = 368;
       break;
     case CLASS_BITSWAP:
       for (size_t i = 0; i < f.swaps.size(); ++i) o.nd |= (1ull << f.swaps[i].first) | (1ull << f.swaps[i].second);
@@ -63,14 +63,14 @@ OpInfo analyse(const FlatOp &f) {
       o.need_tile = o.nd;
       o.tile_ok = nctrl + 2 <= 6 && f.swaps.size() <= 3;
       o.unfused_cost = 0.5 * f.swaps.size() / (1 << nctrl);
-      o.est_bytes = 576 * (uint32_t)f.swaps.size();
+      o.est_bytes = 640 * (uint32_t)f.swaps.size();
       break;
     case CLASS_DIAGONAL:
       o.dg = f.ctrl_mask;
       for (size_t i = 0; i < f.diag_bits.size(); ++i) o.dg |= 1ull << f.diag_bits[i];
       o.tile_ok = f.diag_bits.size() <= 3;  // expands to <= 8 masked-phase terms
       o.unfused_cost = 1.0 / (1 << nctrl);
-      o.est_bytes = 352 * (1u << f.diag_bits.size());
+      o.est_bytes = 368 * (1u << f.diag_bits.size());
       break;
     default:  // CLASS_GENERAL (CLASS_IDENTITY never reaches here)
       for (uint32_t j = 0; j < f.k; ++j) o.nd |= 1ull << f.idx_bits[j];
@@ -276,6 +276,8 @@ struct Emitter {
       for (uint32_t i = 0; i < 3; ++i)
         if ((u >> i) & 1) off |= 1u << P[i];
       mo.h.off[u] = off;
+      // swizzled byte offset (tile_kernel.cu: swz<R>): f64 t ^ ((t>>3)&7), 16 B; f32 t ^ (((t>>4)&7)<<1), 8 B
+      mo.h.soff[u] = sizeof(R) == 8 ? (off ^ ((off >> 3) & 7u)) << 4 : (off ^ (((off >> 4) & 7u) << 1)) << 3;
     }
     mo.h.groups_log2 = T - 3;
     mo.h.nterms = (uint32_t)elems.size();
@@ -287,6 +289,19 @@ struct Emitter {
       d.gmask = e.gmask;
       d.gval = e.gval;
       const bool cond = e.gmask != 0;
+      uint32_t slot = 0;
+      if (cond) {  // the CTA evaluates each distinct condition once (bit `slot` of its condition word)
+        slot = kCondOverflow;
+        for (size_t c = 0; c < pass->conds.size(); ++c)
+          if (pass->conds[c].gmask == e.gmask && pass->conds[c].gval == e.gval) slot = (uint32_t)c;
+        if (slot == kCondOverflow && pass->conds.size() < kCondOverflow) {
+          CondTerm ct;
+          ct.gmask = e.gmask;
+          ct.gval = e.gval;
+          slot = (uint32_t)pass->conds.size();
+          pass->conds.push_back(ct);
+        }
+      }
       uint32_t lc = 0, lm = 0, lv = 0;
       for (uint32_t b = 0; b < 32; ++b) {
         if ((e.lctrl >> b) & 1) lc |= 1u << sub_of(b);
@@ -331,6 +346,7 @@ struct Emitter {
       } else {  // E_DENSE3 (E_X / E_SWAP were lowered above)
         d.op = elem_op(E_DENSE3, 0, 0, cond, rec_bytes);
       }
+      d.op |= slot << kElemCondShift;
       const size_t at = mo.data.size();
       mo.data.resize(at + sizeof(d));
       memcpy(mo.data.data() + at, &d, sizeof(d));
@@ -740,7 +756,7 @@ void emit_pass(const std::vector<FlatOp> &ops, const std::vector<size_t> &taken,
 size_t pass_bytes(const HostPass &p) {
   size_t bytes = 0;
   for (size_t i = 0; i < p.ops.size(); ++i) bytes += sizeof(MicroOp) + ((p.ops[i].data.size() + 15) & ~(size_t)15);
-  return bytes + ((p.gterms.size() + 15) & ~(size_t)15);
+  return bytes + ((p.gterms.size() + 15) & ~(size_t)15) + p.conds.size() * sizeof(CondTerm);
 }
 
 }  // namespace
@@ -806,74 +822,89 @@ void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec
     if (is_blocked) info[i].tile_ok = false;
     remaining.push_back(i);
   }
+  // est_bytes are upper bounds (every op opening its own super-op); real passes are several times
+  // smaller after grouping and folding.  Try optimistic budgets first and fall back towards the
+  // guaranteed one when the emitted pass does not fit the parameter space.
   const uint32_t byte_budget = kMaxPassBytes - 2048;
+  static const uint32_t kBudgetScale[3] = {4, 2, 1};
   while (!remaining.empty()) {
-    uint64_t S_high = 0, pend_d = 0, pend_nd = 0;
-    std::vector<size_t> taken, left;
-    double unfused = 0.0;
-    uint32_t bytes = 0;
-    long single = -1;  // first op that may run alone right now: not blocked, commutes past EVERY earlier op
-    uint64_t seen_d = 0, seen_nd = 0;
-    for (size_t r = 0; r < remaining.size(); ++r) {
-      const size_t idx = remaining[r];
-      const OpInfo &o = info[idx];
-      const bool is_blocked = blocked && (*blocked)[idx];
-      const bool conflict = (o.nd & (pend_d | pend_nd)) || (o.dg & pend_nd);
-      if (single < 0 && !is_blocked && !((o.nd & (seen_d | seen_nd)) || (o.dg & seen_nd))) single = (long)r;
-      seen_d |= o.dg;
-      seen_nd |= o.nd;
-      if (can_tile && !conflict && o.tile_ok && bytes + o.est_bytes <= byte_budget) {
-        const uint64_t need = o.need_tile & ~low_mask & ~S_high;
-        if ((uint32_t)popc(S_high | need) <= m) {
-          S_high |= need;
-          taken.push_back(idx);
-          unfused += o.unfused_cost;
-          bytes += o.est_bytes;
-          continue;
+    bool done = false, stuck = false;
+    for (int attempt = 0; attempt < 3 && !done; ++attempt) {
+      const uint64_t budget = (uint64_t)byte_budget * kBudgetScale[attempt];
+      uint64_t S_high = 0, pend_d = 0, pend_nd = 0;
+      std::vector<size_t> taken, left;
+      double unfused = 0.0;
+      uint64_t bytes = 0;
+      long single = -1;  // first op that may run alone right now: not blocked, commutes past EVERY earlier op
+      uint64_t seen_d = 0, seen_nd = 0;
+      for (size_t r = 0; r < remaining.size(); ++r) {
+        const size_t idx = remaining[r];
+        const OpInfo &o = info[idx];
+        const bool is_blocked = blocked && (*blocked)[idx];
+        const bool conflict = (o.nd & (pend_d | pend_nd)) || (o.dg & pend_nd);
+        if (single < 0 && !is_blocked && !((o.nd & (seen_d | seen_nd)) || (o.dg & seen_nd))) single = (long)r;
+        seen_d |= o.dg;
+        seen_nd |= o.nd;
+        if (can_tile && !conflict && o.tile_ok && bytes + o.est_bytes <= budget) {
+          const uint64_t need = o.need_tile & ~low_mask & ~S_high;
+          if ((uint32_t)popc(S_high | need) <= m) {
+            S_high |= need;
+            taken.push_back(idx);
+            unfused += o.unfused_cost;
+            bytes += o.est_bytes;
+            continue;
+          }
         }
+        pend_d |= o.dg;
+        pend_nd |= o.nd;
+        left.push_back(idx);
       }
-      pend_d |= o.dg;
-      pend_nd |= o.nd;
-      left.push_back(idx);
-    }
-    if (taken.empty() || unfused <= 1.05) {
-      if (single < 0) break;  // everything left is blocked or stuck behind a blocked op
-      // not worth a full sweep: run one op with its per-gate kernel
+      if (taken.empty() || unfused <= 1.05) {
+        if (single < 0) {  // everything left is blocked or stuck behind a blocked op
+          stuck = true;
+          break;
+        }
+        // not worth a full sweep: run one op with its per-gate kernel
+        PlanStep st;
+        st.is_pass = false;
+        st.op_index = remaining[(size_t)single];
+        steps->push_back(st);
+        remaining.erase(remaining.begin() + single);
+        done = true;
+        break;
+      }
       PlanStep st;
-      st.is_pass = false;
-      st.op_index = remaining[(size_t)single];
+      st.is_pass = true;
+      PassHeader &h = st.pass.hdr;
+      memset(&h, 0, sizeof(h));
+      h.T = cfg.T;
+      h.L = cfg.L;
+      h.m = m;
+      // pad the tile-bit set to exactly m bits with the highest unused bits
+      for (int b = (int)n_local - 1; b >= (int)cfg.L && (uint32_t)popc(S_high) < m; --b)
+        if (!((S_high >> b) & 1)) S_high |= 1ull << b;
+      uint32_t c = 0;
+      for (uint32_t b = 0; b < 64; ++b)
+        if ((S_high >> b) & 1) h.hi_pos[c++] = b;
+      for (uint32_t ch = 0; ch < (1u << m); ++ch) {
+        uint64_t off = 0;
+        for (uint32_t i = 0; i < m; ++i)
+          if ((ch >> i) & 1) off |= 1ull << h.hi_pos[i];
+        h.chunk_off[ch] = off;
+      }
+      if (prec == QIP_F32)
+        emit_pass<float>(ops, taken, h, cfg, &st.pass);
+      else
+        emit_pass<double>(ops, taken, h, cfg, &st.pass);
+      if (pass_bytes(st.pass) > kMaxPassBytes && attempt < 2) continue;  // too optimistic: retry with a smaller budget
+      h.n_ops = (uint32_t)st.pass.ops.size();
+      h.n_gterms = (uint32_t)(st.pass.gterms.size() / (prec == QIP_F32 ? sizeof(GlobalTerm<float>) : sizeof(GlobalTerm<double>)));
+      st.pass.n_gates = (uint32_t)taken.size();
       steps->push_back(st);
-      remaining.erase(remaining.begin() + single);
-      continue;
+      remaining.swap(left);
+      done = true;
     }
-    PlanStep st;
-    st.is_pass = true;
-    PassHeader &h = st.pass.hdr;
-    memset(&h, 0, sizeof(h));
-    h.T = cfg.T;
-    h.L = cfg.L;
-    h.m = m;
-    // pad the tile-bit set to exactly m bits with the highest unused bits
-    for (int b = (int)n_local - 1; b >= (int)cfg.L && (uint32_t)popc(S_high) < m; --b)
-      if (!((S_high >> b) & 1)) S_high |= 1ull << b;
-    uint32_t c = 0;
-    for (uint32_t b = 0; b < 64; ++b)
-      if ((S_high >> b) & 1) h.hi_pos[c++] = b;
-    for (uint32_t ch = 0; ch < (1u << m); ++ch) {
-      uint64_t off = 0;
-      for (uint32_t i = 0; i < m; ++i)
-        if ((ch >> i) & 1) off |= 1ull << h.hi_pos[i];
-      h.chunk_off[ch] = off;
-    }
-    if (prec == QIP_F32)
-      emit_pass<float>(ops, taken, h, cfg, &st.pass);
-    else
-      emit_pass<double>(ops, taken, h, cfg, &st.pass);
-    h.n_ops = (uint32_t)st.pass.ops.size();
-    h.n_gterms = (uint32_t)(st.pass.gterms.size() / (prec == QIP_F32 ? sizeof(GlobalTerm<float>) : sizeof(GlobalTerm<double>)));
-    st.pass.n_gates = (uint32_t)taken.size();
-    steps->push_back(st);
-    remaining.swap(left);
+    if (stuck) break;
   }
   if (leftover) *leftover = remaining;
 }
@@ -893,6 +924,10 @@ bool serialise_pass(const HostPass &p, PassParams *out) {
   }
   out->h.gterm_off = (uint32_t)(w - out->recs);
   if (!p.gterms.empty()) memcpy(w, p.gterms.data(), p.gterms.size());
+  w += (p.gterms.size() + 15) & ~(size_t)15;
+  out->h.cond_off = (uint32_t)(w - out->recs);
+  out->h.n_conds = (uint32_t)p.conds.size();
+  if (!p.conds.empty()) memcpy(w, p.conds.data(), p.conds.size() * sizeof(CondTerm));
   out->h.blob_bytes = (uint32_t)bytes;
   return true;
 }

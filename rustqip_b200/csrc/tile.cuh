@@ -38,40 +38,65 @@ enum MicroKind { MK_DENSE = 0, MK_DIAG = 1, MK_EXCH = 2, MK_SUPER = 3 };
 // exchange done with register moves (bit-exact, no FP64 work).
 enum ElemType { E_DENSE1 = 0, E_DENSE1R = 1, E_X = 2, E_PHASE = 3, E_SWAP = 4, E_DENSE3 = 5 };
 
-// Elem::op layout (host-precomputed so the kernel's dispatch is a handful of compares):
-//   bits 0-4   interpreter case id: 0 END (sentinel after the last op of a super-op),
+// Elem::op layout (host-precomputed so the kernel's dispatch is one jump on the case id):
+//   bits 0-5   interpreter case id: 0 END (sentinel after the last op of a super-op),
 //              1-3 real 2x2 on sub-bit 0/1/2 with every pair active, 4-6 complex ditto,
-//              7-9 real 2x2 masked, 10-12 complex 2x2 masked, 13 PHASE, 14 dense 8x8,
+//              7-9 real 2x2 masked (generic), 10-12 complex 2x2 masked, 13 PHASE (generic mask), 14 dense 8x8,
 //              15-17 X (pair exchange by register moves) every pair active, 18-20 X masked,
 //              21 PHASEN: one phase mask, base factor m[0..1] times the product of the CTA-uniform
-//                 conditional factors listed after the record (count in Elem::pad) -- a run of
+//                 conditional factors listed after the record (slot of the per-CTA table in Elem::pad) -- a run of
 //                 controlled phases whose controls lie outside the tile costs one application
+//              22-24 PHASE on every amplitude with sub-bit j set (T, S, Rz ... : straight-line, no mask tests)
+//              25-30 real 2x2 on sub-bit j under ONE control inside the group (CNOT, CRy): 25 + 2*j + w, w = 0/1:
+//                 the control is the lower/higher of the two other sub-bits
+//              31-33 real 2x2 on sub-bit j under BOTH other sub-bits (Toffoli)
+//              34-36 PHASE on the amplitudes with two sub-bits set (CZ, controlled phase): (0,1), (0,2), (1,2)
+//   bits 6-11  slot of the op's CTA-uniform condition in the pass's condition table (kCondOverflow: test
+//              the record's own gmask/gval)
 //   bits 12-19 active mask: 2x2 kinds: bit p <-> the p-th (ascending) sub-index with bit j
 //              clear; PHASE: bit c <-> sub-index c
 //   bits 20-30 record size in 16-byte units (the dense 8x8 matrix follows its record)
-//   bit 31     the op has a CTA-uniform condition (gmask/gval must be tested)
+//   bit 31     the op has a CTA-uniform condition
 static const uint32_t kElemHasCond = 1u << 31;
+static const uint32_t kElemCaseMask = 0x3fu;
+static const uint32_t kElemCondShift = 6;
+static const uint32_t kCondOverflow = 63;  // slots 0..62 index the pass's condition table
 enum ElemCase { EC_END = 0, EC_D1R_FULL = 1, EC_D1C_FULL = 4, EC_D1R_MASK = 7, EC_D1C_MASK = 10, EC_PHASE = 13, EC_DENSE3 = 14,
-                EC_X_FULL = 15, EC_X_MASK = 18, EC_PHASEN = 21 };
+                EC_X_FULL = 15, EC_X_MASK = 18, EC_PHASEN = 21, EC_PHASE_J = 22, EC_D1R_C1 = 25, EC_D1R_C2 = 31,
+                EC_PHASE_2 = 34, EC_N_CASES = 37 };
+// pair mask of "the w-th other sub-bit is set" / "both other sub-bits set"; phase masks of the special cases
+static const uint32_t kPairMaskC1[2] = {0xAu, 0xCu};
+static const uint32_t kPairMaskC2 = 0x8u;
+static const uint32_t kPhaseMaskJ[3] = {0xAAu, 0xCCu, 0xF0u};
+static const uint32_t kPhaseMask2[3] = {0x88u, 0xA0u, 0xC0u};
 inline uint32_t elem_op(uint32_t kind, uint32_t j, uint32_t mask, bool cond, uint32_t size_bytes) {
   uint32_t id;
-  if (kind == E_DENSE1R)
-    id = (mask == 0xfu ? EC_D1R_FULL : EC_D1R_MASK) + j;
-  else if (kind == E_DENSE1)
+  if (kind == E_DENSE1R) {
+    if (mask == 0xfu) id = EC_D1R_FULL + j;
+    else if (mask == kPairMaskC1[0]) id = EC_D1R_C1 + 2 * j;
+    else if (mask == kPairMaskC1[1]) id = EC_D1R_C1 + 2 * j + 1;
+    else if (mask == kPairMaskC2) id = EC_D1R_C2 + j;
+    else id = EC_D1R_MASK + j;
+  } else if (kind == E_DENSE1)
     id = (mask == 0xfu ? EC_D1C_FULL : EC_D1C_MASK) + j;
   else if (kind == E_X)
     id = (mask == 0xfu ? EC_X_FULL : EC_X_MASK) + j;
-  else if (kind == E_PHASE)
+  else if (kind == E_PHASE) {
     id = EC_PHASE;
-  else
+    for (uint32_t q = 0; q < 3; ++q) {
+      if (mask == kPhaseMaskJ[q]) id = EC_PHASE_J + q;
+      if (mask == kPhaseMask2[q]) id = EC_PHASE_2 + q;
+    }
+  } else
     id = EC_DENSE3;
   return id | (mask << 12) | ((size_bytes >> 4) << 20) | (cond ? kElemHasCond : 0u);
 }
-inline uint32_t elem_case(uint32_t op) { return op & 0x1fu; }
+inline uint32_t elem_case(uint32_t op) { return op & kElemCaseMask; }
+inline uint32_t elem_cond_slot(uint32_t op) { return (op >> kElemCondShift) & 63u; }
 inline uint32_t elem_op_phasen(uint32_t mask, uint32_t size_bytes) { return EC_PHASEN | (mask << 12) | ((size_bytes >> 4) << 20); }
 inline uint32_t elem_size_bytes(uint32_t op) { return ((op >> 20) & 0x7ffu) << 4; }
 
-// Device-visible micro-op header (fixed 128 bytes), followed by its data:
+// Device-visible micro-op header (fixed 160 bytes), followed by its data:
 //   MK_DENSE: 2^k x 2^k complex<R> (re,im interleaved), sub-index bit i <-> ins_pos order of targets
 //   MK_DIAG : nterms x DiagTerm<R>
 //   MK_SUPER: nterms elementary records (Elem<R>, dense 8x8 ones followed by 64 complex<R>) + END record
@@ -88,8 +113,10 @@ struct alignas(16) MicroOp {
   uint32_t pad0;
   uint64_t gmask;        // control bits outside the tile: tested against the tile's base index
   uint64_t pad1[3];
+  uint32_t soff[8];      // super: SWIZZLED shared-memory BYTE offset of sub-index u (the XOR swizzle is GF(2)-linear,
+                         // so address(t0 + off[u]) = tile + (swz_bytes(t0) ^ soff[u]))
 };
-static_assert(sizeof(MicroOp) == 128, "MicroOp must be 128 bytes");
+static_assert(sizeof(MicroOp) == 160, "MicroOp must be 160 bytes");
 
 template <typename R>
 struct alignas(16) DiagTerm {  // multiply by (re,im) where (global & gmask)==gval and (local & lmask)==lval
@@ -115,6 +142,10 @@ struct alignas(16) PhaseTerm {  // conditional factor of an EC_PHASEN record
   R re, im;
 };
 
+struct CondTerm {  // entry of a pass's condition table: (base & gmask) == gval, evaluated once per CTA
+  uint64_t gmask, gval;
+};
+
 template <typename R>
 struct GlobalTerm {  // multiply the whole tile by (re,im) where (base & gmask) == gval
   uint64_t gmask, gval;
@@ -130,7 +161,9 @@ struct PassHeader {
   uint32_t gterm_off;                      // byte offset of the GlobalTerm array inside the blob
   uint32_t n_phasen;                       // EC_PHASEN ops in this pass (slots of the per-CTA factor table)
   uint32_t use_tma;                        // set by the launcher: tile moved by TMA tensor copies
-  uint32_t pad_[3];
+  uint32_t n_conds;                        // CondTerm records (<= kCondOverflow) at cond_off inside the blob
+  uint32_t cond_off;
+  uint32_t pad_[1];
 };
 
 // What the kernel receives by value (constant bank).  16-byte aligned so that the records
@@ -152,6 +185,7 @@ struct HostPass {
   PassHeader hdr{};
   std::vector<HostMicroOp> ops;
   std::vector<unsigned char> gterms;  // GlobalTerm<R> records
+  std::vector<CondTerm> conds;        // distinct CTA-uniform conditions of the pass's elementary ops
   uint32_t n_gates = 0;               // reference ops folded into this pass
 };
 

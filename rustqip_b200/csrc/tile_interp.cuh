@@ -92,23 +92,33 @@
 #define QIP_COD(x) "=d"(x)
 #define QIP_COF(x) "=f"(x)
 
-// Defines  template <int G> void NAME(uint32_t tile_saddr, const MicroOp *mo, const unsigned char *data, uint64_t base, const R *tbl)
-// for one precision.  tile_saddr = shared-memory byte address of the tile.
+// Defines  template <int G> void NAME(uint32_t tile_saddr, const MicroOp *mo, const unsigned char *data, uint64_t base,
+//                                     const R *tbl, uint64_t condbits)
+// for one precision.  tile_saddr = shared-memory byte address of the tile; condbits = this CTA's
+// evaluation of the pass's condition table (bit s <-> CondTerm s).
+//
+// Per group: the group counter is expanded with three `t += t & (~0 << p)` steps (inserting a
+// zero bit at position p: low + 2*high = t + high), the 8 addresses are swz(t) ^ soff[u] with the
+// swizzled byte offsets precomputed on the host (the XOR swizzle is GF(2)-linear).  The
+// elementary ops are dispatched by ONE jump on the host-computed case id; every frequent shape
+// (full 2x2, 2x2 under one/two in-group controls, phase on one/two sub-bits) is straight-line
+// code without mask tests.
 #define QIP_DEFINE_RUN_SUPER(NAME, R, T, C, CO, SWZ, ESHIFT)                                                     \
   template <int G>                                                                                              \
   __device__ __forceinline__ void NAME(uint32_t tile_saddr, const MicroOp *mo, const unsigned char *data,      \
-                                       uint64_t base, const R *tbl) {                                           \
+                                       uint64_t base, const R *tbl, uint64_t condbits) {                        \
+    typedef R QipReal;                                                                                          \
     const uint32_t groups = 1u << mo->groups_log2;                                                              \
+    const uint32_t hm0 = ~0u << mo->ins_pos[0], hm1 = ~0u << mo->ins_pos[1], hm2 = ~0u << mo->ins_pos[2];      \
     for (uint32_t g = threadIdx.x; g < groups; g += G * kTileThreads) {                                         \
       const bool two = (G == 2) && (g + kTileThreads < groups); /* warp-uniform */                              \
-      const uint32_t ta = expand_local(g, mo);                                                                  \
-      const uint32_t tb = expand_local(two ? g + kTileThreads : g, mo);                                         \
-      /* the XOR swizzle is GF(2)-linear and ta/tb have zeros at the group's bit positions, so        \
-         swz(t + off[u]) == swz(t) ^ swz(off[u]): one XOR + one ADD per amplitude */                       \
-      const uint32_t sa = SWZ(ta) << ESHIFT, sb = SWZ(tb) << ESHIFT;                                        \
+      uint32_t ta = g, tb = two ? g + kTileThreads : g;                                                         \
+      ta += ta & hm0; ta += ta & hm1; ta += ta & hm2;                                                           \
+      tb += tb & hm0; tb += tb & hm1; tb += tb & hm2;                                                           \
+      const uint32_t sa = SWZ(ta) << ESHIFT, sb = SWZ(tb) << ESHIFT;                                            \
       uint32_t aa[8], ab[8];                                                                                    \
       _Pragma("unroll") for (int u = 0; u < 8; ++u) {                                                           \
-        const uint32_t so = SWZ(mo->off[u]) << ESHIFT;                                                          \
+        const uint32_t so = mo->soff[u];                                                                        \
         aa[u] = tile_saddr + (sa ^ so);                                                                         \
         ab[u] = tile_saddr + (sb ^ so);                                                                         \
       }                                                                                                         \
@@ -122,47 +132,74 @@
       uint32_t op_next = reinterpret_cast<const Elem<R> *>(ep)->op;                                             \
       for (;;) {                                                                                                \
         const uint32_t op = op_next;                                                                            \
-        const uint32_t id = op & 0x1fu;                                                                         \
+        const uint32_t id = op & kElemCaseMask;                                                                 \
         if (id == EC_END) break;                                                                                \
         const Elem<R> *e = reinterpret_cast<const Elem<R> *>(ep);                                               \
         ep += ((op >> 20) & 0x7ffu) << 4;                                                                       \
         op_next = reinterpret_cast<const Elem<R> *>(ep)->op; /* next descriptor in flight during this op */     \
-        if ((int32_t)op < 0 && (base & e->gmask) != e->gval) continue; /* control outside the tile is 0 */      \
-        const uint32_t pm = (op >> 12) & 0xffu;                                                                 \
-        if (id < EC_D1C_FULL) { /* real 2x2, every pair active: H, X, ... */                                    \
-          const R m00 = e->m[0], m01 = e->m[1], m10 = e->m[2], m11 = e->m[3];                                   \
-          const uint32_t j = id - EC_D1R_FULL;                                                                  \
-          _QIP_D1R_FULL(T, C)                                                                                   \
-        } else if (id < EC_D1R_MASK) { /* complex 2x2, every pair active */                                     \
-          const R m0 = e->m[0], m1 = e->m[1], m2 = e->m[2], m3 = e->m[3];                                       \
-          const R m4 = e->m[4], m5 = e->m[5], m6 = e->m[6], m7 = e->m[7];                                       \
-          const R n1 = -m1, n3 = -m3, n5 = -m5, n7 = -m7;                                                       \
-          const uint32_t j = id - EC_D1C_FULL;                                                                  \
-          _QIP_D1C_FULL(T, C)                                                                                   \
-        } else if (id == EC_PHASE) {                                                                            \
-          const R wr = e->m[0], wi = e->m[1];                                                                   \
-          _QIP_PH_BODY(T, C)                                                                                    \
-        } else if (id == EC_PHASEN) { /* run of controlled phases, controls outside the tile: the product */    \
-          const R wr = tbl[2 * e->pad], wi = tbl[2 * e->pad + 1]; /* was formed once per CTA (factor table) */  \
-          _QIP_PH_BODY(T, C)                                                                                    \
-        } else if (id >= EC_X_FULL) { /* X / CNOT / Toffoli-X: pair exchange by register moves */               \
-          const uint32_t xm = id >= EC_X_MASK ? pm : 0xfu;                                                      \
-          const uint32_t j = id >= EC_X_MASK ? id - EC_X_MASK : id - EC_X_FULL;                                 \
-          _QIP_X_BODY(T)                                                                                        \
-        } else if (id < EC_D1C_MASK) { /* real 2x2 under controls inside the group: CNOT, Toffoli */            \
-          const R m00 = e->m[0], m01 = e->m[1], m10 = e->m[2], m11 = e->m[3];                                   \
-          const uint32_t j = id - EC_D1R_MASK;                                                                  \
-          _QIP_D1R_MASKED(T, C)                                                                                 \
-        } else if (id < EC_PHASE) {                                                                             \
-          const R m0 = e->m[0], m1 = e->m[1], m2 = e->m[2], m3 = e->m[3];                                       \
-          const R m4 = e->m[4], m5 = e->m[5], m6 = e->m[6], m7 = e->m[7];                                       \
-          const R n1 = -m1, n3 = -m3, n5 = -m5, n7 = -m7;                                                       \
-          const uint32_t j = id - EC_D1C_MASK;                                                                  \
-          _QIP_D1C_MASKED(T, C)                                                                                 \
+        asm volatile("" ::"r"(op_next));                     /* (keeps the load above the arithmetic) */        \
+        if ((int32_t)op < 0) { /* control outside the tile: evaluated once per CTA */                           \
+          const uint32_t slot = (op >> kElemCondShift) & 63u;                                                   \
+          if (slot != kCondOverflow) {                                                                          \
+            if (!((condbits >> slot) & 1ull)) continue;                                                         \
+          } else if ((base & e->gmask) != e->gval) {                                                            \
+            continue;                                                                                           \
+          }                                                                                                     \
+        }                                                                                                       \
+        /* dispatch: hot shapes first, compare chains (a flat switch is lowered to a balanced compare    \
+           tree plus small jump tables whose target load sits on the critical path) */                        \
+        if (id < EC_D1C_FULL) {                                                                                 \
+          _QIP_LOAD_MR                                                                                          \
+          if (id == EC_D1R_FULL) { _QIP_D1R_U(T, C, 0, 1) _QIP_D1R_U(T, C, 2, 3) _QIP_D1R_U(T, C, 4, 5) _QIP_D1R_U(T, C, 6, 7) } \
+          else if (id == EC_D1R_FULL + 1) { _QIP_D1R_U(T, C, 0, 2) _QIP_D1R_U(T, C, 1, 3) _QIP_D1R_U(T, C, 4, 6) _QIP_D1R_U(T, C, 5, 7) } \
+          else { _QIP_D1R_U(T, C, 0, 4) _QIP_D1R_U(T, C, 1, 5) _QIP_D1R_U(T, C, 2, 6) _QIP_D1R_U(T, C, 3, 7) } \
+        } else if (id >= EC_PHASE_J) {                                                                          \
+          if (id < EC_D1R_C1) { /* every amplitude with sub-bit j set: T, S, Rz, control outside the tile */   \
+            _QIP_LOAD_W                                                                                         \
+            if (id == EC_PHASE_J) { _QIP_PH_U(T, C, 1) _QIP_PH_U(T, C, 3) _QIP_PH_U(T, C, 5) _QIP_PH_U(T, C, 7) } \
+            else if (id == EC_PHASE_J + 1) { _QIP_PH_U(T, C, 2) _QIP_PH_U(T, C, 3) _QIP_PH_U(T, C, 6) _QIP_PH_U(T, C, 7) } \
+            else { _QIP_PH_U(T, C, 4) _QIP_PH_U(T, C, 5) _QIP_PH_U(T, C, 6) _QIP_PH_U(T, C, 7) }                \
+          } else if (id < EC_D1R_C2) { /* one control inside the group: pairs 1,3 or 2,3 of sub-bit j */        \
+            _QIP_LOAD_MR                                                                                        \
+            if (id < EC_D1R_C1 + 2) {                                                                           \
+              if (id == EC_D1R_C1) { _QIP_D1R_U(T, C, 2, 3) _QIP_D1R_U(T, C, 6, 7) }                            \
+              else { _QIP_D1R_U(T, C, 4, 5) _QIP_D1R_U(T, C, 6, 7) }                                            \
+            } else if (id < EC_D1R_C1 + 4) {                                                                    \
+              if (id == EC_D1R_C1 + 2) { _QIP_D1R_U(T, C, 1, 3) _QIP_D1R_U(T, C, 5, 7) }                        \
+              else { _QIP_D1R_U(T, C, 4, 6) _QIP_D1R_U(T, C, 5, 7) }                                            \
+            } else {                                                                                            \
+              if (id == EC_D1R_C1 + 4) { _QIP_D1R_U(T, C, 1, 5) _QIP_D1R_U(T, C, 3, 7) }                        \
+              else { _QIP_D1R_U(T, C, 2, 6) _QIP_D1R_U(T, C, 3, 7) }                                            \
+            }                                                                                                   \
+          } else if (id < EC_PHASE_2) { /* both other sub-bits are controls: pair 3 only */                     \
+            _QIP_LOAD_MR                                                                                        \
+            if (id == EC_D1R_C2) { _QIP_D1R_U(T, C, 6, 7) }                                                     \
+            else if (id == EC_D1R_C2 + 1) { _QIP_D1R_U(T, C, 5, 7) }                                            \
+            else { _QIP_D1R_U(T, C, 3, 7) }                                                                     \
+          } else { /* two sub-bits set: CZ, controlled phase inside the group */                                \
+            _QIP_LOAD_W                                                                                         \
+            if (id == EC_PHASE_2) { _QIP_PH_U(T, C, 3) _QIP_PH_U(T, C, 7) }                                     \
+            else if (id == EC_PHASE_2 + 1) { _QIP_PH_U(T, C, 5) _QIP_PH_U(T, C, 7) }                            \
+            else { _QIP_PH_U(T, C, 6) _QIP_PH_U(T, C, 7) }                                                      \
+          }                                                                                                     \
+        } else if (id < EC_D1R_MASK) {                                                                          \
+          _QIP_LOAD_MC                                                                                          \
+          if (id == EC_D1C_FULL) { _QIP_D1C_U(T, C, 0, 1) _QIP_D1C_U(T, C, 2, 3) _QIP_D1C_U(T, C, 4, 5) _QIP_D1C_U(T, C, 6, 7) } \
+          else if (id == EC_D1C_FULL + 1) { _QIP_D1C_U(T, C, 0, 2) _QIP_D1C_U(T, C, 1, 3) _QIP_D1C_U(T, C, 4, 6) _QIP_D1C_U(T, C, 5, 7) } \
+          else { _QIP_D1C_U(T, C, 0, 4) _QIP_D1C_U(T, C, 1, 5) _QIP_D1C_U(T, C, 2, 6) _QIP_D1C_U(T, C, 3, 7) } \
         } else {                                                                                                \
-          const R *m8 = reinterpret_cast<const R *>(e + 1);                                                     \
-          _QIP_D3_BODY(T, C, CO, R, "a")                                                                        \
-          if (G == 2) { _QIP_D3_BODY(T, C, CO, R, "b") }                                                        \
+          switch (id) {                                                                                         \
+            _QIP_CASES_D1R_MASK(T, C)                                                                           \
+            _QIP_CASES_D1C_MASK(T, C)                                                                           \
+            _QIP_CASES_PHASE_GEN(T, C)                                                                          \
+            _QIP_CASES_X(T)                                                                                     \
+            case EC_DENSE3: {                                                                                   \
+              const R *m8 = reinterpret_cast<const R *>(e + 1);                                                 \
+              _QIP_D3_BODY(T, C, CO, R, "a")                                                                    \
+              if (G == 2) { _QIP_D3_BODY(T, C, CO, R, "b") }                                                    \
+            } break;                                                                                            \
+            default: break;                                                                                     \
+          }                                                                                                     \
         }                                                                                                       \
       }                                                                                                         \
       QIP_ST(T, "a", 0, aa[0]); QIP_ST(T, "a", 1, aa[1]); QIP_ST(T, "a", 2, aa[2]); QIP_ST(T, "a", 3, aa[3]);   \
@@ -175,51 +212,40 @@
   }
 
 // --- bodies (use the local names of QIP_DEFINE_RUN_SUPER) ---
-// "full" ops (every pair active) are straight-line: 4 pairs x G groups of independent
-// arithmetic for the scheduler to interleave; masked ops test one mask bit per pair.
+// Pair p of sub-bit j = the p-th (ascending) sub-index with bit j clear, and its partner:
+//   j=0: (0,1) (2,3) (4,5) (6,7)   j=1: (0,2) (1,3) (4,6) (5,7)   j=2: (0,4) (1,5) (2,6) (3,7)
+// bit 0 of p <-> the lower of the two other sub-bits, bit 1 of p <-> the higher one.
 #define _QIP_D1R_U(T, C, i0, i1)                                        \
   QIP_D1R(T, C, "a", i0, i1, m00, m01, m10, m11);                       \
   if (G == 2) QIP_D1R(T, C, "b", i0, i1, m00, m01, m10, m11);
 #define _QIP_D1R_STEP(T, C, p, i0, i1) \
   if ((pm >> p) & 1u) { _QIP_D1R_U(T, C, i0, i1) }
-#define _QIP_D1R_FULL(T, C)                                             \
-  if (j == 0) {                                                         \
-    _QIP_D1R_U(T, C, 0, 1) _QIP_D1R_U(T, C, 2, 3) _QIP_D1R_U(T, C, 4, 5) _QIP_D1R_U(T, C, 6, 7) \
-  } else if (j == 1) {                                                  \
-    _QIP_D1R_U(T, C, 0, 2) _QIP_D1R_U(T, C, 1, 3) _QIP_D1R_U(T, C, 4, 6) _QIP_D1R_U(T, C, 5, 7) \
-  } else {                                                              \
-    _QIP_D1R_U(T, C, 0, 4) _QIP_D1R_U(T, C, 1, 5) _QIP_D1R_U(T, C, 2, 6) _QIP_D1R_U(T, C, 3, 7) \
-  }
-#define _QIP_D1R_MASKED(T, C)                                           \
-  if (j == 0) {                                                         \
-    _QIP_D1R_STEP(T, C, 0, 0, 1) _QIP_D1R_STEP(T, C, 1, 2, 3) _QIP_D1R_STEP(T, C, 2, 4, 5) _QIP_D1R_STEP(T, C, 3, 6, 7) \
-  } else if (j == 1) {                                                  \
-    _QIP_D1R_STEP(T, C, 0, 0, 2) _QIP_D1R_STEP(T, C, 1, 1, 3) _QIP_D1R_STEP(T, C, 2, 4, 6) _QIP_D1R_STEP(T, C, 3, 5, 7) \
-  } else {                                                              \
-    _QIP_D1R_STEP(T, C, 0, 0, 4) _QIP_D1R_STEP(T, C, 1, 1, 5) _QIP_D1R_STEP(T, C, 2, 2, 6) _QIP_D1R_STEP(T, C, 3, 3, 7) \
-  }
+#define _QIP_LOAD_MR const QipReal m00 = e->m[0], m01 = e->m[1], m10 = e->m[2], m11 = e->m[3];
+#define _QIP_LOAD_PM const uint32_t pm = (op >> 12) & 0xffu;
+#define _QIP_CASES_D1R_MASK(T, C)                                                                                     \
+  case EC_D1R_MASK + 0: { _QIP_LOAD_MR _QIP_LOAD_PM                                                                   \
+    _QIP_D1R_STEP(T, C, 0, 0, 1) _QIP_D1R_STEP(T, C, 1, 2, 3) _QIP_D1R_STEP(T, C, 2, 4, 5) _QIP_D1R_STEP(T, C, 3, 6, 7) } break; \
+  case EC_D1R_MASK + 1: { _QIP_LOAD_MR _QIP_LOAD_PM                                                                   \
+    _QIP_D1R_STEP(T, C, 0, 0, 2) _QIP_D1R_STEP(T, C, 1, 1, 3) _QIP_D1R_STEP(T, C, 2, 4, 6) _QIP_D1R_STEP(T, C, 3, 5, 7) } break; \
+  case EC_D1R_MASK + 2: { _QIP_LOAD_MR _QIP_LOAD_PM                                                                   \
+    _QIP_D1R_STEP(T, C, 0, 0, 4) _QIP_D1R_STEP(T, C, 1, 1, 5) _QIP_D1R_STEP(T, C, 2, 2, 6) _QIP_D1R_STEP(T, C, 3, 3, 7) } break;
 
 #define _QIP_D1C_U(T, C, i0, i1)                                                                \
   QIP_D1C(T, C, "a", i0, i1, m0, m1, m2, m3, m4, m5, m6, m7, n1, n3, n5, n7);                   \
   if (G == 2) QIP_D1C(T, C, "b", i0, i1, m0, m1, m2, m3, m4, m5, m6, m7, n1, n3, n5, n7);
 #define _QIP_D1C_STEP(T, C, p, i0, i1) \
   if ((pm >> p) & 1u) { _QIP_D1C_U(T, C, i0, i1) }
-#define _QIP_D1C_FULL(T, C)                                             \
-  if (j == 0) {                                                         \
-    _QIP_D1C_U(T, C, 0, 1) _QIP_D1C_U(T, C, 2, 3) _QIP_D1C_U(T, C, 4, 5) _QIP_D1C_U(T, C, 6, 7) \
-  } else if (j == 1) {                                                  \
-    _QIP_D1C_U(T, C, 0, 2) _QIP_D1C_U(T, C, 1, 3) _QIP_D1C_U(T, C, 4, 6) _QIP_D1C_U(T, C, 5, 7) \
-  } else {                                                              \
-    _QIP_D1C_U(T, C, 0, 4) _QIP_D1C_U(T, C, 1, 5) _QIP_D1C_U(T, C, 2, 6) _QIP_D1C_U(T, C, 3, 7) \
-  }
-#define _QIP_D1C_MASKED(T, C)                                           \
-  if (j == 0) {                                                         \
-    _QIP_D1C_STEP(T, C, 0, 0, 1) _QIP_D1C_STEP(T, C, 1, 2, 3) _QIP_D1C_STEP(T, C, 2, 4, 5) _QIP_D1C_STEP(T, C, 3, 6, 7) \
-  } else if (j == 1) {                                                  \
-    _QIP_D1C_STEP(T, C, 0, 0, 2) _QIP_D1C_STEP(T, C, 1, 1, 3) _QIP_D1C_STEP(T, C, 2, 4, 6) _QIP_D1C_STEP(T, C, 3, 5, 7) \
-  } else {                                                              \
-    _QIP_D1C_STEP(T, C, 0, 0, 4) _QIP_D1C_STEP(T, C, 1, 1, 5) _QIP_D1C_STEP(T, C, 2, 2, 6) _QIP_D1C_STEP(T, C, 3, 3, 7) \
-  }
+#define _QIP_LOAD_MC                                                \
+  const QipReal m0 = e->m[0], m1 = e->m[1], m2 = e->m[2], m3 = e->m[3];   \
+  const QipReal m4 = e->m[4], m5 = e->m[5], m6 = e->m[6], m7 = e->m[7];   \
+  const QipReal n1 = -m1, n3 = -m3, n5 = -m5, n7 = -m7;
+#define _QIP_CASES_D1C_MASK(T, C)                                                                                     \
+  case EC_D1C_MASK + 0: { _QIP_LOAD_MC _QIP_LOAD_PM                                                                   \
+    _QIP_D1C_STEP(T, C, 0, 0, 1) _QIP_D1C_STEP(T, C, 1, 2, 3) _QIP_D1C_STEP(T, C, 2, 4, 5) _QIP_D1C_STEP(T, C, 3, 6, 7) } break; \
+  case EC_D1C_MASK + 1: { _QIP_LOAD_MC _QIP_LOAD_PM                                                                   \
+    _QIP_D1C_STEP(T, C, 0, 0, 2) _QIP_D1C_STEP(T, C, 1, 1, 3) _QIP_D1C_STEP(T, C, 2, 4, 6) _QIP_D1C_STEP(T, C, 3, 5, 7) } break; \
+  case EC_D1C_MASK + 2: { _QIP_LOAD_MC _QIP_LOAD_PM                                                                   \
+    _QIP_D1C_STEP(T, C, 0, 0, 4) _QIP_D1C_STEP(T, C, 1, 1, 5) _QIP_D1C_STEP(T, C, 2, 2, 6) _QIP_D1C_STEP(T, C, 3, 3, 7) } break;
 
 #define _QIP_X_STEP(T, p, i0, i1)                 \
   if ((xm >> p) & 1u) {                           \
@@ -234,15 +260,28 @@
   } else {                                                              \
     _QIP_X_STEP(T, 0, 0, 4) _QIP_X_STEP(T, 1, 1, 5) _QIP_X_STEP(T, 2, 2, 6) _QIP_X_STEP(T, 3, 3, 7) \
   }
+#define _QIP_CASES_X(T)                                                                            \
+  case EC_X_FULL + 0: case EC_X_FULL + 1: case EC_X_FULL + 2:                                      \
+  case EC_X_MASK + 0: case EC_X_MASK + 1: case EC_X_MASK + 2: {                                    \
+    const uint32_t xm = id >= EC_X_MASK ? (op >> 12) & 0xffu : 0xfu;                               \
+    const uint32_t j = id >= EC_X_MASK ? id - EC_X_MASK : id - EC_X_FULL;                          \
+    _QIP_X_BODY(T)                                                                                 \
+  } break;
 
-#define _QIP_PH_STEP(T, C, c)                       \
-  if ((pm >> c) & 1u) {                             \
-    QIP_PH(T, C, "a", c, wr, wi);                   \
-    if (G == 2) QIP_PH(T, C, "b", c, wr, wi);       \
-  }
+#define _QIP_PH_U(T, C, c)                          \
+  QIP_PH(T, C, "a", c, wr, wi);                     \
+  if (G == 2) QIP_PH(T, C, "b", c, wr, wi);
+#define _QIP_PH_STEP(T, C, c) \
+  if ((pm >> c) & 1u) { _QIP_PH_U(T, C, c) }
 #define _QIP_PH_BODY(T, C)                                                                              \
   _QIP_PH_STEP(T, C, 0) _QIP_PH_STEP(T, C, 1) _QIP_PH_STEP(T, C, 2) _QIP_PH_STEP(T, C, 3)               \
   _QIP_PH_STEP(T, C, 4) _QIP_PH_STEP(T, C, 5) _QIP_PH_STEP(T, C, 6) _QIP_PH_STEP(T, C, 7)
+#define _QIP_LOAD_W const QipReal wr = e->m[0], wi = e->m[1];
+#define _QIP_CASES_PHASE_GEN(T, C)                                                                                    \
+  case EC_PHASE: { _QIP_LOAD_W _QIP_LOAD_PM _QIP_PH_BODY(T, C) } break;                                               \
+  case EC_PHASEN: { /* run of controlled phases, controls outside the tile: the product was formed */                 \
+    const QipReal wr = tbl[2 * e->pad], wi = tbl[2 * e->pad + 1]; /* once per CTA (factor table) */                         \
+    _QIP_LOAD_PM _QIP_PH_BODY(T, C) } break;
 
 // dense 8x8 (composed blocks / user 2-3 qubit matrices): through C++ temporaries
 #define _QIP_D3_BODY(T, C, CO, R, P)                                                       \

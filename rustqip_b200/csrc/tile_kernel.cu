@@ -253,9 +253,9 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
       for (;;) {
         const Elem<R> *e = reinterpret_cast<const Elem<R> *>(ep);
         const uint32_t op = e->op;
-        if ((op & 0x1fu) == EC_END) break;
+        if ((op & kElemCaseMask) == EC_END) break;
         const uint32_t size = ((op >> 20) & 0x7ffu) << 4;
-        if ((op & 0x1fu) == EC_PHASEN) {
+        if ((op & kElemCaseMask) == EC_PHASEN) {
           R wr = e->m[0], wi = e->m[1];
           const PhaseTerm<R> *pt = reinterpret_cast<const PhaseTerm<R> *>(e + 1);
           const uint32_t nt = (size - (uint32_t)sizeof(Elem<R>)) / (uint32_t)sizeof(PhaseTerm<R>);
@@ -272,11 +272,24 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
       }
     }
   }
+  // ... and this CTA's evaluation of the pass's condition table (controls that live outside the
+  // tile): thread s tests condition s, two ballots give the 64-bit word every thread keeps.
+  uint32_t *condw = reinterpret_cast<uint32_t *>(smem + tile_bytes + kMaxPhasen * 16 + 16);
+  if (threadIdx.x < 64) {
+    bool on = false;
+    if (threadIdx.x < h->n_conds) {
+      const CondTerm *ct = reinterpret_cast<const CondTerm *>(pp.recs + h->cond_off) + threadIdx.x;
+      on = (base & ct->gmask) == ct->gval;
+    }
+    const uint32_t bits = __ballot_sync(0xffffffffu, on);
+    if ((threadIdx.x & 31u) == 0) condw[threadIdx.x >> 5] = bits;
+  }
   if (use_tma)
     mbar_wait(mbar, 0);
   else
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  const uint64_t condbits = (uint64_t)condw[0] | ((uint64_t)condw[1] << 32);
 
   // ---- 2. apply ----
   const unsigned char *rec = pp.recs;
@@ -287,9 +300,9 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
     if ((base & mo->gmask) == mo->gmask) {
       if (mo->kind == MK_SUPER) {
         if constexpr (sizeof(R) == 8)
-          run_super_f64<G>(smem_base, mo, data, base, reinterpret_cast<const double *>(tbl));
+          run_super_f64<G>(smem_base, mo, data, base, reinterpret_cast<const double *>(tbl), condbits);
         else
-          run_super_f32<G>(smem_base, mo, data, base, reinterpret_cast<const float *>(tbl));
+          run_super_f32<G>(smem_base, mo, data, base, reinterpret_cast<const float *>(tbl), condbits);
       } else if (mo->kind == MK_DENSE) {
         const R *mat = reinterpret_cast<const R *>(data);
         if (mo->k == 1)
@@ -415,8 +428,8 @@ cudaError_t launch_tile_pass(qip_prec prec, void *psi, uint32_t n_local, PassPar
   alignas(64) CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   pp.h.use_tma = (use_tma && make_tile_map(&tmap, prec, psi, n_local, pp.h)) ? 1u : 0u;
-  // tile | EC_PHASEN factor table | mbarrier
-  const size_t smem = ((size_t)(prec == QIP_F32 ? 8u : 16u) << T) + kMaxPhasen * 16 + 16;
+  // tile | EC_PHASEN factor table | mbarrier | condition word
+  const size_t smem = ((size_t)(prec == QIP_F32 ? 8u : 16u) << T) + kMaxPhasen * 16 + 32;
   const unsigned grid = 1u << (n_local - T);
   if (prec == QIP_F32) {
     if (groups_per_thread == 1)

@@ -49,14 +49,68 @@ static void apply_single(const FlatOp &f, uint32_t n, std::vector<cd> &psi) {
   psi.swap(out);
 }
 
-// elementary op on the 8 register-resident amplitudes of one group (mirrors tile_kernel.cu)
+// elementary op on the 8 register-resident amplitudes of one group (mirrors tile_kernel.cu:
+// the specialised case ids do NOT read the mask field, so the emulator derives the mask from the
+// id as the kernel's straight-line code does and flags a record whose stored mask disagrees)
+static int g_decode_errors = 0;
+
 template <typename R>
-static void run_elem(const Elem<R> &e, const R *mat8, cd a[8], uint64_t base) {
-  if ((e.op & kElemHasCond) && (base & e.gmask) != e.gval) return;
-  const uint32_t id = elem_case(e.op), mask = (e.op >> 12) & 0xff;
+static void run_elem(const Elem<R> &e, const R *mat8, cd a[8], uint64_t base, const CondTerm *conds, uint32_t n_conds) {
+  if (e.op & kElemHasCond) {
+    const uint32_t slot = elem_cond_slot(e.op);
+    bool on = (base & e.gmask) == e.gval;
+    if (slot != kCondOverflow) {
+      if (slot >= n_conds || conds[slot].gmask != e.gmask || conds[slot].gval != e.gval) ++g_decode_errors;
+      else on = (base & conds[slot].gmask) == conds[slot].gval;
+    }
+    if (!on) return;
+  }
+  const uint32_t id = elem_case(e.op);
+  uint32_t mask = (e.op >> 12) & 0xff;
+  enum { K_D1, K_X, K_PH, K_PHN, K_D3 } kind;
+  bool real = false;
+  uint32_t j = 0;
   if (id >= EC_D1R_FULL && id < EC_PHASE) {
-    const bool real = (id >= EC_D1R_FULL && id < EC_D1C_FULL) || (id >= EC_D1R_MASK && id < EC_D1C_MASK);
-    const uint32_t j = (id - 1) % 3;
+    kind = K_D1;
+    real = (id < EC_D1C_FULL) || (id >= EC_D1R_MASK && id < EC_D1C_MASK);
+    j = (id - 1) % 3;
+    if ((id < EC_D1R_MASK) != (mask == 0xf)) ++g_decode_errors;
+  } else if (id >= EC_D1R_C1 && id < EC_D1R_C2) {
+    kind = K_D1;
+    real = true;
+    j = (id - EC_D1R_C1) / 2;
+    const uint32_t want = kPairMaskC1[(id - EC_D1R_C1) % 2];
+    if (mask != want) ++g_decode_errors;
+    mask = want;
+  } else if (id >= EC_D1R_C2 && id < EC_PHASE_2) {
+    kind = K_D1;
+    real = true;
+    j = id - EC_D1R_C2;
+    if (mask != kPairMaskC2) ++g_decode_errors;
+    mask = kPairMaskC2;
+  } else if (id >= EC_X_FULL && id < EC_PHASEN) {
+    kind = K_X;
+    j = (id - EC_X_FULL) % 3;
+    if ((id < EC_X_MASK) != (mask == 0xf)) ++g_decode_errors;
+  } else if (id == EC_PHASEN) {
+    kind = K_PHN;
+  } else if (id == EC_PHASE) {
+    kind = K_PH;
+  } else if (id >= EC_PHASE_J && id < EC_D1R_C1) {
+    kind = K_PH;
+    if (mask != kPhaseMaskJ[id - EC_PHASE_J]) ++g_decode_errors;
+    mask = kPhaseMaskJ[id - EC_PHASE_J];
+  } else if (id >= EC_PHASE_2 && id < EC_N_CASES) {
+    kind = K_PH;
+    if (mask != kPhaseMask2[id - EC_PHASE_2]) ++g_decode_errors;
+    mask = kPhaseMask2[id - EC_PHASE_2];
+  } else if (id == EC_DENSE3) {
+    kind = K_D3;
+  } else {
+    ++g_decode_errors;
+    return;
+  }
+  if (kind == K_D1) {
     uint32_t p = 0;
     for (uint32_t c = 0; c < 8; ++c) {
       if ((c >> j) & 1) continue;
@@ -73,8 +127,7 @@ static void run_elem(const Elem<R> &e, const R *mat8, cd a[8], uint64_t base) {
         a[i1] = cd(e.m[4], e.m[5]) * x + cd(e.m[6], e.m[7]) * y;
       }
     }
-  } else if (id >= EC_X_FULL && id < EC_PHASEN) {
-    const uint32_t j = (id - EC_X_FULL) % 3;
+  } else if (kind == K_X) {
     uint32_t p = 0;
     for (uint32_t c = 0; c < 8; ++c) {
       if ((c >> j) & 1) continue;
@@ -82,7 +135,7 @@ static void run_elem(const Elem<R> &e, const R *mat8, cd a[8], uint64_t base) {
       ++p;
       if (on) std::swap(a[c], a[c | (1u << j)]);
     }
-  } else if (id == EC_PHASEN) {
+  } else if (kind == K_PHN) {
     cd w(e.m[0], e.m[1]);
     const PhaseTerm<R> *t = reinterpret_cast<const PhaseTerm<R> *>(mat8);
     const uint32_t nt = (elem_size_bytes(e.op) - (uint32_t)sizeof(Elem<R>)) / (uint32_t)sizeof(PhaseTerm<R>);
@@ -90,7 +143,7 @@ static void run_elem(const Elem<R> &e, const R *mat8, cd a[8], uint64_t base) {
       if ((base & t[k].gmask) == t[k].gval) w *= cd(t[k].re, t[k].im);
     for (uint32_t c = 0; c < 8; ++c)
       if ((mask >> c) & 1) a[c] *= w;
-  } else if (id == EC_PHASE) {
+  } else if (kind == K_PH) {
     for (uint32_t c = 0; c < 8; ++c)
       if ((mask >> c) & 1) a[c] *= cd(e.m[0], e.m[1]);
   } else {  // EC_DENSE3
@@ -118,6 +171,7 @@ static void run_pass_params(const PassParams &pp, uint32_t n, std::vector<cd> &p
     }
     for (uint64_t t = 0; t < (1ull << T); ++t) tile[t] = psi[base + h.chunk_off[t >> L] + (t & ((1ull << L) - 1))];
     const unsigned char *rp = pp.recs;
+    const CondTerm *conds = reinterpret_cast<const CondTerm *>(pp.recs + h.cond_off);
     for (uint32_t oi = 0; oi < h.n_ops; ++oi) {
       MicroOp mo;
       memcpy(&mo, rp, sizeof(mo));
@@ -144,7 +198,17 @@ static void run_pass_params(const PassParams &pp, uint32_t n, std::vector<cd> &p
           std::swap(tile[t0 + mo.off[0]], tile[t0 + mo.off[1]]);
         } else if (mo.kind == MK_SUPER) {
           cd a[8];
-          for (uint32_t u = 0; u < 8; ++u) a[u] = tile[t0 + mo.off[u]];
+          for (uint32_t u = 0; u < 8; ++u) {
+            const uint32_t off = mo.off[u];
+            const uint32_t want = sizeof(R) == 8 ? (off ^ ((off >> 3) & 7u)) << 4 : (off ^ (((off >> 4) & 7u) << 1)) << 3;
+            if (g == 0 && mo.soff[u] != want) ++g_decode_errors;
+            a[u] = tile[t0 + off];
+          }
+          {  // the kernel expands the group counter with t += t & (~0 << p): must equal the bit insertion
+            uint32_t t = (uint32_t)g;
+            for (uint32_t i = 0; i < 3; ++i) t += t & (~0u << mo.ins_pos[i]);
+            if (mo.ins_n != 3 || mo.lor_mask != 0 || t != (uint32_t)t0) ++g_decode_errors;
+          }
           const unsigned char *ep = data;
           for (;;) {
             Elem<R> e;
@@ -152,7 +216,7 @@ static void run_pass_params(const PassParams &pp, uint32_t n, std::vector<cd> &p
             if (elem_case(e.op) == EC_END) break;
             const R *mat8 = reinterpret_cast<const R *>(ep + sizeof(e));
             ep += elem_size_bytes(e.op);
-            run_elem<R>(e, mat8, a, base);
+            run_elem<R>(e, mat8, a, base, conds, h.n_conds);
           }
           for (uint32_t u = 0; u < 8; ++u) tile[t0 + mo.off[u]] = a[u];
         } else {
@@ -178,6 +242,28 @@ static void run_pass_params(const PassParams &pp, uint32_t n, std::vector<cd> &p
   }
 }
 
+// number of elementary records whose condition did not get a slot of the pass's condition table
+template <typename R>
+static uint64_t count_overflow_conditions(const PassParams &pp) {
+  uint64_t n = 0;
+  const unsigned char *rp = pp.recs;
+  for (uint32_t oi = 0; oi < pp.h.n_ops; ++oi) {
+    MicroOp mo;
+    memcpy(&mo, rp, sizeof(mo));
+    const unsigned char *ep = rp + sizeof(mo);
+    rp += sizeof(mo) + mo.data_bytes;
+    if (mo.kind != MK_SUPER) continue;
+    for (;;) {
+      Elem<R> e;
+      memcpy(&e, ep, sizeof(e));
+      if (elem_case(e.op) == EC_END) break;
+      if ((e.op & kElemHasCond) && elem_cond_slot(e.op) == kCondOverflow) ++n;
+      ep += elem_size_bytes(e.op);
+    }
+  }
+  return n;
+}
+
 extern "C" int emul_schedule(int prec, uint32_t n, const qip_op *ops, size_t n_ops, double *state, uint32_t T,
                              uint32_t L, int fuse_blocks, uint32_t max_k, uint64_t *stats, char *errbuf,
                              size_t errlen) {
@@ -197,9 +283,10 @@ extern "C" int emul_schedule(int prec, uint32_t n, const qip_op *ops, size_t n_o
   if (max_k) cfg.compose_threshold = max_k;
   std::vector<PlanStep> steps;
   plan_passes(flat, n, (qip_prec)prec, cfg, &steps);
+  g_decode_errors = 0;
   std::vector<cd> psi(1ull << n);
   for (uint64_t i = 0; i < (1ull << n); ++i) psi[i] = cd(state[2 * i], state[2 * i + 1]);
-  uint64_t n_pass = 0, n_single = 0, n_micro = 0, n_gates_in_pass = 0;
+  uint64_t n_pass = 0, n_single = 0, n_micro = 0, n_gates_in_pass = 0, n_overflow = 0, max_conds = 0;
   for (size_t s = 0; s < steps.size(); ++s) {
     if (steps[s].is_pass) {
       PassParams pp;
@@ -207,6 +294,8 @@ extern "C" int emul_schedule(int prec, uint32_t n, const qip_op *ops, size_t n_o
         if (errbuf && errlen) snprintf(errbuf, errlen, "pass does not fit the parameter space");
         return -2;
       }
+      n_overflow += prec == QIP_F32 ? count_overflow_conditions<float>(pp) : count_overflow_conditions<double>(pp);
+      if (pp.h.n_conds > max_conds) max_conds = pp.h.n_conds;
       if (prec == QIP_F32)
         run_pass_params<float>(pp, n, psi);
       else
@@ -228,6 +317,12 @@ extern "C" int emul_schedule(int prec, uint32_t n, const qip_op *ops, size_t n_o
     stats[1] = n_single;
     stats[2] = n_micro;
     stats[3] = n_gates_in_pass;
+    stats[4] = n_overflow;
+    stats[5] = max_conds;
+  }
+  if (g_decode_errors) {
+    if (errbuf && errlen) snprintf(errbuf, errlen, "%d records disagree with their case id / condition slot / offsets", g_decode_errors);
+    return -3;
   }
   return 0;
 }

@@ -419,6 +419,27 @@ def test_fused_multi_tile(ctx, dtype, n):
     assert_close(got_unfused, want, dtype)
 
 
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_fused_condition_table_overflow(ctx, dtype):
+    """More distinct controls-outside-the-tile conditions in one pass (175) than the 63 slots of the per-CTA
+    condition word: the rest must take the in-record test.  Tile = index bits 0-4 and 15-21, controls on 5-14."""
+    import itertools
+    n = 22
+    rng = np.random.default_rng(31)
+    ops = []
+    for k in (1, 2, 3):
+        for ctrls in itertools.combinations(range(7, 17), k):
+            tgt = n - 1 - int(rng.integers(3))
+            inner = [gates.x(tgt), gates.h(tgt), gates.t(tgt), gates.mat([tgt], rand_unitary(1, rng).reshape(-1))][int(rng.integers(4))]
+            ops.append(make_control_op(list(ctrls), inner))
+    psi = rand_state(n, dtype, 14)
+    want = qo.run_pipeline(n, ops, state=psi, dtype=dtype)
+    l0 = ctx.kernel_launches()
+    got = gpu_state_apply(ctx, n, ops, psi, fusion=True)
+    assert ctx.kernel_launches() - l0 <= 3
+    assert_close(got, want, dtype)
+
+
 def test_fused_random_circuit_n20(ctx):
     n = 20
     ops = circuits.random_circuit(n, 12, 0x5EED0002, "H,T,CNOT") + circuits.random_circuit(n, 6, 0x5EED0005, "H,CZ,CNOT")

@@ -108,6 +108,30 @@ def test_planner_random_and_qft(emul):
     assert np.max(np.abs(got - qo.run_pipeline(n, ops, state=psi))) < 1e-12
 
 
+def many_condition_circuit(n, outside_qubits, seed):
+    """Gates on the three lowest index bits under every 1-, 2- and 3-subset of `outside_qubits` as controls:
+    92 distinct CTA-uniform conditions for 8 qubits, more than the 63 slots of a pass's condition table."""
+    import itertools
+    rng = np.random.default_rng(seed)
+    ops = []
+    for k in (1, 2, 3):
+        for ctrls in itertools.combinations(outside_qubits, k):
+            tgt = n - 1 - int(rng.integers(3))
+            inner = [gates.x(tgt), gates.h(tgt), gates.t(tgt), gates.mat([tgt], rand_unitary(1, rng).reshape(-1))][int(rng.integers(4))]
+            ops.append(make_control_op(list(ctrls), inner))
+    return ops
+
+
+def test_planner_condition_table_overflow(emul):
+    n, T, Lo = 16, 8, 3
+    ops = many_condition_circuit(n, list(range(5, 13)), 21)  # index bits 3..10: outside the tile (bits 0-2, 11-15)
+    psi = rand_state(n, 22)
+    want = qo.run_pipeline(n, ops, state=psi)
+    got, stats = run_emul(emul, n, ops, psi, T=T, Lo=Lo)
+    assert np.max(np.abs(got - want)) < 1e-12
+    assert stats[0] == 1 and stats[5] == 63 and stats[4] >= 10  # one pass, full table, the rest on the in-record path
+
+
 def test_planner_f32_data_path(emul):
     n = 9
     ops = mixed_circuit(n, 80, 99)
