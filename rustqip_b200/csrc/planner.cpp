@@ -772,6 +772,7 @@ PlanConfig default_plan_config(qip_prec prec, uint32_t n_local) {
   if (const char *e = getenv("QIPB200_TILE_G")) c.groups_per_thread = atoi(e) == 2 ? 2 : 1;
   if (const char *e = getenv("QIPB200_NO_BLOCK_FUSION")) c.fuse_blocks = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_NO_PEEPHOLE")) c.peephole = atoi(e) == 0;
+  if (const char *e = getenv("QIPB200_NO_SEED_SEARCH")) c.seed_search = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_X_MOVES")) c.x_as_moves = atoi(e) != 0;
   if (const char *e = getenv("QIPB200_NO_PHASEN")) c.fold_cond_phases = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_NO_TMA")) c.use_tma = atoi(e) == 0;
@@ -831,34 +832,70 @@ void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec
     bool done = false, stuck = false;
     for (int attempt = 0; attempt < 3 && !done; ++attempt) {
       const uint64_t budget = (uint64_t)byte_budget * kBudgetScale[attempt];
-      uint64_t S_high = 0, pend_d = 0, pend_nd = 0;
-      std::vector<size_t> taken, left;
-      double unfused = 0.0;
-      uint64_t bytes = 0;
-      long single = -1;  // first op that may run alone right now: not blocked, commutes past EVERY earlier op
-      uint64_t seen_d = 0, seen_nd = 0;
-      for (size_t r = 0; r < remaining.size(); ++r) {
-        const size_t idx = remaining[r];
-        const OpInfo &o = info[idx];
-        const bool is_blocked = blocked && (*blocked)[idx];
-        const bool conflict = (o.nd & (pend_d | pend_nd)) || (o.dg & pend_nd);
-        if (single < 0 && !is_blocked && !((o.nd & (seen_d | seen_nd)) || (o.dg & seen_nd))) single = (long)r;
-        seen_d |= o.dg;
-        seen_nd |= o.nd;
-        if (can_tile && !conflict && o.tile_ok && bytes + o.est_bytes <= budget) {
-          const uint64_t need = o.need_tile & ~low_mask & ~S_high;
-          if ((uint32_t)popc(S_high | need) <= m) {
-            S_high |= need;
-            taken.push_back(idx);
-            unfused += o.unfused_cost;
-            bytes += o.est_bytes;
-            continue;
+      // One greedy selection in program order, the tile's high bits pre-seeded with `seed`.
+      struct Pick {
+        uint64_t S_high = 0;
+        std::vector<size_t> taken, left;
+        double unfused = 0.0;
+        long single = -1;  // first op that may run alone right now: not blocked, commutes past EVERY earlier op
+        size_t n_nd = 0;   // non-diagonal gates absorbed (diagonal ones ride along in any pass)
+      };
+      auto select = [&](uint64_t seed) {
+        Pick pk;
+        pk.S_high = seed;
+        uint64_t pend_d = 0, pend_nd = 0, bytes = 0, seen_d = 0, seen_nd = 0;
+        for (size_t r = 0; r < remaining.size(); ++r) {
+          const size_t idx = remaining[r];
+          const OpInfo &o = info[idx];
+          const bool is_blocked = blocked && (*blocked)[idx];
+          const bool conflict = (o.nd & (pend_d | pend_nd)) || (o.dg & pend_nd);
+          if (pk.single < 0 && !is_blocked && !((o.nd & (seen_d | seen_nd)) || (o.dg & seen_nd))) pk.single = (long)r;
+          seen_d |= o.dg;
+          seen_nd |= o.nd;
+          if (can_tile && !conflict && o.tile_ok && bytes + o.est_bytes <= budget) {
+            const uint64_t need = o.need_tile & ~low_mask & ~pk.S_high;
+            if ((uint32_t)popc(pk.S_high | need) <= m) {
+              pk.S_high |= need;
+              pk.taken.push_back(idx);
+              pk.unfused += o.unfused_cost;
+              pk.n_nd += o.nd ? 1 : 0;
+              bytes += o.est_bytes;
+              continue;
+            }
           }
+          pend_d |= o.dg;
+          pend_nd |= o.nd;
+          pk.left.push_back(idx);
         }
-        pend_d |= o.dg;
-        pend_nd |= o.nd;
-        left.push_back(idx);
+        return pk;
+      };
+      Pick best = select(0);
+      if (cfg.seed_search && can_tile) {
+        // The plain greedy fills the tile with the bits of the first gates it meets.  Try reserving slots
+        // for bits that gates left behind need (forward selection, one bit at a time): keep whichever
+        // selection absorbs the most non-diagonal gates.
+        uint64_t seeds = 0;
+        for (uint32_t round = 0; round < m && !best.left.empty(); ++round) {
+          uint64_t cand = 0;
+          for (size_t r = 0; r < best.left.size() && r < 64; ++r) cand |= info[best.left[r]].need_tile & ~low_mask;
+          cand &= ~best.S_high;
+          uint64_t best_bit = 0;
+          for (uint32_t bit = 0; bit < 64; ++bit) {
+            if (!((cand >> bit) & 1)) continue;
+            Pick alt = select(seeds | (1ull << bit));
+            if (alt.n_nd > best.n_nd) {
+              best = std::move(alt);
+              best_bit = 1ull << bit;
+            }
+          }
+          if (!best_bit) break;
+          seeds |= best_bit;
+        }
       }
+      uint64_t S_high = best.S_high;
+      std::vector<size_t> &taken = best.taken, &left = best.left;
+      const double unfused = best.unfused;
+      const long single = best.single;
       if (taken.empty() || unfused <= 1.05) {
         if (single < 0) {  // everything left is blocked or stuck behind a blocked op
           stuck = true;
