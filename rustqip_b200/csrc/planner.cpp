@@ -211,6 +211,12 @@ struct Emitter {
   const PlanConfig *cfg;
   std::vector<Group> open;
   std::vector<GlobalTerm<R>> gterms;
+  // Un-normalised Hadamards: product of the scales not applied yet (a global scalar), and where the last
+  // butterfly record sits so that it can be turned back into a scaled 2x2 if nothing else absorbs the product.
+  double pending_scale = 1.0;
+  long had_op = -1;
+  size_t had_at = 0;
+  uint32_t had_j = 0;
 
   void emit_group(const Group &g) {
     // pad the bit set to 3 with the highest unused tile-local bits (keeps the low bits for the lanes)
@@ -326,12 +332,28 @@ struct Emitter {
         bool real = true;
         for (int q = 0; q < 4; ++q) real &= e.m[q].imag() == 0.0;
         d.op = elem_op(real ? E_DENSE1R : E_DENSE1, j, pm, cond, rec_bytes);
+        cplx mm[4] = {e.m[0], e.m[1], e.m[2], e.m[3]};
+        const bool everywhere = pm == 0xfu && !cond;  // acts on every amplitude of the state
+        const double hs = mm[0].real();
+        const bool is_h = real && everywhere && cfg->unnormalised_h && hs > 0.0 && mm[1].real() == hs && mm[2].real() == hs &&
+                          mm[3].real() == -hs;
+        if (is_h) {  // s*[[1,1],[1,-1]]: butterfly now, scale later
+          d.op = (d.op & ~kElemCaseMask) | (EC_HAD + j);
+          pending_scale *= hs;
+          had_op = (long)pass->ops.size();
+          had_at = mo.data.size();
+          had_j = j;
+        } else if (everywhere && pending_scale != 1.0) {
+          for (int q = 0; q < 4; ++q) mm[q] *= pending_scale;
+          pending_scale = 1.0;
+          had_op = -1;
+        }
         for (int q = 0; q < 4; ++q) {
           if (real) {
-            d.m[q] = (R)e.m[q].real();
+            d.m[q] = (R)mm[q].real();
           } else {
-            d.m[2 * q] = (R)e.m[q].real();
-            d.m[2 * q + 1] = (R)e.m[q].imag();
+            d.m[2 * q] = (R)mm[q].real();
+            d.m[2 * q + 1] = (R)mm[q].imag();
           }
         }
         }
@@ -362,7 +384,12 @@ struct Emitter {
         memcpy(mo.data.data() + at3, &pt, sizeof(pt));
       }
       if (e.type == E_DENSE3) {
-        const std::vector<cplx> M = embed(e.mk, e.mbits, P);
+        std::vector<cplx> M = embed(e.mk, e.mbits, P);
+        if (!cond && pending_scale != 1.0) {  // a dense block touches every amplitude: it takes the pending scale
+          for (size_t q = 0; q < M.size(); ++q) M[q] *= pending_scale;
+          pending_scale = 1.0;
+          had_op = -1;
+        }
         const size_t at2 = mo.data.size();
         mo.data.resize(at2 + 128 * sizeof(R));
         R *w = reinterpret_cast<R *>(mo.data.data() + at2);
@@ -381,6 +408,21 @@ struct Emitter {
     }
     mo.h.data_bytes = (uint32_t)mo.data.size();
     pass->ops.push_back(mo);
+  }
+
+  // End of the pass: a product of Hadamard scales nobody absorbed goes back into the last butterfly,
+  // which becomes an ordinary real 2x2 again.
+  void settle_scale() {
+    if (pending_scale == 1.0) return;
+    Elem<R> d;
+    unsigned char *rec = pass->ops[(size_t)had_op].data.data() + had_at;
+    memcpy(&d, rec, sizeof(d));
+    d.op = (d.op & ~kElemCaseMask) | (EC_D1R_FULL + had_j);
+    d.m[0] = d.m[1] = d.m[2] = (R)pending_scale;
+    d.m[3] = (R)-pending_scale;
+    memcpy(rec, &d, sizeof(d));
+    pending_scale = 1.0;
+    had_op = -1;
   }
 
   // Emit the open groups that touch `lmask` (or all of them).  Groups on disjoint bits commute,
@@ -417,7 +459,7 @@ struct Emitter {
   // Peephole: fold `e` into the last elementary op of a group when both act on the same
   // target bit under the same controls/condition (H.T.H -> one complex 2x2, T after a 2x2 ->
   // a scaled row, two phases on the same mask -> one phase).  Returns true when folded.
-  static bool fold_into(HElem &b, const HElem &e, bool fold_cond) {
+  static bool fold_into(HElem &b, const HElem &e, bool fold_cond, bool keep_real) {
     if (fold_cond && b.type == E_PHASE && e.type == E_PHASE && b.lmask == e.lmask && b.lval == e.lval &&
         (b.gmask != e.gmask || b.gval != e.gval || !b.terms.empty() || !e.terms.empty())) {
       // same amplitudes, different CTA-uniform conditions: keep one op with a list of conditional factors
@@ -453,14 +495,22 @@ struct Emitter {
       b.m[3] = e.m[2] * a1 + e.m[3] * a3;
       return true;
     }
+    // A real 2x2 costs half the FP64 work of a complex one, an (un-normalised) Hadamard a quarter, a phase on one
+    // sub-bit a quarter: folding a non-real phase into a REAL matrix would make it complex and cost more than
+    // the two ops apart.  (Complex matrices absorb phases for free.)
+    auto is_real = [](const HElem &d1) {
+      return d1.m[0].imag() == 0.0 && d1.m[1].imag() == 0.0 && d1.m[2].imag() == 0.0 && d1.m[3].imag() == 0.0;
+    };
     if (b.type == E_DENSE1 && e.type == E_PHASE) {
       if (!e.terms.empty() || !phase_target_ok(e, b)) return false;
+      if (keep_real && is_real(b) && e.m[0].imag() != 0.0) return false;
       b.m[2] *= e.m[0];  // diag(1,w) * M: scales the row of the |1> output
       b.m[3] *= e.m[0];
       return true;
     }
     if (b.type == E_PHASE && e.type == E_DENSE1) {
       if (!b.terms.empty() || !phase_target_ok(b, e)) return false;
+      if (keep_real && is_real(e) && b.m[0].imag() != 0.0) return false;
       HElem d = e;
       d.m[1] *= b.m[0];  // M * diag(1,w): scales the column of the |1> input
       d.m[3] *= b.m[0];
@@ -518,28 +568,51 @@ struct Emitter {
       open.push_back(g);
       return;
     }
-    if (hit.size() == 1 && cfg->peephole) {
-      std::vector<HElem> &el = open[hit[0]].elems;
-      if (fold_into(el.back(), e, cfg->fold_cond_phases)) {
-        open[hit[0]].mask = um;
-        return;
-      }
-      if (cfg->fold_cond_phases && e.type == E_PHASE && e.terms.size() < 48) {
-        // phases commute with each other: look further back through the run of phases for the same mask
-        for (size_t k = el.size(); k-- > 0 && el[k].type == E_PHASE;)
-          if (el[k].lmask == e.lmask && el[k].lval == e.lval && el[k].terms.size() < 48 && fold_into(el[k], e, true)) {
-            open[hit[0]].mask = um;
-            return;
-          }
-      }
-    }
     Group merged;
     merged.mask = um;
     for (size_t h = 0; h < hit.size(); ++h)  // disjoint groups commute: any order
       merged.elems.insert(merged.elems.end(), open[hit[h]].elems.begin(), open[hit[h]].elems.end());
-    merged.elems.push_back(e);
     for (size_t h = hit.size(); h-- > 0;) open.erase(open.begin() + hit[h]);
-    open.push_back(merged);
+    bool folded = false;
+    if (cfg->peephole) {
+      // Fold `e` into an earlier op on the same target (see fold_into), looking back past the ops it
+      // commutes with (disjoint bits, or diagonal on every shared bit): H(a) H(b) T(a) folds T into H(a)'s slot.
+      std::vector<HElem> &el = merged.elems;
+      for (size_t k = el.size(); k-- > 0;) {
+        HElem &prev = el[k];
+        const bool terms_ok = !(e.type == E_PHASE && prev.type == E_PHASE) || (prev.terms.size() < 48 && e.terms.size() < 48);
+        if (terms_ok && fold_into(prev, e, cfg->fold_cond_phases, cfg->keep_real)) {
+          folded = true;
+          if (is_identity(prev)) el.erase(el.begin() + (long)k);  // H.H, X.X, T.T^-1 ...: nothing left to do
+          break;
+        }
+        if (!cfg->lookback || !commute(prev, e)) break;
+      }
+    }
+    if (!folded) merged.elems.push_back(e);
+    if (!merged.elems.empty()) open.push_back(merged);
+  }
+
+  static uint32_t nd_bits(const HElem &h) {
+    switch (h.type) {
+      case E_DENSE1:
+      case E_X:
+        return 1u << h.lb_j;
+      case E_SWAP:
+        return (1u << h.lb_j) | (1u << h.lb_k);
+      case E_PHASE:
+        return 0;
+      default:
+        return h.bits();
+    }
+  }
+  static bool commute(const HElem &a, const HElem &b) { return !(nd_bits(a) & b.bits()) && !(nd_bits(b) & a.bits()); }
+  static bool is_identity(const HElem &h) {
+    const double tol = 1e-15;
+    if (h.type == E_PHASE) return h.terms.empty() && std::abs(h.m[0] - cplx(1, 0)) < tol;
+    if (h.type != E_DENSE1) return false;
+    return std::abs(h.m[0] - cplx(1, 0)) < tol && std::abs(h.m[3] - cplx(1, 0)) < tol && std::abs(h.m[1]) < tol &&
+           std::abs(h.m[2]) < tol;
   }
 
   // ---- wide micro-ops for what does not fit 3 bits ----------------------------------
@@ -749,6 +822,7 @@ void emit_pass(const std::vector<FlatOp> &ops, const std::vector<size_t> &taken,
     em.add(e);
   }
   em.flush_touching(0, true);
+  em.settle_scale();
   pass->gterms.resize(em.gterms.size() * sizeof(GlobalTerm<R>));
   if (!em.gterms.empty()) memcpy(pass->gterms.data(), em.gterms.data(), pass->gterms.size());
 }
@@ -772,7 +846,10 @@ PlanConfig default_plan_config(qip_prec prec, uint32_t n_local) {
   if (const char *e = getenv("QIPB200_TILE_G")) c.groups_per_thread = atoi(e) == 2 ? 2 : 1;
   if (const char *e = getenv("QIPB200_NO_BLOCK_FUSION")) c.fuse_blocks = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_NO_PEEPHOLE")) c.peephole = atoi(e) == 0;
-  if (const char *e = getenv("QIPB200_NO_SEED_SEARCH")) c.seed_search = atoi(e) == 0;
+  if (const char *e = getenv("QIPB200_SEED_SEARCH")) c.seed_search = atoi(e) != 0;
+  if (const char *e = getenv("QIPB200_NO_HAD")) c.unnormalised_h = atoi(e) == 0;
+  if (const char *e = getenv("QIPB200_NO_KEEP_REAL")) c.keep_real = atoi(e) == 0;
+  if (const char *e = getenv("QIPB200_NO_LOOKBACK")) c.lookback = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_X_MOVES")) c.x_as_moves = atoi(e) != 0;
   if (const char *e = getenv("QIPB200_NO_PHASEN")) c.fold_cond_phases = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_NO_TMA")) c.use_tma = atoi(e) == 0;

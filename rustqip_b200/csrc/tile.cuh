@@ -51,6 +51,9 @@ enum ElemType { E_DENSE1 = 0, E_DENSE1R = 1, E_X = 2, E_PHASE = 3, E_SWAP = 4, E
 //                 the control is the lower/higher of the two other sub-bits
 //              31-33 real 2x2 on sub-bit j under BOTH other sub-bits (Toffoli)
 //              34-36 PHASE on the amplitudes with two sub-bits set (CZ, controlled phase): (0,1), (0,2), (1,2)
+//              37-39 UN-NORMALISED Hadamard butterfly on sub-bit j (x+y, x-y: half the FP64 work of a real 2x2);
+//                 the planner folds the pending 1/sqrt(2)^k -- a global scalar, it commutes with everything --
+//                 into a later full 2x2 of the same pass
 //   bits 6-11  slot of the op's CTA-uniform condition in the pass's condition table (kCondOverflow: test
 //              the record's own gmask/gval)
 //   bits 12-19 active mask: 2x2 kinds: bit p <-> the p-th (ascending) sub-index with bit j
@@ -63,7 +66,7 @@ static const uint32_t kElemCondShift = 6;
 static const uint32_t kCondOverflow = 63;  // slots 0..62 index the pass's condition table
 enum ElemCase { EC_END = 0, EC_D1R_FULL = 1, EC_D1C_FULL = 4, EC_D1R_MASK = 7, EC_D1C_MASK = 10, EC_PHASE = 13, EC_DENSE3 = 14,
                 EC_X_FULL = 15, EC_X_MASK = 18, EC_PHASEN = 21, EC_PHASE_J = 22, EC_D1R_C1 = 25, EC_D1R_C2 = 31,
-                EC_PHASE_2 = 34, EC_N_CASES = 37 };
+                EC_PHASE_2 = 34, EC_HAD = 37, EC_N_CASES = 40 };
 // pair mask of "the w-th other sub-bit is set" / "both other sub-bits set"; phase masks of the special cases
 static const uint32_t kPairMaskC1[2] = {0xAu, 0xCu};
 static const uint32_t kPairMaskC2 = 0x8u;
@@ -206,7 +209,11 @@ struct PlanConfig {
   bool use_tma = true;          // move tiles with TMA (cp.async.bulk.tensor, 128B-swizzle tensor map) when the geometry allows
   bool x_as_moves = false;      // X inside a tile as register moves (exact for non-finite amplitudes too) instead of the
                                 // exact-for-finite 0/1 real 2x2; moves cost more issue slots, the FP64 pipe has slack
-  bool seed_search = true;      // tile-bit choice: also try reserving a slot for a bit the greedy left out
+  bool lookback = true;         // peephole: look back past commuting ops for a fold partner; drop ops that cancel
+  bool keep_real = true;        // peephole: do not fold a non-real phase into a real 2x2 (the complex product costs more)
+  bool unnormalised_h = true;   // Hadamards as add/sub butterflies, the scale folded into another gate of the pass
+  bool seed_search = false;     // tile-bit choice: also try reserving slots for bits the greedy left out (fewer passes, but
+                                // more elementary ops; measured slower on the N=30 circuit: 25 passes 309 ms vs 29 passes 302 ms)
   int groups_per_thread = 1;       // register-resident groups per interpreter decode (1: 3 CTAs/SM, 2: 2 CTAs/SM)
   uint32_t compose_threshold = 8;  // >= this many 2x2 gates in one group: compose them into one 8x8
 };

@@ -33,6 +33,16 @@
                "fma.rn." T " q" P "i" #I0 ", %0, q" P "i" #I0 ", t3;\n\t}" ::C(M00),   \
                C(M01), C(M10), C(M11))
 
+// un-normalised Hadamard butterfly on the pair (I0, I1):  x' = x + y ; y' = x - y
+#define QIP_HAD(T, P, I0, I1)                                                     \
+  asm volatile("{\n\t.reg ." T " t1, t2;\n\t"                                    \
+               "add.rn." T " t1, q" P "r" #I0 ", q" P "r" #I1 ";\n\t"             \
+               "add.rn." T " t2, q" P "i" #I0 ", q" P "i" #I1 ";\n\t"             \
+               "sub.rn." T " q" P "r" #I1 ", q" P "r" #I0 ", q" P "r" #I1 ";\n\t" \
+               "sub.rn." T " q" P "i" #I1 ", q" P "i" #I0 ", q" P "i" #I1 ";\n\t" \
+               "mov." T " q" P "r" #I0 ", t1;\n\t"                                \
+               "mov." T " q" P "i" #I0 ", t2;\n\t}" ::)
+
 // complex 2x2 on the pair (I0, I1); operands %0..%7 = m00r m00i m01r m01i m10r m10i m11r m11i,
 // %8..%11 = -m00i -m01i -m10i -m11i (negated once per op in C++)
 #define QIP_D1C(T, C, P, I0, I1, A, B, Cc, D, E, F, G, H, NB, ND, NF, NH)                \
@@ -148,7 +158,11 @@
         }                                                                                                       \
         /* dispatch: hot shapes first, compare chains (a flat switch is lowered to a balanced compare    \
            tree plus small jump tables whose target load sits on the critical path) */                        \
-        if (id < EC_D1C_FULL) {                                                                                 \
+        if (id >= EC_HAD) { /* Hadamard as an add/sub butterfly, scale folded into another gate by the planner */\
+          if (id == EC_HAD) { _QIP_HAD_U(T, 0, 1) _QIP_HAD_U(T, 2, 3) _QIP_HAD_U(T, 4, 5) _QIP_HAD_U(T, 6, 7) } \
+          else if (id == EC_HAD + 1) { _QIP_HAD_U(T, 0, 2) _QIP_HAD_U(T, 1, 3) _QIP_HAD_U(T, 4, 6) _QIP_HAD_U(T, 5, 7) } \
+          else { _QIP_HAD_U(T, 0, 4) _QIP_HAD_U(T, 1, 5) _QIP_HAD_U(T, 2, 6) _QIP_HAD_U(T, 3, 7) }              \
+        } else if (id < EC_D1C_FULL) {                                                                          \
           _QIP_LOAD_MR                                                                                          \
           if (id == EC_D1R_FULL) { _QIP_D1R_U(T, C, 0, 1) _QIP_D1R_U(T, C, 2, 3) _QIP_D1R_U(T, C, 4, 5) _QIP_D1R_U(T, C, 6, 7) } \
           else if (id == EC_D1R_FULL + 1) { _QIP_D1R_U(T, C, 0, 2) _QIP_D1R_U(T, C, 1, 3) _QIP_D1R_U(T, C, 4, 6) _QIP_D1R_U(T, C, 5, 7) } \
@@ -215,6 +229,9 @@
 // Pair p of sub-bit j = the p-th (ascending) sub-index with bit j clear, and its partner:
 //   j=0: (0,1) (2,3) (4,5) (6,7)   j=1: (0,2) (1,3) (4,6) (5,7)   j=2: (0,4) (1,5) (2,6) (3,7)
 // bit 0 of p <-> the lower of the two other sub-bits, bit 1 of p <-> the higher one.
+#define _QIP_HAD_U(T, i0, i1)     \
+  QIP_HAD(T, "a", i0, i1);        \
+  if (G == 2) QIP_HAD(T, "b", i0, i1);
 #define _QIP_D1R_U(T, C, i0, i1)                                        \
   QIP_D1R(T, C, "a", i0, i1, m00, m01, m10, m11);                       \
   if (G == 2) QIP_D1R(T, C, "b", i0, i1, m00, m01, m10, m11);

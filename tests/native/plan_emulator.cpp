@@ -68,7 +68,7 @@ static void run_elem(const Elem<R> &e, const R *mat8, cd a[8], uint64_t base, co
   const uint32_t id = elem_case(e.op);
   uint32_t mask = (e.op >> 12) & 0xff;
   enum { K_D1, K_X, K_PH, K_PHN, K_D3 } kind;
-  bool real = false;
+  bool real = false, had = false;
   uint32_t j = 0;
   if (id >= EC_D1R_FULL && id < EC_PHASE) {
     kind = K_D1;
@@ -100,10 +100,16 @@ static void run_elem(const Elem<R> &e, const R *mat8, cd a[8], uint64_t base, co
     kind = K_PH;
     if (mask != kPhaseMaskJ[id - EC_PHASE_J]) ++g_decode_errors;
     mask = kPhaseMaskJ[id - EC_PHASE_J];
-  } else if (id >= EC_PHASE_2 && id < EC_N_CASES) {
+  } else if (id >= EC_PHASE_2 && id < EC_HAD) {
     kind = K_PH;
     if (mask != kPhaseMask2[id - EC_PHASE_2]) ++g_decode_errors;
     mask = kPhaseMask2[id - EC_PHASE_2];
+  } else if (id >= EC_HAD && id < EC_N_CASES) {
+    kind = K_D1;
+    real = true;
+    j = id - EC_HAD;
+    if (mask != 0xf || (e.op & kElemHasCond)) ++g_decode_errors;
+    had = true;
   } else if (id == EC_DENSE3) {
     kind = K_D3;
   } else {
@@ -119,7 +125,10 @@ static void run_elem(const Elem<R> &e, const R *mat8, cd a[8], uint64_t base, co
       if (!on) continue;
       const uint32_t i0 = c, i1 = c | (1u << j);
       const cd x = a[i0], y = a[i1];
-      if (real) {
+      if (had) {  // un-normalised butterfly: the record's matrix is not read
+        a[i0] = x + y;
+        a[i1] = x - y;
+      } else if (real) {
         a[i0] = (double)e.m[0] * x + (double)e.m[1] * y;
         a[i1] = (double)e.m[2] * x + (double)e.m[3] * y;
       } else {

@@ -14,7 +14,7 @@ from rustqip_b200 import circuits  # noqa: E402
 from rustqip_b200._abi import QipOp, marshal_ops  # noqa: E402
 
 CASES = {0: "END", 1: "D1R_FULL", 4: "D1C_FULL", 7: "D1R_MASK", 10: "D1C_MASK", 13: "PHASE", 14: "DENSE3",
-         15: "X_FULL", 18: "X_MASK", 21: "PHASEN", 22: "PHASE_J", 25: "D1R_C1", 31: "D1R_C2", 34: "PHASE_2"}
+         15: "X_FULL", 18: "X_MASK", 21: "PHASEN", 22: "PHASE_J", 25: "D1R_C1", 31: "D1R_C2", 34: "PHASE_2", 37: "HAD"}
 
 
 def main():
