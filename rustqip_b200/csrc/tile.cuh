@@ -210,7 +210,8 @@ struct PlanConfig {
   bool x_as_moves = false;      // X inside a tile as register moves (exact for non-finite amplitudes too) instead of the
                                 // exact-for-finite 0/1 real 2x2; moves cost more issue slots, the FP64 pipe has slack
   bool lookback = true;         // peephole: look back past commuting ops for a fold partner; drop ops that cancel
-  bool keep_real = true;        // peephole: do not fold a non-real phase into a real 2x2 (the complex product costs more)
+  bool keep_real = false;       // peephole: do not fold a non-real phase into a real 2x2 (less FP64 work, more elementary ops:
+                                // measured 292 ms vs 289 ms on the N=30 circuit -- the interpreter is issue-bound, not FP64-bound)
   bool unnormalised_h = true;   // Hadamards as add/sub butterflies, the scale folded into another gate of the pass
   bool seed_search = false;     // tile-bit choice: also try reserving slots for bits the greedy left out (fewer passes, but
                                 // more elementary ops; measured slower on the N=30 circuit: 25 passes 309 ms vs 29 passes 302 ms)
