@@ -194,6 +194,24 @@ int qipb200_state_exchange_bytes(qipb200_state *state, uint64_t *bytes);
 int qipb200_plan_exchanges(qip_prec prec, uint32_t n_qubits, int world_size, const qip_op *ops,
                            size_t n_ops, uint32_t *needs_exchange);
 
+/* ---- N3: gate-schedule wire format "QIPS" -----------------------------------------
+ * The reference's only export is OpenQASM 2.0 (qip/src/qasm.rs:112-184), which drops MAT
+ * entries; QIPS carries exactly the `qip_op` records this ABI consumes (byte layout:
+ * rustqip_b200/wire.py, rustqip_b200/csrc/wire.cpp).  Host-only: no GPU, no context.
+ *
+ * parse: builds an owned schedule from `len` bytes; on a malformed buffer returns
+ * QIPB200_ERR_INVALID_ARG with a message in errbuf (may be NULL).  The returned records stay valid
+ * until qipb200_schedule_free and can be passed to qipb200_state_apply_schedule /
+ * qipb200_calculate_state as they are.
+ * serialise: returns the number of bytes the schedule needs and writes them when cap suffices
+ * (call with buf=NULL to size the buffer); 0 on a malformed op tree. */
+typedef struct qipb200_schedule qipb200_schedule;
+int qipb200_schedule_parse(const void *buf, size_t len, qipb200_schedule **out, char *errbuf, size_t errlen);
+const qip_op *qipb200_schedule_ops(const qipb200_schedule *s, size_t *n_ops, uint32_t *n_qubits, qip_prec *prec);
+void qipb200_schedule_free(qipb200_schedule *s);
+size_t qipb200_schedule_serialise(qip_prec prec, uint32_t n_qubits, const qip_op *ops, size_t n_ops, void *buf,
+                                  size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -215,12 +215,40 @@ class B200State {
     ctx_.check(qipb200_state_measure_probs(st_, indices.data(), (uint32_t)indices.size(), out.data()));
     return out;
   }
+  // a schedule parsed from the QIPS wire format (owned by the library): builder.rs:423-514 on foreign circuits
+  void apply_parsed(const qip_op *ops, size_t n_ops, bool fusion = true) {
+    ctx_.check(qipb200_state_apply_schedule(st_, ops, n_ops, fusion ? QIPB200_SCHED_DEFAULT : QIPB200_SCHED_NO_FUSION));
+  }
   qipb200_state *get() const { return st_; }
 
  private:
   Context &ctx_;
   size_t n_;
   qipb200_state *st_ = nullptr;
+};
+
+// ---- QIPS schedule wire format: RAII over qipb200_schedule_parse ------------
+class ParsedSchedule {
+ public:
+  ParsedSchedule(const void *bytes, size_t len) {
+    char err[256];
+    if (qipb200_schedule_parse(bytes, len, &s_, err, sizeof(err)) != QIPB200_OK) throw CircuitError(err);
+    ops_ = qipb200_schedule_ops(s_, &n_ops_, &n_qubits_, &prec_);
+  }
+  ~ParsedSchedule() { qipb200_schedule_free(s_); }
+  ParsedSchedule(const ParsedSchedule &) = delete;
+  ParsedSchedule &operator=(const ParsedSchedule &) = delete;
+  const qip_op *ops() const { return ops_; }
+  size_t size() const { return n_ops_; }
+  uint32_t n_qubits() const { return n_qubits_; }
+  qip_prec prec() const { return prec_; }
+
+ private:
+  qipb200_schedule *s_ = nullptr;
+  const qip_op *ops_ = nullptr;
+  size_t n_ops_ = 0;
+  uint32_t n_qubits_ = 0;
+  qip_prec prec_ = QIP_F64;
 };
 
 }  // namespace qip

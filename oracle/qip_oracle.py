@@ -138,6 +138,18 @@ def apply_op_overwrite(n, op, inp, out, input_offset=0, output_offset=0):
     _apply(n, op, inp, out, input_offset, output_offset, False)
 
 
+def apply_op_raw(n, cop, state, dtype=np.complex128):
+    """apply_op_overwrite for an already marshalled `qip_op` record (e.g. one owned by the product library's
+    schedule parser): returns the new state."""
+    prec = prec_of(dtype)
+    state = np.ascontiguousarray(state.astype(dtype, copy=False))
+    out = np.zeros_like(state)
+    f = lib().qo_apply_op_f64 if prec == QIP_F64 else lib().qo_apply_op_f32
+    if f(n, C.byref(cop), state.ctypes.data, state.shape[0], out.ctypes.data, out.shape[0], 0, 0, 0) != 0:
+        raise ValueError("oracle: malformed op")
+    return out
+
+
 def run_pipeline(n, ops, init_index=0, dtype=np.complex128, state=None):
     """The unitary part of LocalBuilder::calculate_state_with_init (builder.rs:406-514):
     state = e_init; arena = 0; per entry: apply_op_overwrite(state -> arena); swap."""

@@ -31,6 +31,7 @@ EXPORTS = [
     "qipb200_state_measure_prob", "qipb200_state_soft_measure", "qipb200_state_collapse",
     "qipb200_state_new_sharded", "qipb200_state_ipc_export", "qipb200_state_ipc_import",
     "qipb200_state_qubit_map", "qipb200_state_exchange_bytes", "qipb200_plan_exchanges",
+    "qipb200_schedule_parse", "qipb200_schedule_ops", "qipb200_schedule_free", "qipb200_schedule_serialise",
 ]
 
 
@@ -88,6 +89,13 @@ def lib():
     L.qipb200_state_exchange_bytes.argtypes = [vp, C.POINTER(u64)]
     L.qipb200_plan_exchanges.restype = i32
     L.qipb200_plan_exchanges.argtypes = [i32, u32, i32, opp, C.c_size_t, vp]
+    L.qipb200_schedule_parse.restype = i32
+    L.qipb200_schedule_parse.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.c_char_p, C.c_size_t]
+    L.qipb200_schedule_ops.restype = opp
+    L.qipb200_schedule_ops.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(u32), C.POINTER(i32)]
+    L.qipb200_schedule_free.restype, L.qipb200_schedule_free.argtypes = None, [vp]
+    L.qipb200_schedule_serialise.restype = C.c_size_t
+    L.qipb200_schedule_serialise.argtypes = [i32, u32, opp, C.c_size_t, vp, C.c_size_t]
     _lib = L
     return L
 

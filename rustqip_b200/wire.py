@@ -108,6 +108,72 @@ def load_schedule(path: str) -> Tuple[int, type, List[MatrixOp]]:
         return n, dt, [_r_op(f, dt) for _ in range(n_ops)]
 
 
+class ParsedSchedule:
+    """A QIPS buffer parsed by the C ABI (`qipb200_schedule_parse`, rustqip_b200/csrc/wire.cpp): the library owns
+    the `qip_op` records; `State.apply_marshalled(sched.ops, sched.n_ops)` runs them without a Python op tree."""
+
+    def __init__(self, data: bytes):
+        import ctypes as C
+
+        from . import _lib
+
+        L = _lib.lib()
+        self._L = L
+        self._h = C.c_void_p()
+        err = C.create_string_buffer(256)
+        buf = (C.c_ubyte * len(data)).from_buffer_copy(data)
+        st = L.qipb200_schedule_parse(buf, len(data), C.byref(self._h), err, len(err))
+        if st != 0:
+            self._h = None
+            raise CircuitError(err.value.decode("utf-8", "replace") or "malformed QIPS schedule", status=st)
+        n_ops, n, prec = C.c_size_t(), C.c_uint32(), C.c_int()
+        self.ops = L.qipb200_schedule_ops(self._h, C.byref(n_ops), C.byref(n), C.byref(prec))
+        self.n_ops, self.n_qubits, self.prec = n_ops.value, n.value, prec.value
+
+    def serialise(self) -> bytes:
+        import ctypes as C
+
+        need = self._L.qipb200_schedule_serialise(self.prec, self.n_qubits, self.ops, self.n_ops, None, 0)
+        out = (C.c_ubyte * need)()
+        got = self._L.qipb200_schedule_serialise(self.prec, self.n_qubits, self.ops, self.n_ops, out, need)
+        if got != need or need == 0:
+            raise CircuitError("qipb200_schedule_serialise failed")
+        return bytes(out)
+
+    def close(self):
+        if self._h:
+            self._L.qipb200_schedule_free(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        self.close()
+
+
+def serialise_ops(n_qubits: int, ops: Sequence[MatrixOp], dtype=np.complex128) -> bytes:
+    """QIPS bytes written by the C ABI from marshalled `qip_op` records (the writer a Rust/C caller uses)."""
+    import ctypes as C
+
+    from . import _lib
+    from ._abi import marshal_ops
+
+    prec = prec_of(dtype)
+    arr, keep = marshal_ops(ops, prec)
+    L = _lib.lib()
+    need = L.qipb200_schedule_serialise(prec, n_qubits, arr, len(ops), None, 0)
+    if need == 0:
+        raise CircuitError("qipb200_schedule_serialise failed")
+    out = (C.c_ubyte * need)()
+    if L.qipb200_schedule_serialise(prec, n_qubits, arr, len(ops), out, need) != need:
+        raise CircuitError("qipb200_schedule_serialise failed")
+    return bytes(out)
+
+
 def dump_state(path: str, state) -> None:
     """Write this rank's shard of a device-resident `State` (canonical layout)."""
     amps = state.download()

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "qipb200.h")).read()
-    declared = set(re.findall(r"^(?:int|void|uint64_t|const char \*)\s*\*?(qipb200_[a-z0-9_]+)\s*\(", hdr, re.M))
+    declared = set(re.findall(r"^(?:int|void|uint64_t|size_t|const char \*|const qip_op \*)\s*\*?(qipb200_[a-z0-9_]+)\s*\(", hdr, re.M))
     assert declared, "no declarations parsed"
     L = _lib.lib()
     missing = [s for s in sorted(declared) if not hasattr(L, s)]

@@ -67,3 +67,63 @@ def test_schedule_and_state_files_on_device(ctx, tmp_path):
     with State(n, np.complex64, ctx) as st3:
         with pytest.raises(CircuitError, match="does not match"):
             wire.load_state(snap, st3)
+
+
+# ---- the same format through the C ABI (qipb200_schedule_parse / _serialise: no GPU needed) ------------
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_c_abi_reader_and_writer_agree_with_the_python_reference(tmp_path, dtype):
+    n = 6
+    ops = _zoo(n)
+    path = os.path.join(tmp_path, "circuit.qips")
+    wire.dump_schedule(path, n, ops, dtype)
+    data = open(path, "rb").read()
+    assert wire.serialise_ops(n, ops, dtype) == data           # C writer == Python writer, byte for byte
+    with wire.ParsedSchedule(data) as sched:                    # C reader ...
+        assert (sched.n_qubits, sched.n_ops) == (n, len(ops))
+        assert sched.serialise() == data                       # ... loses nothing
+        # the parsed records are valid ops for an n-qubit state (reference constructor checks, in the library)
+        from rustqip_b200 import _lib
+        for i in range(sched.n_ops):
+            assert _lib.lib().qipb200_validate_op(None, sched.prec, n, sched.ops[i]) == 0
+        # and they drive the CPU oracle to the same amplitudes as the Python op tree
+        psi = np.ascontiguousarray((np.arange(1, 65) / 100.0).astype(dtype))
+        want = qo.run_pipeline(n, ops, state=psi, dtype=dtype)
+        got = psi.copy()
+        for i in range(sched.n_ops):
+            got = qo.apply_op_raw(n, sched.ops[i], got, dtype)
+        assert np.array_equal(got, want)
+
+
+def test_c_abi_reader_rejects_malformed_buffers(tmp_path):
+    path = os.path.join(tmp_path, "c.qips")
+    wire.dump_schedule(path, 5, _zoo(5))
+    data = open(path, "rb").read()
+    with pytest.raises(CircuitError, match="QIPS"):
+        wire.ParsedSchedule(b"nonsense-nonsense-nonsense-nonsense")
+    for cut in (3, 23, 30, len(data) // 2, len(data) - 1):
+        with pytest.raises(CircuitError, match="truncated"):
+            wire.ParsedSchedule(data[:cut])
+    with pytest.raises(CircuitError, match="trailing"):
+        wire.ParsedSchedule(data + b"\0")
+    huge = bytearray(data)
+    huge[16:24] = (2 ** 60).to_bytes(8, "little")            # announces 2^60 records
+    with pytest.raises(CircuitError, match="truncated"):
+        wire.ParsedSchedule(bytes(huge))
+    bad_kind = bytearray(data)
+    bad_kind[24] = 9
+    with pytest.raises(CircuitError, match="unknown op kind"):
+        wire.ParsedSchedule(bytes(bad_kind))
+
+
+@pytest.mark.gpu
+def test_c_abi_parsed_schedule_runs_on_device(ctx, tmp_path):
+    from rustqip_b200.state import State
+    n = 11
+    ops = _zoo(n)
+    data = wire.serialise_ops(n, ops)
+    want = qo.run_pipeline(n, ops, 3)
+    with wire.ParsedSchedule(data) as sched, State(n, np.complex128, ctx) as st:
+        st.set_basis(3)
+        st.apply_marshalled(sched.ops, sched.n_ops)
+        got = st.download()
+    assert np.max(np.abs(got - want)) < 1e-10
