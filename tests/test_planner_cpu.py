@@ -132,6 +132,30 @@ def test_planner_condition_table_overflow(emul):
     assert stats[0] == 1 and stats[5] == 63 and stats[4] >= 10  # one pass, full table, the rest on the in-record path
 
 
+@pytest.mark.parametrize("fuse", [True, False])
+def test_planner_unnormalised_hadamards(emul, fuse):
+    """Hadamards run as add/sub butterflies; the pending 1/sqrt(2)^k must end up in exactly one later gate of the
+    pass (a full 2x2, a dense block) or back in the last butterfly -- whatever the rest of the pass looks like."""
+    n, T, Lo = 10, 6, 3
+    rng = np.random.default_rng(41)
+    u2 = rand_unitary(2, rng).reshape(-1)
+    cases = {
+        "only H": [gates.h(q) for q in range(n)],
+        "H then conditional gates only": [gates.h(q) for q in range(n)] + [gates.cnot(0, 9), gates.cz(1, 8), gates.toffoli(2, 3, 7)],
+        "H then a dense block": [gates.h(9), gates.h(8), make_matrix_op([8, 9], u2), gates.h(7)],
+        "H between full gates": [gates.h(9), gates.mat([9], rand_unitary(1, rng).reshape(-1)), gates.h(9), gates.h(8),
+                                 gates.rz(8, 0.3), gates.h(8), gates.x(7), gates.h(7)],
+        "H H cancels": [gates.h(5), gates.h(5), gates.h(4), gates.t(4), gates.h(4)],
+        "controlled H is not a global scale": [make_control_op([0], gates.h(9)), gates.h(9), make_control_op([8], gates.h(9))],
+    }
+    for name, ops in cases.items():
+        psi = rand_state(n, 42)
+        want = qo.run_pipeline(n, ops, state=psi)
+        for dtype, tol in ((np.complex128, 1e-12), (np.complex64, 5e-6)):
+            got, _ = run_emul(emul, n, ops, psi, dtype=dtype, T=T, Lo=Lo, fuse=fuse)
+            assert np.max(np.abs(got - want)) < tol, name
+
+
 def test_planner_f32_data_path(emul):
     n = 9
     ops = mixed_circuit(n, 80, 99)
