@@ -451,6 +451,21 @@ struct Emitter {
           }
         if (!placed) packed.push_back(out[i]);
       }
+      if (cfg->fill_on_flush && !all) {
+        // A super-op that leaves with spare bits takes open groups that nothing forces out yet along for the
+        // ride (disjoint bits commute; their later ops simply start a new group): their current ops cost no
+        // shared-memory round trip of their own.
+        for (size_t j = 0; j < packed.size(); ++j)
+          for (size_t i = 0; i < open.size() && popc(packed[j].mask) < 3;) {
+            if (popc(packed[j].mask | open[i].mask) <= 3) {
+              packed[j].mask |= open[i].mask;
+              packed[j].elems.insert(packed[j].elems.end(), open[i].elems.begin(), open[i].elems.end());
+              open.erase(open.begin() + (long)i);
+            } else {
+              ++i;
+            }
+          }
+      }
       out.swap(packed);
     }
     for (size_t i = 0; i < out.size(); ++i) emit_group(out[i]);
@@ -850,6 +865,7 @@ PlanConfig default_plan_config(qip_prec prec, uint32_t n_local) {
   if (const char *e = getenv("QIPB200_NO_HAD")) c.unnormalised_h = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_KEEP_REAL")) c.keep_real = atoi(e) != 0;
   if (const char *e = getenv("QIPB200_NO_LOOKBACK")) c.lookback = atoi(e) == 0;
+  if (const char *e = getenv("QIPB200_NO_FILL")) c.fill_on_flush = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_X_MOVES")) c.x_as_moves = atoi(e) != 0;
   if (const char *e = getenv("QIPB200_NO_PHASEN")) c.fold_cond_phases = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_NO_TMA")) c.use_tma = atoi(e) == 0;

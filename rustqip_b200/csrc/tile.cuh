@@ -209,6 +209,7 @@ struct PlanConfig {
   bool use_tma = true;          // move tiles with TMA (cp.async.bulk.tensor, 128B-swizzle tensor map) when the geometry allows
   bool x_as_moves = false;      // X inside a tile as register moves (exact for non-finite amplitudes too) instead of the
                                 // exact-for-finite 0/1 real 2x2; moves cost more issue slots, the FP64 pipe has slack
+  bool fill_on_flush = true;    // a super-op leaving with spare bits takes small open groups along
   bool lookback = true;         // peephole: look back past commuting ops for a fold partner; drop ops that cancel
   bool keep_real = false;       // peephole: do not fold a non-real phase into a real 2x2 (less FP64 work, more elementary ops:
                                 // measured 292 ms vs 289 ms on the N=30 circuit -- the interpreter is issue-bound, not FP64-bound)

@@ -3,6 +3,8 @@
 // host logic (planner.cpp, opcompile.cpp, serialisation) is validated without a GPU.
 // Built by tests/test_planner_cpu.py into tests/native/_build/; never part of libqipb200.
 #include <complex>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -361,6 +363,14 @@ extern "C" int emul_plan_stats(int prec, uint32_t n, const qip_op *ops, size_t n
     ++n_pass;
     n_micro += steps[s].pass.ops.size();
     n_gates_in_pass += steps[s].pass.n_gates;
+    if (getenv("PLAN_TRACE")) {  // one line per pass: gates, then each micro-op as bits:elems
+      fprintf(stderr, "pass %2llu: %3u gates |", (unsigned long long)n_pass, steps[s].pass.n_gates);
+      for (size_t i = 0; i < steps[s].pass.ops.size(); ++i) {
+        const MicroOp &mo = steps[s].pass.ops[i].h;
+        fprintf(stderr, " {%u,%u,%u}:%u", mo.ins_pos[0], mo.ins_pos[1], mo.ins_pos[2], mo.nterms);
+      }
+      fprintf(stderr, "\n");
+    }
     for (size_t i = 0; i < steps[s].pass.ops.size(); ++i) {
       const MicroOp &mo = steps[s].pass.ops[i].h;
       if (mo.kind == MK_DENSE) dense_k[mo.k]++;
