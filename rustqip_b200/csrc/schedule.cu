@@ -51,7 +51,7 @@ int execute_steps(qipb200_state *s, const std::vector<PlanStep> &steps, const st
         break;
       }
       cudaError_t e = launch_tile_pass(s->prec, s->buf, s->n_local, *pp, cfg.groups_per_thread, cfg.use_tma, ctx->stream,
-                                       &ctx->launches);
+                                       &ctx->launches, cfg.kernel_variant);
       if (e != cudaSuccess) st = report_cuda_error(s, e, "launch_tile_pass");
       ++ctx->tile_launches;
       ctx->fused_gates += steps[i].pass.n_gates;

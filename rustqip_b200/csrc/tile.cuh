@@ -216,6 +216,7 @@ struct PlanConfig {
   bool unnormalised_h = true;   // Hadamards as add/sub butterflies, the scale folded into another gate of the pass
   bool seed_search = false;     // tile-bit choice: also try reserving slots for bits the greedy left out (fewer passes, but
                                 // more elementary ops; measured slower on the N=30 circuit: 25 passes 309 ms vs 29 passes 302 ms)
+  int kernel_variant = 0;          // compile-time experiments of the tile kernel (tile_kernel.cu, template parameter V)
   int groups_per_thread = 1;       // register-resident groups per interpreter decode (1: 3 CTAs/SM, 2: 2 CTAs/SM)
   uint32_t compose_threshold = 8;  // >= this many 2x2 gates in one group: compose them into one 8x8
 };

@@ -183,7 +183,12 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap *map, uint32_t sr
                : "memory");
 }
 
-template <typename R, int G>
+// VAR selects compile-time experiments (QIPB200_TILE_VARIANT; 0 is the measured default, its code does not
+// depend on the others):
+//   VAR & 1: keep the shared-window base in an opaque register (r1o: `S2R SR_CgaCtaId` re-materialised per group, 2.3 %)
+//   VAR & 2: touch the next micro-op's header and first records before the barrier that precedes them
+//          (r1o: 6.8 % of the warp time on the constant-cache miss of that first read)
+template <typename R, int G, int VAR>
 __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
     k_tile_pass(R *__restrict__ psi, const __grid_constant__ PassParams pp, const __grid_constant__ CUtensorMap tmap) {
   typedef typename C2<R>::type V;
@@ -212,7 +217,9 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
   constexpr uint32_t kLow3 = sizeof(R) == 8 ? 3 : 4;  // index bits covered by one 128-byte row
   const uint32_t units = tile_bytes >> 4;
   const uint32_t lmask = (1u << L) - 1u;
-  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+  uint32_t smem_base_v = (uint32_t)__cvta_generic_to_shared(smem);
+  if constexpr ((VAR & 1) != 0) asm volatile("" : "+r"(smem_base_v));
+  const uint32_t smem_base = smem_base_v;
   const bool use_tma = h->use_tma != 0;
   const uint32_t mbar = smem_base + tile_bytes + kMaxPhasen * 16;
   const uint32_t n_boxes = 1u << (m - 3);           // only meaningful with use_tma (m >= 3)
@@ -297,6 +304,13 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
     const MicroOp *mo = reinterpret_cast<const MicroOp *>(rec);
     const unsigned char *data = rec + sizeof(MicroOp);
     rec = data + mo->data_bytes;
+    if constexpr ((VAR & 2) != 0) {
+      if (i + 1 < n_ops) {  // bring the next header and the start of its records into the constant cache now
+        const uint32_t *nx = reinterpret_cast<const uint32_t *>(rec);
+        const uint32_t touch = nx[0] ^ nx[16] ^ nx[32] ^ nx[48];  // 0, 64, 128, 192 bytes in (header + END always exist)
+        asm volatile("" ::"r"(touch));
+      }
+    }
     if ((base & mo->gmask) == mo->gmask) {
       if (mo->kind == MK_SUPER) {
         if constexpr (sizeof(R) == 8)
@@ -378,10 +392,14 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
 
 cudaError_t tile_pass_configure() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(k_tile_pass<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_tile_pass<double, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_tile_pass<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_tile_pass<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  const void *fns[] = {(const void *)k_tile_pass<double, 1, 0>, (const void *)k_tile_pass<double, 2, 0>,
+                       (const void *)k_tile_pass<float, 1, 0>,  (const void *)k_tile_pass<float, 2, 0>,
+                       (const void *)k_tile_pass<double, 1, 1>, (const void *)k_tile_pass<double, 1, 2>,
+                       (const void *)k_tile_pass<double, 1, 3>, (const void *)k_tile_pass<float, 1, 1>,
+                       (const void *)k_tile_pass<float, 1, 2>,  (const void *)k_tile_pass<float, 1, 3>};
+  for (const void *f : fns)
+    if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
+  return cudaSuccess;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -422,8 +440,23 @@ static bool make_tile_map(CUtensorMap *map, qip_prec prec, void *psi, uint32_t n
   return r == CUDA_SUCCESS;
 }
 
+template <typename R>
+static void launch_variant(int groups_per_thread, int variant, unsigned grid, size_t smem, cudaStream_t s, R *psi,
+                           const PassParams &pp, const CUtensorMap &tmap) {
+  if (groups_per_thread != 1) {
+    k_tile_pass<R, 2, 0><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap);
+    return;
+  }
+  switch (variant) {
+    case 1: k_tile_pass<R, 1, 1><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
+    case 2: k_tile_pass<R, 1, 2><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
+    case 3: k_tile_pass<R, 1, 3><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
+    default: k_tile_pass<R, 1, 0><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
+  }
+}
+
 cudaError_t launch_tile_pass(qip_prec prec, void *psi, uint32_t n_local, PassParams &pp, int groups_per_thread,
-                             bool use_tma, cudaStream_t s, uint64_t *launches) {
+                             bool use_tma, cudaStream_t s, uint64_t *launches, int variant) {
   const uint32_t T = pp.h.T;
   alignas(64) CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
@@ -431,17 +464,10 @@ cudaError_t launch_tile_pass(qip_prec prec, void *psi, uint32_t n_local, PassPar
   // tile | EC_PHASEN factor table | mbarrier | condition word
   const size_t smem = ((size_t)(prec == QIP_F32 ? 8u : 16u) << T) + kMaxPhasen * 16 + 32;
   const unsigned grid = 1u << (n_local - T);
-  if (prec == QIP_F32) {
-    if (groups_per_thread == 1)
-      k_tile_pass<float, 1><<<grid, kTileThreads, smem, s>>>((float *)psi, pp, tmap);
-    else
-      k_tile_pass<float, 2><<<grid, kTileThreads, smem, s>>>((float *)psi, pp, tmap);
-  } else {
-    if (groups_per_thread == 1)
-      k_tile_pass<double, 1><<<grid, kTileThreads, smem, s>>>((double *)psi, pp, tmap);
-    else
-      k_tile_pass<double, 2><<<grid, kTileThreads, smem, s>>>((double *)psi, pp, tmap);
-  }
+  if (prec == QIP_F32)
+    launch_variant<float>(groups_per_thread, variant, grid, smem, s, (float *)psi, pp, tmap);
+  else
+    launch_variant<double>(groups_per_thread, variant, grid, smem, s, (double *)psi, pp, tmap);
   ++*launches;
   return cudaGetLastError();
 }
