@@ -66,6 +66,7 @@ bool parse_op(Reader &r, qipb200_schedule *s, size_t amp, qip_op *out, uint32_t 
   if (!r.get(&kind) || !r.get(&n_idx) || !r.get(&n_ctrl)) return fail(err, "schedule truncated (op header)");
   if (kind > QIP_OP_CONTROL) return fail(err, "schedule: unknown op kind");
   if (n_idx > kMaxIndices) return fail(err, "schedule: too many indices in one op");
+  if (kind != QIP_OP_CONTROL && n_ctrl != 0) return fail(err, "schedule: control count on an op that is not a Control");
   memset(out, 0, sizeof(*out));
   out->kind = kind;
   out->n_indices = n_idx;
