@@ -93,6 +93,23 @@ def test_planner_matches_oracle_mixed(emul, n, T, Lo, fuse):
     assert stats[0] > 0  # passes were actually produced
 
 
+@pytest.mark.parametrize("knobs", [
+    {"QIPB200_SEED_SEARCH": "1"}, {"QIPB200_KEEP_REAL": "1"}, {"QIPB200_NO_HAD": "1"}, {"QIPB200_NO_LOOKBACK": "1"},
+    {"QIPB200_NO_FILL": "1"}, {"QIPB200_NO_PEEPHOLE": "1"}, {"QIPB200_NO_PHASEN": "1"}, {"QIPB200_X_MOVES": "1"},
+    {"QIPB200_COMPOSE": "3"}, {"QIPB200_SEED_SEARCH": "1", "QIPB200_KEEP_REAL": "1", "QIPB200_NO_FILL": "1"},
+])
+def test_planner_knobs_keep_parity(emul, monkeypatch, knobs):
+    """Every planner switch (read from the environment at plan time) must leave the amplitudes alone."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    for n, T, Lo, seed in [(10, 7, 3, 5), (9, 6, 2, 6)]:
+        ops = mixed_circuit(n, 100, 2000 + seed) + circuits.random_circuit(n, 6, 90 + seed, "H,T,CNOT") + circuits.qft(n)[:30]
+        psi = rand_state(n, seed)
+        want = qo.run_pipeline(n, ops, state=psi)
+        got, stats = run_emul(emul, n, ops, psi, T=T, Lo=Lo)
+        assert np.max(np.abs(got - want)) < 1e-12, knobs
+
+
 def test_planner_random_and_qft(emul):
     for n, T, Lo in [(10, 6, 3), (12, 8, 3)]:
         ops = circuits.random_circuit(n, 8, 77, "H,T,CNOT") + circuits.random_circuit(n, 4, 78, "H,CZ,CNOT")
