@@ -186,8 +186,9 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap *map, uint32_t sr
 // VAR selects compile-time experiments (QIPB200_TILE_VARIANT; 0 is the measured default, its code does not
 // depend on the others):
 //   VAR & 1: keep the shared-window base in an opaque register (r1o: `S2R SR_CgaCtaId` re-materialised per group, 2.3 %)
-//   VAR & 2: touch the next micro-op's header and first records before the barrier that precedes them
-//          (r1o: 6.8 % of the warp time on the constant-cache miss of that first read)
+//   VAR & 2: touch the next micro-op's header and first records before the barrier that precedes them (the
+//          first read after the barrier carries 6.8 % of the r1o samples; their stall reason is the barrier
+//          itself, so this only helps if a cold constant line hides behind it)
 template <typename R, int G, int VAR>
 __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
     k_tile_pass(R *__restrict__ psi, const __grid_constant__ PassParams pp, const __grid_constant__ CUtensorMap tmap) {
