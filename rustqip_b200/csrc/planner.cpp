@@ -859,7 +859,7 @@ PlanConfig default_plan_config(qip_prec prec, uint32_t n_local) {
   if (const char *e = getenv("QIPB200_TILE_L")) c.L = (uint32_t)atoi(e);
   if (const char *e = getenv("QIPB200_COMPOSE")) c.compose_threshold = (uint32_t)std::max(1, atoi(e));
   if (const char *e = getenv("QIPB200_TILE_G")) c.groups_per_thread = atoi(e) == 2 ? 2 : 1;
-  if (const char *e = getenv("QIPB200_TILE_VARIANT")) c.kernel_variant = atoi(e) & 3;
+  if (const char *e = getenv("QIPB200_TILE_VARIANT")) c.kernel_variant = atoi(e) & 7;
   if (const char *e = getenv("QIPB200_NO_BLOCK_FUSION")) c.fuse_blocks = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_NO_PEEPHOLE")) c.peephole = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_SEED_SEARCH")) c.seed_search = atoi(e) != 0;

@@ -186,6 +186,8 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap *map, uint32_t sr
 // VAR selects compile-time experiments (QIPB200_TILE_VARIANT; 0 is the measured default, its code does not
 // depend on the others):
 //   VAR & 1: keep the shared-window base in an opaque register (r1o: `S2R SR_CgaCtaId` re-materialised per group, 2.3 %)
+//   VAR & 4: next descriptor word loaded one elementary op ahead through an opaque register (r1o: 9 % of the
+//          samples wait on the `LDC` of the op word; the compiler re-materialises the plain C++ prefetch at its use)
 //   VAR & 2: touch the next micro-op's header and first records before the barrier that precedes them (the
 //          first read after the barrier carries 6.8 % of the r1o samples; their stall reason is the barrier
 //          itself, so this only helps if a cold constant line hides behind it)
@@ -201,6 +203,7 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
     QIP_DECL_GROUP("f32", "a");
     if (G == 2) QIP_DECL_GROUP("f32", "b");
   }
+  if constexpr ((VAR & 4) != 0) QIP_DECL_OPWORD();
   extern __shared__ __align__(1024) unsigned char smem[];
   const PassHeader *h = &pp.h;
   const uint32_t T = h->T, L = h->L, m = h->m, n_ops = h->n_ops;
@@ -300,6 +303,8 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
   const uint64_t condbits = (uint64_t)condw[0] | ((uint64_t)condw[1] << 32);
 
   // ---- 2. apply ----
+  uint64_t recs_param = 0;  // VAR & 4: param-space address of pp.recs (ld.param from inline asm)
+  if constexpr ((VAR & 4) != 0) asm volatile("cvta.to.param.u64 %0, %1;" : "=l"(recs_param) : "l"(pp.recs));
   const unsigned char *rec = pp.recs;
   for (uint32_t i = 0; i < n_ops; ++i) {
     const MicroOp *mo = reinterpret_cast<const MicroOp *>(rec);
@@ -315,9 +320,11 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
     if ((base & mo->gmask) == mo->gmask) {
       if (mo->kind == MK_SUPER) {
         if constexpr (sizeof(R) == 8)
-          run_super_f64<G>(smem_base, mo, data, base, reinterpret_cast<const double *>(tbl), condbits);
+          run_super_f64<G, (VAR & 4) != 0>(smem_base, mo, data, base, reinterpret_cast<const double *>(tbl), condbits,
+                                           (uint32_t)recs_param + (uint32_t)(data - pp.recs));
         else
-          run_super_f32<G>(smem_base, mo, data, base, reinterpret_cast<const float *>(tbl), condbits);
+          run_super_f32<G, (VAR & 4) != 0>(smem_base, mo, data, base, reinterpret_cast<const float *>(tbl), condbits,
+                                           (uint32_t)recs_param + (uint32_t)(data - pp.recs));
       } else if (mo->kind == MK_DENSE) {
         const R *mat = reinterpret_cast<const R *>(data);
         if (mo->k == 1)
@@ -397,7 +404,9 @@ cudaError_t tile_pass_configure() {
                        (const void *)k_tile_pass<float, 1, 0>,  (const void *)k_tile_pass<float, 2, 0>,
                        (const void *)k_tile_pass<double, 1, 1>, (const void *)k_tile_pass<double, 1, 2>,
                        (const void *)k_tile_pass<double, 1, 3>, (const void *)k_tile_pass<float, 1, 1>,
-                       (const void *)k_tile_pass<float, 1, 2>,  (const void *)k_tile_pass<float, 1, 3>};
+                       (const void *)k_tile_pass<float, 1, 2>,  (const void *)k_tile_pass<float, 1, 3>,
+                       (const void *)k_tile_pass<double, 1, 4>, (const void *)k_tile_pass<double, 1, 7>,
+                       (const void *)k_tile_pass<float, 1, 4>,  (const void *)k_tile_pass<float, 1, 7>};
   for (const void *f : fns)
     if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
   return cudaSuccess;
@@ -452,6 +461,8 @@ static void launch_variant(int groups_per_thread, int variant, unsigned grid, si
     case 1: k_tile_pass<R, 1, 1><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
     case 2: k_tile_pass<R, 1, 2><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
     case 3: k_tile_pass<R, 1, 3><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
+    case 4: k_tile_pass<R, 1, 4><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
+    case 7: k_tile_pass<R, 1, 7><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
     default: k_tile_pass<R, 1, 0><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
   }
 }
