@@ -113,7 +113,7 @@ struct alignas(16) MicroOp {
   uint32_t groups_log2;  // T - ins_n
   uint32_t nterms;       // diag terms / super elems
   uint32_t data_bytes;   // bytes of data following the header
-  uint32_t pad0;
+  uint32_t pad0;         // super: 1 when every record's case id is covered by the PTX record loop (tile_interp_ptx.cuh)
   uint64_t gmask;        // control bits outside the tile: tested against the tile's base index
   uint64_t pad1[3];
   uint32_t soff[8];      // super: SWIZZLED shared-memory BYTE offset of sub-index u (the XOR swizzle is GF(2)-linear,

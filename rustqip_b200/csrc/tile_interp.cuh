@@ -114,8 +114,8 @@
 // elementary ops are dispatched by ONE jump on the host-computed case id; every frequent shape
 // (full 2x2, 2x2 under one/two in-group controls, phase on one/two sub-bits) is straight-line
 // code without mask tests.
-#define QIP_DEFINE_RUN_SUPER(NAME, R, T, C, CO, SWZ, ESHIFT)                                                     \
-  template <int G, int PF>                                                                                      \
+#define QIP_DEFINE_RUN_SUPER(NAME, R, T, C, CO, SWZ, ESHIFT, PTXFN)                                              \
+  template <int G, int PF, int PX>                                                                              \
   __device__ __forceinline__ void NAME(uint32_t tile_saddr, const MicroOp *mo, const unsigned char *data,      \
                                        uint64_t base, const R *tbl, uint64_t condbits, uint32_t data_param) {   \
     typedef R QipReal;                                                                                          \
@@ -139,6 +139,9 @@
         QIP_LD(T, "b", 0, ab[0]); QIP_LD(T, "b", 1, ab[1]); QIP_LD(T, "b", 2, ab[2]); QIP_LD(T, "b", 3, ab[3]); \
         QIP_LD(T, "b", 4, ab[4]); QIP_LD(T, "b", 5, ab[5]); QIP_LD(T, "b", 6, ab[6]); QIP_LD(T, "b", 7, ab[7]); \
       }                                                                                                         \
+      if (PX && G == 1 && mo->pad0) { /* experiment: the whole record loop as one PTX block */                  \
+        PTXFN(data_param, condbits, base, (uint32_t)__cvta_generic_to_shared(tbl));                             \
+      } else {                                                                                                  \
       const unsigned char *ep = data;                                                                           \
       uint32_t pe = data_param; /* PF: the same position as a PARAM-space address (for ld.param in asm) */      \
       uint32_t op_next = 0;                                                                                     \
@@ -230,6 +233,7 @@
           }                                                                                                     \
         }                                                                                                       \
       }                                                                                                         \
+      } /* !PX */                                                                                               \
       QIP_ST(T, "a", 0, aa[0]); QIP_ST(T, "a", 1, aa[1]); QIP_ST(T, "a", 2, aa[2]); QIP_ST(T, "a", 3, aa[3]);   \
       QIP_ST(T, "a", 4, aa[4]); QIP_ST(T, "a", 5, aa[5]); QIP_ST(T, "a", 6, aa[6]); QIP_ST(T, "a", 7, aa[7]);   \
       if (two) {                                                                                                \

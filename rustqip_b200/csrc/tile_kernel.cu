@@ -23,6 +23,7 @@
 #include "tile.cuh"
 #include "tile_launch.cuh"
 #include "tile_interp.cuh"
+#include "tile_interp_ptx.cuh"
 
 #include <cstring>
 
@@ -68,8 +69,10 @@ __device__ __forceinline__ uint32_t expand_local(uint32_t g, const MicroOp *mo) 
 __device__ __forceinline__ uint32_t swz_d(uint32_t t) { return t ^ ((t >> 3) & 7u); }
 __device__ __forceinline__ uint32_t swz_f(uint32_t t) { return t ^ (((t >> 4) & 7u) << 1); }
 
-QIP_DEFINE_RUN_SUPER(run_super_f64, double, "f64", QIP_CD, QIP_COD, swz_d, 4)
-QIP_DEFINE_RUN_SUPER(run_super_f32, float, "f32", QIP_CF, QIP_COF, swz_f, 3)
+QIP_DEFINE_RUN_ELEMS_PTX(run_elems_ptx_f64, "f64", "32", "40", "48", "56", "64", "72", "80", "88", "16")
+QIP_DEFINE_RUN_ELEMS_PTX(run_elems_ptx_f32, "f32", "32", "36", "40", "44", "48", "52", "56", "60", "8")
+QIP_DEFINE_RUN_SUPER(run_super_f64, double, "f64", QIP_CD, QIP_COD, swz_d, 4, run_elems_ptx_f64)
+QIP_DEFINE_RUN_SUPER(run_super_f32, float, "f32", QIP_CF, QIP_COF, swz_f, 3, run_elems_ptx_f32)
 
 // ---- wide micro-ops (more than 3 involved bits): rare -----------------------------------
 template <typename R, int K>
@@ -188,6 +191,8 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap *map, uint32_t sr
 //   VAR & 1: keep the shared-window base in an opaque register (r1o: `S2R SR_CgaCtaId` re-materialised per group, 2.3 %)
 //   VAR & 4: next descriptor word loaded one elementary op ahead through an opaque register (r1o: 9 % of the
 //          samples wait on the `LDC` of the op word; the compiler re-materialises the plain C++ prefetch at its use)
+//   VAR & 8: the record loop of a super-op as one PTX block with `brx.idx` dispatch (tile_interp_ptx.cuh), for the
+//          super-ops the planner marked (MicroOp::pad0)
 //   VAR & 2: touch the next micro-op's header and first records before the barrier that precedes them (the
 //          first read after the barrier carries 6.8 % of the r1o samples; their stall reason is the barrier
 //          itself, so this only helps if a cold constant line hides behind it)
@@ -304,7 +309,7 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
 
   // ---- 2. apply ----
   uint64_t recs_param = 0;  // VAR & 4: param-space address of pp.recs (ld.param from inline asm)
-  if constexpr ((VAR & 4) != 0) asm volatile("cvta.to.param.u64 %0, %1;" : "=l"(recs_param) : "l"(pp.recs));
+  if constexpr ((VAR & 12) != 0) asm volatile("cvta.to.param.u64 %0, %1;" : "=l"(recs_param) : "l"(pp.recs));
   const unsigned char *rec = pp.recs;
   for (uint32_t i = 0; i < n_ops; ++i) {
     const MicroOp *mo = reinterpret_cast<const MicroOp *>(rec);
@@ -320,10 +325,10 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
     if ((base & mo->gmask) == mo->gmask) {
       if (mo->kind == MK_SUPER) {
         if constexpr (sizeof(R) == 8)
-          run_super_f64<G, (VAR & 4) != 0>(smem_base, mo, data, base, reinterpret_cast<const double *>(tbl), condbits,
+          run_super_f64<G, (VAR & 4) != 0, (VAR & 8) != 0>(smem_base, mo, data, base, reinterpret_cast<const double *>(tbl), condbits,
                                            (uint32_t)recs_param + (uint32_t)(data - pp.recs));
         else
-          run_super_f32<G, (VAR & 4) != 0>(smem_base, mo, data, base, reinterpret_cast<const float *>(tbl), condbits,
+          run_super_f32<G, (VAR & 4) != 0, (VAR & 8) != 0>(smem_base, mo, data, base, reinterpret_cast<const float *>(tbl), condbits,
                                            (uint32_t)recs_param + (uint32_t)(data - pp.recs));
       } else if (mo->kind == MK_DENSE) {
         const R *mat = reinterpret_cast<const R *>(data);
@@ -406,7 +411,9 @@ cudaError_t tile_pass_configure() {
                        (const void *)k_tile_pass<double, 1, 3>, (const void *)k_tile_pass<float, 1, 1>,
                        (const void *)k_tile_pass<float, 1, 2>,  (const void *)k_tile_pass<float, 1, 3>,
                        (const void *)k_tile_pass<double, 1, 4>, (const void *)k_tile_pass<double, 1, 7>,
-                       (const void *)k_tile_pass<float, 1, 4>,  (const void *)k_tile_pass<float, 1, 7>};
+                       (const void *)k_tile_pass<float, 1, 4>,  (const void *)k_tile_pass<float, 1, 7>,
+                       (const void *)k_tile_pass<double, 1, 8>, (const void *)k_tile_pass<double, 1, 9>,
+                       (const void *)k_tile_pass<float, 1, 8>,  (const void *)k_tile_pass<float, 1, 9>};
   for (const void *f : fns)
     if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
   return cudaSuccess;
@@ -463,6 +470,8 @@ static void launch_variant(int groups_per_thread, int variant, unsigned grid, si
     case 3: k_tile_pass<R, 1, 3><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
     case 4: k_tile_pass<R, 1, 4><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
     case 7: k_tile_pass<R, 1, 7><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
+    case 8: k_tile_pass<R, 1, 8><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
+    case 9: k_tile_pass<R, 1, 9><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
     default: k_tile_pass<R, 1, 0><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
   }
 }
