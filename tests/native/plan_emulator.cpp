@@ -342,6 +342,86 @@ extern "C" int emul_schedule(int prec, uint32_t n, const qip_op *ops, size_t n_o
   return 0;
 }
 
+// The epoch loop of a sharded state (schedule.cu: run_fused) without the sharding: ops whose non-diagonal bits
+// touch `remote_bits` are BLOCKED (as if a rank index held those qubits); each epoch plans and runs what may
+// run, then "migrates" for the first blocked op that is left (here: simply unblocks it) and starts over.
+// Validates the commutation rules of plan_passes(blocked, leftover, dep) on one address space.
+extern "C" int emul_schedule_blocked(int prec, uint32_t n, const qip_op *ops, size_t n_ops, double *state, uint32_t T,
+                                     uint32_t L, uint64_t remote_bits, uint64_t *stats, char *errbuf, size_t errlen) {
+  std::vector<FlatOp> flat(n_ops);
+  std::vector<DepMasks> dep_all(n_ops);
+  std::vector<char> blocked_all(n_ops, 0);
+  for (size_t i = 0; i < n_ops; ++i) {
+    std::string err;
+    int st = compile_op(&ops[i], (qip_prec)prec, n, &flat[i], &err);
+    if (st != QIPB200_OK) {
+      if (errbuf && errlen) snprintf(errbuf, errlen, "%s", err.c_str());
+      return st;
+    }
+    op_dependency_masks(flat[i], &dep_all[i]);
+    blocked_all[i] = (dep_all[i].nd & remote_bits) ? 1 : 0;
+  }
+  PlanConfig cfg = default_plan_config((qip_prec)prec, n);
+  if (T) cfg.T = T;
+  if (L) cfg.L = L;
+  g_decode_errors = 0;
+  std::vector<cd> psi(1ull << n);
+  for (uint64_t i = 0; i < (1ull << n); ++i) psi[i] = cd(state[2 * i], state[2 * i + 1]);
+  std::vector<size_t> remaining(n_ops);
+  for (size_t i = 0; i < n_ops; ++i) remaining[i] = i;
+  uint64_t epochs = 0, n_pass = 0;
+  while (!remaining.empty()) {
+    ++epochs;
+    std::vector<FlatOp> local(remaining.size());
+    std::vector<char> blocked(remaining.size());
+    std::vector<DepMasks> dep(remaining.size());
+    for (size_t r = 0; r < remaining.size(); ++r) {
+      local[r] = flat[remaining[r]];
+      blocked[r] = blocked_all[remaining[r]];
+      dep[r] = dep_all[remaining[r]];
+    }
+    std::vector<PlanStep> steps;
+    std::vector<size_t> left;
+    plan_passes(local, n, (qip_prec)prec, cfg, &steps, &blocked, &left, &dep);
+    for (size_t s = 0; s < steps.size(); ++s) {
+      if (steps[s].is_pass) {
+        PassParams pp;
+        if (!serialise_pass(steps[s].pass, &pp)) return -2;
+        if (prec == QIP_F32)
+          run_pass_params<float>(pp, n, psi);
+        else
+          run_pass_params<double>(pp, n, psi);
+        ++n_pass;
+      } else {
+        if (blocked[steps[s].op_index]) return -4;  // a blocked op must never be scheduled
+        apply_single(local[steps[s].op_index], n, psi);
+      }
+    }
+    if (left.empty()) break;
+    size_t first_blocked = left.size();
+    for (size_t i = 0; i < left.size(); ++i)
+      if (blocked[left[i]]) {
+        first_blocked = i;
+        break;
+      }
+    if (first_blocked == left.size()) return -5;  // no progress and nothing to migrate for
+    blocked_all[remaining[left[first_blocked]]] = 0;
+    std::vector<size_t> next;
+    for (size_t i = 0; i < left.size(); ++i) next.push_back(remaining[left[i]]);
+    remaining.swap(next);
+  }
+  for (uint64_t i = 0; i < (1ull << n); ++i) {
+    state[2 * i] = psi[i].real();
+    state[2 * i + 1] = psi[i].imag();
+  }
+  if (stats) {
+    stats[0] = n_pass;
+    stats[1] = epochs;
+  }
+  if (g_decode_errors) return -3;
+  return 0;
+}
+
 // plan only (no amplitudes): pass / single-step counts for big circuits
 extern "C" int emul_plan_stats(int prec, uint32_t n, const qip_op *ops, size_t n_ops, uint32_t T, uint32_t L,
                                int fuse_blocks, uint32_t max_k, uint64_t *stats) {

@@ -34,6 +34,9 @@ def emul():
     L.emul_schedule.restype = C.c_int
     L.emul_schedule.argtypes = [C.c_int, C.c_uint32, C.POINTER(QipOp), C.c_size_t, C.c_void_p, C.c_uint32,
                                 C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_char_p, C.c_size_t]
+    L.emul_schedule_blocked.restype = C.c_int
+    L.emul_schedule_blocked.argtypes = [C.c_int, C.c_uint32, C.POINTER(QipOp), C.c_size_t, C.c_void_p, C.c_uint32,
+                                        C.c_uint32, C.c_uint64, C.c_void_p, C.c_char_p, C.c_size_t]
     L.emul_plan_stats.restype = C.c_int
     L.emul_plan_stats.argtypes = [C.c_int, C.c_uint32, C.POINTER(QipOp), C.c_size_t, C.c_uint32, C.c_uint32,
                                   C.c_int, C.c_uint32, C.c_void_p]
@@ -171,6 +174,25 @@ def test_planner_unnormalised_hadamards(emul, fuse):
         for dtype, tol in ((np.complex128, 1e-12), (np.complex64, 5e-6)):
             got, _ = run_emul(emul, n, ops, psi, dtype=dtype, T=T, Lo=Lo, fuse=fuse)
             assert np.max(np.abs(got - want)) < tol, name
+
+
+@pytest.mark.parametrize("n,T,Lo,remote", [(10, 6, 3, 0b11 << 8), (11, 7, 3, 0b111 << 8), (9, 6, 2, 1 << 8)])
+def test_planner_epochs_with_blocked_ops(emul, n, T, Lo, remote):
+    """The epoch loop of a sharded state on one address space: ops that act non-diagonally on the `remote` index
+    bits are blocked until 'their' migration; everything that overtakes them must commute with them."""
+    for seed in (1, 2, 3):
+        ops = mixed_circuit(n, 90, 3000 + seed) + circuits.random_circuit(n, 5, 70 + seed, "H,T,CNOT") + circuits.qft(n)[:25]
+        psi = rand_state(n, 30 + seed)
+        want = qo.run_pipeline(n, ops, state=psi)
+        arr, keep = marshal_ops(ops, prec_of(np.complex128))
+        st = np.ascontiguousarray(psi.astype(np.complex128))
+        stats = np.zeros(64, dtype=np.uint64)
+        err = C.create_string_buffer(256)
+        rc = emul.emul_schedule_blocked(prec_of(np.complex128), n, arr, len(ops), st.ctypes.data, T, Lo, remote,
+                                        stats.ctypes.data, err, 256)
+        assert rc == 0, (rc, err.value)
+        assert np.max(np.abs(st - want)) < 1e-12
+        assert stats[1] > 1  # it really went through several epochs
 
 
 def test_planner_f32_data_path(emul):
