@@ -77,6 +77,13 @@ uint64_t qipb200_kernel_launches(const qipb200_ctx *ctx);
 /* out4 = { all kernels, fused tile passes, NVLink exchange kernels, reference ops folded into tile passes }. */
 int qipb200_launch_stats(const qipb200_ctx *ctx, uint64_t *out4);
 
+/* Optional device timing by category (absent in the reference): while enabled, every fused tile pass and every
+ * NVLink exchange (kernel + its two flag barriers) is bracketed by a CUDA-event pair on the context's stream.
+ * profile_read synchronises the stream and returns
+ *   out4 = { tile-pass ms, tile passes, exchange ms, exchanges }  since the previous read, then resets. */
+int qipb200_profile_enable(qipb200_ctx *ctx, int on);
+int qipb200_profile_read(qipb200_ctx *ctx, double *out4);
+
 /* Validate an op exactly as the reference's constructors do
  * (qip/src/state_ops/matrix_ops.rs:12-122: non-empty indices, len(dense)==4^k,
  * sparse row count 2^k and no empty row, equal swap halves, >=1 control) plus
@@ -137,6 +144,12 @@ int qipb200_state_apply_schedule(qipb200_state *state, const qip_op *ops, size_t
 
 /* sum |a|^2 over the (local) state: prob_magnitude, measurement_ops.rs:11-13. */
 int qipb200_state_norm2(qipb200_state *state, double *out);
+
+/* max over the (local) amplitudes of max(|re_a - re_b|, |im_a - im_b|), computed on the device: the
+ * comparison behind the fused-vs-unfused parity checks at sizes no host oracle reaches (two 16 GiB
+ * states at N=30).  Both states must live on the same context and have the same shape and layout.
+ * Replaces nothing in the reference (its tests compare Vecs on the host). */
+int qipb200_state_max_abs_diff(qipb200_state *a, qipb200_state *b, double *out);
 
 /* Block until everything queued on the state's stream has finished. */
 int qipb200_state_sync(qipb200_state *state);

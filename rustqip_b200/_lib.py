@@ -23,11 +23,11 @@ _lib = None
 # every symbol include/qipb200.h declares
 EXPORTS = [
     "qipb200_abi_version", "qipb200_init", "qipb200_shutdown", "qipb200_last_error",
-    "qipb200_kernel_launches", "qipb200_launch_stats", "qipb200_stream_handle", "qipb200_validate_op", "qipb200_apply_op",
+    "qipb200_kernel_launches", "qipb200_launch_stats", "qipb200_stream_handle", "qipb200_profile_enable", "qipb200_profile_read", "qipb200_validate_op", "qipb200_apply_op",
     "qipb200_apply_op_overwrite", "qipb200_apply_ops", "qipb200_state_new", "qipb200_state_free",
     "qipb200_state_set_basis", "qipb200_state_upload", "qipb200_state_download",
     "qipb200_state_apply_op", "qipb200_state_apply_schedule", "qipb200_state_norm2",
-    "qipb200_state_sync", "qipb200_calculate_state", "qipb200_state_measure_probs",
+    "qipb200_state_sync", "qipb200_state_max_abs_diff", "qipb200_calculate_state", "qipb200_state_measure_probs",
     "qipb200_state_measure_prob", "qipb200_state_soft_measure", "qipb200_state_collapse",
     "qipb200_state_new_sharded", "qipb200_state_ipc_export", "qipb200_state_ipc_import",
     "qipb200_state_qubit_map", "qipb200_state_exchange_bytes", "qipb200_plan_exchanges",
@@ -53,6 +53,8 @@ def lib():
     L.qipb200_last_error.restype, L.qipb200_last_error.argtypes = C.c_char_p, [vp]
     L.qipb200_stream_handle.restype, L.qipb200_stream_handle.argtypes = i32, [vp, C.POINTER(vp)]
     L.qipb200_launch_stats.restype, L.qipb200_launch_stats.argtypes = i32, [vp, vp]
+    L.qipb200_profile_enable.restype, L.qipb200_profile_enable.argtypes = i32, [vp, i32]
+    L.qipb200_profile_read.restype, L.qipb200_profile_read.argtypes = i32, [vp, vp]
     L.qipb200_kernel_launches.restype, L.qipb200_kernel_launches.argtypes = u64, [vp]
     L.qipb200_validate_op.restype, L.qipb200_validate_op.argtypes = i32, [vp, i32, u32, opp]
     for name in ("qipb200_apply_op", "qipb200_apply_op_overwrite"):
@@ -70,6 +72,8 @@ def lib():
     L.qipb200_state_apply_schedule.argtypes = [vp, opp, C.c_size_t, u32]
     L.qipb200_state_norm2.restype, L.qipb200_state_norm2.argtypes = i32, [vp, C.POINTER(C.c_double)]
     L.qipb200_state_sync.restype, L.qipb200_state_sync.argtypes = i32, [vp]
+    L.qipb200_state_max_abs_diff.restype = i32
+    L.qipb200_state_max_abs_diff.argtypes = [vp, vp, C.POINTER(C.c_double)]
     L.qipb200_calculate_state.restype = i32
     L.qipb200_calculate_state.argtypes = [vp, i32, u32, u64, opp, C.c_size_t, u32, vp]
     L.qipb200_state_measure_probs.restype = i32

@@ -144,3 +144,20 @@ def config4(n: int = 26, blocks: int = 200, k: int = 4, seed: int = 0x5EED0004) 
         u = haar_unitary(k, rng)
         ops.append(gates.mat(p[:k], u.reshape(-1)))
     return ops
+
+
+def sharded_parity_circuit(n: int, g: int, seed: int = 5) -> List[MatrixOp]:
+    """Every op kind on the rank-held qubits 0..g-1 of a 2^g-way sharded n-qubit state (g may be 0), then
+    random layers and a QFT prefix that touch them repeatedly: the circuit of the multi-GPU parity checks
+    (tests/dist_worker.py) and of bench.py's `parity_ok` leg, small enough for the CPU oracle."""
+    from .ops import make_matrix_op, make_swap_op
+    rng = np.random.default_rng(seed)
+    u2 = np.linalg.qr(rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4)))[0]
+    hi = max(g - 1, 0)
+    ops = [gates.h(0), gates.cnot(0, n - 1), gates.cnot(n - 1, 0), gates.t(0), gates.cz(0, 3),
+           gates.cphase(2, 0, 0.3), gates.h(hi), gates.x(0), gates.toffoli(0, 1, 2), gates.toffoli(3, 4, 0),
+           make_swap_op([0], [n - 2]), gates.rz(0, 0.4), make_matrix_op([0, 5], u2.reshape(-1)),
+           make_matrix_op([4, hi], u2.reshape(-1)), make_swap_op([0], [hi]) if hi > 0 else gates.h(1)]
+    ops += random_circuit(n, 6, 1234 + n, "H,T,CNOT") + random_circuit(n, 4, 99 + n, "H,CZ,CNOT")
+    ops += qft(n)[: 3 * n]
+    return ops

@@ -121,6 +121,12 @@ extern "C" void qipb200_shutdown(qipb200_ctx *ctx) {
   if (ctx->d_out) cudaFree(ctx->d_out);
   if (ctx->d_scalar) cudaFree(ctx->d_scalar);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  for (int cat = 0; cat < 2; ++cat)
+    for (size_t i = 0; i < ctx->prof_events[cat].size(); ++i) {
+      cudaEventDestroy(ctx->prof_events[cat][i].first);
+      cudaEventDestroy(ctx->prof_events[cat][i].second);
+    }
+  for (size_t i = 0; i < ctx->prof_pool.size(); ++i) cudaEventDestroy(ctx->prof_pool[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -146,6 +152,31 @@ extern "C" int qipb200_launch_stats(const qipb200_ctx *ctx, uint64_t *out4) {
   return QIPB200_OK;
 }
 
+extern "C" int qipb200_profile_enable(qipb200_ctx *ctx, int on) {
+  if (!ctx) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "profile_enable: ctx is NULL");
+  ctx->profile = on != 0;
+  return QIPB200_OK;
+}
+
+extern "C" int qipb200_profile_read(qipb200_ctx *ctx, double *out4) {
+  if (!ctx || !out4) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "profile_read: NULL argument");
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int cat = 0; cat < 2; ++cat) {
+    double ms = 0.0;
+    for (size_t i = 0; i < ctx->prof_events[cat].size(); ++i) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, ctx->prof_events[cat][i].first, ctx->prof_events[cat][i].second) == cudaSuccess) ms += t;
+      ctx->prof_pool.push_back(ctx->prof_events[cat][i].first);
+      ctx->prof_pool.push_back(ctx->prof_events[cat][i].second);
+    }
+    out4[2 * cat] = ms;
+    out4[2 * cat + 1] = (double)ctx->prof_events[cat].size();
+    ctx->prof_events[cat].clear();
+  }
+  return QIPB200_OK;
+}
+
 extern "C" int qipb200_validate_op(const qipb200_ctx *ctx, qip_prec prec, uint32_t n_qubits, const qip_op *op) {
   std::string err;
   int st = validate_op(op, prec, n_qubits, &err);
@@ -165,6 +196,8 @@ int host_apply(qipb200_ctx *ctx, qip_prec prec, uint32_t n, const qip_op *op, co
   if (!ctx) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "ctx is NULL (call qipb200_init first; there is no CPU path)");
   if ((!input && input_len) || (!output && output_len))
     return set_err(ctx, QIPB200_ERR_INVALID_ARG, "apply_op: NULL amplitude buffer");
+  if (n > 40 || input_len > (1ull << 40) || output_len > (1ull << 40))  // keeps len * amp_bytes far from wrapping
+    return set_err(ctx, QIPB200_ERR_SIZE_MISMATCH, "apply_op: buffer length out of range");
   FlatOp f;
   std::string err;
   int st = compile_op(op, prec, n, &f, &err);
@@ -266,6 +299,7 @@ int exchange_bits(qipb200_state *s, uint32_t R, uint32_t l) {
   const int rb = (s->rank >> r) & 1;
   uint32_t s_bit = s->n_local - 1;
   if (s_bit == l) s_bit = s->n_local - 2;
+  ProfileScope prof(ctx, 1);
   CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch,
                               s->flags + kFlagErrorSlot, ctx->stream, &ctx->launches));
   CU(ctx, launch_pair_exchange(s->prec, s->buf, s->peer_buf[partner], s->n_local, l, s_bit, rb, ctx->stream,
@@ -545,7 +579,8 @@ extern "C" int qipb200_state_upload(qipb200_state *s, const void *host, uint64_t
   if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
   qipb200_ctx *ctx = s->ctx;
   if (!host && len) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "upload: host pointer is NULL");
-  if (offset + len > (1ull << s->n_local)) return set_err(ctx, QIPB200_ERR_SIZE_MISMATCH, "upload: range exceeds the local state");
+  if (len > (1ull << s->n_local) || offset > (1ull << s->n_local) - len)
+    return set_err(ctx, QIPB200_ERR_SIZE_MISMATCH, "upload: range exceeds the local state");
   CU(ctx, cudaSetDevice(ctx->device));
   if (!layout_is_identity(s)) {
     int st = restore_layout(s);
@@ -561,7 +596,8 @@ extern "C" int qipb200_state_download(qipb200_state *s, void *host, uint64_t off
   if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
   qipb200_ctx *ctx = s->ctx;
   if (!host && len) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "download: host pointer is NULL");
-  if (offset + len > (1ull << s->n_local)) return set_err(ctx, QIPB200_ERR_SIZE_MISMATCH, "download: range exceeds the local state");
+  if (len > (1ull << s->n_local) || offset > (1ull << s->n_local) - len)
+    return set_err(ctx, QIPB200_ERR_SIZE_MISMATCH, "download: range exceeds the local state");
   CU(ctx, cudaSetDevice(ctx->device));
   if (!layout_is_identity(s)) {
     int st = restore_layout(s);
@@ -595,6 +631,20 @@ extern "C" int qipb200_state_norm2(qipb200_state *s, double *out) {
   qipb200_ctx *ctx = s->ctx;
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, launch_norm2(s->prec, s->buf, 1ull << s->n_local, ctx->d_scalar, ctx->stream, &ctx->launches));
+  CU(ctx, cudaMemcpyAsync(out, ctx->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(ctx, cudaStreamSynchronize(ctx->stream));
+  return QIPB200_OK;
+}
+
+extern "C" int qipb200_state_max_abs_diff(qipb200_state *a, qipb200_state *b, double *out) {
+  if (!a || !b || !out) return set_err(a ? a->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "max_abs_diff: NULL argument");
+  qipb200_ctx *ctx = a->ctx;
+  if (a->ctx != b->ctx || a->prec != b->prec || a->n != b->n || a->world != b->world || a->rank != b->rank)
+    return set_err(ctx, QIPB200_ERR_SIZE_MISMATCH, "max_abs_diff: the two states differ in context, precision or shape");
+  if (a->phys_of_logical != b->phys_of_logical)
+    return set_err(ctx, QIPB200_ERR_UNSUPPORTED, "max_abs_diff: the two sharded states hold different qubit layouts");
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, launch_max_abs_diff(a->prec, a->buf, b->buf, 1ull << a->n_local, ctx->d_scalar, ctx->stream, &ctx->launches));
   CU(ctx, cudaMemcpyAsync(out, ctx->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   return QIPB200_OK;
@@ -748,22 +798,30 @@ extern "C" int qipb200_state_soft_measure(qipb200_state *s, const uint64_t *indi
   const uint64_t clen = 1ull << chunk_log2;
   const size_t ab = amp_bytes(s->prec);
   std::vector<char> host(clen * ab);
-  CU(ctx, cudaMemcpyAsync(host.data(), (const char *)s->buf + c * clen * ab, clen * ab, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
-  uint64_t idx = 0;  // the reference leaves measured_indx = 0 when the scan never crosses
-  for (uint64_t i = 0; i < clen; ++i) {
-    double re, im;
-    if (s->prec == QIP_F32) {
-      re = ((const float *)host.data())[2 * i];
-      im = ((const float *)host.data())[2 * i + 1];
-    } else {
-      re = ((const double *)host.data())[2 * i];
-      im = ((const double *)host.data())[2 * i + 1];
-    }
-    rem -= re * re + im * im;
-    if (rem <= 0.0) {
-      idx = c * clen + i;
-      break;
+  // The device-reduced chunk sums and this serial scan add in different orders: when r lands within
+  // rounding of a chunk boundary the scan of chunk c may end just short of the crossing.  The reference's
+  // single serial scan would simply go on, so do the same: keep scanning the following chunks, and only
+  // after the last one leave measured_indx = 0 (measurement_ops.rs:166-172: "never crossed").
+  uint64_t idx = 0;
+  bool crossed = false;
+  for (; c < chunks && !crossed; ++c) {
+    CU(ctx, cudaMemcpyAsync(host.data(), (const char *)s->buf + c * clen * ab, clen * ab, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint64_t i = 0; i < clen; ++i) {
+      double re, im;
+      if (s->prec == QIP_F32) {
+        re = ((const float *)host.data())[2 * i];
+        im = ((const float *)host.data())[2 * i + 1];
+      } else {
+        re = ((const double *)host.data())[2 * i];
+        im = ((const double *)host.data())[2 * i + 1];
+      }
+      rem -= re * re + im * im;
+      if (rem <= 0.0) {
+        idx = c * clen + i;
+        crossed = true;
+        break;
+      }
     }
   }
   uint64_t m = 0;  // extract_bits(measured_indx, [n-1-index]) (measurement_ops.rs:174-175)

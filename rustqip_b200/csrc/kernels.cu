@@ -557,6 +557,39 @@ cudaError_t launch_norm2(qip_prec prec, const void *psi, uint64_t len, double *d
   return cudaGetLastError();
 }
 
+// max over the amplitudes of max(|re_a - re_b|, |im_a - im_b|): the device-side comparison behind
+// qipb200_state_max_abs_diff (fused-vs-unfused parity checks at sizes no host oracle reaches).
+// Non-negative doubles order like their bit patterns, so the reduction is an atomicMax on u64;
+// a NaN difference is reported as +inf.
+template <typename R>
+__global__ void __launch_bounds__(kThreads) k_maxdiff(const R *__restrict__ a, const R *__restrict__ b, uint64_t len,
+                                                      unsigned long long *out) {
+  double acc = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x; i < len; i += (uint64_t)gridDim.x * kThreads) {
+    typename Vec2<R>::type x = *reinterpret_cast<const typename Vec2<R>::type *>(a + 2 * i);
+    typename Vec2<R>::type y = *reinterpret_cast<const typename Vec2<R>::type *>(b + 2 * i);
+    double d0 = fabs((double)x.x - (double)y.x), d1 = fabs((double)x.y - (double)y.y);
+    if (d0 != d0 || d1 != d1) d0 = __longlong_as_double(0x7ff0000000000000ll);
+    acc = fmax(acc, fmax(d0, d1));
+  }
+  for (int o = 16; o > 0; o >>= 1) acc = fmax(acc, __shfl_down_sync(0xffffffffu, acc, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(acc));
+}
+
+cudaError_t launch_max_abs_diff(qip_prec prec, const void *a, const void *b, uint64_t len, double *d_out, cudaStream_t s,
+                                uint64_t *launches) {
+  cudaError_t e = cudaMemsetAsync(d_out, 0, sizeof(double), s);
+  if (e != cudaSuccess) return e;
+  unsigned grid = (unsigned)std::min<uint64_t>((len + kThreads - 1) / kThreads, 148ull * 16);
+  if (grid == 0) grid = 1;
+  if (prec == QIP_F32)
+    k_maxdiff<float><<<grid, kThreads, 0, s>>>((const float *)a, (const float *)b, len, (unsigned long long *)d_out);
+  else
+    k_maxdiff<double><<<grid, kThreads, 0, s>>>((const double *)a, (const double *)b, len, (unsigned long long *)d_out);
+  ++*launches;
+  return cudaGetLastError();
+}
+
 template <typename R>
 __global__ void k_set_one(R *psi, uint64_t index) {
   psi[2 * index] = (R)1;

@@ -37,6 +37,9 @@ cudaError_t launch_gather(qip_prec prec, const FlatOp &f, uint32_t n_qubits, con
 // sum |a|^2 into *d_out (a device double, zeroed by the launcher).
 cudaError_t launch_norm2(qip_prec prec, const void *psi, uint64_t len, double *d_out, cudaStream_t s,
                          uint64_t *launches);
+// max over amplitudes of max(|re_a-re_b|, |im_a-im_b|) into *d_out (a device double).
+cudaError_t launch_max_abs_diff(qip_prec prec, const void *a, const void *b, uint64_t len, double *d_out, cudaStream_t s,
+                                uint64_t *launches);
 cudaError_t launch_set_basis(qip_prec prec, void *psi, uint64_t len, uint64_t index, bool owns_index,
                              cudaStream_t s, uint64_t *launches);
 

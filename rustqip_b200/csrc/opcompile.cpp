@@ -96,12 +96,15 @@ int validate_op(const qip_op *op, qip_prec prec, uint32_t n_qubits, std::string 
       break;
     }
     case QIP_OP_SPARSE: {
-      if (!cur->sp_rowptr || (!cur->sp_col && cur->sp_rowptr[0] != cur->sp_rowptr[1]))
-        return fail(err, QIPB200_ERR_INVALID_ARG, "Sparse op without data");
+      // the row count is checked BEFORE sp_rowptr is touched: a record with n_rows = 0 (e.g. from a parsed,
+      // untrusted schedule) owns a one-element rowptr
+      if (!cur->sp_rowptr) return fail(err, QIPB200_ERR_INVALID_ARG, "Sparse op without data");
       if (kop > 20) return fail(err, QIPB200_ERR_UNSUPPORTED, "sparse op on more than 20 qubits");
       if (cur->n_entries != (1ull << kop))
         return fail(err, QIPB200_ERR_SIZE_MISMATCH,
                     fmt("Sparse matrix has %llu rows versus expected 2^%llu", cur->n_entries, kop));
+      if (!cur->sp_col && cur->sp_rowptr[0] != cur->sp_rowptr[1])
+        return fail(err, QIPB200_ERR_INVALID_ARG, "Sparse op without data");
       for (uint64_t r = 0; r < (1ull << kop); ++r) {
         if (cur->sp_rowptr[r + 1] <= cur->sp_rowptr[r])
           return fail(err, QIPB200_ERR_SIZE_MISMATCH,

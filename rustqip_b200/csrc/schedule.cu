@@ -50,6 +50,7 @@ int execute_steps(qipb200_state *s, const std::vector<PlanStep> &steps, const st
         st = report_error(s, QIPB200_ERR_UNSUPPORTED, "internal: fused pass exceeds the kernel parameter space");
         break;
       }
+      ProfileScope prof(ctx, 0);
       cudaError_t e = launch_tile_pass(s->prec, s->buf, s->n_local, *pp, cfg.groups_per_thread, cfg.use_tma, ctx->stream,
                                        &ctx->launches, cfg.kernel_variant);
       if (e != cudaSuccess) st = report_cuda_error(s, e, "launch_tile_pass");
@@ -68,11 +69,12 @@ int execute_steps(qipb200_state *s, const std::vector<PlanStep> &steps, const st
 // "blocked"; later ops may overtake them only when they commute); when nothing more can run, the
 // first blocked op's qubit is migrated over NVLink (one exchange) and the next epoch starts.
 int run_fused(qipb200_state *s, const qip_op *ops, size_t n_ops, const std::vector<uint64_t> &next_use) {
-  static bool configured = false;
-  if (!configured) {
+  // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting and a process may hold contexts on
+  // several GPUs: the opt-in is tracked per context (a context is bound to one device and driven by one thread).
+  if (!s->ctx->tile_configured) {
     cudaError_t e = tile_pass_configure();
     if (e != cudaSuccess) return report_cuda_error(s, e, "cudaFuncSetAttribute(tile pass)");
-    configured = true;
+    s->ctx->tile_configured = true;
   }
   const PlanConfig cfg = default_plan_config(s->prec, s->n_local);
   std::vector<size_t> remaining(n_ops);

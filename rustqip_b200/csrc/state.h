@@ -5,6 +5,7 @@
 
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "opcompile.h"
@@ -18,6 +19,12 @@ struct qipb200_ctx {
   uint64_t tile_launches = 0;      // fused tile passes among `launches`
   uint64_t exchange_launches = 0;  // NVLink pair-exchange kernels among `launches`
   uint64_t fused_gates = 0;        // reference ops folded into tile passes
+  bool tile_configured = false;    // the tile kernels' > 48 KiB shared-memory opt-in was done on this device
+  // optional per-category device timing (qipb200_profile_enable): CUDA-event pairs recorded on `stream`
+  // around every fused tile pass [0] and every NVLink exchange incl. its two flag barriers [1]
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[2];
+  std::vector<cudaEvent_t> prof_pool;
   // staging buffers of the host-buffer drop-ins (qipb200_apply_op*)
   void *d_in = nullptr, *d_out = nullptr;
   size_t d_in_bytes = 0, d_out_bytes = 0;
@@ -48,6 +55,34 @@ struct qipb200_state {
 };
 
 namespace qipb200 {
+
+// RAII bracket of one profiled region (no-op unless ctx->profile).
+struct ProfileScope {
+  qipb200_ctx *ctx;
+  int cat;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ProfileScope(qipb200_ctx *c, int category) : ctx(c), cat(category) {
+    if (!ctx->profile) return;
+    auto take = [&]() {
+      cudaEvent_t e = nullptr;
+      if (!ctx->prof_pool.empty()) {
+        e = ctx->prof_pool.back();
+        ctx->prof_pool.pop_back();
+      } else if (cudaEventCreate(&e) != cudaSuccess) {
+        e = nullptr;
+      }
+      return e;
+    };
+    e0 = take();
+    e1 = take();
+    if (e0) cudaEventRecord(e0, ctx->stream);
+  }
+  ~ProfileScope() {
+    if (!e0 || !e1) return;
+    cudaEventRecord(e1, ctx->stream);
+    ctx->prof_events[cat].push_back(std::make_pair(e0, e1));
+  }
+};
 
 inline size_t amp_bytes(qip_prec p) { return p == QIP_F32 ? 8 : 16; }
 

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -90,6 +91,7 @@ bool parse_op(Reader &r, qipb200_schedule *s, size_t amp, qip_op *out, uint32_t 
       uint64_t n_rows;
       if (!r.get(&n_rows)) return fail(err, "schedule truncated (sparse rows)");
       if (n_rows > r.left / 8) return fail(err, "schedule truncated (sparse rows)");
+      if (n_idx > 20 || n_rows != (1ull << n_idx)) return fail(err, "schedule: Sparse record whose row count is not 2^n_indices");
       s->u64s.emplace_back();
       std::vector<uint64_t> &rowptr = s->u64s.back();
       rowptr.reserve((size_t)n_rows + 1);
@@ -189,21 +191,29 @@ int qipb200_schedule_parse(const void *buf, size_t len, qipb200_schedule **out, 
   std::string err;
   uint32_t magic, version, prec, n;
   uint64_t n_ops;
-  qipb200_schedule *s = new qipb200_schedule();
-  bool ok = r.get(&magic) && r.get(&version) && r.get(&prec) && r.get(&n) && r.get(&n_ops);
-  if (!ok)
-    err = "schedule truncated (file header)";
-  else if (magic != kMagic || version != 1 || prec > QIP_F64)
-    ok = fail(&err, "not a QIPS version-1 schedule");
-  else if (n_ops > r.left / 9)  // every record has at least a 9-byte header
-    ok = fail(&err, "schedule truncated (fewer records than announced)");
-  if (ok) {
-    s->n_qubits = n;
-    s->prec = (int)prec;
-    const size_t amp = prec == QIP_F32 ? 8 : 16;
-    s->ops.resize((size_t)n_ops);
-    for (uint64_t i = 0; ok && i < n_ops; ++i) ok = parse_op(r, s, amp, &s->ops[(size_t)i], 0, &err);
-    if (ok && r.left != 0) ok = fail(&err, "schedule: trailing bytes after the last record");
+  qipb200_schedule *s = new (std::nothrow) qipb200_schedule();
+  if (!s) return QIPB200_ERR_OOM;
+  bool ok = false;
+  try {  // the parser allocates through std::vector: an allocation failure is a status, never an abort
+    ok = r.get(&magic) && r.get(&version) && r.get(&prec) && r.get(&n) && r.get(&n_ops);
+    if (!ok)
+      err = "schedule truncated (file header)";
+    else if (magic != kMagic || version != 1 || prec > QIP_F64)
+      ok = fail(&err, "not a QIPS version-1 schedule");
+    else if (n_ops > r.left / 9)  // every record has at least a 9-byte header
+      ok = fail(&err, "schedule truncated (fewer records than announced)");
+    if (ok) {
+      s->n_qubits = n;
+      s->prec = (int)prec;
+      const size_t amp = prec == QIP_F32 ? 8 : 16;
+      s->ops.resize((size_t)n_ops);
+      for (uint64_t i = 0; ok && i < n_ops; ++i) ok = parse_op(r, s, amp, &s->ops[(size_t)i], 0, &err);
+      if (ok && r.left != 0) ok = fail(&err, "schedule: trailing bytes after the last record");
+    }
+  } catch (const std::bad_alloc &) {
+    if (errbuf && errlen) snprintf(errbuf, errlen, "out of host memory while parsing the schedule");
+    delete s;
+    return QIPB200_ERR_OOM;
   }
   if (!ok) {
     if (errbuf && errlen) snprintf(errbuf, errlen, "%s", err.c_str());

@@ -45,6 +45,16 @@ class Context:
         _lib.check(_lib.lib().qipb200_launch_stats(self._h, out), self._h)
         return {"all": int(out[0]), "tile_passes": int(out[1]), "exchanges": int(out[2]), "fused_gates": int(out[3])}
 
+    def profile(self, on: bool):
+        """Bracket every fused tile pass / NVLink exchange with CUDA events on the context's stream."""
+        _lib.check(_lib.lib().qipb200_profile_enable(self._h, 1 if on else 0), self._h)
+
+    def profile_read(self):
+        """dict(tile_ms, tile_passes, exchange_ms, exchanges) since the previous read (synchronises the stream)."""
+        out = (C.c_double * 4)()
+        _lib.check(_lib.lib().qipb200_profile_read(self._h, out), self._h)
+        return {"tile_ms": out[0], "tile_passes": int(out[1]), "exchange_ms": out[2], "exchanges": int(out[3])}
+
     def kernel_launches(self) -> int:
         return int(_lib.lib().qipb200_kernel_launches(self._h))
 
@@ -163,6 +173,12 @@ class State:
 
     def sync(self):
         self._chk(_lib.lib().qipb200_state_sync(self._h))
+
+    def max_abs_diff(self, other: "State") -> float:
+        """max over amplitudes of max(|d re|, |d im|) against another state of the same shape (on the device)."""
+        v = C.c_double()
+        self._chk(_lib.lib().qipb200_state_max_abs_diff(self._h, other._h, C.byref(v)))
+        return v.value
 
     # -- measurement_ops.rs ---------------------------------------------------
     def measure_probs(self, indices: Sequence[int]) -> np.ndarray:

@@ -13,9 +13,8 @@ def main():
     import torch
     import torch.distributed as dist
     from oracle import qip_oracle as qo
-    from rustqip_b200 import circuits, gates
+    from rustqip_b200 import circuits
     from rustqip_b200.dist import gather_state, init_sharded_state
-    from rustqip_b200.ops import make_matrix_op, make_swap_op
     from rustqip_b200.state import Context
 
     local_rank = int(os.environ["LOCAL_RANK"])
@@ -25,17 +24,10 @@ def main():
     g = (world - 1).bit_length()
     ctx = Context(local_rank)
     failures = 0
-    rng = np.random.default_rng(5)
-    u2 = np.linalg.qr(rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4)))[0]
     for n, dtype, fusion in [(12, np.complex128, False), (14, np.complex128, True), (15, np.complex64, True),
                              (17, np.complex128, True)]:
-        # gates on rank-held qubits (0..g-1) of every kind + a random circuit touching them repeatedly
-        ops = [gates.h(0), gates.cnot(0, n - 1), gates.cnot(n - 1, 0), gates.t(0), gates.cz(0, 3),
-               gates.cphase(2, 0, 0.3), gates.h(g - 1), gates.x(0), gates.toffoli(0, 1, 2), gates.toffoli(3, 4, 0),
-               make_swap_op([0], [n - 2]), gates.rz(0, 0.4), make_matrix_op([0, 5], u2.reshape(-1)),
-               make_matrix_op([4, g - 1], u2.reshape(-1)), make_swap_op([0], [g - 1]) if g > 1 else gates.h(1)]
-        ops += circuits.random_circuit(n, 6, 1234 + n, "H,T,CNOT") + circuits.random_circuit(n, 4, 99 + n, "H,CZ,CNOT")
-        ops += circuits.qft(n)[: 3 * n]
+        # gates on rank-held qubits (0..g-1) of every kind + random circuits touching them repeatedly
+        ops = circuits.sharded_parity_circuit(n, g)
         st = init_sharded_state(n, dtype, ctx)
         st.set_basis(5)
         st.apply_schedule(ops, fusion=fusion)
