@@ -77,6 +77,21 @@ uint64_t qipb200_kernel_launches(const qipb200_ctx *ctx);
 /* out4 = { all kernels, fused tile passes, NVLink exchange kernels, reference ops folded into tile passes }. */
 int qipb200_launch_stats(const qipb200_ctx *ctx, uint64_t *out4);
 
+/* Generated kernels (absent in the reference): fused tile passes of big states are compiled by NVRTC into
+ * kernels specialised to the pass (rustqip_b200/csrc/jit_codegen.cpp); a pass whose kernel is still being compiled
+ * in the background runs the generic kernel meanwhile.  With wait != 0 this call blocks until the background
+ * compilations have finished.  out4 = { tile passes run by generated kernels, all tile passes (this context),
+ * programs compiled so far (process, valid with wait), their total compile time in ms (valid with wait) };
+ * `note` (may be NULL) receives the reason the generated path was last declined, if any.
+ * Environment: QIPB200_JIT = off | async (default from 22 local qubits) | sync (compile before launching). */
+int qipb200_jit_stats(qipb200_ctx *ctx, int wait, double *out4, char *note, size_t note_len);
+/* Host-only (no GPU, ctx-free): plan the schedule for an n-qubit single-device state, generate and NVRTC-compile
+ * the kernel of every fused pass into the process-wide cache (a later qipb200_state_apply_schedule of the same
+ * schedule then starts on generated kernels at once).  out5 = { passes, passes covered by the generator, compiled
+ * without error, wall ms, sum of per-program compile ms }; `log` (may be NULL) receives the last compiler message. */
+int qipb200_jit_precompile(qip_prec prec, uint32_t n_qubits, const qip_op *ops, size_t n_ops, double *out5, char *log,
+                           size_t log_len);
+
 /* Optional device timing by category (absent in the reference): while enabled, every fused tile pass and every
  * NVLink exchange (kernel + its two flag barriers) is bracketed by a CUDA-event pair on the context's stream.
  * profile_read synchronises the stream and returns

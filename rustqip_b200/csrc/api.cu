@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -19,6 +20,8 @@
 #include "kernels.cuh"
 #include "opcompile.h"
 #include "schedule.h"
+#include "tile.cuh"
+#include "jit_codegen.h"
 #include "state.h"
 
 using namespace qipb200;
@@ -127,6 +130,7 @@ extern "C" void qipb200_shutdown(qipb200_ctx *ctx) {
       cudaEventDestroy(ctx->prof_events[cat][i].second);
     }
   for (size_t i = 0; i < ctx->prof_pool.size(); ++i) cudaEventDestroy(ctx->prof_pool[i]);
+  jit_unload(&ctx->jit_loaded);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -149,6 +153,69 @@ extern "C" int qipb200_launch_stats(const qipb200_ctx *ctx, uint64_t *out4) {
   out4[1] = ctx->tile_launches;
   out4[2] = ctx->exchange_launches;
   out4[3] = ctx->fused_gates;
+  return QIPB200_OK;
+}
+
+// Host-only (no GPU, no context): plan `ops` for an n-qubit single-device state, generate the specialised source
+// of every fused pass and compile it with NVRTC for sm_100a.  out[0] = passes planned, out[1] = passes the
+// generator covered, out[2] = of those compiled without error, out[3] = total NVRTC wall time (ms, all passes in
+// parallel on the worker pool), out[4] = sum of the per-program compile times (ms).
+extern "C" int qipb200_jit_precompile(qip_prec prec, uint32_t n_qubits, const qip_op *ops, size_t n_ops, double *out5,
+                                      char *log, size_t log_len) {
+  if (!out5 || (!ops && n_ops)) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "jit_precompile: NULL argument");
+  for (int i = 0; i < 5; ++i) out5[i] = 0.0;
+  if (log && log_len) log[0] = 0;
+  std::string why;
+  if (!jit_available(&why) && why.find("driver") == std::string::npos) {  // the driver is only needed to LAUNCH
+    if (log && log_len) snprintf(log, log_len, "%s", why.c_str());
+    return set_err(nullptr, QIPB200_ERR_UNSUPPORTED, why);
+  }
+  std::vector<FlatOp> flat(n_ops);
+  for (size_t i = 0; i < n_ops; ++i) {
+    std::string err;
+    int st = compile_op(&ops[i], prec, n_qubits, &flat[i], &err);
+    if (st != QIPB200_OK) return set_err(nullptr, st, err);
+  }
+  const PlanConfig cfg = default_plan_config(prec, n_qubits);
+  std::vector<PlanStep> steps;
+  plan_passes(flat, n_qubits, prec, cfg, &steps);
+  std::vector<std::string> sources;
+  for (size_t i = 0; i < steps.size(); ++i) {
+    if (!steps[i].is_pass) continue;
+    out5[0] += 1;
+    JitProgram prog;
+    if (!jit_generate(steps[i].pass, prec, &prog, &why)) {
+      if (log && log_len) snprintf(log, log_len, "declined: %s", why.c_str());
+      continue;
+    }
+    out5[1] += 1;
+    sources.push_back(prog.source);
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  for (size_t i = 0; i < sources.size(); ++i) (void)jit_request(sources[i], false);
+  for (size_t i = 0; i < sources.size(); ++i) {
+    std::shared_ptr<const JitCubin> c = jit_request(sources[i], true);
+    if (c && c->ok) {
+      out5[2] += 1;
+      out5[4] += c->compile_ms;
+    } else if (log && log_len && c) {
+      snprintf(log, log_len, "%s", c->log.c_str());
+    }
+  }
+  out5[3] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return QIPB200_OK;
+}
+
+extern "C" int qipb200_jit_stats(qipb200_ctx *ctx, int wait, double *out4, char *note, size_t note_len) {
+  if (!ctx || !out4) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "jit_stats: NULL argument");
+  uint64_t n = 0;
+  double ms = 0.0;
+  if (wait) jit_wait_all(&n, &ms);
+  out4[0] = (double)ctx->jit_launches;
+  out4[1] = (double)ctx->tile_launches;
+  out4[2] = (double)n;
+  out4[3] = ms;
+  if (note && note_len) snprintf(note, note_len, "%s", ctx->jit_note.c_str());
   return QIPB200_OK;
 }
 

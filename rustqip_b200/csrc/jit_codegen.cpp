@@ -1,0 +1,752 @@
+// jit_codegen.cpp -- see jit_codegen.h.  Pure host C++.
+//
+// Reference semantics being specialised: one pass = the sequential product of the reference's per-entry
+// sweeps (qip/src/builder.rs:423-514, qip-iterators/src/matrix_ops.rs:127-152) restricted to gates whose
+// non-diagonal bits are tile bits; the arithmetic of every elementary op is issued in exactly the order of the
+// interpreter kernel (tile_interp.cuh), with terms whose coefficient is exactly 0 dropped and coefficients of
+// exactly +-1 turned into add/sub -- both exact for finite amplitudes, so the two kernels agree bit for bit
+// (up to the sign of zero) and the interpreter's oracle parity carries over.
+#include "jit_codegen.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <sstream>
+
+namespace qipb200 {
+
+namespace {
+
+struct Cond {
+  uint64_t gmask, gval;
+};
+
+struct PhTerm {
+  uint64_t gmask, gval;
+  double re, im;
+};
+
+// decoded elementary record
+struct DElem {
+  enum Kind { D1, X, PH, PHN, D3, HAD } kind = D1;
+  bool real = false;
+  uint32_t j = 0;
+  uint32_t mask = 0;       // pair mask (D1/X/HAD: bit p <-> p-th pair) or amplitude mask (PH/PHN)
+  int cond = -1;           // index into the program's condition list
+  double m[8] = {0};       // D1: real m00 m01 m10 m11 | complex (re,im) x 4; PH/PHN: w
+  std::vector<double> m8;  // D3: 64 complex, row-major
+  uint32_t slot = 0;       // PHN: factor-table slot
+};
+
+template <typename R>
+bool decode_super(const HostMicroOp &mo, const HostPass &pass, std::vector<Cond> &conds, std::vector<DElem> *out,
+                  std::vector<std::vector<PhTerm>> *phn_terms, std::vector<std::pair<double, double>> *phn_base,
+                  std::string *why) {
+  const unsigned char *ep = mo.data.data();
+  const unsigned char *end = ep + mo.data.size();
+  for (;;) {
+    if (ep + sizeof(Elem<R>) > end) {
+      *why = "truncated super-op record list";
+      return false;
+    }
+    Elem<R> e;
+    memcpy(&e, ep, sizeof(e));
+    const uint32_t id = elem_case(e.op);
+    if (id == EC_END) break;
+    const uint32_t size = elem_size_bytes(e.op);
+    const unsigned char *tail = ep + sizeof(e);
+    ep += size;
+    DElem d;
+    d.mask = (e.op >> 12) & 0xffu;
+    if (e.op & kElemHasCond) {
+      uint64_t gm = e.gmask, gv = e.gval;
+      const uint32_t slot = elem_cond_slot(e.op);
+      if (slot != kCondOverflow) {
+        if (slot >= pass.conds.size()) {
+          *why = "condition slot out of range";
+          return false;
+        }
+        gm = pass.conds[slot].gmask;
+        gv = pass.conds[slot].gval;
+      }
+      int found = -1;
+      for (size_t c = 0; c < conds.size(); ++c)
+        if (conds[c].gmask == gm && conds[c].gval == gv) found = (int)c;
+      if (found < 0) {
+        Cond c = {gm, gv};
+        found = (int)conds.size();
+        conds.push_back(c);
+      }
+      d.cond = found;
+    }
+    auto load_real = [&]() {
+      for (int q = 0; q < 4; ++q) d.m[q] = (double)e.m[q];
+      d.real = true;
+    };
+    auto load_cplx = [&]() {
+      for (int q = 0; q < 8; ++q) d.m[q] = (double)e.m[q];
+      d.real = false;
+    };
+    if (id >= EC_D1R_FULL && id < EC_D1C_FULL) {
+      d.kind = DElem::D1, d.j = id - EC_D1R_FULL, d.mask = 0xf, load_real();
+    } else if (id >= EC_D1C_FULL && id < EC_D1R_MASK) {
+      d.kind = DElem::D1, d.j = id - EC_D1C_FULL, d.mask = 0xf, load_cplx();
+    } else if (id >= EC_D1R_MASK && id < EC_D1C_MASK) {
+      d.kind = DElem::D1, d.j = id - EC_D1R_MASK, load_real();
+    } else if (id >= EC_D1C_MASK && id < EC_PHASE) {
+      d.kind = DElem::D1, d.j = id - EC_D1C_MASK, load_cplx();
+    } else if (id == EC_PHASE) {
+      d.kind = DElem::PH, d.m[0] = (double)e.m[0], d.m[1] = (double)e.m[1];
+    } else if (id == EC_DENSE3) {
+      d.kind = DElem::D3;
+      d.m8.resize(128);
+      const R *w = reinterpret_cast<const R *>(tail);
+      for (int q = 0; q < 128; ++q) d.m8[q] = (double)w[q];
+    } else if (id >= EC_X_FULL && id < EC_X_MASK) {
+      d.kind = DElem::X, d.j = id - EC_X_FULL, d.mask = 0xf;
+    } else if (id >= EC_X_MASK && id < EC_PHASEN) {
+      d.kind = DElem::X, d.j = id - EC_X_MASK;
+    } else if (id == EC_PHASEN) {
+      d.kind = DElem::PHN;
+      d.slot = (uint32_t)phn_terms->size();
+      phn_base->push_back(std::make_pair((double)e.m[0], (double)e.m[1]));
+      std::vector<PhTerm> terms;
+      const uint32_t nt = (size - (uint32_t)sizeof(Elem<R>)) / (uint32_t)sizeof(PhaseTerm<R>);
+      for (uint32_t k = 0; k < nt; ++k) {
+        PhaseTerm<R> pt;
+        memcpy(&pt, tail + k * sizeof(pt), sizeof(pt));
+        PhTerm t = {pt.gmask, pt.gval, (double)pt.re, (double)pt.im};
+        terms.push_back(t);
+      }
+      phn_terms->push_back(terms);
+    } else if (id >= EC_PHASE_J && id < EC_D1R_C1) {
+      d.kind = DElem::PH, d.mask = kPhaseMaskJ[id - EC_PHASE_J], d.m[0] = (double)e.m[0], d.m[1] = (double)e.m[1];
+    } else if (id >= EC_D1R_C1 && id < EC_D1R_C2) {
+      d.kind = DElem::D1, d.j = (id - EC_D1R_C1) / 2, d.mask = kPairMaskC1[(id - EC_D1R_C1) % 2], load_real();
+    } else if (id >= EC_D1R_C2 && id < EC_PHASE_2) {
+      d.kind = DElem::D1, d.j = id - EC_D1R_C2, d.mask = kPairMaskC2, load_real();
+    } else if (id >= EC_PHASE_2 && id < EC_HAD) {
+      d.kind = DElem::PH, d.mask = kPhaseMask2[id - EC_PHASE_2], d.m[0] = (double)e.m[0], d.m[1] = (double)e.m[1];
+    } else if (id >= EC_HAD && id < EC_N_CASES) {
+      d.kind = DElem::HAD, d.j = id - EC_HAD, d.mask = 0xf;
+    } else {
+      *why = "unknown elementary case id";
+      return false;
+    }
+    out->push_back(d);
+  }
+  return true;
+}
+
+// ---- source emission --------------------------------------------------------------------------
+struct Gen {
+  bool f64;
+  std::ostringstream o;
+  std::vector<double> pool;  // |value| of every pooled constant
+  int nv = 0;
+  uint32_t renamed = 0;
+
+  std::string fresh() {
+    char b[24];
+    snprintf(b, sizeof(b), "v%d", nv++);
+    return b;
+  }
+  // expression of constant v (never called with 0 / +-1 by the chain emitter)
+  std::string K(double v) {
+    const double a = std::fabs(v);
+    size_t i = 0;
+    for (; i < pool.size(); ++i)
+      if (pool[i] == a) break;
+    if (i == pool.size()) pool.push_back(a);
+    char b[40];
+    snprintf(b, sizeof(b), v < 0 ? "(-p.c[%zu])" : "p.c[%zu]", i);
+    return b;
+  }
+  // acc = c0*v0; acc = fma(c1, v1, acc); ...   in this order, zero terms dropped, +-1 as add/sub
+  std::string chain(const std::vector<std::pair<double, std::string>> &terms) {
+    std::string acc;
+    for (size_t i = 0; i < terms.size(); ++i) {
+      const double c = terms[i].first;
+      const std::string &v = terms[i].second;
+      if (c == 0.0) continue;
+      if (acc.empty()) {
+        if (c == 1.0) acc = v;
+        else if (c == -1.0) acc = "(-" + v + ")";
+        else acc = "(" + K(c) + " * " + v + ")";
+      } else {
+        if (c == 1.0) acc = "(" + acc + " + " + v + ")";
+        else if (c == -1.0) acc = "(" + acc + " - " + v + ")";
+        else acc = "QFMA(" + K(c) + ", " + v + ", " + acc + ")";
+      }
+    }
+    if (acc.empty()) acc = f64 ? "0.0" : "0.0f";
+    return acc;
+  }
+};
+
+uint32_t swz_units(bool f64, uint32_t t) { return f64 ? (t ^ ((t >> 3) & 7u)) : (t ^ (((t >> 4) & 7u) << 1)); }
+
+}  // namespace
+
+bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::string *why) {
+  std::string dummy;
+  if (!why) why = &dummy;
+  const PassHeader &h = pass.hdr;
+  const bool f64 = prec == QIP_F64;
+  const uint32_t T = h.T, L = h.L, m = h.m;
+  const uint32_t low3 = f64 ? 3 : 4;
+  const uint32_t amp = f64 ? 16 : 8;
+  const uint32_t kThreads = 256, kWarpBits = 3, kLaneBits = 5;
+  if (T < 11 || T > 14) return *why = "tile too small/large for the generated kernel", false;
+  if (m < 3 || L < low3 || (1u << (L - low3)) > 256) return *why = "geometry has no TMA boxes", false;
+  if (pass.ops.empty()) return *why = "empty pass", false;
+  const uint32_t n_it_bits = T - 3 - kWarpBits - kLaneBits;
+  const uint32_t NIT = 1u << n_it_bits;
+  const char *RT = f64 ? "double" : "float";
+
+  // ---- decode ----
+  std::vector<Cond> conds;
+  std::vector<std::vector<PhTerm>> phn_terms;
+  std::vector<std::pair<double, double>> phn_base;
+  std::vector<std::vector<DElem>> supers;
+  std::vector<uint32_t> pmask;  // tile-local bit mask of each super-op
+  std::vector<std::vector<uint32_t>> pbits;
+  for (size_t i = 0; i < pass.ops.size(); ++i) {
+    const HostMicroOp &mo = pass.ops[i];
+    if (mo.h.kind != MK_SUPER || mo.h.ins_n != 3 || mo.h.lor_mask != 0 || mo.h.gmask != 0)
+      return *why = "pass holds a wide micro-op", false;
+    std::vector<DElem> el;
+    const bool ok = f64 ? decode_super<double>(mo, pass, conds, &el, &phn_terms, &phn_base, why)
+                        : decode_super<float>(mo, pass, conds, &el, &phn_terms, &phn_base, why);
+    if (!ok) return false;
+    supers.push_back(el);
+    std::vector<uint32_t> pb(mo.h.ins_pos, mo.h.ins_pos + 3);
+    pbits.push_back(pb);
+    pmask.push_back((1u << pb[0]) | (1u << pb[1]) | (1u << pb[2]));
+    if (pb[0] >= pb[1] || pb[1] >= pb[2] || pb[2] >= T) return *why = "malformed super-op bit list", false;
+  }
+  if (conds.size() > kThreads) return *why = "more than 256 CTA-uniform conditions", false;
+  const size_t S = supers.size();
+  const size_t NC = conds.size(), NPH = phn_terms.size();
+  size_t NPT = 0;
+  for (size_t i = 0; i < NPH; ++i) NPT += phn_terms[i].size();
+  if (NPH > 1024) return *why = "too many conditional phase runs", false;
+  const size_t gsz = f64 ? sizeof(GlobalTerm<double>) : sizeof(GlobalTerm<float>);
+  const size_t NG = pass.gterms.size() / gsz;
+
+  // ---- thread maps: segments of super-ops that share their three warp-id bits ----
+  const uint32_t all_bits = (1u << T) - 1u;
+  std::vector<uint32_t> wmask(S);
+  std::vector<bool> cta_barrier_before(S, false);
+  for (size_t s = 0; s < S;) {
+    uint32_t free_bits = all_bits & ~pmask[s];
+    size_t e = s + 1;
+    while (e < S && __builtin_popcount(free_bits & ~pmask[e]) >= (int)kWarpBits) free_bits &= ~pmask[e++];
+    uint32_t w = 0;
+    for (int b = (int)T - 1; b >= 0 && __builtin_popcount(w) < (int)kWarpBits; --b)
+      if ((free_bits >> b) & 1) w |= 1u << b;
+    for (size_t k = s; k < e; ++k) wmask[k] = w;
+    cta_barrier_before[s] = s != 0;
+    s = e;
+  }
+
+  Gen g;
+  g.f64 = f64;
+  std::ostringstream fn;  // the so_K functions
+  uint32_t n_elems = 0;
+  for (size_t s = 0; s < S; ++s) {
+    // lane / iteration bits of this super-op
+    uint32_t avail = all_bits & ~pmask[s] & ~wmask[s];
+    std::vector<uint32_t> lane;  // tile bit of lane bit k
+    const uint32_t n_classes = f64 ? 3 : 4;
+    for (uint32_t k = 0; k < n_classes; ++k) {
+      // bank-group bit k of a swizzled address is t_k ^ t_{k+3} (f64) / t_k (k = 0), t_k ^ t_{k+3} (f32, k >= 1)
+      int pick = -1;
+      if ((avail >> k) & 1) pick = (int)k;
+      else if ((f64 || k >= 1) && k + 3 < T && ((avail >> (k + 3)) & 1)) pick = (int)(k + 3);
+      if (pick >= 0) {
+        lane.push_back((uint32_t)pick);
+        avail &= ~(1u << pick);
+      }
+    }
+    for (uint32_t b = 0; b < T && lane.size() < kLaneBits; ++b)
+      if ((avail >> b) & 1) {
+        lane.push_back(b);
+        avail &= ~(1u << b);
+      }
+    std::vector<uint32_t> itb;
+    for (uint32_t b = 0; b < T; ++b)
+      if ((avail >> b) & 1) itb.push_back(b);
+    if (lane.size() != kLaneBits || itb.size() != n_it_bits) return *why = "internal: thread map", false;
+    std::vector<uint32_t> dst(8);  // tid bit -> tile bit
+    for (uint32_t k = 0; k < kLaneBits; ++k) dst[k] = lane[k];
+    {
+      uint32_t k = 0;
+      for (uint32_t b = 0; b < T; ++b)
+        if ((wmask[s] >> b) & 1) dst[kLaneBits + k++] = b;
+    }
+
+    fn << "// super-op " << s << ": sub-bits {" << pbits[s][0] << "," << pbits[s][1] << "," << pbits[s][2] << "}, warp bits 0x"
+       << std::hex << wmask[s] << std::dec << "\n";
+    fn << "QIP_DEV void so_" << s << "(unsigned char* sm, const unsigned tid, const JP& p, const unsigned* condw, const "
+       << RT << "* tbl, const " << RT << "* gt) {\n";
+    fn << "  unsigned t = 0u;\n";
+    for (uint32_t k = 0; k < 8;) {
+      uint32_t len = 1;
+      while (k + len < 8 && dst[k + len] == dst[k] + len) ++len;
+      fn << "  t |= ((tid >> " << k << ") & " << ((1u << len) - 1u) << "u) << " << dst[k] << ";\n";
+      k += len;
+    }
+    fn << (f64 ? "  t ^= (t >> 3) & 7u;\n  const unsigned a0 = t << 4;\n" : "  t ^= ((t >> 4) & 7u) << 1;\n  const unsigned a0 = t << 3;\n");
+    // condition words this super-op tests
+    {
+      uint32_t words = 0;
+      for (size_t i = 0; i < supers[s].size(); ++i)
+        if (supers[s][i].cond >= 0) words |= 1u << (supers[s][i].cond >> 5);
+      for (uint32_t w = 0; w < 8; ++w)
+        if ((words >> w) & 1) fn << "  const unsigned cw" << w << " = condw[" << w << "];\n";
+    }
+    const bool last = s + 1 == S;
+    if (last && NG) fn << "  const bool hasg = condw[8] != 0u;\n  const " << RT << " gr = gt[0], gi = gt[1];\n";
+    if (NIT > 1) fn << "#pragma unroll 1\n  for (unsigned it = 0; it < " << NIT << "u; ++it) {\n";
+    else fn << "  {\n";
+    {
+      std::string a = "a0";
+      for (uint32_t k = 0; k < n_it_bits; ++k) {
+        char b[96];
+        snprintf(b, sizeof(b), " ^ (((it >> %u) & 1u) * %uu)", k, swz_units(f64, 1u << itb[k]) * amp);
+        a += b;
+      }
+      fn << "    const unsigned a = " << a << ";\n";
+    }
+    // the 8 addresses: XOR part (swizzle-modified bits) + additive part
+    uint32_t soff[8], xpart[8], apart[8];
+    std::vector<uint32_t> xs;
+    for (uint32_t u = 0; u < 8; ++u) {
+      uint32_t off = 0;
+      for (uint32_t i = 0; i < 3; ++i)
+        if ((u >> i) & 1) off |= 1u << pbits[s][i];
+      soff[u] = swz_units(f64, off) * amp;
+      xpart[u] = soff[u] & 0x70u;
+      apart[u] = soff[u] & ~0x70u;
+      if (xpart[u] && std::find(xs.begin(), xs.end(), xpart[u]) == xs.end()) xs.push_back(xpart[u]);
+    }
+    for (size_t i = 0; i < xs.size(); ++i) fn << "    const unsigned ax" << xs[i] << " = a ^ " << xs[i] << "u;\n";
+    auto addr = [&](uint32_t u) {
+      std::ostringstream x;
+      if (xpart[u]) x << "ax" << xpart[u];
+      else x << "a";
+      if (apart[u]) x << " + " << apart[u] << "u";
+      return x.str();
+    };
+    std::string vr[8], vi[8];
+    for (uint32_t u = 0; u < 8; ++u) {
+      const std::string q = g.fresh();
+      fn << "    const QV " << q << " = *reinterpret_cast<const QV*>(sm + " << addr(u) << ");\n";
+      vr[u] = q + ".x";
+      vi[u] = q + ".y";
+    }
+    // ---- elementary ops ----
+    for (size_t ei = 0; ei < supers[s].size(); ++ei) {
+      const DElem &d = supers[s][ei];
+      ++n_elems;
+      const bool cond = d.cond >= 0;
+      std::string ctest;
+      if (cond) {
+        char b[64];
+        snprintf(b, sizeof(b), "((cw%d >> %d) & 1u)", d.cond >> 5, d.cond & 31);
+        ctest = b;
+      }
+      // new values of the amplitudes this op changes: (u, new re expr, new im expr)
+      struct Upd {
+        uint32_t u;
+        std::string re, im;
+      };
+      std::vector<Upd> upd;
+      auto pairs_of = [&](uint32_t j, uint32_t mask, std::vector<std::pair<uint32_t, uint32_t>> *pr) {
+        uint32_t pidx = 0;
+        for (uint32_t c = 0; c < 8; ++c) {
+          if ((c >> j) & 1) continue;
+          if ((mask >> pidx) & 1) pr->push_back(std::make_pair(c, c | (1u << j)));
+          ++pidx;
+        }
+      };
+      typedef std::vector<std::pair<double, std::string>> Terms;
+      if (d.kind == DElem::X || (d.kind == DElem::D1 && d.real && d.m[0] == 0.0 && d.m[3] == 0.0 && d.m[1] == 1.0 && d.m[2] == 1.0)) {
+        std::vector<std::pair<uint32_t, uint32_t>> pr;
+        pairs_of(d.j, d.mask, &pr);
+        if (!cond) {  // pure renaming: no instruction at all, exact for every bit pattern
+          for (size_t k = 0; k < pr.size(); ++k) {
+            std::swap(vr[pr[k].first], vr[pr[k].second]);
+            std::swap(vi[pr[k].first], vi[pr[k].second]);
+          }
+          ++g.renamed;
+          continue;
+        }
+        for (size_t k = 0; k < pr.size(); ++k) {
+          Upd a = {pr[k].first, vr[pr[k].second], vi[pr[k].second]}, b = {pr[k].second, vr[pr[k].first], vi[pr[k].first]};
+          upd.push_back(a);
+          upd.push_back(b);
+        }
+      } else if (d.kind == DElem::HAD) {
+        std::vector<std::pair<uint32_t, uint32_t>> pr;
+        pairs_of(d.j, d.mask, &pr);
+        for (size_t k = 0; k < pr.size(); ++k) {
+          const uint32_t x = pr[k].first, y = pr[k].second;
+          Upd a = {x, "(" + vr[x] + " + " + vr[y] + ")", "(" + vi[x] + " + " + vi[y] + ")"};
+          Upd b = {y, "(" + vr[x] + " - " + vr[y] + ")", "(" + vi[x] + " - " + vi[y] + ")"};
+          upd.push_back(a);
+          upd.push_back(b);
+        }
+      } else if (d.kind == DElem::D1) {
+        std::vector<std::pair<uint32_t, uint32_t>> pr;
+        pairs_of(d.j, d.mask, &pr);
+        for (size_t k = 0; k < pr.size(); ++k) {
+          const uint32_t x = pr[k].first, y = pr[k].second;
+          const std::string &xr = vr[x], &xi = vi[x], &yr = vr[y], &yi = vi[y];
+          Upd a, b;
+          a.u = x;
+          b.u = y;
+          if (d.real) {  // tile_interp.cuh QIP_D1R: x' = fma(m00, x, m01*y); y' = fma(m10, x, m11*y)
+            const double m00 = d.m[0], m01 = d.m[1], m10 = d.m[2], m11 = d.m[3];
+            a.re = g.chain(Terms{{m01, yr}, {m00, xr}});
+            a.im = g.chain(Terms{{m01, yi}, {m00, xi}});
+            b.re = g.chain(Terms{{m11, yr}, {m10, xr}});
+            b.im = g.chain(Terms{{m11, yi}, {m10, xi}});
+          } else {  // QIP_D1C
+            const double m00r = d.m[0], m00i = d.m[1], m01r = d.m[2], m01i = d.m[3], m10r = d.m[4], m10i = d.m[5],
+                         m11r = d.m[6], m11i = d.m[7];
+            a.re = g.chain(Terms{{m01r, yr}, {-m01i, yi}, {m00r, xr}, {-m00i, xi}});
+            a.im = g.chain(Terms{{m01r, yi}, {m01i, yr}, {m00r, xi}, {m00i, xr}});
+            b.re = g.chain(Terms{{m11r, yr}, {-m11i, yi}, {m10r, xr}, {-m10i, xi}});
+            b.im = g.chain(Terms{{m11r, yi}, {m11i, yr}, {m10r, xi}, {m10i, xr}});
+          }
+          upd.push_back(a);
+          upd.push_back(b);
+        }
+      } else if (d.kind == DElem::PH) {  // QIP_PH: re' = fma(wr, re, -(wi*im)); im' = fma(wr, im, wi*re)
+        for (uint32_t c = 0; c < 8; ++c) {
+          if (!((d.mask >> c) & 1)) continue;
+          Upd a = {c, g.chain(Terms{{-d.m[1], vi[c]}, {d.m[0], vr[c]}}), g.chain(Terms{{d.m[1], vr[c]}, {d.m[0], vi[c]}})};
+          upd.push_back(a);
+        }
+      } else if (d.kind == DElem::PHN) {  // factor formed once per CTA (table behind the tile)
+        const std::string wr = g.fresh(), wi = g.fresh();
+        fn << "    const " << RT << " " << wr << " = tbl[" << 2 * d.slot << "], " << wi << " = tbl[" << 2 * d.slot + 1 << "];\n";
+        for (uint32_t c = 0; c < 8; ++c) {
+          if (!((d.mask >> c) & 1)) continue;
+          Upd a = {c, "QFMA(" + wr + ", " + vr[c] + ", -(" + wi + " * " + vi[c] + "))",
+                   "QFMA(" + wr + ", " + vi[c] + ", (" + wi + " * " + vr[c] + "))"};
+          upd.push_back(a);
+        }
+      } else {  // D3: dense 8x8, rows in order, re = fma(mr, xr, re); re = fma(-mi, xi, re); im likewise
+        for (uint32_t u = 0; u < 8; ++u) {
+          Terms tr, ti;
+          for (uint32_t v = 0; v < 8; ++v) {
+            const double mr = d.m8[2 * (u * 8 + v)], mi = d.m8[2 * (u * 8 + v) + 1];
+            tr.push_back(std::make_pair(mr, vr[v]));
+            tr.push_back(std::make_pair(-mi, vi[v]));
+            ti.push_back(std::make_pair(mr, vi[v]));
+            ti.push_back(std::make_pair(mi, vr[v]));
+          }
+          Upd a = {u, g.chain(tr), g.chain(ti)};
+          upd.push_back(a);
+        }
+      }
+      // materialise (all right-hand sides refer to the OLD names)
+      std::vector<std::string> nr(upd.size()), ni(upd.size());
+      for (size_t k = 0; k < upd.size(); ++k) {
+        nr[k] = g.fresh();
+        ni[k] = g.fresh();
+      }
+      if (!cond) {
+        for (size_t k = 0; k < upd.size(); ++k)
+          fn << "    const " << RT << " " << nr[k] << " = " << upd[k].re << ", " << ni[k] << " = " << upd[k].im << ";\n";
+      } else {
+        for (size_t k = 0; k < upd.size(); ++k)
+          fn << "    " << RT << " " << nr[k] << " = " << vr[upd[k].u] << ", " << ni[k] << " = " << vi[upd[k].u] << ";\n";
+        fn << "    if (" << ctest << ") {\n";
+        for (size_t k = 0; k < upd.size(); ++k)
+          fn << "      " << nr[k] << " = " << upd[k].re << "; " << ni[k] << " = " << upd[k].im << ";\n";
+        fn << "    }\n";
+      }
+      for (size_t k = 0; k < upd.size(); ++k) {
+        vr[upd[k].u] = nr[k];
+        vi[upd[k].u] = ni[k];
+      }
+    }
+    if (last && NG) {  // CTA-uniform phase product, folded into the last write of every amplitude
+      std::string nr[8], ni[8];
+      for (uint32_t u = 0; u < 8; ++u) {
+        nr[u] = g.fresh();
+        ni[u] = g.fresh();
+        fn << "    " << RT << " " << nr[u] << " = " << vr[u] << ", " << ni[u] << " = " << vi[u] << ";\n";
+      }
+      fn << "    if (hasg) {\n";
+      for (uint32_t u = 0; u < 8; ++u)
+        fn << "      " << nr[u] << " = QFMA(gr, " << vr[u] << ", -(gi * " << vi[u] << ")); " << ni[u] << " = QFMA(gr, " << vi[u]
+           << ", (gi * " << vr[u] << "));\n";
+      fn << "    }\n";
+      for (uint32_t u = 0; u < 8; ++u) {
+        vr[u] = nr[u];
+        vi[u] = ni[u];
+      }
+    }
+    for (uint32_t u = 0; u < 8; ++u) {
+      const std::string q = g.fresh();
+      fn << "    { QV " << q << "; " << q << ".x = " << vr[u] << "; " << q << ".y = " << vi[u] << "; *reinterpret_cast<QV*>(sm + "
+         << addr(u) << ") = " << q << "; }\n";
+    }
+    fn << "  }\n}\n\n";
+  }
+
+  // ---- parameter block ----
+  const uint32_t NBOX = 1u << (m - 3);
+  const size_t NK = g.pool.size();
+  std::ostringstream src;
+  src << "// generated by rustqip_b200/csrc/jit_codegen.cpp -- one fused tile pass, specialised\n";
+  src << "typedef unsigned long long u64;\n";
+  src << "#define TILE_T " << T << "\n#define TILE_L " << L << "\n#define TILE_M " << m << "\n#define LOW3 " << low3 << "\n";
+  src << "#define NBOX " << NBOX << "\n#define NC " << NC << "\n#define NPH " << NPH << "\n#define NPT " << NPT << "\n#define NG " << NG
+      << "\n#define NK " << NK << "\n";
+  src << "#define TILE_BYTES " << (amp << T) << "u\n#define BOX_BYTES " << (amp << (L + 3)) << "u\n";
+  const uint32_t tbl_bytes = (uint32_t)(((NPH * 2 * (f64 ? 8 : 4)) + 15) & ~(size_t)15);
+  const uint32_t off_tbl = amp << T, off_gt = off_tbl + tbl_bytes, off_condw = off_gt + 16, off_mbar = off_condw + 48;
+  src << "#define OFF_TBL " << off_tbl << "u\n#define OFF_GT " << off_gt << "u\n#define OFF_CONDW " << off_condw << "u\n#define OFF_MBAR "
+      << off_mbar << "u\n";
+  src << "typedef " << RT << " R;\n";
+  src << "struct JP {\n  u64 box_off[NBOX];\n";
+  if (NC) src << "  u64 cm[NC], cv[NC];\n";
+  if (NPT) src << "  u64 ptm[NPT], ptv[NPT];\n";
+  if (NG) src << "  u64 gm[NG], gv[NG];\n";
+  if (NK) src << "  R c[NK];\n";
+  if (NPT) src << "  R ptw[2 * NPT];\n";
+  if (NPH) src << "  R pw[2 * NPH];\n";
+  if (NG) src << "  R gw[2 * NG];\n";
+  src << "  unsigned hi_pos[8];\n";
+  if (NPH) src << "  unsigned pt_begin[NPH + 1];\n";
+  src << "};\n";
+  src << R"(#ifdef QIP_JIT_HOST
+#include <cmath>
+#include <cstring>
+#define QIP_DEV static inline
+#define QFMA(a, b, c) std::fma((a), (b), (c))
+struct alignas(2 * sizeof(R)) QV { R x, y; };
+#else
+#define QIP_DEV __device__ __forceinline__
+#define QFMA(a, b, c) fma((a), (b), (c))
+)";
+  src << (f64 ? "typedef double2 QV;\n" : "typedef float2 QV;\n");
+  src << "#endif\n\n";
+  src << fn.str();
+
+  // prelude: per-CTA condition word, conditional-phase factor table, CTA-uniform global factor
+  const bool has_prelude = NC || NPH || NG;
+  src << "QIP_DEV void prelude(unsigned char* sm, const unsigned tid, const JP& p, const u64 base) {\n";
+  src << "  unsigned* condw = reinterpret_cast<unsigned*>(sm + OFF_CONDW);\n  (void)condw; (void)base; (void)tid;\n";
+  if (NC) {
+    src << "  {\n    bool on = false;\n    if (tid < NC) on = (base & p.cm[tid]) == p.cv[tid];\n";
+    src << "#ifdef QIP_JIT_HOST\n    if (on) condw[tid >> 5] |= 1u << (tid & 31u);\n#else\n";
+    src << "    const unsigned bits = __ballot_sync(0xffffffffu, on);\n    if ((tid & 31u) == 0u) condw[tid >> 5] = bits;\n#endif\n  }\n";
+  }
+  if (NPH) {
+    src << "  {\n    R* tbl = reinterpret_cast<R*>(sm + OFF_TBL);\n    for (unsigned e = tid; e < NPH; e += " << kThreads << "u) {\n";
+    src << "      R wr = p.pw[2 * e], wi = p.pw[2 * e + 1];\n";
+    src << "      for (unsigned k = p.pt_begin[e]; k < p.pt_begin[e + 1]; ++k) {\n";
+    src << "        if ((base & p.ptm[k]) != p.ptv[k]) continue;\n";
+    src << "        const R nr = wr * p.ptw[2 * k] - wi * p.ptw[2 * k + 1];\n";
+    src << "        wi = wr * p.ptw[2 * k + 1] + wi * p.ptw[2 * k];\n        wr = nr;\n      }\n";
+    src << "      tbl[2 * e] = wr;\n      tbl[2 * e + 1] = wi;\n    }\n  }\n";
+  }
+  if (NG) {
+    src << "  if (tid == " << kThreads - 1 << "u) {\n    R gr = (R)1, gi = (R)0;\n    unsigned hasg = 0u;\n";
+    src << "    for (unsigned k = 0; k < NG; ++k) {\n      if ((base & p.gm[k]) != p.gv[k]) continue;\n";
+    src << "      const R nr = gr * p.gw[2 * k] - gi * p.gw[2 * k + 1];\n      gi = gr * p.gw[2 * k + 1] + gi * p.gw[2 * k];\n      gr = nr;\n      hasg = 1u;\n    }\n";
+    src << "    R* gt = reinterpret_cast<R*>(sm + OFF_GT);\n    gt[0] = gr;\n    gt[1] = gi;\n    condw[8] = hasg;\n  }\n";
+  }
+  src << "}\n\n";
+
+  // tile base index: the tile counter with zero bits inserted at the high tile bit positions
+  src << "QIP_DEV u64 tile_base(const JP& p, u64 tile) {\n  u64 base = tile << TILE_L;\n";
+  src << "  for (unsigned i = 0; i < TILE_M; ++i) {\n    const unsigned q = p.hi_pos[i];\n";
+  src << "    base = ((base >> q) << (q + 1)) | (base & ((1ull << q) - 1ull));\n  }\n  return base;\n}\n\n";
+
+  // ---- host harness (validation without a GPU) ----
+  src << "#ifdef QIP_JIT_HOST\n";
+  src << "extern \"C\" void qip_host_pass(R* psi, const JP* pp, unsigned n_local) {\n  const JP& p = *pp;\n";
+  src << "  static unsigned char sm[OFF_MBAR + 64];\n  const u64 tiles = 1ull << (n_local - TILE_T);\n";
+  src << "  for (u64 tile = 0; tile < tiles; ++tile) {\n    const u64 base = tile_base(p, tile);\n";
+  src << "    for (unsigned t = 0; t < (1u << TILE_T); ++t) {\n      u64 idx = base + (t & ((1u << TILE_L) - 1u));\n";
+  src << "      for (unsigned i = 0; i < TILE_M; ++i) if ((t >> (TILE_L + i)) & 1u) idx |= 1ull << p.hi_pos[i];\n";
+  src << (f64 ? "      const unsigned s = t ^ ((t >> 3) & 7u);\n" : "      const unsigned s = t ^ (((t >> 4) & 7u) << 1);\n");
+  src << "      memcpy(sm + s * sizeof(QV), psi + 2 * idx, sizeof(QV));\n    }\n";
+  src << "    memset(sm + OFF_CONDW, 0, 48);\n";
+  src << "    for (unsigned tid = 0; tid < " << kThreads << "u; ++tid) prelude(sm, tid, p, base);\n";
+  for (size_t s = 0; s < S; ++s)
+    src << "    for (unsigned tid = 0; tid < " << kThreads << "u; ++tid) so_" << s
+        << "(sm, tid, p, reinterpret_cast<const unsigned*>(sm + OFF_CONDW), reinterpret_cast<const R*>(sm + OFF_TBL), "
+           "reinterpret_cast<const R*>(sm + OFF_GT));\n";
+  src << "    for (unsigned t = 0; t < (1u << TILE_T); ++t) {\n      u64 idx = base + (t & ((1u << TILE_L) - 1u));\n";
+  src << "      for (unsigned i = 0; i < TILE_M; ++i) if ((t >> (TILE_L + i)) & 1u) idx |= 1ull << p.hi_pos[i];\n";
+  src << (f64 ? "      const unsigned s = t ^ ((t >> 3) & 7u);\n" : "      const unsigned s = t ^ (((t >> 4) & 7u) << 1);\n");
+  src << "      memcpy(psi + 2 * idx, sm + s * sizeof(QV), sizeof(QV));\n    }\n  }\n}\n";
+  src << "#else\n";
+
+  // ---- device kernel ----
+  src << R"(struct alignas(64) CUtensorMap { u64 opaque[16]; };
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void box_coords(const JP& p, u64 idx, int* c) {
+  const unsigned h1 = p.hi_pos[0], h2 = p.hi_pos[1], h3 = p.hi_pos[2];
+  c[0] = (int)((idx >> LOW3) & ((1ull << (h1 - LOW3)) - 1ull));
+  c[1] = (int)((idx >> h1) & ((1ull << (h2 - h1)) - 1ull));
+  c[2] = (int)((idx >> h2) & ((1ull << (h3 - h2)) - 1ull));
+  c[3] = (int)(idx >> h3);
+}
+extern "C" __global__ void __launch_bounds__(256, 3)
+qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) unsigned char sm[];
+  const unsigned tid = threadIdx.x;
+  const u64 base = tile_base(p, (u64)blockIdx.x);
+  const unsigned smb = (unsigned)__cvta_generic_to_shared(sm);
+  const unsigned mbar = smb + OFF_MBAR;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(TILE_BYTES) : "memory");
+#pragma unroll 1
+    for (unsigned b = 0; b < NBOX; ++b) {
+      int c[4];
+      box_coords(p, base + p.box_off[b], c);
+      asm volatile(
+          "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+              smb + b * BOX_BYTES),
+          "l"(&tmap), "r"(mbar), "r"(0), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3])
+          : "memory");
+    }
+  }
+)";
+  src << "  prelude(sm, tid, p, base);\n";
+  if (has_prelude) src << "  __syncthreads();\n";
+  src << "  const unsigned* condw = reinterpret_cast<const unsigned*>(sm + OFF_CONDW);\n";
+  src << "  const R* tbl = reinterpret_cast<const R*>(sm + OFF_TBL);\n  const R* gt = reinterpret_cast<const R*>(sm + OFF_GT);\n";
+  src << "  mbar_wait(mbar, 0u);\n";
+  uint32_t n_bar = 0, n_ws = 0;
+  for (size_t s = 0; s < S; ++s) {
+    if (s) {
+      if (cta_barrier_before[s]) {
+        src << "  __syncthreads();\n";
+        ++n_bar;
+      } else {
+        src << "  __syncwarp();\n";
+        ++n_ws;
+      }
+    }
+    src << "  so_" << s << "(sm, tid, p, condw, tbl, gt);\n";
+  }
+  src << R"(  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll 1
+    for (unsigned b = 0; b < NBOX; ++b) {
+      int c[4];
+      box_coords(p, base + p.box_off[b], c);
+      asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(&tmap),
+                   "r"(smb + b * BOX_BYTES), "r"(0), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3])
+                   : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+  (void)psi;
+}
+#endif
+)";
+
+  // ---- the JP blob, in declaration order ----
+  std::vector<unsigned char> blob;
+  auto put = [&](const void *ptr, size_t n) {
+    const unsigned char *b = static_cast<const unsigned char *>(ptr);
+    blob.insert(blob.end(), b, b + n);
+  };
+  auto put_real = [&](double v) {
+    if (f64) put(&v, 8);
+    else {
+      const float f = (float)v;
+      put(&f, 4);
+    }
+  };
+  for (uint32_t b = 0; b < NBOX; ++b) put(&h.chunk_off[b << 3], 8);
+  for (size_t i = 0; i < NC; ++i) put(&conds[i].gmask, 8);
+  for (size_t i = 0; i < NC; ++i) put(&conds[i].gval, 8);
+  for (size_t i = 0; i < NPH; ++i)
+    for (size_t k = 0; k < phn_terms[i].size(); ++k) put(&phn_terms[i][k].gmask, 8);
+  for (size_t i = 0; i < NPH; ++i)
+    for (size_t k = 0; k < phn_terms[i].size(); ++k) put(&phn_terms[i][k].gval, 8);
+  std::vector<double> gre(NG), gim(NG);
+  {
+    std::vector<uint64_t> gm(NG), gv(NG);
+    for (size_t i = 0; i < NG; ++i) {
+      if (f64) {
+        GlobalTerm<double> t;
+        memcpy(&t, pass.gterms.data() + i * gsz, gsz);
+        gm[i] = t.gmask, gv[i] = t.gval, gre[i] = t.re, gim[i] = t.im;
+      } else {
+        GlobalTerm<float> t;
+        memcpy(&t, pass.gterms.data() + i * gsz, gsz);
+        gm[i] = t.gmask, gv[i] = t.gval, gre[i] = t.re, gim[i] = t.im;
+      }
+    }
+    for (size_t i = 0; i < NG; ++i) put(&gm[i], 8);
+    for (size_t i = 0; i < NG; ++i) put(&gv[i], 8);
+  }
+  for (size_t i = 0; i < NK; ++i) put_real(g.pool[i]);
+  for (size_t i = 0; i < NPH; ++i)
+    for (size_t k = 0; k < phn_terms[i].size(); ++k) {
+      put_real(phn_terms[i][k].re);
+      put_real(phn_terms[i][k].im);
+    }
+  for (size_t i = 0; i < NPH; ++i) {
+    put_real(phn_base[i].first);
+    put_real(phn_base[i].second);
+  }
+  for (size_t i = 0; i < NG; ++i) {
+    put_real(gre[i]);
+    put_real(gim[i]);
+  }
+  for (uint32_t i = 0; i < 8; ++i) put(&h.hi_pos[i], 4);
+  if (NPH) {
+    uint32_t at = 0;
+    for (size_t i = 0; i < NPH; ++i) {
+      put(&at, 4);
+      at += (uint32_t)phn_terms[i].size();
+    }
+    put(&at, 4);
+  }
+  while (blob.size() % 8) blob.push_back(0);  // sizeof(JP): the struct is 8-byte aligned
+
+  out->source = src.str();
+  out->params.swap(blob);
+  out->smem_bytes = off_mbar + 64;
+  out->threads = kThreads;
+  out->tiles_log2_sub = T;
+  out->n_super = (uint32_t)S;
+  out->n_elems = n_elems;
+  out->n_cta_barriers = n_bar;
+  out->n_warp_syncs = n_ws;
+  out->n_renamed = g.renamed;
+  out->n_consts = (uint32_t)NK;
+  return true;
+}
+
+}  // namespace qipb200

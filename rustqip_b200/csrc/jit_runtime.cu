@@ -1,0 +1,287 @@
+// jit_runtime.cu -- see jit_runtime.h.
+#include "jit_runtime.h"
+
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <chrono>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <unordered_map>
+
+namespace qipb200 {
+
+namespace {
+
+// ---- NVRTC through dlopen: the library must load (and the interpreter path work) without it ----
+struct Nvrtc {
+  void *h = nullptr;
+  nvrtcResult (*create)(nvrtcProgram *, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
+  nvrtcResult (*compile)(nvrtcProgram, int, const char *const *) = nullptr;
+  nvrtcResult (*cubin_size)(nvrtcProgram, size_t *) = nullptr;
+  nvrtcResult (*cubin)(nvrtcProgram, char *) = nullptr;
+  nvrtcResult (*log_size)(nvrtcProgram, size_t *) = nullptr;
+  nvrtcResult (*log)(nvrtcProgram, char *) = nullptr;
+  nvrtcResult (*destroy)(nvrtcProgram *) = nullptr;
+  std::string why;
+  bool ok = false;
+};
+
+Nvrtc &nvrtc() {
+  static Nvrtc n;
+  static std::once_flag once;
+  std::call_once(once, [&]() {
+    const char *names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so"};
+    for (const char *nm : names)
+      if ((n.h = dlopen(nm, RTLD_NOW | RTLD_LOCAL))) break;
+    if (!n.h) {
+      n.why = std::string("libnvrtc not found: ") + dlerror();
+      return;
+    }
+#define QIP_SYM(field, name)                                     \
+  *(void **)(&n.field) = dlsym(n.h, name);                       \
+  if (!n.field) {                                                \
+    n.why = std::string("libnvrtc lacks ") + name;               \
+    return;                                                      \
+  }
+    QIP_SYM(create, "nvrtcCreateProgram")
+    QIP_SYM(compile, "nvrtcCompileProgram")
+    QIP_SYM(cubin_size, "nvrtcGetCUBINSize")
+    QIP_SYM(cubin, "nvrtcGetCUBIN")
+    QIP_SYM(log_size, "nvrtcGetProgramLogSize")
+    QIP_SYM(log, "nvrtcGetProgramLog")
+    QIP_SYM(destroy, "nvrtcDestroyProgram")
+#undef QIP_SYM
+    n.ok = true;
+  });
+  return n;
+}
+
+// ---- driver API through the runtime's entry-point query (no link-time dependency on libcuda) ----
+struct Driver {
+  CUresult (*module_load)(CUmodule *, const void *) = nullptr;
+  CUresult (*module_get)(CUfunction *, CUmodule, const char *) = nullptr;
+  CUresult (*module_unload)(CUmodule) = nullptr;
+  CUresult (*func_set_attr)(CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*launch)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **) = nullptr;
+  CUresult (*err_name)(CUresult, const char **) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+
+Driver &driver() {
+  static Driver d;
+  static std::once_flag once;
+  std::call_once(once, [&]() {
+    auto get = [&](const char *name, void **fp) {
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint(name, fp, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !*fp) {
+        (void)cudaGetLastError();
+        d.why = std::string("driver entry point missing: ") + name;
+        return false;
+      }
+      return true;
+    };
+    if (!get("cuModuleLoadData", (void **)&d.module_load) || !get("cuModuleGetFunction", (void **)&d.module_get) ||
+        !get("cuModuleUnload", (void **)&d.module_unload) || !get("cuFuncSetAttribute", (void **)&d.func_set_attr) ||
+        !get("cuLaunchKernel", (void **)&d.launch) || !get("cuGetErrorName", (void **)&d.err_name))
+      return;
+    d.ok = true;
+  });
+  return d;
+}
+
+std::shared_ptr<JitCubin> compile_now(const std::string &source) {
+  std::shared_ptr<JitCubin> out = std::make_shared<JitCubin>();
+  Nvrtc &n = nvrtc();
+  if (!n.ok) {
+    out->log = n.why;
+    return out;
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  nvrtcProgram prog;
+  if (n.create(&prog, source.c_str(), "qip_pass.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) {
+    out->log = "nvrtcCreateProgram failed";
+    return out;
+  }
+  // sm_100a SASS directly (no PTX JIT by the driver); implicit mul+add contraction off: the generated source
+  // spells every FMA out, in the interpreter kernel's order
+  const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo", "-default-device"};
+  const nvrtcResult r = n.compile(prog, 5, opts);
+  size_t ls = 0;
+  if (n.log_size(prog, &ls) == NVRTC_SUCCESS && ls > 1) {
+    out->log.resize(ls);
+    n.log(prog, &out->log[0]);
+  }
+  if (r == NVRTC_SUCCESS) {
+    size_t cs = 0;
+    if (n.cubin_size(prog, &cs) == NVRTC_SUCCESS && cs) {
+      out->image.resize(cs);
+      out->ok = n.cubin(prog, out->image.data()) == NVRTC_SUCCESS;
+    }
+  }
+  n.destroy(&prog);
+  out->compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return out;
+}
+
+// ---- process-wide cache + background workers ----
+struct Entry {
+  std::shared_ptr<const JitCubin> cubin;  // null while pending
+  bool pending = false;
+};
+
+struct Cache {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::unordered_map<std::string, Entry> map;  // keyed by the source text itself
+  std::deque<std::string> queue;
+  std::vector<std::thread> workers;
+  unsigned in_flight = 0;
+  uint64_t n_compiled = 0;
+  double total_ms = 0.0;
+  bool stop = false;
+
+  void start_workers() {
+    if (!workers.empty()) return;
+    unsigned nthr = std::thread::hardware_concurrency();
+    if (const char *e = getenv("QIPB200_JIT_THREADS")) nthr = (unsigned)std::max(1, atoi(e));
+    nthr = std::max(1u, std::min(nthr, 32u));
+    for (unsigned i = 0; i < nthr; ++i) workers.emplace_back([this]() { this->worker(); });
+  }
+  void worker() {
+    for (;;) {
+      std::string src;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&]() { return stop || !queue.empty(); });
+        if (stop) return;
+        src.swap(queue.front());
+        queue.pop_front();
+      }
+      std::shared_ptr<JitCubin> c = compile_now(src);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        Entry &e = map[src];
+        e.cubin = c;
+        e.pending = false;
+        --in_flight;
+        ++n_compiled;
+        total_ms += c->compile_ms;
+      }
+      cv.notify_all();
+    }
+  }
+  ~Cache() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stop = true;
+    }
+    cv.notify_all();
+    for (std::thread &t : workers) t.join();
+  }
+};
+
+Cache &cache() {
+  static Cache *c = new Cache();  // intentionally leaked at exit when workers are still compiling
+  return *c;
+}
+
+}  // namespace
+
+bool jit_available(std::string *why) {
+  if (!nvrtc().ok) {
+    if (why) *why = nvrtc().why;
+    return false;
+  }
+  if (!driver().ok) {
+    if (why) *why = driver().why;
+    return false;
+  }
+  return true;
+}
+
+std::shared_ptr<const JitCubin> jit_request(const std::string &source, bool wait) {
+  Cache &c = cache();
+  std::unique_lock<std::mutex> lk(c.mu);
+  Entry &e = c.map[source];
+  if (e.cubin) return e.cubin;
+  if (!e.pending) {
+    e.pending = true;
+    ++c.in_flight;
+    c.queue.push_back(source);
+    c.start_workers();
+    c.cv.notify_all();
+  }
+  if (!wait) return nullptr;
+  c.cv.wait(lk, [&]() { return c.map[source].cubin != nullptr; });
+  return c.map[source].cubin;
+}
+
+void jit_wait_all(uint64_t *n_compiled, double *total_ms) {
+  Cache &c = cache();
+  std::unique_lock<std::mutex> lk(c.mu);
+  c.cv.wait(lk, [&]() { return c.in_flight == 0; });
+  if (n_compiled) *n_compiled = c.n_compiled;
+  if (total_ms) *total_ms = c.total_ms;
+}
+
+cudaError_t jit_launch(const std::shared_ptr<const JitCubin> &cubin, std::vector<std::pair<const JitCubin *, JitLoaded>> *loaded,
+                       const JitProgram &prog, void *psi, uint32_t n_local, const CUtensorMap &tmap, cudaStream_t stream,
+                       std::string *err) {
+  Driver &d = driver();
+  if (!d.ok || !cubin || !cubin->ok) {
+    if (err) *err = !d.ok ? d.why : "no cubin";
+    return cudaErrorNotSupported;
+  }
+  JitLoaded *L = nullptr;
+  for (size_t i = 0; i < loaded->size(); ++i)
+    if ((*loaded)[i].first == cubin.get()) L = &(*loaded)[i].second;
+  auto fail = [&](CUresult r, const char *what) {
+    const char *nm = nullptr;
+    d.err_name(r, &nm);
+    if (err) *err = std::string(what) + ": " + (nm ? nm : "?");
+    return cudaErrorUnknown;
+  };
+  if (!L) {
+    JitLoaded nl;
+    CUresult r = d.module_load(&nl.mod, cubin->image.data());
+    if (r != CUDA_SUCCESS) return fail(r, "cuModuleLoadData");
+    r = d.module_get(&nl.fn, nl.mod, "qip_pass");
+    if (r != CUDA_SUCCESS) return fail(r, "cuModuleGetFunction");
+    r = d.func_set_attr(nl.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)prog.smem_bytes);
+    if (r != CUDA_SUCCESS) return fail(r, "cuFuncSetAttribute(max dynamic shared memory)");
+    loaded->push_back(std::make_pair(cubin.get(), nl));
+    L = &loaded->back().second;
+  }
+  alignas(64) CUtensorMap tm = tmap;
+  void *args[3] = {&psi, const_cast<unsigned char *>(prog.params.data()), &tm};
+  const unsigned grid = 1u << (n_local - prog.tiles_log2_sub);
+  const CUresult r = d.launch(L->fn, grid, 1, 1, prog.threads, 1, 1, prog.smem_bytes, (CUstream)stream, args, nullptr);
+  if (r != CUDA_SUCCESS) return fail(r, "cuLaunchKernel");
+  return cudaSuccess;
+}
+
+void jit_unload(std::vector<std::pair<const JitCubin *, JitLoaded>> *loaded) {
+  Driver &d = driver();
+  if (d.ok)
+    for (size_t i = 0; i < loaded->size(); ++i)
+      if ((*loaded)[i].second.mod) d.module_unload((*loaded)[i].second.mod);
+  loaded->clear();
+}
+
+JitMode jit_mode_from_env(uint32_t n_local) {
+  if (const char *e = getenv("QIPB200_JIT")) {
+    if (!strcmp(e, "off") || !strcmp(e, "0")) return JIT_OFF;
+    if (!strcmp(e, "sync")) return JIT_SYNC;
+    if (!strcmp(e, "async") || !strcmp(e, "1")) return JIT_ASYNC;
+  }
+  // below ~2^22 amplitudes a pass takes microseconds: compiling a kernel for it never pays off
+  return n_local >= 22 ? JIT_ASYNC : JIT_OFF;
+}
+
+}  // namespace qipb200

@@ -1,0 +1,56 @@
+// jit_runtime.h -- compiles the generated pass kernels (jit_codegen) with NVRTC for sm_100a and launches them.
+//
+// Tiered execution: a pass whose specialised kernel is not compiled yet runs through the interpreter kernel
+// (tile_kernel.cu) while a background worker pool compiles it; the next run of the same pass STRUCTURE (the
+// numeric gate constants, tile geometry and conditions are kernel parameters, not part of the key) finds the
+// cubin in the process-wide cache.  Both kernels issue the same arithmetic, so mixing them is invisible in the
+// results.  QIPB200_JIT = off | async (default for big states) | sync (compile before launching; tests).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "jit_codegen.h"
+
+namespace qipb200 {
+
+enum JitMode { JIT_OFF = 0, JIT_ASYNC = 1, JIT_SYNC = 2 };
+
+struct JitCubin {  // one compiled program (host memory, device independent)
+  std::vector<char> image;
+  std::string log;
+  bool ok = false;
+  double compile_ms = 0.0;
+};
+
+struct JitLoaded {  // per (context == device): a loaded module of one cubin
+  CUmodule mod = nullptr;
+  CUfunction fn = nullptr;
+};
+
+// NVRTC + the driver entry points could be resolved in this process.
+bool jit_available(std::string *why);
+
+// Ask for the cubin of `source`: returns it when ready, nullptr when it is (now) being compiled in the
+// background; with wait = true blocks until the compilation finishes.  Thread-safe.
+std::shared_ptr<const JitCubin> jit_request(const std::string &source, bool wait);
+
+// Block until the background queue is empty; returns the number of programs compiled so far and the
+// total compile time spent (sum over programs, ms).
+void jit_wait_all(uint64_t *n_compiled, double *total_ms);
+
+// Load (once per context) and launch.  `loaded` is the context's module cache keyed by the cubin pointer.
+cudaError_t jit_launch(const std::shared_ptr<const JitCubin> &cubin, std::vector<std::pair<const JitCubin *, JitLoaded>> *loaded,
+                       const JitProgram &prog, void *psi, uint32_t n_local, const CUtensorMap &tmap, cudaStream_t stream,
+                       std::string *err);
+
+void jit_unload(std::vector<std::pair<const JitCubin *, JitLoaded>> *loaded);
+
+JitMode jit_mode_from_env(uint32_t n_local);
+
+}  // namespace qipb200

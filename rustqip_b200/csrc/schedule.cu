@@ -10,10 +10,14 @@
 // when a rank-held qubit has to be migrated; an exchange is a fusion barrier.
 #include "schedule.h"
 
+#include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "../../include/qipb200.h"
+#include "jit_codegen.h"
+#include "jit_runtime.h"
 #include "tile.cuh"
 #include "tile_launch.cuh"
 
@@ -44,7 +48,46 @@ int execute_steps(qipb200_state *s, const std::vector<PlanStep> &steps, const st
   qipb200_ctx *ctx = s->ctx;
   int st = QIPB200_OK;
   PassParams *pp = new PassParams();
+  // Generated kernels (jit_codegen / jit_runtime): every pass is turned into specialised source; a pass whose
+  // cubin is ready runs it, the others run the interpreter kernel while the background workers compile.
+  const JitMode jmode = cfg.use_tma && cfg.groups_per_thread == 1 && cfg.kernel_variant == 0 ? jit_mode_from_env(s->n_local) : JIT_OFF;
+  std::vector<JitProgram> progs(steps.size());
+  std::vector<char> have_prog(steps.size(), 0);
+  if (jmode != JIT_OFF && jit_available(&ctx->jit_note)) {
+    for (size_t i = 0; i < steps.size(); ++i) {
+      if (!steps[i].is_pass) continue;
+      std::string why;
+      if (jit_generate(steps[i].pass, s->prec, &progs[i], &why)) {
+        have_prog[i] = 1;
+        (void)jit_request(progs[i].source, false);  // all compilations of this schedule start now, in parallel
+      } else {
+        ctx->jit_note = why;
+      }
+    }
+  }
   for (size_t i = 0; i < steps.size() && st == QIPB200_OK; ++i) {
+    if (steps[i].is_pass && have_prog[i]) {
+      alignas(64) CUtensorMap tmap;
+      memset(&tmap, 0, sizeof(tmap));
+      if (make_tile_map(&tmap, s->prec, s->buf, s->n_local, steps[i].pass.hdr)) {
+        std::shared_ptr<const JitCubin> cubin = jit_request(progs[i].source, jmode == JIT_SYNC);
+        if (cubin && !cubin->ok) ctx->jit_note = "NVRTC: " + cubin->log;
+        if (cubin && cubin->ok) {
+          ProfileScope prof(ctx, 0);
+          std::string err;
+          cudaError_t e = jit_launch(cubin, &ctx->jit_loaded, progs[i], s->buf, s->n_local, tmap, ctx->stream, &err);
+          if (e == cudaSuccess) {
+            ++ctx->launches;
+            ++ctx->tile_launches;
+            ++ctx->jit_launches;
+            ctx->fused_gates += steps[i].pass.n_gates;
+            continue;
+          }
+          ctx->jit_note = err;  // fall through to the interpreter kernel
+          (void)cudaGetLastError();
+        }
+      }
+    }
     if (steps[i].is_pass) {
       if (!serialise_pass(steps[i].pass, pp)) {
         st = report_error(s, QIPB200_ERR_UNSUPPORTED, "internal: fused pass exceeds the kernel parameter space");

@@ -8,6 +8,7 @@
 #include <utility>
 #include <vector>
 
+#include "jit_runtime.h"
 #include "opcompile.h"
 
 struct qipb200_ctx {
@@ -19,6 +20,9 @@ struct qipb200_ctx {
   uint64_t tile_launches = 0;      // fused tile passes among `launches`
   uint64_t exchange_launches = 0;  // NVLink pair-exchange kernels among `launches`
   uint64_t fused_gates = 0;        // reference ops folded into tile passes
+  uint64_t jit_launches = 0;       // tile passes among `tile_launches` that ran a generated (specialised) kernel
+  std::vector<std::pair<const qipb200::JitCubin *, qipb200::JitLoaded>> jit_loaded;  // modules loaded on this device
+  std::string jit_note;            // why the generated-kernel path was not taken last time (diagnostics)
   bool tile_configured = false;    // the tile kernels' > 48 KiB shared-memory opt-in was done on this device
   // optional per-category device timing (qipb200_profile_enable): CUDA-event pairs recorded on `stream`
   // around every fused tile pass [0] and every NVLink exchange incl. its two flag barriers [1]

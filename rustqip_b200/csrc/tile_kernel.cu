@@ -443,7 +443,7 @@ static EncodeTiledFn encode_tiled_fn() {
 
 // Tensor map of the local state for one pass (see the comment above mbar_init).  Returns false
 // when the geometry does not fit (then the pass runs with the cp.async path).
-static bool make_tile_map(CUtensorMap *map, qip_prec prec, void *psi, uint32_t n_local, const PassHeader &h) {
+bool make_tile_map(CUtensorMap *map, qip_prec prec, void *psi, uint32_t n_local, const PassHeader &h) {
   EncodeTiledFn enc = encode_tiled_fn();
   const uint32_t low3 = prec == QIP_F64 ? 3 : 4;
   if (!enc || h.m < 3 || h.L < low3 || h.T > n_local) return false;

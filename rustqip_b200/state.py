@@ -45,6 +45,14 @@ class Context:
         _lib.check(_lib.lib().qipb200_launch_stats(self._h, out), self._h)
         return {"all": int(out[0]), "tile_passes": int(out[1]), "exchanges": int(out[2]), "fused_gates": int(out[3])}
 
+    def jit_stats(self, wait: bool = False):
+        """Generated-kernel statistics; wait=True blocks until the background NVRTC compilations are done."""
+        out = (C.c_double * 4)()
+        note = C.create_string_buffer(512)
+        _lib.check(_lib.lib().qipb200_jit_stats(self._h, 1 if wait else 0, out, note, 512), self._h)
+        return {"jit_passes": int(out[0]), "tile_passes": int(out[1]), "programs_compiled": int(out[2]),
+                "compile_ms_total": out[3], "note": note.value.decode("utf-8", "replace")}
+
     def profile(self, on: bool):
         """Bracket every fused tile pass / NVLink exchange with CUDA events on the context's stream."""
         _lib.check(_lib.lib().qipb200_profile_enable(self._h, 1 if on else 0), self._h)

@@ -10,7 +10,11 @@
 #include <vector>
 
 #include "../../rustqip_b200/csrc/opcompile.h"
+#include "../../rustqip_b200/csrc/jit_codegen.h"
 #include "../../rustqip_b200/csrc/tile.cuh"
+
+#include <dlfcn.h>
+#include <unistd.h>
 
 using namespace qipb200;
 typedef std::complex<double> cd;
@@ -478,4 +482,124 @@ extern "C" int emul_plan_stats(int prec, uint32_t n, const qip_op *ops, size_t n
   stats[0] = n_pass; stats[1] = n_single; stats[2] = n_micro; stats[3] = n_gates_in_pass;
   stats[4] = dense_k[0]; /* super-ops */ stats[5] = exch; /* elementary ops */ stats[6] = dense_k[2] + dense_k[3]; stats[7] = diag_terms; stats[8] = dense_k[1];
   return 0;
+}
+
+
+// ---- generated (JIT) pass kernels, compiled for the HOST ------------------------------------------------
+// Same planner, but every pass is turned into specialised source by jit_generate (rustqip_b200/csrc/jit_codegen.cpp),
+// compiled with g++ -DQIP_JIT_HOST and run on the host copy of the state: the code generator (thread maps,
+// addressing, renaming, zero/one folding, parameter block layout) is validated against the oracle without a GPU.
+// stats: [0] passes run through generated code, [1] passes the generator declined (emulated instead),
+//        [2] single-op steps, [3] CTA barriers, [4] warp syncs, [5] renamed (instruction-free) ops, [6] elementary ops
+extern "C" int emul_schedule_jit(int prec, uint32_t n, const qip_op *ops, size_t n_ops, void *state, uint32_t T, uint32_t L,
+                                 const char *workdir, uint64_t *stats, char *errbuf, size_t errlen) {
+  std::vector<FlatOp> flat(n_ops);
+  for (size_t i = 0; i < n_ops; ++i) {
+    std::string err;
+    int st = compile_op(&ops[i], (qip_prec)prec, n, &flat[i], &err);
+    if (st != QIPB200_OK) {
+      if (errbuf && errlen) snprintf(errbuf, errlen, "%s", err.c_str());
+      return st;
+    }
+  }
+  PlanConfig cfg = default_plan_config((qip_prec)prec, n);
+  if (T) cfg.T = T;
+  if (L) cfg.L = L;
+  std::vector<PlanStep> steps;
+  plan_passes(flat, n, (qip_prec)prec, cfg, &steps);
+  const uint64_t N = 1ull << n;
+  uint64_t st_[8] = {0};
+  for (size_t s = 0; s < steps.size(); ++s) {
+    if (!steps[s].is_pass) {  // single op through the reference-semantics gather (via complex<double>)
+      std::vector<cd> psi(N);
+      if (prec == QIP_F32) {
+        const float *f = (const float *)state;
+        for (uint64_t i = 0; i < N; ++i) psi[i] = cd(f[2 * i], f[2 * i + 1]);
+      } else {
+        const double *f = (const double *)state;
+        for (uint64_t i = 0; i < N; ++i) psi[i] = cd(f[2 * i], f[2 * i + 1]);
+      }
+      apply_single(flat[steps[s].op_index], n, psi);
+      for (uint64_t i = 0; i < N; ++i) {
+        if (prec == QIP_F32) {
+          ((float *)state)[2 * i] = (float)psi[i].real();
+          ((float *)state)[2 * i + 1] = (float)psi[i].imag();
+        } else {
+          ((double *)state)[2 * i] = psi[i].real();
+          ((double *)state)[2 * i + 1] = psi[i].imag();
+        }
+      }
+      ++st_[2];
+      continue;
+    }
+    JitProgram prog;
+    std::string why;
+    if (!jit_generate(steps[s].pass, (qip_prec)prec, &prog, &why)) {
+      if (errbuf && errlen) snprintf(errbuf, errlen, "generator declined pass %zu: %s", s, why.c_str());
+      ++st_[1];
+      return -4;
+    }
+    char base[512];
+    snprintf(base, sizeof(base), "%s/jitpass_%d_%zu", workdir, (int)getpid(), s);
+    const std::string cu = std::string(base) + ".cpp", so = std::string(base) + ".so";
+    FILE *f = fopen(cu.c_str(), "w");
+    if (!f) return -5;
+    fwrite(prog.source.data(), 1, prog.source.size(), f);
+    fclose(f);
+    const std::string cmd = "/usr/bin/g++ -x c++ -std=c++17 -O1 -ffp-contract=off -DQIP_JIT_HOST -fPIC -shared -o " + so + " " + cu + " 2> " +
+                            std::string(base) + ".log";
+    if (system(cmd.c_str()) != 0) {
+      if (errbuf && errlen) snprintf(errbuf, errlen, "g++ failed on the generated source of pass %zu (see %s.log)", s, base);
+      return -6;
+    }
+    void *h = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!h) {
+      if (errbuf && errlen) snprintf(errbuf, errlen, "dlopen: %s", dlerror());
+      return -7;
+    }
+    typedef void (*Fn)(void *, const void *, unsigned);
+    Fn fn = (Fn)dlsym(h, "qip_host_pass");
+    if (!fn) return -8;
+    fn(state, prog.params.data(), n);
+    dlclose(h);
+    unlink(so.c_str());
+    ++st_[0];
+    st_[3] += prog.n_cta_barriers;
+    st_[4] += prog.n_warp_syncs;
+    st_[5] += prog.n_renamed;
+    st_[6] += prog.n_elems;
+  }
+  if (stats) memcpy(stats, st_, sizeof(st_));
+  return 0;
+}
+
+// Source + parameter block of every pass of a schedule (no execution): for offline inspection (nvcc / cuobjdump).
+extern "C" int emul_dump_jit(int prec, uint32_t n, const qip_op *ops, size_t n_ops, const char *prefix) {
+  std::vector<FlatOp> flat(n_ops);
+  for (size_t i = 0; i < n_ops; ++i) {
+    std::string err;
+    if (compile_op(&ops[i], (qip_prec)prec, n, &flat[i], &err) != QIPB200_OK) return -1;
+  }
+  PlanConfig cfg = default_plan_config((qip_prec)prec, n);
+  std::vector<PlanStep> steps;
+  plan_passes(flat, n, (qip_prec)prec, cfg, &steps);
+  int k = 0;
+  for (size_t s = 0; s < steps.size(); ++s) {
+    if (!steps[s].is_pass) continue;
+    JitProgram prog;
+    std::string why;
+    char name[512];
+    if (!jit_generate(steps[s].pass, (qip_prec)prec, &prog, &why)) {
+      fprintf(stderr, "pass %zu declined: %s\n", s, why.c_str());
+      continue;
+    }
+    snprintf(name, sizeof(name), "%s_%03d.cu", prefix, k++);
+    FILE *f = fopen(name, "w");
+    if (!f) return -2;
+    fwrite(prog.source.data(), 1, prog.source.size(), f);
+    fclose(f);
+    fprintf(stderr, "%s: %u super-ops, %u elems (%u renamed), %u CTA barriers, %u warp syncs, %u consts, %zu param bytes\n", name,
+            prog.n_super, prog.n_elems, prog.n_renamed, prog.n_cta_barriers, prog.n_warp_syncs, prog.n_consts, prog.params.size());
+  }
+  return k;
 }

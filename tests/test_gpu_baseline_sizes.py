@@ -45,12 +45,23 @@ def test_config4_n26_full_circuit_vs_oracle(ctx):
     assert _max_rel(got, want) <= 1e-10
 
 
-@pytest.mark.parametrize("fusion", [True, False])
-def test_config2_n28_first_gates_vs_oracle(ctx, fusion):
+_WANT = {}
+
+
+def _oracle_config2_prefix(n, ops):
+    if n not in _WANT:
+        _WANT[n] = qo.run_pipeline(n, ops, 0, np.complex128)
+    return _WANT[n]
+
+
+@pytest.mark.parametrize("mode", ["jit", "interpreter", "unfused"])
+def test_config2_n28_first_gates_vs_oracle(ctx, monkeypatch, mode):
     """BASELINE configs[1] at its own size (N=28 f64, 4 GiB): the H layer and the first 102 generated gates."""
+    monkeypatch.setenv("QIPB200_JIT", "sync" if mode == "jit" else "off")
+    fusion = mode != "unfused"
     n = 28
     ops = circuits.config2(n, 40)[:130]
-    want = qo.run_pipeline(n, ops, 0, np.complex128)
+    want = _oracle_config2_prefix(n, ops)
     with State(n, np.complex128, ctx) as st:
         st.set_basis(0)
         st.apply_schedule(ops, fusion=fusion)
@@ -60,8 +71,11 @@ def test_config2_n28_first_gates_vs_oracle(ctx, fusion):
     assert _max_rel(got, want) <= 1e-10
 
 
-def test_bench_workload_n30_f64_fused_equals_unfused(ctx):
-    """The headline workload at full size: 940 gates on a 16 GiB state, fused passes vs one sweep per gate."""
+@pytest.mark.parametrize("jit", ["sync", "off"])
+def test_bench_workload_n30_f64_fused_equals_unfused(ctx, monkeypatch, jit):
+    """The headline workload at full size: 940 gates on a 16 GiB state, fused passes (generated kernels / the
+    interpreter kernel) vs one sweep per gate."""
+    monkeypatch.setenv("QIPB200_JIT", jit)
     n = 30
     ops = circuits.random_circuit(n, 40, 0x5EED0002, "H,T,CNOT")
     with State(n, np.complex128, ctx) as a, State(n, np.complex128, ctx) as b:
@@ -77,8 +91,10 @@ def test_bench_workload_n30_f64_fused_equals_unfused(ctx):
     assert d <= 1e-10 * 2.0 ** (-n / 2)
 
 
-def test_qft_n30_f32_fused_equals_unfused(ctx):
+@pytest.mark.parametrize("jit", ["sync", "off"])
+def test_qft_n30_f32_fused_equals_unfused(ctx, monkeypatch, jit):
     """configs[2] at full size: N=30 f32 QFT (480 gate applications), fused vs per-gate on the device."""
+    monkeypatch.setenv("QIPB200_JIT", jit)
     n = 30
     ops = circuits.qft(n)
     with State(n, np.complex64, ctx) as a, State(n, np.complex64, ctx) as b:
