@@ -512,15 +512,20 @@ def run_b200(args):
                         cst.set_basis(0)
                         cst.apply_marshalled(carr, len(cops), fus)
                     cstep()
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    cst.sync()
-                    e0.record(stream)
+                    ctx.jit_stats(wait=True)  # generated kernels of this schedule compiled
                     cstep()
-                    e1.record(stream)
-                    cst.sync()
-                    e1.synchronize()
-                    cms = e0.elapsed_time(e1)
-                    res[label] = {"ms": cms, "gate_apps_per_s": len(cops) / (cms / 1e3),
+                    reps_ms = []
+                    for _ in range(3):
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        cst.sync()
+                        e0.record(stream)
+                        cstep()
+                        e1.record(stream)
+                        cst.sync()
+                        e1.synchronize()
+                        reps_ms.append(e0.elapsed_time(e1))
+                    cms = float(np.median(reps_ms))
+                    res[label] = {"ms": cms, "ms_repeats": reps_ms, "gate_apps_per_s": len(cops) / (cms / 1e3),
                                   "effective_state_GBps": len(cops) / (cms / 1e3) * 2 * camp * (1 << cn) / 1e9}
                 res["gates"] = len(cops)
                 other[cname] = res
