@@ -62,6 +62,13 @@ int qipb200_abi_version(void);
  * gate kernels run on.  Fails with QIPB200_ERR_CUDA when no usable sm_100
  * device exists -- there is no CPU path. */
 int qipb200_init(qipb200_ctx **ctx, int device_id);
+/* One context over SEVERAL devices of this process (n_devices a power of two; device_ids == NULL means 0..n-1):
+ * the drop-in for a single-process host such as LocalBuilder::calculate_state_with_init
+ * (qip/src/builder.rs:400-519), which has no notion of ranks.  States created on it with qipb200_state_new are
+ * sharded over the devices by their top log2(n_devices) index bits; every state call is served by one host thread
+ * per device inside the library, the devices map each other with CUDA peer access (NVLink / NVSwitch) and run
+ * the same exchange kernels as the one-process-per-GPU path.  upload/download address the whole 2^n vector. */
+int qipb200_init_multi(qipb200_ctx **ctx, int n_devices, const int *device_ids);
 void qipb200_shutdown(qipb200_ctx *ctx);
 
 /* Message of the last failing call on `ctx` (or, with ctx == NULL, of the last
@@ -157,7 +164,9 @@ int qipb200_state_apply_op(qipb200_state *state, const qip_op *op);
 int qipb200_state_apply_schedule(qipb200_state *state, const qip_op *ops, size_t n_ops,
                                  uint32_t flags);
 
-/* sum |a|^2 over the (local) state: prob_magnitude, measurement_ops.rs:11-13. */
+/* sum |a|^2 over the WHOLE state: prob_magnitude, measurement_ops.rs:11-13.  On a sharded state the call is
+ * COLLECTIVE (every rank calls it; the per-rank sums are added through the peers' reduction slots over NVLink)
+ * and every rank receives the same total. */
 int qipb200_state_norm2(qipb200_state *state, double *out);
 
 /* max over the (local) amplitudes of max(|re_a - re_b|, |im_a - im_b|), computed on the device: the
@@ -176,7 +185,11 @@ int qipb200_state_sync(qipb200_state *state);
 int qipb200_calculate_state(qipb200_ctx *ctx, qip_prec prec, uint32_t n_qubits, uint64_t init_index,
                             const qip_op *ops, size_t n_ops, uint32_t flags, void *host_out);
 
-/* ---- measurement on the device (qip/src/state_ops/measurement_ops.rs) ---------- */
+/* ---- measurement on the device (qip/src/state_ops/measurement_ops.rs) ----------
+ * On a sharded state all four calls are COLLECTIVE: every rank calls with the same arguments and every rank
+ * receives the result for the whole 2^n vector (histograms / scalars are summed across the ranks in rank order
+ * through peer-mapped reduction slots, so the values are bit-identical on all ranks and can be fed to
+ * qipb200_state_collapse as they are).  measure_probs is limited to 16 measured qubits there. */
 
 /* measure_probs (measurement_ops.rs:115-127): out[m] for m in 0..2^n_indices,
  * bit i of m <-> indices[i].  `out` is HOST memory of 2^n_indices doubles. */

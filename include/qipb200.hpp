@@ -158,6 +158,12 @@ class Context {
     int st = qipb200_init(&ctx_, device);
     if (st != QIPB200_OK) throw CircuitError(qipb200_last_error(nullptr), st);  // no CPU fallback
   }
+  // ONE context over several devices of this process (a power-of-two count): states created on it are sharded
+  // over the devices inside the library -- what a single-process host like LocalBuilder needs to use a whole box
+  explicit Context(const std::vector<int> &devices) {
+    int st = qipb200_init_multi(&ctx_, (int)devices.size(), devices.data());
+    if (st != QIPB200_OK) throw CircuitError(qipb200_last_error(nullptr), st);
+  }
   ~Context() { qipb200_shutdown(ctx_); }
   Context(const Context &) = delete;
   Context &operator=(const Context &) = delete;
@@ -209,6 +215,14 @@ class B200State {
     double v = 0;
     ctx_.check(qipb200_state_norm2(st_, &v));
     return v;
+  }
+  uint64_t soft_measure(const std::vector<uint64_t> &indices, double r) {  // measurement_ops.rs:153-176, draw supplied
+    uint64_t m = 0;
+    ctx_.check(qipb200_state_soft_measure(st_, indices.data(), (uint32_t)indices.size(), r, &m));
+    return m;
+  }
+  void collapse(const std::vector<uint64_t> &indices, uint64_t measured, double prob) {  // measure_state, :220-269
+    ctx_.check(qipb200_state_collapse(st_, indices.data(), (uint32_t)indices.size(), measured, prob));
   }
   std::vector<double> measure_probs(const std::vector<uint64_t> &indices) {  // measurement_ops.rs:115-127
     std::vector<double> out(size_t(1) << indices.size());

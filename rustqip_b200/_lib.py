@@ -12,7 +12,7 @@ from ._abi import QipOp
 from .errors import B200Unavailable, CircuitError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libqipb200.so")
+SO_PATH = os.environ.get("QIPB200_LIB") or os.path.join(_HERE, "libqipb200.so")  # QIPB200_LIB: a development build
 IPC_HANDLE_BYTES = 64
 
 SCHED_DEFAULT = 0
@@ -22,7 +22,7 @@ _lib = None
 
 # every symbol include/qipb200.h declares
 EXPORTS = [
-    "qipb200_abi_version", "qipb200_init", "qipb200_shutdown", "qipb200_last_error",
+    "qipb200_abi_version", "qipb200_init", "qipb200_init_multi", "qipb200_shutdown", "qipb200_last_error",
     "qipb200_kernel_launches", "qipb200_launch_stats", "qipb200_stream_handle", "qipb200_jit_stats", "qipb200_jit_precompile", "qipb200_profile_enable", "qipb200_profile_read", "qipb200_validate_op", "qipb200_apply_op",
     "qipb200_apply_op_overwrite", "qipb200_apply_ops", "qipb200_state_new", "qipb200_state_free",
     "qipb200_state_set_basis", "qipb200_state_upload", "qipb200_state_download",
@@ -49,6 +49,7 @@ def lib():
     opp = C.POINTER(QipOp)
     L.qipb200_abi_version.restype = i32
     L.qipb200_init.restype, L.qipb200_init.argtypes = i32, [C.POINTER(vp), i32]
+    L.qipb200_init_multi.restype, L.qipb200_init_multi.argtypes = i32, [C.POINTER(vp), i32, vp]
     L.qipb200_shutdown.restype, L.qipb200_shutdown.argtypes = None, [vp]
     L.qipb200_last_error.restype, L.qipb200_last_error.argtypes = C.c_char_p, [vp]
     L.qipb200_stream_handle.restype, L.qipb200_stream_handle.argtypes = i32, [vp, C.POINTER(vp)]

@@ -11,7 +11,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <new>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -64,6 +66,44 @@ int grow(qipb200_ctx *ctx, void **p, size_t *have, size_t need) {
   return QIPB200_OK;
 }
 
+// No C++ exception may cross the C boundary (the library allocates through std::vector / std::string):
+// an allocation failure becomes QIPB200_ERR_OOM, anything else QIPB200_ERR_INVALID_ARG with its message.
+template <typename F>
+int guarded(const qipb200_ctx *ctx, F f) {
+  try {
+    return f();
+  } catch (const std::bad_alloc &) {
+    return set_err(ctx, QIPB200_ERR_OOM, "out of host memory");
+  } catch (const std::exception &e) {
+    return set_err(ctx, QIPB200_ERR_INVALID_ARG, std::string("internal error: ") + e.what());
+  }
+}
+
+// Run f(shard, rank) on every shard of a multi-device state, one host thread per device (the shards are
+// ordinary sharded states: their exchange kernels wait for each other on the GPUs, so they must be driven
+// concurrently, exactly as the one-process-per-GPU model drives them).  First failing status wins.
+template <typename F>
+int each_shard(qipb200_state *p, F f) {
+  const size_t G = p->shards.size();
+  std::vector<int> st(G, QIPB200_OK);
+  auto run = [&](size_t r) {
+    try {
+      st[r] = f(p->shards[r], (int)r);
+    } catch (const std::bad_alloc &) {
+      st[r] = set_err(p->shards[r]->ctx, QIPB200_ERR_OOM, "out of host memory");
+    } catch (const std::exception &e) {
+      st[r] = set_err(p->shards[r]->ctx, QIPB200_ERR_INVALID_ARG, std::string("internal error: ") + e.what());
+    }
+  };
+  std::vector<std::thread> th;
+  for (size_t r = 1; r < G; ++r) th.emplace_back(run, r);
+  run(0);
+  for (std::thread &t : th) t.join();
+  for (size_t r = 0; r < G; ++r)
+    if (st[r] != QIPB200_OK) return set_err(p->ctx, st[r], p->shards[r]->ctx->err);
+  return QIPB200_OK;
+}
+
 bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 int ilog2(int x) {
   int l = 0;
@@ -79,9 +119,65 @@ int ilog2(int x) {
 
 extern "C" int qipb200_abi_version(void) { return 1000; }
 
+static int init_device_ctx(qipb200_ctx **out, int device_id);
+
 extern "C" int qipb200_init(qipb200_ctx **out, int device_id) {
   if (!out) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "qipb200_init: ctx out-pointer is NULL");
   *out = nullptr;
+  return guarded(nullptr, [&]() { return init_device_ctx(out, device_id); });
+}
+
+extern "C" int qipb200_init_multi(qipb200_ctx **out, int n_devices, const int *device_ids) {
+  if (!out) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "qipb200_init_multi: ctx out-pointer is NULL");
+  *out = nullptr;
+  if (!is_pow2(n_devices) || n_devices > kMaxWorld)
+    return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "qipb200_init_multi: n_devices must be a power of two <= 16");
+  return guarded(nullptr, [&]() {
+    qipb200_ctx *parent = new qipb200_ctx();
+    for (int i = 0; i < n_devices; ++i) {
+      const int dev = device_ids ? device_ids[i] : i;
+      for (int j = 0; j < i; ++j)
+        if (parent->children[j]->device == dev) {
+          qipb200_shutdown(parent);
+          return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "qipb200_init_multi: a device is listed twice");
+        }
+      qipb200_ctx *c = nullptr;
+      int st = init_device_ctx(&c, dev);
+      if (st != QIPB200_OK) {
+        qipb200_shutdown(parent);
+        return st;  // message already in the thread-local slot
+      }
+      c->parent = parent;
+      parent->children.push_back(c);
+    }
+    // every device maps every other one (NVLink / NVSwitch peer access: the exchange kernels load and store
+    // the partner's shard directly)
+    for (int i = 0; i < n_devices; ++i) {
+      cudaSetDevice(parent->children[i]->device);
+      for (int j = 0; j < n_devices; ++j) {
+        if (i == j) continue;
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, parent->children[i]->device, parent->children[j]->device);
+        cudaError_t e = can ? cudaDeviceEnablePeerAccess(parent->children[j]->device, 0) : cudaErrorPeerAccessUnsupported;
+        if (e == cudaErrorPeerAccessAlreadyEnabled) {
+          cudaGetLastError();
+          e = cudaSuccess;
+        }
+        if (e != cudaSuccess) {
+          int st = cuda_fail(nullptr, e, "cudaDeviceEnablePeerAccess");
+          qipb200_shutdown(parent);
+          return st == QIPB200_ERR_CUDA ? QIPB200_ERR_COMM : st;
+        }
+      }
+    }
+    parent->device = parent->children[0]->device;
+    parent->sm_count = parent->children[0]->sm_count;
+    *out = parent;
+    return (int)QIPB200_OK;
+  });
+}
+
+static int init_device_ctx(qipb200_ctx **out, int device_id) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) {
@@ -118,11 +214,17 @@ extern "C" int qipb200_init(qipb200_ctx **out, int device_id) {
 
 extern "C" void qipb200_shutdown(qipb200_ctx *ctx) {
   if (!ctx) return;
+  if (!ctx->children.empty() || (!ctx->stream && !ctx->d_scalar)) {  // multi-device parent: owns its children
+    for (size_t i = 0; i < ctx->children.size(); ++i) qipb200_shutdown(ctx->children[i]);
+    delete ctx;
+    return;
+  }
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->d_in) cudaFree(ctx->d_in);
   if (ctx->d_out) cudaFree(ctx->d_out);
   if (ctx->d_scalar) cudaFree(ctx->d_scalar);
+  if (ctx->pool_buf) cudaFree(ctx->pool_buf);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   for (int cat = 0; cat < 2; ++cat)
     for (size_t i = 0; i < ctx->prof_events[cat].size(); ++i) {
@@ -141,11 +243,16 @@ extern "C" const char *qipb200_last_error(const qipb200_ctx *ctx) {
 
 extern "C" int qipb200_stream_handle(const qipb200_ctx *ctx, void **stream) {
   if (!ctx || !stream) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "stream_handle: NULL argument");
-  *stream = (void *)ctx->stream;
+  *stream = (void *)(ctx->children.empty() ? ctx->stream : ctx->children[0]->stream);
   return QIPB200_OK;
 }
 
-extern "C" uint64_t qipb200_kernel_launches(const qipb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t qipb200_kernel_launches(const qipb200_ctx *ctx) {
+  if (!ctx) return 0;
+  uint64_t n = ctx->launches;
+  for (size_t i = 0; i < ctx->children.size(); ++i) n += ctx->children[i]->launches;
+  return n;
+}
 
 extern "C" int qipb200_launch_stats(const qipb200_ctx *ctx, uint64_t *out4) {
   if (!ctx || !out4) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "launch_stats: NULL argument");
@@ -153,6 +260,13 @@ extern "C" int qipb200_launch_stats(const qipb200_ctx *ctx, uint64_t *out4) {
   out4[1] = ctx->tile_launches;
   out4[2] = ctx->exchange_launches;
   out4[3] = ctx->fused_gates;
+  for (size_t i = 0; i < ctx->children.size(); ++i) {  // multi-device context: summed over the devices
+    const qipb200_ctx *c = ctx->children[i];
+    out4[0] += c->launches;
+    out4[1] += c->tile_launches;
+    out4[2] += c->exchange_launches;
+    out4[3] += i == 0 ? c->fused_gates : 0;  // every device folds the same gates: count them once
+  }
   return QIPB200_OK;
 }
 
@@ -213,6 +327,11 @@ extern "C" int qipb200_jit_stats(qipb200_ctx *ctx, int wait, double *out4, char 
   if (wait) jit_wait_all(&n, &ms);
   out4[0] = (double)ctx->jit_launches;
   out4[1] = (double)ctx->tile_launches;
+  for (size_t i = 0; i < ctx->children.size(); ++i) {
+    out4[0] += (double)ctx->children[i]->jit_launches;
+    out4[1] += (double)ctx->children[i]->tile_launches;
+    if (!ctx->children[i]->jit_note.empty()) ctx->jit_note = ctx->children[i]->jit_note;
+  }
   out4[2] = (double)n;
   out4[3] = ms;
   if (note && note_len) snprintf(note, note_len, "%s", ctx->jit_note.c_str());
@@ -222,11 +341,19 @@ extern "C" int qipb200_jit_stats(qipb200_ctx *ctx, int wait, double *out4, char 
 extern "C" int qipb200_profile_enable(qipb200_ctx *ctx, int on) {
   if (!ctx) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "profile_enable: ctx is NULL");
   ctx->profile = on != 0;
+  for (size_t i = 0; i < ctx->children.size(); ++i) ctx->children[i]->profile = on != 0;
   return QIPB200_OK;
 }
 
 extern "C" int qipb200_profile_read(qipb200_ctx *ctx, double *out4) {
   if (!ctx || !out4) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "profile_read: NULL argument");
+  if (!ctx->children.empty()) {  // multi-device context: the first device's timings (all devices run the same steps)
+    for (size_t i = 1; i < ctx->children.size(); ++i) {
+      double drop[4];
+      qipb200_profile_read(ctx->children[i], drop);
+    }
+    return qipb200_profile_read(ctx->children[0], out4);
+  }
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   for (int cat = 0; cat < 2; ++cat) {
@@ -245,10 +372,12 @@ extern "C" int qipb200_profile_read(qipb200_ctx *ctx, double *out4) {
 }
 
 extern "C" int qipb200_validate_op(const qipb200_ctx *ctx, qip_prec prec, uint32_t n_qubits, const qip_op *op) {
-  std::string err;
-  int st = validate_op(op, prec, n_qubits, &err);
-  if (st != QIPB200_OK) return set_err(ctx, st, err);
-  return QIPB200_OK;
+  return guarded(ctx, [&]() -> int {
+    std::string err;
+    int st = validate_op(op, prec, n_qubits, &err);
+    if (st != QIPB200_OK) return set_err(ctx, st, err);
+    return (int)QIPB200_OK;
+  });
 }
 
 // ===================================================================================
@@ -261,6 +390,12 @@ int host_apply(qipb200_ctx *ctx, qip_prec prec, uint32_t n, const qip_op *op, co
                uint64_t input_len, void *output, uint64_t output_len, uint64_t input_offset,
                uint64_t output_offset, bool accumulate) {
   if (!ctx) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "ctx is NULL (call qipb200_init first; there is no CPU path)");
+  if (!ctx->children.empty()) {  // a multi-device context serves the host-buffer drop-ins on its first device
+    qipb200_ctx *parent = ctx;
+    int st = host_apply(parent->children[0], prec, n, op, input, input_len, output, output_len, input_offset, output_offset, accumulate);
+    if (st != QIPB200_OK) parent->err = parent->children[0]->err;
+    return st;
+  }
   if ((!input && input_len) || (!output && output_len))
     return set_err(ctx, QIPB200_ERR_INVALID_ARG, "apply_op: NULL amplitude buffer");
   if (n > 40 || input_len > (1ull << 40) || output_len > (1ull << 40))  // keeps len * amp_bytes far from wrapping
@@ -288,13 +423,13 @@ int host_apply(qipb200_ctx *ctx, qip_prec prec, uint32_t n, const qip_op *op, co
 extern "C" int qipb200_apply_op(qipb200_ctx *ctx, qip_prec prec, uint32_t n, const qip_op *op, const void *input,
                                 uint64_t input_len, void *output, uint64_t output_len, uint64_t input_offset,
                                 uint64_t output_offset) {
-  return host_apply(ctx, prec, n, op, input, input_len, output, output_len, input_offset, output_offset, true);
+  return guarded(ctx, [&]() { return host_apply(ctx, prec, n, op, input, input_len, output, output_len, input_offset, output_offset, true); });
 }
 
 extern "C" int qipb200_apply_op_overwrite(qipb200_ctx *ctx, qip_prec prec, uint32_t n, const qip_op *op,
                                           const void *input, uint64_t input_len, void *output,
                                           uint64_t output_len, uint64_t input_offset, uint64_t output_offset) {
-  return host_apply(ctx, prec, n, op, input, input_len, output, output_len, input_offset, output_offset, false);
+  return guarded(ctx, [&]() { return host_apply(ctx, prec, n, op, input, input_len, output, output_len, input_offset, output_offset, false); });
 }
 
 // ===================================================================================
@@ -325,11 +460,18 @@ int state_alloc(qipb200_ctx *ctx, qip_prec prec, uint32_t n, int rank, int world
   s->bytes = amp_bytes(prec) << s->n_local;
   s->phys_of_logical.resize(n);
   for (uint32_t b = 0; b < n; ++b) s->phys_of_logical[b] = b;
-  cudaError_t e = cudaMalloc(&s->buf, s->bytes);
+  cudaError_t e = cudaSuccess;
+  if (ctx->pool_buf && ctx->pool_bytes == s->bytes) {  // the buffer a freed state of this size left behind
+    s->buf = ctx->pool_buf;
+    ctx->pool_buf = nullptr;
+    ctx->pool_bytes = 0;
+  } else {
+    e = cudaMalloc(&s->buf, s->bytes);
+  }
   if (e == cudaSuccess) e = cudaMemsetAsync(s->buf, 0, s->bytes, ctx->stream);
   if (e == cudaSuccess && world > 1) {
-    e = cudaMalloc((void **)&s->flags, kFlagWords * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMemsetAsync(s->flags, 0, kFlagWords * sizeof(uint32_t), ctx->stream);
+    e = cudaMalloc((void **)&s->flags, kFlagAllocBytes);  // flag page + reduction slot (dist.cuh)
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->flags, 0, kFlagAllocBytes, ctx->stream);
   }
   if (e != cudaSuccess) {
     int st = cuda_fail(ctx, e, "qipb200_state_new");
@@ -606,32 +748,118 @@ int compile_and_localize(qipb200_state *s, const qip_op *op, FlatOp *f, const ui
 
 }  // namespace qipb200
 
+// ---- multi-device (single process) states ---------------------------------------------------
+namespace {
+
+double *comm_of(uint32_t *flags) { return reinterpret_cast<double *>(reinterpret_cast<char *>(flags) + kCommOffsetBytes); }
+
+int multi_state_new(qipb200_ctx *parent, qip_prec prec, uint32_t n, qipb200_state **out) {
+  const int G = (int)parent->children.size();
+  qipb200_state *p = new qipb200_state();
+  p->ctx = parent;
+  p->prec = prec;
+  p->n = n;
+  p->world = 1;
+  p->n_local = n;
+  for (int r = 0; r < G; ++r) {
+    qipb200_state *sh = nullptr;
+    int st = state_alloc(parent->children[r], prec, n, r, G, &sh);
+    if (st != QIPB200_OK) {
+      set_err(parent, st, parent->children[r]->err);
+      for (size_t i = 0; i < p->shards.size(); ++i) qipb200_state_free(p->shards[i]);
+      delete p;
+      return st;
+    }
+    p->shards.push_back(sh);
+  }
+  for (int r = 0; r < G; ++r) {  // peers are plain device pointers here: peer access was enabled by init_multi
+    qipb200_state *sh = p->shards[r];
+    sh->peer_buf.assign(G, nullptr);
+    sh->peer_flags.assign(G, nullptr);
+    sh->peer_comm.assign(G, nullptr);
+    for (int t = 0; t < G; ++t) {
+      sh->peer_buf[t] = p->shards[t]->buf;
+      sh->peer_flags[t] = p->shards[t]->flags;
+      sh->peer_comm[t] = comm_of(p->shards[t]->flags);
+    }
+    sh->ipc_ready = true;
+    cudaSetDevice(sh->ctx->device);
+    cudaStreamSynchronize(sh->ctx->stream);  // the zero fill of buffer and flag page, before any peer touches them
+  }
+  *out = p;
+  return QIPB200_OK;
+}
+
+// out[0..count) (device, on the rank's stream) <- sum over all ranks of their out[]; collective.
+int allreduce_sum(qipb200_state *s, double *d_vec, uint32_t count) {
+  qipb200_ctx *ctx = s->ctx;
+  if (s->world == 1) return QIPB200_OK;
+  if (!s->ipc_ready) return set_err(ctx, QIPB200_ERR_COMM, "sharded state: peers not mapped (call qipb200_state_ipc_import)");
+  if (count > (uint32_t)kCommDoubles) return set_err(ctx, QIPB200_ERR_UNSUPPORTED, "cross-rank reduction larger than the reduction slot");
+  CU(ctx, cudaMemcpyAsync(comm_of(s->flags), d_vec, count * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch, s->flags + kFlagErrorSlot,
+                              ctx->stream, &ctx->launches));
+  CU(ctx, launch_comm_sum(s->peer_comm.data(), s->world, d_vec, count, ctx->stream, &ctx->launches));
+  CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch, s->flags + kFlagErrorSlot,
+                              ctx->stream, &ctx->launches));
+  return QIPB200_OK;
+}
+
+}  // namespace
+
 extern "C" int qipb200_state_new(qipb200_ctx *ctx, qip_prec prec, uint32_t n_qubits, qipb200_state **state) {
-  return state_alloc(ctx, prec, n_qubits, 0, 1, state);
+  return guarded(ctx, [&]() -> int {
+    if (ctx && !ctx->children.empty()) {
+      if (!state) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "state out-pointer is NULL");
+      *state = nullptr;
+      if (ctx->children.size() == 1) return state_alloc(ctx->children[0], prec, n_qubits, 0, 1, state);
+      return multi_state_new(ctx, prec, n_qubits, state);
+    }
+    return state_alloc(ctx, prec, n_qubits, 0, 1, state);
+  });
 }
 
 extern "C" int qipb200_state_new_sharded(qipb200_ctx *ctx, qip_prec prec, uint32_t n_qubits, int rank,
                                          int world_size, qipb200_state **state) {
-  return state_alloc(ctx, prec, n_qubits, rank, world_size, state);
+  if (ctx && !ctx->children.empty())
+    return set_err(ctx, QIPB200_ERR_INVALID_ARG, "state_new_sharded: a multi-device context shards its states itself (use qipb200_state_new)");
+  return guarded(ctx, [&]() { return state_alloc(ctx, prec, n_qubits, rank, world_size, state); });
 }
 
 extern "C" void qipb200_state_free(qipb200_state *s) {
   if (!s) return;
-  cudaSetDevice(s->ctx->device);
-  cudaStreamSynchronize(s->ctx->stream);
-  for (int t = 0; t < (int)s->peer_buf.size(); ++t) {
-    if (t == s->rank) continue;
-    if (s->peer_buf[t]) cudaIpcCloseMemHandle(s->peer_buf[t]);
-    if (s->peer_flags[t]) cudaIpcCloseMemHandle(s->peer_flags[t]);
+  if (!s->shards.empty()) {
+    for (size_t i = 0; i < s->shards.size(); ++i) {  // all work must have drained before any buffer goes away
+      cudaSetDevice(s->shards[i]->ctx->device);
+      cudaStreamSynchronize(s->shards[i]->ctx->stream);
+    }
+    for (size_t i = 0; i < s->shards.size(); ++i) qipb200_state_free(s->shards[i]);
+    delete s;
+    return;
   }
-  if (s->buf) cudaFree(s->buf);
+  qipb200_ctx *ctx = s->ctx;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (s->ipc_mapped)
+    for (int t = 0; t < (int)s->peer_buf.size(); ++t) {
+      if (t == s->rank) continue;
+      if (s->peer_buf[t]) cudaIpcCloseMemHandle(s->peer_buf[t]);
+      if (s->peer_flags[t]) cudaIpcCloseMemHandle(s->peer_flags[t]);
+    }
+  if (s->buf) {
+    if (s->world == 1 && !ctx->pool_buf) {  // keep one buffer for the next state of this size
+      ctx->pool_buf = s->buf;
+      ctx->pool_bytes = s->bytes;
+    } else {
+      cudaFree(s->buf);
+    }
+  }
   if (s->scratch) cudaFree(s->scratch);
   if (s->flags) cudaFree(s->flags);
   delete s;
 }
 
-extern "C" int qipb200_state_set_basis(qipb200_state *s, uint64_t index) {
-  if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
+static int set_basis_impl(qipb200_state *s, uint64_t index) {
   qipb200_ctx *ctx = s->ctx;
   if (index >> s->n) return set_err(ctx, QIPB200_ERR_BAD_INDEX, "initial index out of range");
   CU(ctx, cudaSetDevice(ctx->device));
@@ -642,43 +870,72 @@ extern "C" int qipb200_state_set_basis(qipb200_state *s, uint64_t index) {
   return QIPB200_OK;
 }
 
-extern "C" int qipb200_state_upload(qipb200_state *s, const void *host, uint64_t offset, uint64_t len) {
+extern "C" int qipb200_state_set_basis(qipb200_state *s, uint64_t index) {
   if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
+  return guarded(s->ctx, [&]() -> int {
+    if (!s->shards.empty()) {
+      if (index >> s->n) return set_err(s->ctx, QIPB200_ERR_BAD_INDEX, "initial index out of range");
+      return each_shard(s, [&](qipb200_state *sh, int) { return set_basis_impl(sh, index); });
+    }
+    return set_basis_impl(s, index);
+  });
+}
+
+static int transfer_impl(qipb200_state *s, void *host, uint64_t offset, uint64_t len, bool upload) {
   qipb200_ctx *ctx = s->ctx;
-  if (!host && len) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "upload: host pointer is NULL");
+  const char *what = upload ? "upload" : "download";
+  if (!host && len) return set_err(ctx, QIPB200_ERR_INVALID_ARG, std::string(what) + ": host pointer is NULL");
   if (len > (1ull << s->n_local) || offset > (1ull << s->n_local) - len)
-    return set_err(ctx, QIPB200_ERR_SIZE_MISMATCH, "upload: range exceeds the local state");
+    return set_err(ctx, QIPB200_ERR_SIZE_MISMATCH, std::string(what) + ": range exceeds the local state");
   CU(ctx, cudaSetDevice(ctx->device));
   if (!layout_is_identity(s)) {
     int st = restore_layout(s);
     if (st != QIPB200_OK) return st;
   }
   const size_t ab = amp_bytes(s->prec);
-  CU(ctx, cudaMemcpyAsync((char *)s->buf + offset * ab, host, len * ab, cudaMemcpyHostToDevice, ctx->stream));
+  if (len) {
+    if (upload)
+      CU(ctx, cudaMemcpyAsync((char *)s->buf + offset * ab, host, len * ab, cudaMemcpyHostToDevice, ctx->stream));
+    else
+      CU(ctx, cudaMemcpyAsync(host, (const char *)s->buf + offset * ab, len * ab, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   CU(ctx, cudaStreamSynchronize(ctx->stream));
+  if (s->world > 1 && s->ipc_ready) return check_barrier_error(s);
   return QIPB200_OK;
+}
+
+// A multi-device state is addressed as ONE 2^n vector: the range is cut at the shard boundaries.  Every shard
+// takes part even when its piece is empty (restoring the canonical layout is a collective exchange).
+static int multi_transfer(qipb200_state *p, void *host, uint64_t offset, uint64_t len, bool upload) {
+  if (!host && len) return set_err(p->ctx, QIPB200_ERR_INVALID_ARG, "upload/download: host pointer is NULL");
+  if (len > (1ull << p->n) || offset > (1ull << p->n) - len)
+    return set_err(p->ctx, QIPB200_ERR_SIZE_MISMATCH, "upload/download: range exceeds the state");
+  const size_t ab = amp_bytes(p->prec);
+  return each_shard(p, [&](qipb200_state *sh, int r) {
+    const uint64_t lo = (uint64_t)r << sh->n_local, hi = lo + (1ull << sh->n_local);
+    const uint64_t a = std::max(lo, offset), b = std::min(hi, offset + len);
+    if (b <= a) return transfer_impl(sh, host, 0, 0, upload);
+    return transfer_impl(sh, (char *)host + (a - offset) * ab, a - lo, b - a, upload);
+  });
+}
+
+extern "C" int qipb200_state_upload(qipb200_state *s, const void *host, uint64_t offset, uint64_t len) {
+  if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
+  return guarded(s->ctx, [&]() -> int {
+    if (!s->shards.empty()) return multi_transfer(s, const_cast<void *>(host), offset, len, true);
+    return transfer_impl(s, const_cast<void *>(host), offset, len, true);
+  });
 }
 
 extern "C" int qipb200_state_download(qipb200_state *s, void *host, uint64_t offset, uint64_t len) {
   if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
-  qipb200_ctx *ctx = s->ctx;
-  if (!host && len) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "download: host pointer is NULL");
-  if (len > (1ull << s->n_local) || offset > (1ull << s->n_local) - len)
-    return set_err(ctx, QIPB200_ERR_SIZE_MISMATCH, "download: range exceeds the local state");
-  CU(ctx, cudaSetDevice(ctx->device));
-  if (!layout_is_identity(s)) {
-    int st = restore_layout(s);
-    if (st != QIPB200_OK) return st;
-  }
-  const size_t ab = amp_bytes(s->prec);
-  CU(ctx, cudaMemcpyAsync(host, (const char *)s->buf + offset * ab, len * ab, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(ctx, cudaStreamSynchronize(ctx->stream));
-  if (s->world > 1) return check_barrier_error(s);
-  return QIPB200_OK;
+  return guarded(s->ctx, [&]() -> int {
+    if (!s->shards.empty()) return multi_transfer(s, host, offset, len, false);
+    return transfer_impl(s, host, offset, len, false);
+  });
 }
 
-extern "C" int qipb200_state_apply_op(qipb200_state *s, const qip_op *op) {
-  if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
+static int apply_op_impl(qipb200_state *s, const qip_op *op) {
   CU(s->ctx, cudaSetDevice(s->ctx->device));
   FlatOp f;
   int st = compile_and_localize(s, op, &f, nullptr);
@@ -686,25 +943,53 @@ extern "C" int qipb200_state_apply_op(qipb200_state *s, const qip_op *op) {
   return apply_flat_local(s, f);
 }
 
+extern "C" int qipb200_state_apply_op(qipb200_state *s, const qip_op *op) {
+  if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
+  return guarded(s->ctx, [&]() -> int {
+    if (!s->shards.empty()) return each_shard(s, [&](qipb200_state *sh, int) { return apply_op_impl(sh, op); });
+    return apply_op_impl(s, op);
+  });
+}
+
 extern "C" int qipb200_state_apply_schedule(qipb200_state *s, const qip_op *ops, size_t n_ops, uint32_t flags) {
   if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
   if (!ops && n_ops) return set_err(s->ctx, QIPB200_ERR_INVALID_ARG, "schedule: ops is NULL");
-  CU(s->ctx, cudaSetDevice(s->ctx->device));
-  return run_schedule(s, ops, n_ops, flags);
+  return guarded(s->ctx, [&]() -> int {
+    auto one = [&](qipb200_state *sh, int) -> int {
+      CU(sh->ctx, cudaSetDevice(sh->ctx->device));
+      return run_schedule(sh, ops, n_ops, flags);
+    };
+    if (!s->shards.empty()) return each_shard(s, one);
+    return one(s, 0);
+  });
 }
 
-extern "C" int qipb200_state_norm2(qipb200_state *s, double *out) {
-  if (!s || !out) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "norm2: NULL argument");
+// sum |a|^2 of the WHOLE state: on a sharded state the per-rank sums are all-reduced (collective call).
+static int norm2_impl(qipb200_state *s, double *out) {
   qipb200_ctx *ctx = s->ctx;
   CU(ctx, cudaSetDevice(ctx->device));
   CU(ctx, launch_norm2(s->prec, s->buf, 1ull << s->n_local, ctx->d_scalar, ctx->stream, &ctx->launches));
+  int st = allreduce_sum(s, ctx->d_scalar, 1);
+  if (st != QIPB200_OK) return st;
   CU(ctx, cudaMemcpyAsync(out, ctx->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
   return QIPB200_OK;
 }
 
-extern "C" int qipb200_state_max_abs_diff(qipb200_state *a, qipb200_state *b, double *out) {
-  if (!a || !b || !out) return set_err(a ? a->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "max_abs_diff: NULL argument");
+extern "C" int qipb200_state_norm2(qipb200_state *s, double *out) {
+  if (!s || !out) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "norm2: NULL argument");
+  return guarded(s->ctx, [&]() -> int {
+    if (!s->shards.empty()) {
+      std::vector<double> v(s->shards.size(), 0.0);
+      int st = each_shard(s, [&](qipb200_state *sh, int r) { return norm2_impl(sh, &v[r]); });
+      *out = v[0];
+      return st;
+    }
+    return norm2_impl(s, out);
+  });
+}
+
+static int max_abs_diff_impl(qipb200_state *a, qipb200_state *b, double *out) {
   qipb200_ctx *ctx = a->ctx;
   if (a->ctx != b->ctx || a->prec != b->prec || a->n != b->n || a->world != b->world || a->rank != b->rank)
     return set_err(ctx, QIPB200_ERR_SIZE_MISMATCH, "max_abs_diff: the two states differ in context, precision or shape");
@@ -717,12 +1002,34 @@ extern "C" int qipb200_state_max_abs_diff(qipb200_state *a, qipb200_state *b, do
   return QIPB200_OK;
 }
 
-extern "C" int qipb200_state_sync(qipb200_state *s) {
-  if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
+extern "C" int qipb200_state_max_abs_diff(qipb200_state *a, qipb200_state *b, double *out) {
+  if (!a || !b || !out) return set_err(a ? a->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "max_abs_diff: NULL argument");
+  return guarded(a->ctx, [&]() -> int {
+    if (a->shards.size() != b->shards.size())
+      return set_err(a->ctx, QIPB200_ERR_SIZE_MISMATCH, "max_abs_diff: the two states differ in context, precision or shape");
+    if (!a->shards.empty()) {
+      std::vector<double> v(a->shards.size(), 0.0);
+      int st = each_shard(a, [&](qipb200_state *sh, int r) { return max_abs_diff_impl(sh, b->shards[r], &v[r]); });
+      *out = *std::max_element(v.begin(), v.end());
+      return st;
+    }
+    return max_abs_diff_impl(a, b, out);
+  });
+}
+
+static int sync_impl(qipb200_state *s) {
   CU(s->ctx, cudaSetDevice(s->ctx->device));
   CU(s->ctx, cudaStreamSynchronize(s->ctx->stream));
   if (s->world > 1 && s->ipc_ready) return check_barrier_error(s);
   return QIPB200_OK;
+}
+
+extern "C" int qipb200_state_sync(qipb200_state *s) {
+  if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
+  return guarded(s->ctx, [&]() -> int {
+    if (!s->shards.empty()) return each_shard(s, [&](qipb200_state *sh, int) { return sync_impl(sh); });
+    return sync_impl(s);
+  });
 }
 
 extern "C" int qipb200_calculate_state(qipb200_ctx *ctx, qip_prec prec, uint32_t n_qubits, uint64_t init_index,
@@ -758,34 +1065,36 @@ extern "C" int qipb200_apply_ops(qipb200_ctx *ctx, qip_prec prec, uint32_t n, co
   if (n_ops == 1)  // matrix_ops.rs:167
     return qipb200_apply_op(ctx, prec, n, ops, input, input_len, output, output_len, input_offset, output_offset);
   // Sequential product on the full state, accumulated into `output` (see header: Q5).
-  if (input_offset != 0 || output_offset != 0 || input_len != (1ull << n) || output_len != (1ull << n))
+  if (n > 40 || input_offset != 0 || output_offset != 0 || input_len != (1ull << n) || output_len != (1ull << n))
     return set_err(ctx, QIPB200_ERR_UNSUPPORTED, "apply_ops with several ops needs full-length buffers and zero offsets");
-  qipb200_state *s = nullptr;
-  int st = qipb200_state_new(ctx, prec, n, &s);
-  if (st != QIPB200_OK) return st;
-  st = qipb200_state_upload(s, input, 0, input_len);
-  if (st == QIPB200_OK) st = qipb200_state_apply_schedule(s, ops, n_ops, QIPB200_SCHED_DEFAULT);
-  std::vector<char> tmp;
-  if (st == QIPB200_OK) {
-    tmp.resize(output_len * ab);
-    st = qipb200_state_download(s, tmp.data(), 0, output_len);
-  }
-  qipb200_state_free(s);
-  if (st != QIPB200_OK) return st;
-  if (prec == QIP_F32) {
-    float *o = (float *)output;
-    const float *t = (const float *)tmp.data();
-    for (uint64_t i = 0; i < 2 * output_len; ++i) o[i] += t[i];
-  } else {
-    double *o = (double *)output;
-    const double *t = (const double *)tmp.data();
-    for (uint64_t i = 0; i < 2 * output_len; ++i) o[i] += t[i];
-  }
-  return QIPB200_OK;
+  return guarded(ctx, [&]() -> int {
+    qipb200_state *s = nullptr;
+    int st = qipb200_state_new(ctx, prec, n, &s);
+    if (st != QIPB200_OK) return st;
+    st = qipb200_state_upload(s, input, 0, input_len);
+    if (st == QIPB200_OK) st = qipb200_state_apply_schedule(s, ops, n_ops, QIPB200_SCHED_DEFAULT);
+    std::vector<char> tmp;
+    if (st == QIPB200_OK) {
+      tmp.resize(output_len * ab);
+      st = qipb200_state_download(s, tmp.data(), 0, output_len);
+    }
+    qipb200_state_free(s);
+    if (st != QIPB200_OK) return st;
+    if (prec == QIP_F32) {
+      float *o = (float *)output;
+      const float *t = (const float *)tmp.data();
+      for (uint64_t i = 0; i < 2 * output_len; ++i) o[i] += t[i];
+    } else {
+      double *o = (double *)output;
+      const double *t = (const double *)tmp.data();
+      for (uint64_t i = 0; i < 2 * output_len; ++i) o[i] += t[i];
+    }
+    return (int)QIPB200_OK;
+  });
 }
 
 // ===================================================================================
-// measurement
+// measurement (collective on a sharded state: every rank calls, every rank gets the answer)
 // ===================================================================================
 
 namespace {
@@ -802,14 +1111,11 @@ int check_indices(qipb200_state *s, const uint64_t *indices, uint32_t n_indices)
   return QIPB200_OK;
 }
 
-}  // namespace
-
-extern "C" int qipb200_state_measure_probs(qipb200_state *s, const uint64_t *indices, uint32_t n_indices, double *out) {
-  if (!s || !out) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "measure_probs: NULL argument");
+int measure_probs_impl(qipb200_state *s, const uint64_t *indices, uint32_t n_indices, double *out) {
   qipb200_ctx *ctx = s->ctx;
-  int st = check_indices(s, indices, n_indices);
-  if (st != QIPB200_OK) return st;
   if (n_indices > 26) return set_err(ctx, QIPB200_ERR_UNSUPPORTED, "measure_probs: more than 26 measured qubits");
+  if (s->world > 1 && (1u << n_indices) > (uint32_t)kCommDoubles)
+    return set_err(ctx, QIPB200_ERR_UNSUPPORTED, "measure_probs on a sharded state: more than 16 measured qubits");
   CU(ctx, cudaSetDevice(ctx->device));
   uint32_t bitpos[32];
   for (uint32_t i = 0; i < n_indices; ++i) bitpos[i] = s->phys_of_logical[s->n - 1 - (uint32_t)indices[i]];
@@ -817,35 +1123,20 @@ extern "C" int qipb200_state_measure_probs(qipb200_state *s, const uint64_t *ind
   CU(ctx, cudaMallocAsync((void **)&d_hist, sizeof(double) << n_indices, ctx->stream));
   CU(ctx, launch_measure_probs(s->prec, s->buf, 1ull << s->n_local, (uint64_t)s->rank << s->n_local, bitpos,
                                n_indices, d_hist, ctx->stream, &ctx->launches));
-  CU(ctx, cudaMemcpyAsync(out, d_hist, sizeof(double) << n_indices, cudaMemcpyDeviceToHost, ctx->stream));
+  // measurement_ops.rs:115-127 sums over the WHOLE vector: per-rank histograms are added across the ranks
+  int st = allreduce_sum(s, d_hist, 1u << n_indices);
+  if (st == QIPB200_OK)
+    CU(ctx, cudaMemcpyAsync(out, d_hist, sizeof(double) << n_indices, cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaFreeAsync(d_hist, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
-  return QIPB200_OK;
+  return st;
 }
 
-extern "C" int qipb200_state_measure_prob(qipb200_state *s, uint64_t measured, const uint64_t *indices,
-                                          uint32_t n_indices, double *out) {
-  if (!s || !out) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "measure_prob: NULL argument");
-  int st = check_indices(s, indices, n_indices);
-  if (st != QIPB200_OK) return st;
-  if (n_indices > 26) return set_err(s->ctx, QIPB200_ERR_UNSUPPORTED, "measure_prob: more than 26 measured qubits");
-  std::vector<double> probs(1ull << n_indices);
-  st = qipb200_state_measure_probs(s, indices, n_indices, probs.data());
-  if (st != QIPB200_OK) return st;
-  *out = (measured >> n_indices) ? 0.0 : probs[measured];
-  return QIPB200_OK;
-}
-
-extern "C" int qipb200_state_soft_measure(qipb200_state *s, const uint64_t *indices, uint32_t n_indices, double r,
-                                          uint64_t *measured) {
-  if (!s || !measured) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "soft_measure: NULL argument");
+// The serial scan of measurement_ops.rs:166-172 over this rank's amplitudes, starting with `rem` left of the
+// draw: per-chunk sums on the device, chunk search on the host, then a scan of the chunk holding the crossing
+// (and of the following ones when rounding leaves the chunk-level search one step short).
+int local_scan(qipb200_state *s, double rem, bool *crossed, uint64_t *idx_out) {
   qipb200_ctx *ctx = s->ctx;
-  int st = check_indices(s, indices, n_indices);
-  if (st != QIPB200_OK) return st;
-  if (s->world > 1) return set_err(ctx, QIPB200_ERR_UNSUPPORTED, "soft_measure on a sharded state: sample per rank via measure_probs");
-  CU(ctx, cudaSetDevice(ctx->device));
-  // Inverse-CDF sampling (measurement_ops.rs:153-176 is a serial scan): per-chunk sums on the
-  // device, chunk search on the host, then a scan of the one chunk that contains the crossing.
   const uint64_t len = 1ull << s->n_local;
   const uint32_t chunk_log2 = s->n_local > 12 ? 12 : s->n_local;
   const uint64_t chunks = len >> chunk_log2;
@@ -856,7 +1147,6 @@ extern "C" int qipb200_state_soft_measure(qipb200_state *s, const uint64_t *indi
   CU(ctx, cudaMemcpyAsync(sums.data(), d_sums, chunks * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(ctx, cudaFreeAsync(d_sums, ctx->stream));
   CU(ctx, cudaStreamSynchronize(ctx->stream));
-  double rem = r;  // full-length input: r * 1 (measurement_ops.rs:160-165)
   uint64_t c = 0;
   for (; c + 1 < chunks; ++c) {
     if (rem - sums[c] <= 0.0) break;
@@ -865,13 +1155,9 @@ extern "C" int qipb200_state_soft_measure(qipb200_state *s, const uint64_t *indi
   const uint64_t clen = 1ull << chunk_log2;
   const size_t ab = amp_bytes(s->prec);
   std::vector<char> host(clen * ab);
-  // The device-reduced chunk sums and this serial scan add in different orders: when r lands within
-  // rounding of a chunk boundary the scan of chunk c may end just short of the crossing.  The reference's
-  // single serial scan would simply go on, so do the same: keep scanning the following chunks, and only
-  // after the last one leave measured_indx = 0 (measurement_ops.rs:166-172: "never crossed").
-  uint64_t idx = 0;
-  bool crossed = false;
-  for (; c < chunks && !crossed; ++c) {
+  *crossed = false;
+  *idx_out = 0;
+  for (; c < chunks && !*crossed; ++c) {
     CU(ctx, cudaMemcpyAsync(host.data(), (const char *)s->buf + c * clen * ab, clen * ab, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     for (uint64_t i = 0; i < clen; ++i) {
@@ -885,11 +1171,70 @@ extern "C" int qipb200_state_soft_measure(qipb200_state *s, const uint64_t *indi
       }
       rem -= re * re + im * im;
       if (rem <= 0.0) {
-        idx = c * clen + i;
-        crossed = true;
+        *idx_out = c * clen + i;
+        *crossed = true;
         break;
       }
     }
+  }
+  return QIPB200_OK;
+}
+
+int soft_measure_impl(qipb200_state *s, const uint64_t *indices, uint32_t n_indices, double r, uint64_t *measured) {
+  qipb200_ctx *ctx = s->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
+  uint64_t idx = 0;  // the reference leaves measured_indx = 0 when the scan never crosses
+  if (s->world == 1) {
+    bool crossed = false;
+    int st = local_scan(s, r, &crossed, &idx);  // full-length input: r * 1 (measurement_ops.rs:160-165)
+    if (st != QIPB200_OK) return st;
+  } else {
+    // The reference scans the whole vector in index order: restore the canonical layout (rank r then holds
+    // indices [r 2^nl, (r+1) 2^nl)), all-gather the per-rank totals, let every rank scan its own shard with the
+    // part of the draw the lower ranks left over, all-gather (crossed, index): the lowest crossing rank wins.
+    if (!layout_is_identity(s)) {
+      int st = restore_layout(s);
+      if (st != QIPB200_OK) return st;
+    }
+    const int W = s->world;
+    double *d_vec = nullptr;
+    CU(ctx, cudaMallocAsync((void **)&d_vec, 2 * W * sizeof(double), ctx->stream));
+    CU(ctx, cudaMemsetAsync(d_vec, 0, 2 * W * sizeof(double), ctx->stream));
+    CU(ctx, launch_norm2(s->prec, s->buf, 1ull << s->n_local, ctx->d_scalar, ctx->stream, &ctx->launches));
+    CU(ctx, cudaMemcpyAsync(d_vec + s->rank, ctx->d_scalar, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    int st = allreduce_sum(s, d_vec, (uint32_t)W);
+    std::vector<double> tot(2 * W, 0.0);
+    if (st == QIPB200_OK) {
+      CU(ctx, cudaMemcpyAsync(tot.data(), d_vec, W * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(ctx, cudaStreamSynchronize(ctx->stream));
+      double rem = r;
+      for (int t = 0; t < s->rank; ++t) rem -= tot[t];
+      bool crossed = false;
+      uint64_t li = 0;
+      if (rem <= 0.0 && s->rank > 0) {
+        crossed = true;  // the draw ran out below this rank: a serial scan arriving here stops at the first element
+      } else {
+        st = local_scan(s, rem, &crossed, &li);
+      }
+      std::vector<double> mine(2 * W, 0.0);
+      mine[2 * s->rank] = crossed ? 1.0 : 0.0;
+      mine[2 * s->rank + 1] = (double)(((uint64_t)s->rank << s->n_local) + li);  // < 2^40: exact in a double
+      if (st == QIPB200_OK) {
+        CU(ctx, cudaMemcpyAsync(d_vec, mine.data(), 2 * W * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        st = allreduce_sum(s, d_vec, (uint32_t)(2 * W));
+      }
+      if (st == QIPB200_OK) {
+        CU(ctx, cudaMemcpyAsync(tot.data(), d_vec, 2 * W * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int t = 0; t < W; ++t)
+          if (tot[2 * t] != 0.0) {
+            idx = (uint64_t)tot[2 * t + 1];
+            break;
+          }
+      }
+    }
+    CU(ctx, cudaFreeAsync(d_vec, ctx->stream));
+    if (st != QIPB200_OK) return st;
   }
   uint64_t m = 0;  // extract_bits(measured_indx, [n-1-index]) (measurement_ops.rs:174-175)
   for (uint32_t i = 0; i < n_indices; ++i) m |= ((idx >> (s->n - 1 - indices[i])) & 1ull) << i;
@@ -897,12 +1242,8 @@ extern "C" int qipb200_state_soft_measure(qipb200_state *s, const uint64_t *indi
   return QIPB200_OK;
 }
 
-extern "C" int qipb200_state_collapse(qipb200_state *s, const uint64_t *indices, uint32_t n_indices,
-                                      uint64_t measured, double measured_prob) {
-  if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
+int collapse_impl(qipb200_state *s, const uint64_t *indices, uint32_t n_indices, uint64_t measured, double measured_prob) {
   qipb200_ctx *ctx = s->ctx;
-  int st = check_indices(s, indices, n_indices);
-  if (st != QIPB200_OK) return st;
   if (measured_prob == 0.0) return QIPB200_OK;  // measurement_ops.rs:230: untouched
   CU(ctx, cudaSetDevice(ctx->device));
   uint64_t row_mask = 0, measured_mask = 0;
@@ -922,8 +1263,69 @@ extern "C" int qipb200_state_collapse(qipb200_state *s, const uint64_t *indices,
   return QIPB200_OK;
 }
 
+}  // namespace
+
+extern "C" int qipb200_state_measure_probs(qipb200_state *s, const uint64_t *indices, uint32_t n_indices, double *out) {
+  if (!s || !out) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "measure_probs: NULL argument");
+  return guarded(s->ctx, [&]() -> int {
+    int st = check_indices(s, indices, n_indices);
+    if (st != QIPB200_OK) return st;
+    if (!s->shards.empty()) {
+      if (n_indices > 16) return set_err(s->ctx, QIPB200_ERR_UNSUPPORTED, "measure_probs on a sharded state: more than 16 measured qubits");
+      std::vector<std::vector<double>> v(s->shards.size(), std::vector<double>((size_t)1 << n_indices));
+      st = each_shard(s, [&](qipb200_state *sh, int r) { return measure_probs_impl(sh, indices, n_indices, v[r].data()); });
+      if (st == QIPB200_OK) memcpy(out, v[0].data(), sizeof(double) << n_indices);
+      return st;
+    }
+    return measure_probs_impl(s, indices, n_indices, out);
+  });
+}
+
+extern "C" int qipb200_state_measure_prob(qipb200_state *s, uint64_t measured, const uint64_t *indices,
+                                          uint32_t n_indices, double *out) {
+  if (!s || !out) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "measure_prob: NULL argument");
+  return guarded(s->ctx, [&]() -> int {
+    int st = check_indices(s, indices, n_indices);
+    if (st != QIPB200_OK) return st;
+    if (n_indices > 26) return set_err(s->ctx, QIPB200_ERR_UNSUPPORTED, "measure_prob: more than 26 measured qubits");
+    std::vector<double> probs(1ull << n_indices);
+    st = qipb200_state_measure_probs(s, indices, n_indices, probs.data());
+    if (st != QIPB200_OK) return st;
+    *out = (measured >> n_indices) ? 0.0 : probs[measured];
+    return (int)QIPB200_OK;
+  });
+}
+
+extern "C" int qipb200_state_soft_measure(qipb200_state *s, const uint64_t *indices, uint32_t n_indices, double r,
+                                          uint64_t *measured) {
+  if (!s || !measured) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "soft_measure: NULL argument");
+  return guarded(s->ctx, [&]() -> int {
+    int st = check_indices(s, indices, n_indices);
+    if (st != QIPB200_OK) return st;
+    if (!s->shards.empty()) {
+      std::vector<uint64_t> v(s->shards.size(), 0);
+      st = each_shard(s, [&](qipb200_state *sh, int rk) { return soft_measure_impl(sh, indices, n_indices, r, &v[rk]); });
+      *measured = v[0];
+      return st;
+    }
+    return soft_measure_impl(s, indices, n_indices, r, measured);
+  });
+}
+
+extern "C" int qipb200_state_collapse(qipb200_state *s, const uint64_t *indices, uint32_t n_indices,
+                                      uint64_t measured, double measured_prob) {
+  if (!s) return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "state is NULL");
+  return guarded(s->ctx, [&]() -> int {
+    int st = check_indices(s, indices, n_indices);
+    if (st != QIPB200_OK) return st;
+    if (!s->shards.empty())
+      return each_shard(s, [&](qipb200_state *sh, int) { return collapse_impl(sh, indices, n_indices, measured, measured_prob); });
+    return collapse_impl(s, indices, n_indices, measured, measured_prob);
+  });
+}
+
 // ===================================================================================
-// multi-GPU plumbing
+// multi-GPU plumbing (one process per GPU: CUDA IPC)
 // ===================================================================================
 
 extern "C" int qipb200_state_ipc_export(qipb200_state *s, void *amp_handle, void *flag_handle) {
@@ -945,44 +1347,52 @@ extern "C" int qipb200_state_ipc_import(qipb200_state *s, const void *amp_handle
   if (!s || !amp_handles || !flag_handles) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "ipc_import: NULL argument");
   qipb200_ctx *ctx = s->ctx;
   if (s->world == 1) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "ipc_import: not a sharded state");
-  CU(ctx, cudaSetDevice(ctx->device));
-  s->peer_buf.assign(s->world, nullptr);
-  s->peer_flags.assign(s->world, nullptr);
-  for (int t = 0; t < s->world; ++t) {
-    if (t == s->rank) {
-      s->peer_buf[t] = s->buf;
-      s->peer_flags[t] = s->flags;
-      continue;
+  if (s->ipc_ready) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "ipc_import: peers are already mapped");
+  return guarded(ctx, [&]() -> int {
+    CU(ctx, cudaSetDevice(ctx->device));
+    s->peer_buf.assign(s->world, nullptr);
+    s->peer_flags.assign(s->world, nullptr);
+    s->peer_comm.assign(s->world, nullptr);
+    s->ipc_mapped = true;
+    for (int t = 0; t < s->world; ++t) {
+      if (t == s->rank) {
+        s->peer_buf[t] = s->buf;
+        s->peer_flags[t] = s->flags;
+        s->peer_comm[t] = comm_of(s->flags);
+        continue;
+      }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char *)amp_handles + (size_t)t * QIPB200_IPC_HANDLE_BYTES, sizeof(h));
+      cudaError_t e = cudaIpcOpenMemHandle(&s->peer_buf[t], h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        cuda_fail(ctx, e, "cudaIpcOpenMemHandle(amplitudes)");
+        return (int)QIPB200_ERR_COMM;
+      }
+      memcpy(&h, (const char *)flag_handles + (size_t)t * QIPB200_IPC_HANDLE_BYTES, sizeof(h));
+      void *fp = nullptr;
+      e = cudaIpcOpenMemHandle(&fp, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        cuda_fail(ctx, e, "cudaIpcOpenMemHandle(flags)");
+        return (int)QIPB200_ERR_COMM;
+      }
+      s->peer_flags[t] = (uint32_t *)fp;
+      s->peer_comm[t] = comm_of((uint32_t *)fp);
     }
-    cudaIpcMemHandle_t h;
-    memcpy(&h, (const char *)amp_handles + (size_t)t * QIPB200_IPC_HANDLE_BYTES, sizeof(h));
-    cudaError_t e = cudaIpcOpenMemHandle(&s->peer_buf[t], h, cudaIpcMemLazyEnablePeerAccess);
-    if (e != cudaSuccess) {
-      cuda_fail(ctx, e, "cudaIpcOpenMemHandle(amplitudes)");
-      return QIPB200_ERR_COMM;
-    }
-    memcpy(&h, (const char *)flag_handles + (size_t)t * QIPB200_IPC_HANDLE_BYTES, sizeof(h));
-    void *fp = nullptr;
-    e = cudaIpcOpenMemHandle(&fp, h, cudaIpcMemLazyEnablePeerAccess);
-    if (e != cudaSuccess) {
-      cuda_fail(ctx, e, "cudaIpcOpenMemHandle(flags)");
-      return QIPB200_ERR_COMM;
-    }
-    s->peer_flags[t] = (uint32_t *)fp;
-  }
-  s->ipc_ready = true;
-  return QIPB200_OK;
+    s->ipc_ready = true;
+    return (int)QIPB200_OK;
+  });
 }
 
 extern "C" int qipb200_state_qubit_map(qipb200_state *s, uint32_t *bit_of_qubit) {
   if (!s || !bit_of_qubit) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "qubit_map: NULL argument");
-  for (uint32_t q = 0; q < s->n; ++q) bit_of_qubit[q] = s->phys_of_logical[s->n - 1 - q];
+  const qipb200_state *src = s->shards.empty() ? s : s->shards[0];
+  for (uint32_t q = 0; q < s->n; ++q) bit_of_qubit[q] = src->phys_of_logical[s->n - 1 - q];
   return QIPB200_OK;
 }
 
 extern "C" int qipb200_state_exchange_bytes(qipb200_state *s, uint64_t *bytes) {
   if (!s || !bytes) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "exchange_bytes: NULL argument");
-  *bytes = s->exchange_bytes;
+  *bytes = s->shards.empty() ? s->exchange_bytes : s->shards[0]->exchange_bytes;
   return QIPB200_OK;
 }
 
@@ -990,17 +1400,19 @@ extern "C" int qipb200_plan_exchanges(qip_prec prec, uint32_t n_qubits, int worl
                                       size_t n_ops, uint32_t *needs_exchange) {
   if (!is_pow2(world_size) || (!ops && n_ops) || !needs_exchange)
     return set_err(nullptr, QIPB200_ERR_INVALID_ARG, "plan_exchanges: bad argument");
-  const uint32_t n_local = n_qubits - (uint32_t)ilog2(world_size);
-  for (size_t i = 0; i < n_ops; ++i) {
-    FlatOp f;
-    std::string err;
-    int st = compile_op(&ops[i], prec, n_qubits, &f, &err);
-    if (st != QIPB200_OK) return set_err(nullptr, st, err);
-    std::vector<uint32_t> nd;
-    nondiag_bits(f, &nd);
-    uint32_t cnt = 0;
-    for (size_t j = 0; j < nd.size(); ++j) cnt += nd[j] >= n_local;
-    needs_exchange[i] = cnt;
-  }
-  return QIPB200_OK;
+  return guarded(nullptr, [&]() -> int {
+    const uint32_t n_local = n_qubits - (uint32_t)ilog2(world_size);
+    for (size_t i = 0; i < n_ops; ++i) {
+      FlatOp f;
+      std::string err;
+      int st = compile_op(&ops[i], prec, n_qubits, &f, &err);
+      if (st != QIPB200_OK) return set_err(nullptr, st, err);
+      std::vector<uint32_t> nd;
+      nondiag_bits(f, &nd);
+      uint32_t cnt = 0;
+      for (size_t j = 0; j < nd.size(); ++j) cnt += nd[j] >= n_local;
+      needs_exchange[i] = cnt;
+    }
+    return (int)QIPB200_OK;
+  });
 }

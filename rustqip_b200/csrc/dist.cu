@@ -108,4 +108,35 @@ cudaError_t launch_flag_barrier(uint32_t *const *peer_flags, uint32_t *my_flags,
   return cudaGetLastError();
 }
 
+// ---- small all-reduce through the peers' reduction slots ----------------------------------
+struct CommSumArgs {
+  const double *comm[kMaxWorld];
+  int world;
+  uint32_t count;
+};
+
+__global__ void __launch_bounds__(256) k_comm_sum(double *__restrict__ out, const CommSumArgs a) {
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= a.count) return;
+  double acc = 0.0;
+  for (int t = 0; t < a.world; ++t) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(a.comm[t] + i) : "memory");
+    acc += v;
+  }
+  out[i] = acc;
+}
+
+cudaError_t launch_comm_sum(const double *const *peer_comm, int world, double *out, uint32_t count, cudaStream_t s,
+                            uint64_t *launches) {
+  if (world > kMaxWorld || count > (uint32_t)kCommDoubles) return cudaErrorInvalidValue;
+  CommSumArgs a;
+  for (int t = 0; t < world; ++t) a.comm[t] = peer_comm[t];
+  a.world = world;
+  a.count = count;
+  k_comm_sum<<<(count + 255u) / 256u, 256, 0, s>>>(out, a);
+  ++*launches;
+  return cudaGetLastError();
+}
+
 }  // namespace qipb200

@@ -12,6 +12,11 @@ namespace qipb200 {
 static const int kMaxWorld = 16;
 static const int kFlagErrorSlot = 32;   // flags[kFlagErrorSlot] != 0 => a barrier timed out
 static const int kFlagWords = 64;
+// The flag page is followed, in the same (peer-mapped) allocation, by one reduction slot of kCommDoubles doubles:
+// small cross-rank sums (measurement histograms, norms, sampling prefixes) are exchanged through it.
+static const int kCommDoubles = 1 << 16;
+static const size_t kCommOffsetBytes = 256;
+static const size_t kFlagAllocBytes = kCommOffsetBytes + (size_t)kCommDoubles * sizeof(double);
 
 // Trade the half-shard selected by local bit `l` with the partner's (see dist.cu).
 // rb = this rank's value of the rank bit being migrated; s_bit = pair-ownership bit.
@@ -21,5 +26,10 @@ cudaError_t launch_pair_exchange(qip_prec prec, void *mine, void *peer, uint32_t
 // All-rank barrier through peer-mapped flag pages; stream-ordered.
 cudaError_t launch_flag_barrier(uint32_t *const *peer_flags, uint32_t *my_flags, int rank, int world,
                                 uint32_t epoch, uint32_t *error_word, cudaStream_t s, uint64_t *launches);
+
+// out[i] = sum over ranks t (ascending: the same order, hence the same bits, on every rank) of comm_t[i], where
+// comm_t is rank t's reduction slot read over NVLink.  The caller brackets it with flag barriers.
+cudaError_t launch_comm_sum(const double *const *peer_comm, int world, double *out, uint32_t count, cudaStream_t s,
+                            uint64_t *launches);
 
 }  // namespace qipb200

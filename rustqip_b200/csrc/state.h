@@ -23,6 +23,14 @@ struct qipb200_ctx {
   uint64_t jit_launches = 0;       // tile passes among `tile_launches` that ran a generated (specialised) kernel
   std::vector<std::pair<const qipb200::JitCubin *, qipb200::JitLoaded>> jit_loaded;  // modules loaded on this device
   std::string jit_note;            // why the generated-kernel path was not taken last time (diagnostics)
+  // multi-device context (qipb200_init_multi): one child context per device, owned by the parent; states created
+  // on the parent are sharded over the children inside this one process (peer access instead of CUDA IPC)
+  std::vector<qipb200_ctx *> children;
+  qipb200_ctx *parent = nullptr;
+  // one released state buffer kept for the next state of the same size (qipb200_calculate_state re-allocates
+  // 2^n amplitudes per call otherwise)
+  void *pool_buf = nullptr;
+  size_t pool_bytes = 0;
   bool tile_configured = false;    // the tile kernels' > 48 KiB shared-memory opt-in was done on this device
   // optional per-category device timing (qipb200_profile_enable): CUDA-event pairs recorded on `stream`
   // around every fused tile pass [0] and every NVLink exchange incl. its two flag barriers [1]
@@ -53,6 +61,9 @@ struct qipb200_state {
   std::vector<void *> peer_buf;
   uint32_t *flags = nullptr;  // world slots, written by peers
   std::vector<uint32_t *> peer_flags;
+  std::vector<const double *> peer_comm;  // every rank's reduction slot (behind its flag page, dist.cuh)
+  std::vector<qipb200_state *> shards;    // parent state of a multi-device context: one sharded state per device
+  bool ipc_mapped = false;                // peers were mapped with cudaIpcOpenMemHandle (to be closed on free)
   uint32_t epoch = 0;
   uint64_t exchange_bytes = 0;
   bool ipc_ready = false;

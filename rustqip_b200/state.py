@@ -20,14 +20,23 @@ from .ops import MatrixOp
 class Context:
     """One CUDA device + stream (qipb200_ctx).  One process per GPU."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """device: one CUDA device id, or a list of ids (a power-of-two count): ONE context over several devices
+        of this process (qipb200_init_multi) whose states are sharded over them inside the library."""
         self._h = C.c_void_p()
         L = _lib.lib()
-        st = L.qipb200_init(C.byref(self._h), int(device))
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*[int(d) for d in device])
+            st = L.qipb200_init_multi(C.byref(self._h), len(device), ids)
+            self.device = int(device[0])
+            self.devices = [int(d) for d in device]
+        else:
+            st = L.qipb200_init(C.byref(self._h), int(device))
+            self.device = int(device)
+            self.devices = [int(device)]
         if st != 0:
             msg = L.qipb200_last_error(None).decode("utf-8", "replace")
             raise B200Unavailable(msg)
-        self.device = int(device)
 
     @property
     def handle(self):

@@ -18,8 +18,10 @@ ROOT = os.path.dirname(HERE)
 SO = os.path.join(HERE, "native", "_build", "libplan_emul.so")
 SRCS = [os.path.join(HERE, "native", "plan_emulator.cpp"),
         os.path.join(ROOT, "rustqip_b200", "csrc", "planner.cpp"),
-        os.path.join(ROOT, "rustqip_b200", "csrc", "opcompile.cpp")]
+        os.path.join(ROOT, "rustqip_b200", "csrc", "opcompile.cpp"),
+        os.path.join(ROOT, "rustqip_b200", "csrc", "jit_codegen.cpp")]
 HDRS = [os.path.join(ROOT, "rustqip_b200", "csrc", "tile.cuh"),
+        os.path.join(ROOT, "rustqip_b200", "csrc", "jit_codegen.h"),
         os.path.join(ROOT, "rustqip_b200", "csrc", "opcompile.h"),
         os.path.join(ROOT, "include", "qip_op.h")]
 
@@ -29,7 +31,7 @@ def emul():
     os.makedirs(os.path.dirname(SO), exist_ok=True)
     stale = not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in SRCS + HDRS)
     if stale:
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SO] + SRCS)
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SO] + SRCS + ["-ldl"])
     L = C.CDLL(SO)
     L.emul_schedule.restype = C.c_int
     L.emul_schedule.argtypes = [C.c_int, C.c_uint32, C.POINTER(QipOp), C.c_size_t, C.c_void_p, C.c_uint32,
