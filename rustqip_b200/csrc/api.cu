@@ -642,9 +642,16 @@ int launch_local_op(qipb200_state *s, const FlatOp &f) {
     case CLASS_IDENTITY:
       return QIPB200_OK;
     case CLASS_DIAGONAL:
-      if (f.diag_bits.size() > (size_t)kMaxDiagParamK || __builtin_popcountll(cm) > kMaxIns) break;
-      CU(ctx, launch_diag(s->prec, s->buf, nl, cm, f.diag_bits, f.diag, ctx->stream, &ctx->launches));
-      return QIPB200_OK;
+      if (__builtin_popcountll(cm) > kMaxIns) break;
+      if (f.diag_bits.size() <= (size_t)kMaxDiagParamK) {
+        CU(ctx, launch_diag(s->prec, s->buf, nl, cm, f.diag_bits, f.diag, ctx->stream, &ctx->launches));
+        return QIPB200_OK;
+      }
+      if (f.diag_bits.size() <= 10) {
+        CU(ctx, launch_diag_wide(s->prec, s->buf, nl, cm, f.diag_bits, f.diag, ctx->stream, &ctx->launches));
+        return QIPB200_OK;
+      }
+      break;
     case CLASS_FLIP:
       CU(ctx, launch_flip(s->prec, s->buf, nl, cm, f.tgt_sorted[0], ctx->stream, &ctx->launches));
       return QIPB200_OK;
@@ -657,6 +664,13 @@ int launch_local_op(qipb200_state *s, const FlatOp &f) {
       if (f.tgt_sorted.size() <= (size_t)kMaxRegK &&
           __builtin_popcountll(cm) + f.tgt_sorted.size() <= (size_t)kMaxIns) {
         CU(ctx, launch_dense(s->prec, s->buf, nl, f, ctx->stream, &ctx->launches));
+        return QIPB200_OK;
+      }
+      // k = 5..10 in place (the reference applies any k through the same row loop, qubit_iterators.rs:23-55)
+      if (f.tgt_sorted.size() >= 5 && f.tgt_sorted.size() <= 10 &&
+          __builtin_popcountll(cm) + f.tgt_sorted.size() <= (size_t)kMaxIns && nl >= f.tgt_sorted.size() + __builtin_popcountll(cm) &&
+          (f.tgt_sorted.size() == 5 || nl - (uint32_t)__builtin_popcountll(cm) >= 8)) {
+        CU(ctx, launch_dense_wide(s->prec, s->buf, nl, f, ctx->stream, &ctx->launches));
         return QIPB200_OK;
       }
       break;

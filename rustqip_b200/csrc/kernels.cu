@@ -16,6 +16,7 @@
 // enough independent loads in flight per SM.
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <cstdio>
 
 namespace qipb200 {
@@ -215,6 +216,179 @@ cudaError_t launch_dense(qip_prec prec, void *psi, uint32_t n_local, const FlatO
 }
 
 // ---------------------------------------------------------------------------------
+// K2 dense block on 5 target bits, in place: the 32 amplitudes of a group live in the registers of
+// one thread (as for k <= 4), the 32 x 32 matrix in shared memory (16 KiB f64), read with broadcast
+// 16-byte loads -- one LDS per four FMAs, every lane of a warp asks for the same entry.  Lanes run
+// over neighbouring groups, so both the 32 loads and the 32 stores of a warp-instruction cover
+// contiguous runs (the lowest non-target bits are the lane bits).  FP64: 128 FMA per amplitude, 4 flop/B
+// beyond the HBM ridge of a B200 -- this kernel is FP64-pipe bound, not HBM bound.
+// Two output rows are accumulated at a time (four independent FMA chains).
+// ---------------------------------------------------------------------------------
+struct WideArgs {
+  InsArgs ins;
+  uint64_t ctrl_mask;
+  uint64_t n_items;
+  uint64_t off[32];  // amplitude offset of sub-index u (k = 5)
+};
+
+template <typename R>
+__global__ void __launch_bounds__(128)
+    k_dense5(R *__restrict__ psi, const R *__restrict__ mat, const __grid_constant__ WideArgs a) {
+  typedef typename Vec2<R>::type V;
+  __shared__ V m[32 * 32];
+  for (int i = threadIdx.x; i < 32 * 32; i += 128) m[i] = reinterpret_cast<const V *>(mat)[i];
+  __syncthreads();
+  const uint64_t w = (uint64_t)blockIdx.x * 128 + threadIdx.x;
+  if (w >= a.n_items) return;
+  const uint64_t base = expand_index(w, a.ins) | a.ctrl_mask;
+  V x[32];
+#pragma unroll
+  for (int v = 0; v < 32; ++v) x[v] = *reinterpret_cast<const V *>(psi + 2 * (base + a.off[v]));
+#pragma unroll 1
+  for (int u = 0; u < 32; u += 2) {
+    R r0 = (R)0, i0 = (R)0, r1 = (R)0, i1 = (R)0;
+    const V *row0 = m + u * 32, *row1 = row0 + 32;
+#pragma unroll
+    for (int v = 0; v < 32; ++v) {
+      const V c0 = row0[v], c1 = row1[v];
+      r0 = fma(c0.x, x[v].x, r0);
+      r0 = fma(-c0.y, x[v].y, r0);
+      i0 = fma(c0.x, x[v].y, i0);
+      i0 = fma(c0.y, x[v].x, i0);
+      r1 = fma(c1.x, x[v].x, r1);
+      r1 = fma(-c1.y, x[v].y, r1);
+      i1 = fma(c1.x, x[v].y, i1);
+      i1 = fma(c1.y, x[v].x, i1);
+    }
+    V o0, o1;
+    o0.x = r0, o0.y = i0, o1.x = r1, o1.y = i1;
+    *reinterpret_cast<V *>(psi + 2 * (base + a.off[u])) = o0;  // the group is this thread's alone: its inputs are in x[]
+    *reinterpret_cast<V *>(psi + 2 * (base + a.off[u + 1])) = o1;
+  }
+}
+
+// Dense block on 6..10 target bits, in place: a CTA stages 2^k groups' worth of amplitudes (x 2^c
+// neighbouring groups, k + c = 12: 4096 amplitudes) in shared memory, every thread accumulates 16 outputs
+// from the staged inputs and the matrix (read through L1/L2: all lanes of a warp share the entry), the tile
+// is written back after a barrier.  Compute bound by a wide margin (2^k complex MACs per amplitude):
+// correctness and "never unsupported" rather than speed-of-light.
+struct BigArgs {
+  InsArgs ins;        // target + control positions (ascending)
+  uint64_t ctrl_mask;
+  uint64_t n_tiles;
+  uint32_t k, c;      // c = companion groups per tile (log2)
+  uint64_t off[10];   // amplitude offset of target bit i
+};
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+    k_dense_big(R *__restrict__ psi, const R *__restrict__ mat, const __grid_constant__ BigArgs a) {
+  typedef typename Vec2<R>::type V;
+  extern __shared__ __align__(16) unsigned char smem_big[];
+  V *x = reinterpret_cast<V *>(smem_big);  // x[v * C + cc]
+  const uint32_t S = 1u << a.k, C = 1u << a.c;
+  const uint64_t tile = blockIdx.x;
+  if (tile >= a.n_tiles) return;
+  for (uint32_t e = threadIdx.x; e < S * C; e += 256) {
+    const uint32_t v = e >> a.c, cc = e & (C - 1u);
+    uint64_t idx = expand_index(tile * C + cc, a.ins) | a.ctrl_mask;
+    for (uint32_t i = 0; i < a.k; ++i)
+      if ((v >> i) & 1u) idx += a.off[i];
+    x[e] = *reinterpret_cast<const V *>(psi + 2 * idx);
+  }
+  __syncthreads();
+  const uint32_t per = (S * C) / 256u;  // outputs per thread (16 for k + c = 12)
+  V out[16];
+  const uint32_t cc = threadIdx.x & (C - 1u), u0 = threadIdx.x >> a.c, ustep = 256u >> a.c;
+  for (uint32_t q = 0; q < per; ++q) {
+    const uint32_t u = u0 + q * ustep;
+    const V *row = reinterpret_cast<const V *>(mat) + (size_t)u * S;
+    R re = (R)0, im = (R)0;
+    for (uint32_t v = 0; v < S; ++v) {
+      const V cm = __ldg(row + v);
+      const V xv = x[v * C + cc];
+      re = fma(cm.x, xv.x, re);
+      re = fma(-cm.y, xv.y, re);
+      im = fma(cm.x, xv.y, im);
+      im = fma(cm.y, xv.x, im);
+    }
+    out[q].x = re;
+    out[q].y = im;
+  }
+  __syncthreads();
+  for (uint32_t q = 0; q < per; ++q) {
+    const uint32_t u = u0 + q * ustep;
+    uint64_t idx = expand_index(tile * C + cc, a.ins) | a.ctrl_mask;
+    for (uint32_t i = 0; i < a.k; ++i)
+      if ((u >> i) & 1u) idx += a.off[i];
+    *reinterpret_cast<V *>(psi + 2 * idx) = out[q];
+  }
+}
+
+template <typename R>
+static cudaError_t launch_dense_wide_t(R *psi, uint32_t n_local, const FlatOp &f, cudaStream_t s, uint64_t *launches) {
+  const uint32_t K = (uint32_t)f.tgt_sorted.size();
+  const size_t S = (size_t)1 << K;
+  // the matrix travels through a stream-ordered device allocation (16 KiB .. 16 MiB)
+  std::vector<R> host(2 * S * S);
+  for (size_t i = 0; i < S * S; ++i) {
+    host[2 * i] = (R)f.m_sorted[i].real();
+    host[2 * i + 1] = (R)f.m_sorted[i].imag();
+  }
+  R *d_mat = nullptr;
+  cudaError_t e = cudaMallocAsync((void **)&d_mat, host.size() * sizeof(R), s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyAsync(d_mat, host.data(), host.size() * sizeof(R), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // `host` is pageable and leaves scope
+  if (e != cudaSuccess) {
+    cudaFreeAsync(d_mat, s);
+    return e;
+  }
+  const uint32_t n_ins = K + (uint32_t)__builtin_popcountll(f.ctrl_mask);
+  if (K == 5) {
+    WideArgs a;
+    if (!build_ins(f.ctrl_mask, f.tgt_sorted.data(), K, &a.ins)) return cudaFreeAsync(d_mat, s), cudaErrorInvalidValue;
+    a.ctrl_mask = f.ctrl_mask;
+    for (uint32_t u = 0; u < 32; ++u) {
+      uint64_t off = 0;
+      for (uint32_t i = 0; i < K; ++i)
+        if ((u >> i) & 1) off |= 1ull << f.tgt_sorted[i];
+      a.off[u] = off;
+    }
+    a.n_items = 1ull << (n_local - n_ins);
+    k_dense5<R><<<(unsigned)((a.n_items + 127) / 128), 128, 0, s>>>(psi, d_mat, a);
+  } else {
+    BigArgs a;
+    if (!build_ins(f.ctrl_mask, f.tgt_sorted.data(), K, &a.ins)) return cudaFreeAsync(d_mat, s), cudaErrorInvalidValue;
+    a.ctrl_mask = f.ctrl_mask;
+    a.k = K;
+    const uint32_t groups_log2 = n_local - n_ins;
+    a.c = std::min<uint32_t>(12u - std::min(12u, K), groups_log2);
+    if (K + a.c < 8) a.c = std::min<uint32_t>(8u - K, groups_log2);  // at least one output per thread
+    if ((1u << (K + a.c)) < 256u || ((1u << (K + a.c)) / 256u) > 16u) return cudaFreeAsync(d_mat, s), cudaErrorInvalidValue;
+    for (uint32_t i = 0; i < K; ++i) a.off[i] = 1ull << f.tgt_sorted[i];
+    a.n_tiles = 1ull << (groups_log2 - a.c);
+    const size_t smem = ((size_t)2 * sizeof(R)) << (K + a.c);
+    // > 48 KiB of dynamic shared memory is a per-device opt-in: set it on the current device every time (cheap)
+    e = cudaFuncSetAttribute((const void *)k_dense_big<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return cudaFreeAsync(d_mat, s), e;
+    k_dense_big<R><<<(unsigned)a.n_tiles, 256, smem, s>>>(psi, d_mat, a);
+  }
+  ++*launches;
+  e = cudaGetLastError();
+  cudaFreeAsync(d_mat, s);
+  return e;
+}
+
+cudaError_t launch_dense_wide(qip_prec prec, void *psi, uint32_t n_local, const FlatOp &f, cudaStream_t s,
+                              uint64_t *launches) {
+  const size_t K = f.tgt_sorted.size();
+  if (K < 5 || K > 10 || K + (size_t)__builtin_popcountll(f.ctrl_mask) > (size_t)kMaxIns) return cudaErrorInvalidValue;
+  return prec == QIP_F32 ? launch_dense_wide_t<float>((float *)psi, n_local, f, s, launches)
+                         : launch_dense_wide_t<double>((double *)psi, n_local, f, s, launches);
+}
+
+// ---------------------------------------------------------------------------------
 // K5 diagonal: a[i] *= d[sub(i)] on the amplitudes whose control bits are all 1.
 // After promotion (opcompile.cpp) T/S/Z/CZ/controlled-phase are a single scalar on
 // a bit mask: only 1/2 .. 1/4 of the state is touched.
@@ -282,6 +456,74 @@ cudaError_t launch_diag(qip_prec prec, void *psi, uint32_t n_local, uint64_t ctr
                         uint64_t *launches) {
   return prec == QIP_F32 ? launch_diag_t<float>((float *)psi, n_local, ctrl_mask, bits, d, s, launches)
                          : launch_diag_t<double>((double *)psi, n_local, ctrl_mask, bits, d, s, launches);
+}
+
+// Diagonal on 5..10 bits: the table (<= 1024 entries) is staged in shared memory per CTA; grid-stride over
+// the touched amplitudes.  HBM bound like k_diag: one read + one write per touched amplitude.
+struct DiagWideArgs {
+  InsArgs ins;  // control positions only
+  uint64_t ctrl_mask;
+  uint64_t n_items;
+  uint32_t n_bits;
+  uint32_t bits[10];
+};
+
+template <typename R>
+__global__ void __launch_bounds__(kThreads)
+    k_diag_wide(R *__restrict__ psi, const R *__restrict__ table, const __grid_constant__ DiagWideArgs a) {
+  typedef typename Vec2<R>::type V;
+  __shared__ V tb[1024];
+  const uint32_t entries = 1u << a.n_bits;
+  for (uint32_t i = threadIdx.x; i < entries; i += kThreads) tb[i] = reinterpret_cast<const V *>(table)[i];
+  __syncthreads();
+  for (uint64_t w = (uint64_t)blockIdx.x * kThreads + threadIdx.x; w < a.n_items; w += (uint64_t)gridDim.x * kThreads) {
+    const uint64_t i = expand_index(w, a.ins) | a.ctrl_mask;
+    uint32_t u = 0;
+    for (uint32_t j = 0; j < a.n_bits; ++j) u |= (uint32_t)((i >> a.bits[j]) & 1ull) << j;
+    const V d = tb[u];
+    V v = *reinterpret_cast<const V *>(psi + 2 * i);
+    const R re = v.x, im = v.y;
+    v.x = fma(d.x, re, -d.y * im);
+    v.y = fma(d.x, im, d.y * re);
+    *reinterpret_cast<V *>(psi + 2 * i) = v;
+  }
+}
+
+template <typename R>
+static cudaError_t launch_diag_wide_t(R *psi, uint32_t n_local, uint64_t ctrl_mask, const std::vector<uint32_t> &bits,
+                                      const std::vector<cplx> &d, cudaStream_t s, uint64_t *launches) {
+  DiagWideArgs a;
+  if (bits.size() > 10 || d.size() != ((size_t)1 << bits.size())) return cudaErrorInvalidValue;
+  if (!build_ins(ctrl_mask, nullptr, 0, &a.ins)) return cudaErrorInvalidValue;
+  a.ctrl_mask = ctrl_mask;
+  a.n_bits = (uint32_t)bits.size();
+  for (size_t j = 0; j < bits.size(); ++j) a.bits[j] = bits[j];
+  a.n_items = 1ull << (n_local - a.ins.n_ins);
+  std::vector<R> host(2 * d.size());
+  for (size_t u = 0; u < d.size(); ++u) {
+    host[2 * u] = (R)d[u].real();
+    host[2 * u + 1] = (R)d[u].imag();
+  }
+  R *d_tab = nullptr;
+  cudaError_t e = cudaMallocAsync((void **)&d_tab, host.size() * sizeof(R), s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyAsync(d_tab, host.data(), host.size() * sizeof(R), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) {
+    const unsigned grid = (unsigned)std::min<uint64_t>((a.n_items + kThreads - 1) / kThreads, 148ull * 32);
+    k_diag_wide<R><<<grid ? grid : 1, kThreads, 0, s>>>(psi, d_tab, a);
+    ++*launches;
+    e = cudaGetLastError();
+  }
+  cudaFreeAsync(d_tab, s);
+  return e;
+}
+
+cudaError_t launch_diag_wide(qip_prec prec, void *psi, uint32_t n_local, uint64_t ctrl_mask,
+                             const std::vector<uint32_t> &bits, const std::vector<cplx> &d, cudaStream_t s,
+                             uint64_t *launches) {
+  return prec == QIP_F32 ? launch_diag_wide_t<float>((float *)psi, n_local, ctrl_mask, bits, d, s, launches)
+                         : launch_diag_wide_t<double>((double *)psi, n_local, ctrl_mask, bits, d, s, launches);
 }
 
 // ---------------------------------------------------------------------------------

@@ -21,6 +21,13 @@ cudaError_t launch_dense(qip_prec prec, void *psi, uint32_t n_local, const FlatO
 cudaError_t launch_diag(qip_prec prec, void *psi, uint32_t n_local, uint64_t ctrl_mask,
                         const std::vector<uint32_t> &bits, const std::vector<cplx> &d, cudaStream_t s,
                         uint64_t *launches);
+// Dense blocks on 5..10 target bits, in place (k = 5: groups in registers, matrix in shared memory; k >= 6: staged
+// through shared memory, matrix through L1/L2), and diagonals on 5..10 bits (table in shared memory).
+cudaError_t launch_dense_wide(qip_prec prec, void *psi, uint32_t n_local, const FlatOp &f, cudaStream_t s,
+                              uint64_t *launches);
+cudaError_t launch_diag_wide(qip_prec prec, void *psi, uint32_t n_local, uint64_t ctrl_mask,
+                             const std::vector<uint32_t> &bits, const std::vector<cplx> &d, cudaStream_t s,
+                             uint64_t *launches);
 cudaError_t launch_flip(qip_prec prec, void *psi, uint32_t n_local, uint64_t ctrl_mask, uint32_t tbit,
                         cudaStream_t s, uint64_t *launches);
 cudaError_t launch_bitswap(qip_prec prec, void *psi, uint32_t n_local, uint64_t ctrl_mask, uint32_t p,
