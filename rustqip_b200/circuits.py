@@ -158,6 +158,11 @@ def sharded_parity_circuit(n: int, g: int, seed: int = 5) -> List[MatrixOp]:
            gates.cphase(2, 0, 0.3), gates.h(hi), gates.x(0), gates.toffoli(0, 1, 2), gates.toffoli(3, 4, 0),
            make_swap_op([0], [n - 2]), gates.rz(0, 0.4), make_matrix_op([0, 5], u2.reshape(-1)),
            make_matrix_op([4, hi], u2.reshape(-1)), make_swap_op([0], [hi]) if hi > 0 else gates.h(1)]
+    # a dense 5-qubit block and a 6-qubit diagonal that include rank-held qubits (in-place wide kernels after migration)
+    u5 = np.linalg.qr(rng.standard_normal((32, 32)) + 1j * rng.standard_normal((32, 32)))[0]
+    ops += [make_matrix_op([0, 5, 2, 7, n - 1], u5.reshape(-1)),
+            make_matrix_op([hi, 1, 6, 3, 8, n - 2] if hi != 1 else [0, 1, 6, 3, 8, n - 2],
+                           np.diag(np.exp(1j * rng.standard_normal(64))).reshape(-1))]
     ops += random_circuit(n, 6, 1234 + n, "H,T,CNOT") + random_circuit(n, 4, 99 + n, "H,CZ,CNOT")
     ops += qft(n)[: 3 * n]
     return ops
