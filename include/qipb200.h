@@ -253,6 +253,15 @@ void qipb200_schedule_free(qipb200_schedule *s);
 size_t qipb200_schedule_serialise(qip_prec prec, uint32_t n_qubits, const qip_op *ops, size_t n_ops, void *buf,
                                   size_t cap);
 
+/* State files "QIPA" (checkpoint / resume; the reference keeps its state in two Vecs for the duration of one call,
+ * qip/src/builder.rs:406-407, and has no equivalent): one file per shard -- 40-byte header {magic "QIPA", version 1,
+ * prec, n_qubits, rank, world, first_index, n_amplitudes} followed by the shard's amplitudes in canonical index
+ * order, streamed through a 64 MiB bounce buffer.  load checks the header against the target state.  On a
+ * multi-device state (qipb200_init_multi) the shards go to "<path>.<rank>".  Byte-compatible with
+ * rustqip_b200.wire.dump_state / load_state. */
+int qipb200_state_save(qipb200_state *state, const char *path);
+int qipb200_state_load(qipb200_state *state, const char *path);
+
 #ifdef __cplusplus
 }
 #endif

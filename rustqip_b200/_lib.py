@@ -31,7 +31,7 @@ EXPORTS = [
     "qipb200_state_measure_prob", "qipb200_state_soft_measure", "qipb200_state_collapse",
     "qipb200_state_new_sharded", "qipb200_state_ipc_export", "qipb200_state_ipc_import",
     "qipb200_state_qubit_map", "qipb200_state_exchange_bytes", "qipb200_plan_exchanges",
-    "qipb200_schedule_parse", "qipb200_schedule_ops", "qipb200_schedule_free", "qipb200_schedule_serialise",
+    "qipb200_state_save", "qipb200_state_load", "qipb200_schedule_parse", "qipb200_schedule_ops", "qipb200_schedule_free", "qipb200_schedule_serialise",
 ]
 
 
@@ -98,6 +98,8 @@ def lib():
     L.qipb200_state_exchange_bytes.argtypes = [vp, C.POINTER(u64)]
     L.qipb200_plan_exchanges.restype = i32
     L.qipb200_plan_exchanges.argtypes = [i32, u32, i32, opp, C.c_size_t, vp]
+    L.qipb200_state_save.restype, L.qipb200_state_save.argtypes = i32, [vp, C.c_char_p]
+    L.qipb200_state_load.restype, L.qipb200_state_load.argtypes = i32, [vp, C.c_char_p]
     L.qipb200_schedule_parse.restype = i32
     L.qipb200_schedule_parse.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.c_char_p, C.c_size_t]
     L.qipb200_schedule_ops.restype = opp

@@ -1108,6 +1108,84 @@ extern "C" int qipb200_apply_ops(qipb200_ctx *ctx, qip_prec prec, uint32_t n, co
 }
 
 // ===================================================================================
+// N3: state files ("QIPA" v1, one file per shard; layout in rustqip_b200/wire.py) -- checkpoint / resume
+// ===================================================================================
+
+namespace {
+
+struct QipaHeader {
+  uint32_t magic, version, prec, n_qubits, rank, world;
+  uint64_t first_index, n_amplitudes;
+};
+static_assert(sizeof(QipaHeader) == 40, "QIPA header is 40 bytes");
+const uint32_t kQipaMagic = 0x41504951u;
+const size_t kFileChunkBytes = 64u << 20;  // host bounce buffer: the shard never sits in host memory as a whole
+
+int state_file_impl(qipb200_state *s, const char *path, bool save) {
+  qipb200_ctx *ctx = s->ctx;
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (!layout_is_identity(s)) {  // files hold the canonical layout (collective on a sharded state)
+    int st = restore_layout(s);
+    if (st != QIPB200_OK) return st;
+  }
+  const size_t ab = amp_bytes(s->prec);
+  const uint64_t len = 1ull << s->n_local;
+  FILE *f = fopen(path, save ? "wb" : "rb");
+  if (!f) return set_err(ctx, QIPB200_ERR_INVALID_ARG, std::string("state file: cannot open ") + path);
+  QipaHeader h;
+  int st = QIPB200_OK;
+  if (save) {
+    h.magic = kQipaMagic, h.version = 1, h.prec = (uint32_t)s->prec, h.n_qubits = s->n, h.rank = (uint32_t)s->rank;
+    h.world = (uint32_t)s->world, h.first_index = (uint64_t)s->rank << s->n_local, h.n_amplitudes = len;
+    if (fwrite(&h, sizeof(h), 1, f) != 1) st = set_err(ctx, QIPB200_ERR_INVALID_ARG, "state file: write failed");
+  } else {
+    if (fread(&h, sizeof(h), 1, f) != 1 || h.magic != kQipaMagic || h.version != 1)
+      st = set_err(ctx, QIPB200_ERR_INVALID_ARG, "not a QIPA version-1 state file");
+    else if (h.prec != (uint32_t)s->prec || h.n_qubits != s->n || h.rank != (uint32_t)s->rank || h.world != (uint32_t)s->world ||
+             h.n_amplitudes != len)
+      st = set_err(ctx, QIPB200_ERR_SIZE_MISMATCH, "state file does not match the target state (prec/n/rank/world/length)");
+  }
+  std::vector<char> bounce;
+  if (st == QIPB200_OK) bounce.resize((size_t)std::min<uint64_t>(kFileChunkBytes, len * ab));
+  for (uint64_t done = 0; st == QIPB200_OK && done < len * ab;) {
+    const size_t n = (size_t)std::min<uint64_t>(bounce.size(), len * ab - done);
+    cudaError_t e;
+    if (save) {
+      e = cudaMemcpyAsync(bounce.data(), (const char *)s->buf + done, n, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) st = cuda_fail(ctx, e, "state file: device -> host");
+      else if (fwrite(bounce.data(), 1, n, f) != n) st = set_err(ctx, QIPB200_ERR_INVALID_ARG, "state file: write failed");
+    } else {
+      if (fread(bounce.data(), 1, n, f) != n) {
+        st = set_err(ctx, QIPB200_ERR_INVALID_ARG, "state file truncated");
+        break;
+      }
+      e = cudaMemcpyAsync((char *)s->buf + done, bounce.data(), n, cudaMemcpyHostToDevice, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) st = cuda_fail(ctx, e, "state file: host -> device");
+    }
+    done += n;
+  }
+  if (st == QIPB200_OK && !save && fgetc(f) != EOF) st = set_err(ctx, QIPB200_ERR_INVALID_ARG, "state file: trailing bytes");
+  if (fclose(f) != 0 && st == QIPB200_OK && save) st = set_err(ctx, QIPB200_ERR_INVALID_ARG, "state file: close failed");
+  return st;
+}
+
+int state_file(qipb200_state *s, const char *path, bool save) {
+  if (!s || !path) return set_err(s ? s->ctx : nullptr, QIPB200_ERR_INVALID_ARG, "state file: NULL argument");
+  return guarded(s->ctx, [&]() -> int {
+    if (!s->shards.empty())  // multi-device state: one file per shard, "<path>.<rank>"
+      return each_shard(s, [&](qipb200_state *sh, int r) { return state_file_impl(sh, (std::string(path) + "." + std::to_string(r)).c_str(), save); });
+    return state_file_impl(s, path, save);
+  });
+}
+
+}  // namespace
+
+extern "C" int qipb200_state_save(qipb200_state *s, const char *path) { return state_file(s, path, true); }
+extern "C" int qipb200_state_load(qipb200_state *s, const char *path) { return state_file(s, path, false); }
+
+// ===================================================================================
 // measurement (collective on a sharded state: every rank calls, every rank gets the answer)
 // ===================================================================================
 

@@ -197,6 +197,13 @@ class State:
         self._chk(_lib.lib().qipb200_state_max_abs_diff(self._h, other._h, C.byref(v)))
         return v.value
 
+    # -- N3: QIPA state files through the C ABI (checkpoint / resume) ----------------
+    def save(self, path: str):
+        self._chk(_lib.lib().qipb200_state_save(self._h, str(path).encode()))
+
+    def load(self, path: str):
+        self._chk(_lib.lib().qipb200_state_load(self._h, str(path).encode()))
+
     # -- measurement_ops.rs ---------------------------------------------------
     def measure_probs(self, indices: Sequence[int]) -> np.ndarray:
         idx = np.ascontiguousarray(np.asarray(list(indices), dtype=np.uint64))

@@ -67,6 +67,24 @@ def test_schedule_and_state_files_on_device(ctx, tmp_path):
     with State(n, np.complex64, ctx) as st3:
         with pytest.raises(CircuitError, match="does not match"):
             wire.load_state(snap, st3)
+    # the same file format through the C ABI (qipb200_state_save / _load): byte-identical files, cross-readable
+    snap_c = os.path.join(tmp_path, "s_c.qipa")
+    with State(n, np.complex128, ctx) as st4:
+        st4.set_basis(3)
+        st4.apply_schedule(loaded[:40])
+        st4.save(snap_c)
+    assert open(snap_c, "rb").read() == open(snap, "rb").read()
+    with State(n, np.complex128, ctx) as st5:
+        st5.load(snap)                     # written by the Python writer, read by the library
+        st5.apply_schedule(loaded[40:])
+        assert np.max(np.abs(st5.download() - want)) < 1e-10
+    with State(n, np.complex64, ctx) as st6:
+        with pytest.raises(CircuitError, match="does not match"):
+            st6.load(snap_c)
+    with State(n, np.complex128, ctx) as st7:
+        open(snap_c, "ab").write(b"x")
+        with pytest.raises(CircuitError, match="trailing"):
+            st7.load(snap_c)
 
 
 # ---- the same format through the C ABI (qipb200_schedule_parse / _serialise: no GPU needed) ------------
