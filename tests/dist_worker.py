@@ -40,29 +40,39 @@ def main():
         got = gather_state(st)
         draws = (1e-9, 0.3, 0.62, 0.999999)
         samples = [st.soft_measure([0, 2, n - 1], r) for r in draws]
-        mprob = st.measure_prob(1, [1, 0])
-        st.collapse([1, 0], 1, mprob)
+        p10 = st.measure_probs([1, 0])
+        mval = int(np.argmax(p10))          # collapse onto the likeliest outcome of qubits (1, 0): never probability 0
+        mprob = st.measure_prob(mval, [1, 0])
+        st.collapse([1, 0], mval, mprob)
         norm_post = st.norm2()
         post = gather_state(st)
         gathered = [None] * world
-        dist.all_gather_object(gathered, (norm_all, probs.tolist(), samples, norm_post))
+        dist.all_gather_object(gathered, (norm_all, probs.tolist(), samples, norm_post, mval, mprob))
         st.free()
         if rank == 0:
             want = qo.run_pipeline(n, ops, 5, dtype)
             tol = 1e-10 if dtype == np.complex128 else 1e-5
             ptol = 1e-12 if dtype == np.complex128 else 1e-5
             err = float(np.max(np.abs(got.astype(np.complex128) - want.astype(np.complex128))))
-            ok = err <= tol and abs(norm_all - 1.0) < 1e-4
-            # every rank received the same collective results
-            ok = ok and all(g == gathered[0] for g in gathered)
             wprobs = qo.measure_probs(n, [0, n - 1, 3], want).astype(np.float64)
-            ok = ok and bool(np.allclose(probs, wprobs, atol=ptol)) and abs(p1 - qo.measure_prob(n, 1, [0], want)) < ptol
-            # sampling: the scan runs over OUR amplitudes (the GPU state), as the reference's would
-            # (the device scan accumulates in f64 for either precision: compare with the f64 scan of the same amplitudes)
-            ok = ok and samples == [qo.soft_measure(n, [0, 2, n - 1], got.astype(np.complex128), r) for r in draws]
             wpost = np.zeros_like(got)
-            qo.measure_state(n, [1, 0], 1, mprob, got, wpost)
-            ok = ok and bool(np.allclose(post, wpost, rtol=1e-5 if dtype == np.complex64 else 1e-13, atol=0)) and abs(norm_post - 1.0) < 1e-4
+            qo.measure_state(n, [1, 0], mval, mprob, got, wpost)
+            checks = {
+                "amplitudes": err <= tol,
+                "norm": abs(norm_all - 1.0) < 1e-4,
+                # every rank received the same collective results
+                "ranks_agree": all(g == gathered[0] for g in gathered),
+                "measure_probs": bool(np.allclose(probs, wprobs, atol=ptol)),
+                "measure_prob": abs(p1 - qo.measure_prob(n, 1, [0], want)) < ptol,
+                # sampling: the scan runs over OUR amplitudes (the GPU state), as the reference's would (the device
+                # scan accumulates in f64 for either precision: compare with the f64 scan of the same amplitudes)
+                "soft_measure": samples == [qo.soft_measure(n, [0, 2, n - 1], got.astype(np.complex128), r) for r in draws],
+                "collapse": bool(np.allclose(post, wpost, rtol=1e-5 if dtype == np.complex64 else 1e-13, atol=0)),
+                "norm_after_collapse": abs(norm_post - 1.0) < 1e-4,
+            }
+            ok = all(checks.values())
+            if not ok:
+                print("  failed checks:", [k for k, v in checks.items() if not v], "samples", samples, flush=True)
             print("n=%d %s fusion=%s world=%d: max err %.3e, norm %.12f, probs/samples/collapse checked, exchanged %.1f MiB/rank -> %s" % (
                 n, np.dtype(dtype).name, fusion, world, err, norm_all, exch / 2 ** 20, "OK" if ok else "FAIL"), flush=True)
             failures += 0 if ok else 1
