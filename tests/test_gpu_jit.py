@@ -38,8 +38,11 @@ def test_generated_kernels_match_oracle_and_interpreter(ctx, monkeypatch, dtype,
     assert_close(got, want, dtype)
     ref, n0 = run(ctx, n, ops, psi, monkeypatch, "off")
     assert n0 == 0
-    # same arithmetic in the same order (zero terms dropped, +-1 as add/sub: exact for finite values)
-    assert np.array_equal(got, ref)
+    # same arithmetic in the same order on the amplitudes (zero terms dropped, +-1 as add/sub: exact for finite
+    # values); only the per-CTA scalar products (global phase, conditional-phase tables) may be contracted
+    # differently by the two compilers: agreement to a few ulp instead of the oracle tolerance
+    scale = float(np.max(np.abs(ref)))
+    assert float(np.max(np.abs(got.astype(np.complex128) - ref.astype(np.complex128)))) <= (1e-14 if dtype == np.complex128 else 2e-6) * scale
 
 
 @pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
@@ -79,4 +82,4 @@ def test_async_mode_converges_to_generated_kernels(ctx, monkeypatch):
     second, njit = run(ctx, n, ops, psi, monkeypatch, "async")
     t1 = ctx.jit_stats()
     assert njit == t1["tile_passes"] - t0["tile_passes"] and njit >= 1
-    assert np.array_equal(first, second)
+    assert float(np.max(np.abs(first - second))) <= 1e-14 * float(np.max(np.abs(first)))
