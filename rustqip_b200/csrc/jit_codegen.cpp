@@ -341,10 +341,95 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
       if (apart[u]) x << " + " << apart[u] << "u";
       return x.str();
     };
+    // ---- conditional exchanges folded into the addresses ----
+    // An X under a CTA-uniform condition (CNOT / Toffoli whose control lies outside the tile) cannot be a static
+    // renaming; as arithmetic it costs four predicated moves per amplitude.  When it is the FIRST thing that
+    // happens to its amplitudes it is a conditional choice of the LOAD address instead (one select per amplitude),
+    // when it is the LAST thing, of the STORE address.
+    const std::vector<DElem> &els = supers[s];
+    auto is_xlike = [](const DElem &d) {
+      return d.kind == DElem::X || (d.kind == DElem::D1 && d.real && d.m[0] == 0.0 && d.m[3] == 0.0 && d.m[1] == 1.0 && d.m[2] == 1.0);
+    };
+    auto pairs_list = [](uint32_t j, uint32_t mask, std::vector<std::pair<uint32_t, uint32_t>> *pr) {
+      uint32_t pidx = 0;
+      for (uint32_t c = 0; c < 8; ++c) {
+        if ((c >> j) & 1) continue;
+        if ((mask >> pidx) & 1) pr->push_back(std::make_pair(c, c | (1u << j)));
+        ++pidx;
+      }
+    };
+    auto amps_of = [&](const DElem &d) -> uint32_t {
+      if (d.kind == DElem::D3) return 0xffu;
+      if (d.kind == DElem::PH || d.kind == DElem::PHN) return d.mask;
+      std::vector<std::pair<uint32_t, uint32_t>> pr;
+      pairs_list(d.j, d.mask, &pr);
+      uint32_t a = 0;
+      for (size_t k = 0; k < pr.size(); ++k) a |= (1u << pr[k].first) | (1u << pr[k].second);
+      return a;
+    };
+    std::vector<char> folded(els.size(), 0);
+    int lf_cond[8], sf_cond[8];
+    uint32_t lf_other[8], sf_other[8];
+    for (uint32_t u = 0; u < 8; ++u) lf_cond[u] = sf_cond[u] = -1, lf_other[u] = sf_other[u] = u;
+    {
+      uint32_t slot_of[8], dirty = 0;
+      for (uint32_t u = 0; u < 8; ++u) slot_of[u] = u;
+      for (size_t ei = 0; ei < els.size(); ++ei) {
+        const DElem &d = els[ei];
+        const uint32_t am = amps_of(d);
+        if (is_xlike(d)) {
+          std::vector<std::pair<uint32_t, uint32_t>> pr;
+          pairs_list(d.j, d.mask, &pr);
+          if (d.cond < 0) {  // static renaming: follows the names, touches nothing
+            for (size_t k = 0; k < pr.size(); ++k) std::swap(slot_of[pr[k].first], slot_of[pr[k].second]);
+            continue;
+          }
+          if (!(am & dirty)) {
+            for (size_t k = 0; k < pr.size(); ++k) {
+              const uint32_t sx = slot_of[pr[k].first], sy = slot_of[pr[k].second];
+              lf_cond[sx] = lf_cond[sy] = d.cond;
+              lf_other[sx] = sy;
+              lf_other[sy] = sx;
+            }
+            folded[ei] = 1;
+          }
+        }
+        dirty |= am;
+      }
+      uint32_t later = 0;
+      for (size_t ei = els.size(); ei-- > 0;) {
+        if (folded[ei]) continue;
+        const DElem &d = els[ei];
+        const uint32_t am = amps_of(d);
+        if (is_xlike(d) && d.cond >= 0 && !(am & later)) {
+          std::vector<std::pair<uint32_t, uint32_t>> pr;
+          pairs_list(d.j, d.mask, &pr);
+          for (size_t k = 0; k < pr.size(); ++k) {
+            sf_cond[pr[k].first] = sf_cond[pr[k].second] = d.cond;
+            sf_other[pr[k].first] = pr[k].second;
+            sf_other[pr[k].second] = pr[k].first;
+          }
+          folded[ei] = 1;
+        }
+        later |= am;
+      }
+    }
+    auto cond_test = [](int c) {
+      char b[64];
+      snprintf(b, sizeof(b), "((cw%d >> %d) & 1u)", c >> 5, c & 31);
+      return std::string(b);
+    };
+    auto sel_addr = [&](uint32_t u, int c, uint32_t other, const char *tag) {
+      if (c < 0) return addr(u);
+      const std::string nm = std::string(tag) + std::to_string(u);
+      fn << "    const unsigned " << nm << " = " << cond_test(c) << " ? (" << addr(other) << ") : (" << addr(u) << ");\n";
+      return nm;
+    };
     std::string vr[8], vi[8];
     for (uint32_t u = 0; u < 8; ++u) {
+      const std::string la = sel_addr(u, lf_cond[u], lf_other[u], "la");
       const std::string q = g.fresh();
-      fn << "    const QV " << q << " = *reinterpret_cast<const QV*>(sm + " << addr(u) << ");\n";
+      fn << "    const QV " << q << " = *reinterpret_cast<const QV*>(sm + " << la << ");\n";
       vr[u] = q + ".x";
       vi[u] = q + ".y";
     }
@@ -352,6 +437,10 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
     for (size_t ei = 0; ei < supers[s].size(); ++ei) {
       const DElem &d = supers[s][ei];
       ++n_elems;
+      if (folded[ei]) {  // became a conditional load / store address
+        ++g.renamed;
+        continue;
+      }
       const bool cond = d.cond >= 0;
       std::string ctest;
       if (cond) {
@@ -495,9 +584,10 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
       }
     }
     for (uint32_t u = 0; u < 8; ++u) {
+      const std::string sa = sel_addr(u, sf_cond[u], sf_other[u], "sa");
       const std::string q = g.fresh();
       fn << "    { QV " << q << "; " << q << ".x = " << vr[u] << "; " << q << ".y = " << vi[u] << "; *reinterpret_cast<QV*>(sm + "
-         << addr(u) << ") = " << q << "; }\n";
+         << sa << ") = " << q << "; }\n";
     }
     fn << "  }\n}\n\n";
   }
