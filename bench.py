@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--depth", type=int, default=40)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--gate-set", default="H,T,CNOT")
+    ap.add_argument("--seed", type=lambda x: int(x, 0), default=0x5EED0002, help="generator seed of the random workload")
+    ap.add_argument("--config5", action="store_true",
+                    help="BASELINE configs[4] exactly: depth-30 random {H,CZ,CNOT}, seed 0x5EED0005 (N = n-local + log2 gpus: 33 at 8 GPUs)")
     ap.add_argument("--workload", default="random", choices=["random", "qft", "dense4"],
                     help="random: depth-D random layers (BASELINE metric / configs[1], [4]); qft: configs[2]; dense4: configs[3]")
     ap.add_argument("--no-fusion", action="store_true", help="one kernel sweep per gate")
@@ -135,9 +138,9 @@ def build_workload(args, world):
         ops = circuits.config4(n, blocks=args.depth)
         name = "N=%d %s H^n then %d dense 4-qubit Haar blocks on seeded random qubits (BASELINE configs[3])" % (n, args.dtype, args.depth)
     else:
-        ops = circuits.random_circuit(n, args.depth, 0x5EED0002, args.gate_set)
-        name = "N=%d %s depth-%d random {%s} from |0>, layer 0 = H^n (SURVEY 8d generator, seed 0x5EED0002)" % (
-            n, args.dtype, args.depth, args.gate_set)
+        ops = circuits.random_circuit(n, args.depth, args.seed, args.gate_set)
+        name = "N=%d %s depth-%d random {%s} from |0>, layer 0 = H^n (SURVEY 8d generator, seed 0x%X)" % (
+            n, args.dtype, args.depth, args.gate_set, args.seed)
     return n, ops, name
 
 
@@ -604,6 +607,8 @@ def run_b200(args):
 
 def main():
     args = parse_args()
+    if args.config5:
+        args.gate_set, args.depth, args.seed = "H,CZ,CNOT", 30, 0x5EED0005
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -15,6 +15,8 @@
 // release/acquire), launched on the same stream before and after the trade.
 #include "dist.cuh"
 
+#include <cstdlib>
+
 namespace qipb200 {
 
 static const int kThreads = 256;
@@ -26,20 +28,38 @@ struct ExArgs {
   uint64_t n_items;
 };
 
-template <typename V>
+// U independent pairs per thread: U remote 16-byte loads in flight per lane (NVLink round trips are ~2 us; the
+// link needs a few MB outstanding per direction).  Items of one thread are a CTA-stride apart, so every
+// warp-instruction still covers contiguous runs.
+template <typename V, int U>
 __global__ void __launch_bounds__(kThreads)
     k_pair_exchange(V *__restrict__ mine, V *__restrict__ peer, const ExArgs a) {
-  const uint64_t w = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (w >= a.n_items) return;
-  uint64_t idx = w;
-  idx = ((idx >> a.pos_lo) << (a.pos_lo + 1)) | (idx & ((1ull << a.pos_lo) - 1ull));
-  idx = ((idx >> a.pos_hi) << (a.pos_hi + 1)) | (idx & ((1ull << a.pos_hi) - 1ull));
-  const uint64_t i = idx | a.fixed;
-  const uint64_t j = i ^ a.flip;
-  const V x = mine[i];
-  const V y = peer[j];  // NVLink load
-  mine[i] = y;
-  peer[j] = x;          // NVLink store
+  const uint64_t w0 = (uint64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
+  uint64_t ii[U], jj[U];
+  V x[U], y[U];
+  bool on[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const uint64_t w = w0 + (uint64_t)u * kThreads;
+    on[u] = w < a.n_items;
+    uint64_t idx = on[u] ? w : 0;
+    idx = ((idx >> a.pos_lo) << (a.pos_lo + 1)) | (idx & ((1ull << a.pos_lo) - 1ull));
+    idx = ((idx >> a.pos_hi) << (a.pos_hi + 1)) | (idx & ((1ull << a.pos_hi) - 1ull));
+    ii[u] = idx | a.fixed;
+    jj[u] = ii[u] ^ a.flip;
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (on[u]) y[u] = peer[jj[u]];  // NVLink loads, all issued before the first use
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (on[u]) x[u] = mine[ii[u]];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (on[u]) {
+      mine[ii[u]] = y[u];
+      peer[jj[u]] = x[u];  // NVLink store (posted)
+    }
 }
 
 cudaError_t launch_pair_exchange(qip_prec prec, void *mine, void *peer, uint32_t n_local, uint32_t l,
@@ -51,11 +71,26 @@ cudaError_t launch_pair_exchange(qip_prec prec, void *mine, void *peer, uint32_t
   a.fixed = ((uint64_t)(rb ? 0 : 1) << l) | ((uint64_t)(rb ? 1 : 0) << s_bit);
   a.flip = 1ull << l;
   a.n_items = 1ull << (n_local - 2);
-  const unsigned grid = (unsigned)((a.n_items + kThreads - 1) / kThreads);
-  if (prec == QIP_F32)
-    k_pair_exchange<float2><<<grid, kThreads, 0, s>>>((float2 *)mine, (float2 *)peer, a);
-  else
-    k_pair_exchange<double2><<<grid, kThreads, 0, s>>>((double2 *)mine, (double2 *)peer, a);
+  static const int unroll = []() {
+    const char *e = getenv("QIPB200_EXCH_UNROLL");
+    const int u = e ? atoi(e) : 4;
+    return u == 1 || u == 2 || u == 4 || u == 8 ? u : 4;
+  }();
+#define QIP_EXCH(UU)                                                                                        \
+  {                                                                                                         \
+    const unsigned grid = (unsigned)((a.n_items + (uint64_t)kThreads * UU - 1) / ((uint64_t)kThreads * UU)); \
+    if (prec == QIP_F32)                                                                                    \
+      k_pair_exchange<float2, UU><<<grid, kThreads, 0, s>>>((float2 *)mine, (float2 *)peer, a);             \
+    else                                                                                                    \
+      k_pair_exchange<double2, UU><<<grid, kThreads, 0, s>>>((double2 *)mine, (double2 *)peer, a);          \
+  }
+  switch (unroll) {
+    case 1: QIP_EXCH(1) break;
+    case 2: QIP_EXCH(2) break;
+    case 8: QIP_EXCH(8) break;
+    default: QIP_EXCH(4) break;
+  }
+#undef QIP_EXCH
   ++*launches;
   return cudaGetLastError();
 }
