@@ -435,11 +435,7 @@ def run_b200(args):
     # normalised (whole state, all-reduced over the ranks); (ii) an oracle-sized circuit with every op kind on the
     # rank-held qubits, run on these very ranks through the same schedule path, equals the CPU oracle.
     tolp = 1e-10 if args.dtype == "f64" else 1e-5
-    nrm = st.norm2()
-    if world > 1:
-        t = torch.tensor([nrm], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t)
-        nrm = float(t.item())
+    nrm = st.norm2()  # collective on a sharded state: already the whole-state sum, identical on every rank
     pn = 17
     pops = circuits_mod().sharded_parity_circuit(pn, (world - 1).bit_length())
     pst = State(pn, dtype, ctx, rank=rank, world_size=world)
