@@ -240,13 +240,58 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
   const uint32_t all_bits = (1u << T) - 1u;
   std::vector<uint32_t> wmask(S);
   std::vector<bool> cta_barrier_before(S, false);
+  // Bank groups: with the 128-byte XOR swizzle the 16-byte bank group of tile-local index t is (t ^ t>>3) & 7 for
+  // f64 (8-byte bank pair (t0, t1^t4, t2^t5, t3^t6) for f32).  A quarter warp (half warp for f32) is conflict free
+  // iff its lane bits reach every bank-group bit: bank bit k needs tile bit k or k+3 among the lane bits (f32: bit 0
+  // alone for k = 0).  A bank bit whose providers all sit in the sub-bits is lost anyway (inherent 2-way conflict);
+  // the warp-id bits must not take the last provider away.  Measured (r2c): with warp bits chosen blindly the average
+  // conflict degree was 1.85 and the pass was bound by shared-memory bandwidth (2 x 64 KiB per super-op and tile).
+  const uint32_t n_bank_bits = f64 ? 3 : 4;
+  auto providers = [&](uint32_t k) -> uint32_t {  // tile bits that toggle bank bit k
+    if (!f64 && k == 0) return 1u;
+    return ((1u << k) | (1u << (k + 3))) & all_bits;
+  };
+  auto lost_bank_bits = [&](uint32_t taken) {  // bank bits no lane bit can reach once `taken` bits are gone
+    uint32_t n = 0;
+    for (uint32_t k = 0; k < n_bank_bits; ++k) n += (providers(k) & ~taken) == 0;
+    return n;
+  };
+  // extra conflicts (log2, summed over the super-ops s..e-1) caused by using `w` as warp bits, beyond the inherent ones
+  auto extra_cost = [&](size_t s, size_t e, uint32_t w) {
+    uint32_t c = 0;
+    for (size_t k = s; k < e; ++k) c += lost_bank_bits(pmask[k] | w) - lost_bank_bits(pmask[k]);
+    return c;
+  };
+  auto best_warp_bits = [&](size_t s, size_t e, uint32_t free_bits, uint32_t *cost) {
+    uint32_t best = 0, best_cost = ~0u;
+    std::vector<uint32_t> fb;
+    for (int b = (int)T - 1; b >= 0; --b)
+      if ((free_bits >> b) & 1) fb.push_back((uint32_t)b);
+    for (size_t i = 0; i < fb.size(); ++i)
+      for (size_t j = i + 1; j < fb.size(); ++j)
+        for (size_t k = j + 1; k < fb.size(); ++k) {
+          const uint32_t w = (1u << fb[i]) | (1u << fb[j]) | (1u << fb[k]);
+          const uint32_t c = extra_cost(s, e, w);
+          if (c < best_cost) best = w, best_cost = c;  // first hit wins ties: the highest bits
+        }
+    *cost = best_cost;
+    return best;
+  };
   for (size_t s = 0; s < S;) {
     uint32_t free_bits = all_bits & ~pmask[s];
+    uint32_t cost = 0;
+    uint32_t w = best_warp_bits(s, s + 1, free_bits, &cost);
     size_t e = s + 1;
-    while (e < S && __builtin_popcount(free_bits & ~pmask[e]) >= (int)kWarpBits) free_bits &= ~pmask[e++];
-    uint32_t w = 0;
-    for (int b = (int)T - 1; b >= 0 && __builtin_popcount(w) < (int)kWarpBits; --b)
-      if ((free_bits >> b) & 1) w |= 1u << b;
+    // extend the segment while three common free bits exist that cost no bank conflict: a CTA barrier is far
+    // cheaper than a 2-way conflict on every access of a super-op
+    while (e < S && __builtin_popcount(free_bits & ~pmask[e]) >= (int)kWarpBits) {
+      uint32_t c2 = 0;
+      const uint32_t w2 = best_warp_bits(s, e + 1, free_bits & ~pmask[e], &c2);
+      if (c2 > cost) break;
+      free_bits &= ~pmask[e++];
+      w = w2;
+      cost = c2;
+    }
     for (size_t k = s; k < e; ++k) wmask[k] = w;
     cta_barrier_before[s] = s != 0;
     s = e;
@@ -310,6 +355,19 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
     }
     const bool last = s + 1 == S;
     if (last && NG) fn << "  const bool hasg = condw[8] != 0u;\n  const " << RT << " gr = gt[0], gi = gt[1];\n";
+    // conditional-phase factors (one broadcast shared-memory read each) are loop invariants: read them once per
+    // super-op, not once per group (the compiler cannot prove that the group's stores leave the table alone)
+    std::vector<char> phn_hoisted(phn_terms.size(), 0);
+    if (NIT > 1) {
+      uint32_t budget = 12;
+      for (size_t ei = 0; ei < supers[s].size() && budget; ++ei)
+        if (supers[s][ei].kind == DElem::PHN && !phn_hoisted[supers[s][ei].slot]) {
+          const uint32_t sl = supers[s][ei].slot;
+          fn << "  const " << RT << " pw" << sl << "r = tbl[" << 2 * sl << "], pw" << sl << "i = tbl[" << 2 * sl + 1 << "];\n";
+          phn_hoisted[sl] = 1;
+          --budget;
+        }
+    }
     if (NIT > 1) fn << "#pragma unroll 1\n  for (unsigned it = 0; it < " << NIT << "u; ++it) {\n";
     else fn << "  {\n";
     {
@@ -522,8 +580,14 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
           upd.push_back(a);
         }
       } else if (d.kind == DElem::PHN) {  // factor formed once per CTA (table behind the tile)
-        const std::string wr = g.fresh(), wi = g.fresh();
-        fn << "    const " << RT << " " << wr << " = tbl[" << 2 * d.slot << "], " << wi << " = tbl[" << 2 * d.slot + 1 << "];\n";
+        std::string wr, wi;
+        if (phn_hoisted[d.slot]) {
+          wr = "pw" + std::to_string(d.slot) + "r";
+          wi = "pw" + std::to_string(d.slot) + "i";
+        } else {
+          wr = g.fresh(), wi = g.fresh();
+          fn << "    const " << RT << " " << wr << " = tbl[" << 2 * d.slot << "], " << wi << " = tbl[" << 2 * d.slot + 1 << "];\n";
+        }
         for (uint32_t c = 0; c < 8; ++c) {
           if (!((d.mask >> c) & 1)) continue;
           Upd a = {c, "QFMA(" + wr + ", " + vr[c] + ", -(" + wi + " * " + vi[c] + "))",
