@@ -287,7 +287,6 @@ struct Emitter {
     }
     mo.h.groups_log2 = T - 3;
     mo.h.nterms = (uint32_t)elems.size();
-    bool ptx_ok = true;
     for (size_t i = 0; i < elems.size(); ++i) {
       const HElem &e = elems[i];
       Elem<R> d;
@@ -369,11 +368,6 @@ struct Emitter {
         d.op = elem_op(E_DENSE3, 0, 0, cond, rec_bytes);
       }
       d.op |= slot << kElemCondShift;
-      {  // case ids the single-block PTX record loop covers (tile_interp_ptx.cuh; experiment, see MicroOp::pad0)
-        const uint32_t id = d.op & kElemCaseMask;
-        const bool covered = (id >= EC_D1R_FULL && id < EC_D1R_MASK) || id == EC_PHASE || (id >= EC_PHASEN && id < EC_N_CASES);
-        ptx_ok = ptx_ok && covered;
-      }
       const size_t at = mo.data.size();
       mo.data.resize(at + sizeof(d));
       memcpy(mo.data.data() + at, &d, sizeof(d));
@@ -412,7 +406,6 @@ struct Emitter {
       memcpy(mo.data.data() + at, &endrec, sizeof(endrec));
     }
     mo.h.data_bytes = (uint32_t)mo.data.size();
-    mo.h.pad0 = ptx_ok ? 1u : 0u;
     pass->ops.push_back(mo);
   }
 
@@ -865,7 +858,6 @@ PlanConfig default_plan_config(qip_prec prec, uint32_t n_local) {
   if (const char *e = getenv("QIPB200_TILE_L")) c.L = (uint32_t)atoi(e);
   if (const char *e = getenv("QIPB200_COMPOSE")) c.compose_threshold = (uint32_t)std::max(1, atoi(e));
   if (const char *e = getenv("QIPB200_TILE_G")) c.groups_per_thread = atoi(e) == 2 ? 2 : 1;
-  if (const char *e = getenv("QIPB200_TILE_VARIANT")) c.kernel_variant = atoi(e) & 15;
   if (const char *e = getenv("QIPB200_NO_BLOCK_FUSION")) c.fuse_blocks = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_NO_PEEPHOLE")) c.peephole = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_SEED_SEARCH")) c.seed_search = atoi(e) != 0;

@@ -50,7 +50,7 @@ int execute_steps(qipb200_state *s, const std::vector<PlanStep> &steps, const st
   PassParams *pp = new PassParams();
   // Generated kernels (jit_codegen / jit_runtime): every pass is turned into specialised source; a pass whose
   // cubin is ready runs it, the others run the interpreter kernel while the background workers compile.
-  const JitMode jmode = cfg.use_tma && cfg.groups_per_thread == 1 && cfg.kernel_variant == 0 ? jit_mode_from_env(s->n_local) : JIT_OFF;
+  const JitMode jmode = cfg.use_tma && cfg.groups_per_thread == 1 ? jit_mode_from_env(s->n_local) : JIT_OFF;
   std::vector<JitProgram> progs(steps.size());
   std::vector<char> have_prog(steps.size(), 0);
   if (jmode != JIT_OFF && jit_available(&ctx->jit_note)) {
@@ -95,7 +95,7 @@ int execute_steps(qipb200_state *s, const std::vector<PlanStep> &steps, const st
       }
       ProfileScope prof(ctx, 0);
       cudaError_t e = launch_tile_pass(s->prec, s->buf, s->n_local, *pp, cfg.groups_per_thread, cfg.use_tma, ctx->stream,
-                                       &ctx->launches, cfg.kernel_variant);
+                                       &ctx->launches);
       if (e != cudaSuccess) st = report_cuda_error(s, e, "launch_tile_pass");
       ++ctx->tile_launches;
       ctx->fused_gates += steps[i].pass.n_gates;

@@ -113,7 +113,7 @@ struct alignas(16) MicroOp {
   uint32_t groups_log2;  // T - ins_n
   uint32_t nterms;       // diag terms / super elems
   uint32_t data_bytes;   // bytes of data following the header
-  uint32_t pad0;         // super: 1 when every record's case id is covered by the PTX record loop (tile_interp_ptx.cuh)
+  uint32_t pad0;
   uint64_t gmask;        // control bits outside the tile: tested against the tile's base index
   uint64_t pad1[3];
   uint32_t soff[8];      // super: SWIZZLED shared-memory BYTE offset of sub-index u (the XOR swizzle is GF(2)-linear,
@@ -216,7 +216,6 @@ struct PlanConfig {
   bool unnormalised_h = true;   // Hadamards as add/sub butterflies, the scale folded into another gate of the pass
   bool seed_search = false;     // tile-bit choice: also try reserving slots for bits the greedy left out (fewer passes, but
                                 // more elementary ops; measured slower on the N=30 circuit: 25 passes 309 ms vs 29 passes 302 ms)
-  int kernel_variant = 0;          // compile-time experiments of the tile kernel (tile_kernel.cu, template parameter V)
   int groups_per_thread = 1;       // register-resident groups per interpreter decode (1: 3 CTAs/SM, 2: 2 CTAs/SM)
   uint32_t compose_threshold = 8;  // >= this many 2x2 gates in one group: compose them into one 8x8
 };

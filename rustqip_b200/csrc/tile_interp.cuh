@@ -11,7 +11,6 @@
 // Macro parameters:  T = "f64" | "f32";  P = "a" | "b" (group);  I0, I1 = sub-indices.
 #pragma once
 
-#define QIP_DECL_OPWORD() asm volatile(".reg .b32 qopn;")
 #define QIP_DECL_GROUP(T, P)                                                                        \
   asm volatile(".reg ." T " q" P "r0, q" P "r1, q" P "r2, q" P "r3, q" P "r4, q" P "r5, q" P "r6, q" P \
                "r7, q" P "i0, q" P "i1, q" P "i2, q" P "i3, q" P "i4, q" P "i5, q" P "i6, q" P "i7;")
@@ -114,10 +113,10 @@
 // elementary ops are dispatched by ONE jump on the host-computed case id; every frequent shape
 // (full 2x2, 2x2 under one/two in-group controls, phase on one/two sub-bits) is straight-line
 // code without mask tests.
-#define QIP_DEFINE_RUN_SUPER(NAME, R, T, C, CO, SWZ, ESHIFT, PTXFN)                                              \
-  template <int G, int PF, int PX>                                                                              \
+#define QIP_DEFINE_RUN_SUPER(NAME, R, T, C, CO, SWZ, ESHIFT)                                              \
+  template <int G>                                                                                              \
   __device__ __forceinline__ void NAME(uint32_t tile_saddr, const MicroOp *mo, const unsigned char *data,      \
-                                       uint64_t base, const R *tbl, uint64_t condbits, uint32_t data_param) {   \
+                                       uint64_t base, const R *tbl, uint64_t condbits) {                        \
     typedef R QipReal;                                                                                          \
     const uint32_t groups = 1u << mo->groups_log2;                                                              \
     const uint32_t hm0 = ~0u << mo->ins_pos[0], hm1 = ~0u << mo->ins_pos[1], hm2 = ~0u << mo->ins_pos[2];      \
@@ -139,32 +138,17 @@
         QIP_LD(T, "b", 0, ab[0]); QIP_LD(T, "b", 1, ab[1]); QIP_LD(T, "b", 2, ab[2]); QIP_LD(T, "b", 3, ab[3]); \
         QIP_LD(T, "b", 4, ab[4]); QIP_LD(T, "b", 5, ab[5]); QIP_LD(T, "b", 6, ab[6]); QIP_LD(T, "b", 7, ab[7]); \
       }                                                                                                         \
-      if (PX && G == 1 && mo->pad0) { /* experiment: the whole record loop as one PTX block */                  \
-        PTXFN(data_param, condbits, base, (uint32_t)__cvta_generic_to_shared(tbl));                             \
-      } else {                                                                                                  \
+      {                                                                                                         \
       const unsigned char *ep = data;                                                                           \
-      uint32_t pe = data_param; /* PF: the same position as a PARAM-space address (for ld.param in asm) */      \
-      uint32_t op_next = 0;                                                                                     \
-      if (PF) asm volatile("ld.param.u32 qopn, [%0];" ::"r"(pe));                                               \
-      else op_next = reinterpret_cast<const Elem<R> *>(ep)->op;                                                 \
+      uint32_t op_next = reinterpret_cast<const Elem<R> *>(ep)->op;                                             \
       for (;;) {                                                                                                \
-        uint32_t op = op_next;                                                                                  \
-        if (PF) asm volatile("mov.b32 %0, qopn;" : "=r"(op));                                                   \
+        const uint32_t op = op_next;                                                                            \
         const uint32_t id = op & kElemCaseMask;                                                                 \
         if (id == EC_END) break;                                                                                \
         const Elem<R> *e = reinterpret_cast<const Elem<R> *>(ep);                                               \
         ep += ((op >> 20) & 0x7ffu) << 4;                                                                       \
-        if (PF) { /* experiment: the plain load below is re-materialised at its use (a second ld.param at the  \
-                     loop tail, the early one is dead), and an asm OUTPUT is copied into the loop-carried  \
-                     register right behind the load.  So the word goes into a NAMED PTX register (like the \
-                     amplitudes): fetched here, read at the top of the next iteration, nothing waits for   \
-                     it in between. */                                                                      \
-          pe += ((op >> 20) & 0x7ffu) << 4;                                                                     \
-          asm volatile("ld.param.u32 qopn, [%0];" ::"r"(pe));                                                   \
-        } else {                                                                                                \
-          op_next = reinterpret_cast<const Elem<R> *>(ep)->op; /* next descriptor in flight during this op */   \
-          asm volatile("" ::"r"(op_next));                     /* (keeps the load above the arithmetic) */      \
-        }                                                                                                       \
+        op_next = reinterpret_cast<const Elem<R> *>(ep)->op; /* next descriptor in flight during this op */     \
+        asm volatile("" ::"r"(op_next));                     /* (keeps the load above the arithmetic) */        \
         if ((int32_t)op < 0) { /* control outside the tile: evaluated once per CTA */                           \
           const uint32_t slot = (op >> kElemCondShift) & 63u;                                                   \
           if (slot != kCondOverflow) {                                                                          \
@@ -233,7 +217,7 @@
           }                                                                                                     \
         }                                                                                                       \
       }                                                                                                         \
-      } /* !PX */                                                                                               \
+      }                                                                                                         \
       QIP_ST(T, "a", 0, aa[0]); QIP_ST(T, "a", 1, aa[1]); QIP_ST(T, "a", 2, aa[2]); QIP_ST(T, "a", 3, aa[3]);   \
       QIP_ST(T, "a", 4, aa[4]); QIP_ST(T, "a", 5, aa[5]); QIP_ST(T, "a", 6, aa[6]); QIP_ST(T, "a", 7, aa[7]);   \
       if (two) {                                                                                                \

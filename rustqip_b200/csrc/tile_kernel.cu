@@ -23,7 +23,6 @@
 #include "tile.cuh"
 #include "tile_launch.cuh"
 #include "tile_interp.cuh"
-#include "tile_interp_ptx.cuh"
 
 #include <cstring>
 
@@ -69,10 +68,8 @@ __device__ __forceinline__ uint32_t expand_local(uint32_t g, const MicroOp *mo) 
 __device__ __forceinline__ uint32_t swz_d(uint32_t t) { return t ^ ((t >> 3) & 7u); }
 __device__ __forceinline__ uint32_t swz_f(uint32_t t) { return t ^ (((t >> 4) & 7u) << 1); }
 
-QIP_DEFINE_RUN_ELEMS_PTX(run_elems_ptx_f64, "f64", "32", "40", "48", "56", "64", "72", "80", "88", "16")
-QIP_DEFINE_RUN_ELEMS_PTX(run_elems_ptx_f32, "f32", "32", "36", "40", "44", "48", "52", "56", "60", "8")
-QIP_DEFINE_RUN_SUPER(run_super_f64, double, "f64", QIP_CD, QIP_COD, swz_d, 4, run_elems_ptx_f64)
-QIP_DEFINE_RUN_SUPER(run_super_f32, float, "f32", QIP_CF, QIP_COF, swz_f, 3, run_elems_ptx_f32)
+QIP_DEFINE_RUN_SUPER(run_super_f64, double, "f64", QIP_CD, QIP_COD, swz_d, 4)
+QIP_DEFINE_RUN_SUPER(run_super_f32, float, "f32", QIP_CF, QIP_COF, swz_f, 3)
 
 // ---- wide micro-ops (more than 3 involved bits): rare -----------------------------------
 template <typename R, int K>
@@ -186,17 +183,12 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap *map, uint32_t sr
                : "memory");
 }
 
-// VAR selects compile-time experiments (QIPB200_TILE_VARIANT; 0 is the measured default, its code does not
-// depend on the others):
-//   VAR & 1: keep the shared-window base in an opaque register (r1o: `S2R SR_CgaCtaId` re-materialised per group, 2.3 %)
-//   VAR & 4: next descriptor word loaded one elementary op ahead through an opaque register (r1o: 9 % of the
-//          samples wait on the `LDC` of the op word; the compiler re-materialises the plain C++ prefetch at its use)
-//   VAR & 8: the record loop of a super-op as one PTX block with `brx.idx` dispatch (tile_interp_ptx.cuh), for the
-//          super-ops the planner marked (MicroOp::pad0)
-//   VAR & 2: touch the next micro-op's header and first records before the barrier that precedes them (the
-//          first read after the barrier carries 6.8 % of the r1o samples; their stall reason is the barrier
-//          itself, so this only helps if a cold constant line hides behind it)
-template <typename R, int G, int VAR>
+// (Round 1 carried four compile-time experiments of this interpreter -- opaque shared-window base, header touch
+// before the barrier, descriptor word software-pipelined through a named PTX register, the record loop as one PTX
+// block with brx.idx dispatch.  Measured in round 2 (profiles/r2c_interpreter_variants_ab.txt, N=30 f64 circuit):
+// 288.8 ms default vs 288.8 / 324.6 / 286.1 / 285.2 / 293.6 ms: nothing beyond 1.2 %.  They were deleted; the pass
+// is bound by its shared-memory round trips, and the generated kernels (jit_codegen.cpp) are the product path.)
+template <typename R, int G>
 __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
     k_tile_pass(R *__restrict__ psi, const __grid_constant__ PassParams pp, const __grid_constant__ CUtensorMap tmap) {
   typedef typename C2<R>::type V;
@@ -208,7 +200,6 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
     QIP_DECL_GROUP("f32", "a");
     if (G == 2) QIP_DECL_GROUP("f32", "b");
   }
-  if constexpr ((VAR & 4) != 0) QIP_DECL_OPWORD();
   extern __shared__ __align__(1024) unsigned char smem[];
   const PassHeader *h = &pp.h;
   const uint32_t T = h->T, L = h->L, m = h->m, n_ops = h->n_ops;
@@ -226,9 +217,7 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
   constexpr uint32_t kLow3 = sizeof(R) == 8 ? 3 : 4;  // index bits covered by one 128-byte row
   const uint32_t units = tile_bytes >> 4;
   const uint32_t lmask = (1u << L) - 1u;
-  uint32_t smem_base_v = (uint32_t)__cvta_generic_to_shared(smem);
-  if constexpr ((VAR & 1) != 0) asm volatile("" : "+r"(smem_base_v));
-  const uint32_t smem_base = smem_base_v;
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
   const bool use_tma = h->use_tma != 0;
   const uint32_t mbar = smem_base + tile_bytes + kMaxPhasen * 16;
   const uint32_t n_boxes = 1u << (m - 3);           // only meaningful with use_tma (m >= 3)
@@ -308,28 +297,17 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
   const uint64_t condbits = (uint64_t)condw[0] | ((uint64_t)condw[1] << 32);
 
   // ---- 2. apply ----
-  uint64_t recs_param = 0;  // VAR & 4: param-space address of pp.recs (ld.param from inline asm)
-  if constexpr ((VAR & 12) != 0) asm volatile("cvta.to.param.u64 %0, %1;" : "=l"(recs_param) : "l"(pp.recs));
   const unsigned char *rec = pp.recs;
   for (uint32_t i = 0; i < n_ops; ++i) {
     const MicroOp *mo = reinterpret_cast<const MicroOp *>(rec);
     const unsigned char *data = rec + sizeof(MicroOp);
     rec = data + mo->data_bytes;
-    if constexpr ((VAR & 2) != 0) {
-      if (i + 1 < n_ops) {  // bring the next header and the start of its records into the constant cache now
-        const uint32_t *nx = reinterpret_cast<const uint32_t *>(rec);
-        const uint32_t touch = nx[0] ^ nx[16] ^ nx[32] ^ nx[48];  // 0, 64, 128, 192 bytes in (header + END always exist)
-        asm volatile("" ::"r"(touch));
-      }
-    }
     if ((base & mo->gmask) == mo->gmask) {
       if (mo->kind == MK_SUPER) {
         if constexpr (sizeof(R) == 8)
-          run_super_f64<G, (VAR & 4) != 0, (VAR & 8) != 0>(smem_base, mo, data, base, reinterpret_cast<const double *>(tbl), condbits,
-                                           (uint32_t)recs_param + (uint32_t)(data - pp.recs));
+          run_super_f64<G>(smem_base, mo, data, base, reinterpret_cast<const double *>(tbl), condbits);
         else
-          run_super_f32<G, (VAR & 4) != 0, (VAR & 8) != 0>(smem_base, mo, data, base, reinterpret_cast<const float *>(tbl), condbits,
-                                           (uint32_t)recs_param + (uint32_t)(data - pp.recs));
+          run_super_f32<G>(smem_base, mo, data, base, reinterpret_cast<const float *>(tbl), condbits);
       } else if (mo->kind == MK_DENSE) {
         const R *mat = reinterpret_cast<const R *>(data);
         if (mo->k == 1)
@@ -405,21 +383,10 @@ __global__ void __launch_bounds__(kTileThreads, (G == 1 ? 3 : 2))
 
 cudaError_t tile_pass_configure() {
   cudaError_t e;
-  // the measured default and its two-groups-per-thread sibling: required
-  const void *fns[] = {(const void *)k_tile_pass<double, 1, 0>, (const void *)k_tile_pass<double, 2, 0>,
-                       (const void *)k_tile_pass<float, 1, 0>, (const void *)k_tile_pass<float, 2, 0>};
+  const void *fns[] = {(const void *)k_tile_pass<double, 1>, (const void *)k_tile_pass<double, 2>,
+                       (const void *)k_tile_pass<float, 1>, (const void *)k_tile_pass<float, 2>};
   for (const void *f : fns)
     if ((e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)) != cudaSuccess) return e;
-  // experiment instantiations (QIPB200_TILE_VARIANT): best effort, a failure here must not touch the default path
-  const void *exp_fns[] = {(const void *)k_tile_pass<double, 1, 1>, (const void *)k_tile_pass<double, 1, 2>,
-                           (const void *)k_tile_pass<double, 1, 3>, (const void *)k_tile_pass<float, 1, 1>,
-                           (const void *)k_tile_pass<float, 1, 2>,  (const void *)k_tile_pass<float, 1, 3>,
-                           (const void *)k_tile_pass<double, 1, 4>, (const void *)k_tile_pass<double, 1, 7>,
-                           (const void *)k_tile_pass<float, 1, 4>,  (const void *)k_tile_pass<float, 1, 7>,
-                           (const void *)k_tile_pass<double, 1, 8>, (const void *)k_tile_pass<double, 1, 9>,
-                           (const void *)k_tile_pass<float, 1, 8>,  (const void *)k_tile_pass<float, 1, 9>};
-  for (const void *f : exp_fns)
-    if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess) (void)cudaGetLastError();
   return cudaSuccess;
 }
 
@@ -461,27 +428,8 @@ bool make_tile_map(CUtensorMap *map, qip_prec prec, void *psi, uint32_t n_local,
   return r == CUDA_SUCCESS;
 }
 
-template <typename R>
-static void launch_variant(int groups_per_thread, int variant, unsigned grid, size_t smem, cudaStream_t s, R *psi,
-                           const PassParams &pp, const CUtensorMap &tmap) {
-  if (groups_per_thread != 1) {
-    k_tile_pass<R, 2, 0><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap);
-    return;
-  }
-  switch (variant) {
-    case 1: k_tile_pass<R, 1, 1><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
-    case 2: k_tile_pass<R, 1, 2><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
-    case 3: k_tile_pass<R, 1, 3><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
-    case 4: k_tile_pass<R, 1, 4><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
-    case 7: k_tile_pass<R, 1, 7><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
-    case 8: k_tile_pass<R, 1, 8><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
-    case 9: k_tile_pass<R, 1, 9><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
-    default: k_tile_pass<R, 1, 0><<<grid, kTileThreads, smem, s>>>(psi, pp, tmap); break;
-  }
-}
-
 cudaError_t launch_tile_pass(qip_prec prec, void *psi, uint32_t n_local, PassParams &pp, int groups_per_thread,
-                             bool use_tma, cudaStream_t s, uint64_t *launches, int variant) {
+                             bool use_tma, cudaStream_t s, uint64_t *launches) {
   const uint32_t T = pp.h.T;
   alignas(64) CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
@@ -489,10 +437,17 @@ cudaError_t launch_tile_pass(qip_prec prec, void *psi, uint32_t n_local, PassPar
   // tile | EC_PHASEN factor table | mbarrier | condition word
   const size_t smem = ((size_t)(prec == QIP_F32 ? 8u : 16u) << T) + kMaxPhasen * 16 + 32;
   const unsigned grid = 1u << (n_local - T);
-  if (prec == QIP_F32)
-    launch_variant<float>(groups_per_thread, variant, grid, smem, s, (float *)psi, pp, tmap);
-  else
-    launch_variant<double>(groups_per_thread, variant, grid, smem, s, (double *)psi, pp, tmap);
+  if (prec == QIP_F32) {
+    if (groups_per_thread == 2)
+      k_tile_pass<float, 2><<<grid, kTileThreads, smem, s>>>((float *)psi, pp, tmap);
+    else
+      k_tile_pass<float, 1><<<grid, kTileThreads, smem, s>>>((float *)psi, pp, tmap);
+  } else {
+    if (groups_per_thread == 2)
+      k_tile_pass<double, 2><<<grid, kTileThreads, smem, s>>>((double *)psi, pp, tmap);
+    else
+      k_tile_pass<double, 1><<<grid, kTileThreads, smem, s>>>((double *)psi, pp, tmap);
+  }
   ++*launches;
   return cudaGetLastError();
 }

@@ -21,8 +21,7 @@ bool make_tile_map(CUtensorMap *map, qip_prec prec, void *psi, uint32_t n_local,
 // Run one serialised pass (passed by value as a kernel parameter) over the local state.
 // groups_per_thread: 1 (3 CTAs/SM) or 2 (2 CTAs/SM, descriptors decoded once per two groups).
 // use_tma: move the tile with TMA tensor copies when the pass geometry allows (m >= 3).
-// variant: compile-time kernel experiments (tile_kernel.cu: template parameter V), 0 = default.
 cudaError_t launch_tile_pass(qip_prec prec, void *psi, uint32_t n_local, PassParams &pp, int groups_per_thread,
-                             bool use_tma, cudaStream_t s, uint64_t *launches, int variant = 0);
+                             bool use_tma, cudaStream_t s, uint64_t *launches);
 
 }  // namespace qipb200

@@ -229,10 +229,6 @@ static void run_pass_params(const PassParams &pp, uint32_t n, std::vector<cd> &p
             Elem<R> e;
             memcpy(&e, ep, sizeof(e));
             if (elem_case(e.op) == EC_END) break;
-            if (g == 0 && mo.pad0) {  // marked for the PTX record loop: only the case ids that loop implements
-              const uint32_t id = elem_case(e.op);
-              if (!((id >= EC_D1R_FULL && id < EC_D1R_MASK) || id == EC_PHASE || (id >= EC_PHASEN && id < EC_N_CASES))) ++g_decode_errors;
-            }
             const R *mat8 = reinterpret_cast<const R *>(ep + sizeof(e));
             ep += elem_size_bytes(e.op);
             run_elem<R>(e, mat8, a, base, conds, h.n_conds);
