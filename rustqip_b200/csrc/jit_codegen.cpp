@@ -28,112 +28,91 @@ struct PhTerm {
   double re, im;
 };
 
-// decoded elementary record
+// elementary op of a group, ready for emission (sub-index coordinates, K = bits of the group)
 struct DElem {
-  enum Kind { D1, X, PH, PHN, D3, HAD } kind = D1;
+  enum Kind { D1, X, PH, PHN, DK, HAD } kind = D1;
   bool real = false;
-  uint32_t j = 0;
-  uint32_t mask = 0;       // pair mask (D1/X/HAD: bit p <-> p-th pair) or amplitude mask (PH/PHN)
+  uint32_t j = 0;          // D1 / X / HAD: target sub-bit
+  uint32_t lc = 0;         // D1 / X: control sub-mask
+  uint32_t lm = 0, lv = 0; // PH / PHN: acts on sub-indices c with (c & lm) == lv
   int cond = -1;           // index into the program's condition list
-  double m[8] = {0};       // D1: real m00 m01 m10 m11 | complex (re,im) x 4; PH/PHN: w
-  std::vector<double> m8;  // D3: 64 complex, row-major
+  double m[8] = {0};       // D1: real m00 m01 m10 m11 | complex (re,im) x 4; PH: w
+  std::vector<uint32_t> mb;  // DK: sub-bits of the dense block (ascending)
+  std::vector<double> mk;    // DK: 2^k x 2^k complex (re,im), row-major
   uint32_t slot = 0;       // PHN: factor-table slot
 };
 
-template <typename R>
-bool decode_super(const HostMicroOp &mo, const HostPass &pass, std::vector<Cond> &conds, std::vector<DElem> *out,
-                  std::vector<std::vector<PhTerm>> *phn_terms, std::vector<std::pair<double, double>> *phn_base,
-                  std::string *why) {
-  const unsigned char *ep = mo.data.data();
-  const unsigned char *end = ep + mo.data.size();
-  for (;;) {
-    if (ep + sizeof(Elem<R>) > end) {
-      *why = "truncated super-op record list";
-      return false;
-    }
-    Elem<R> e;
-    memcpy(&e, ep, sizeof(e));
-    const uint32_t id = elem_case(e.op);
-    if (id == EC_END) break;
-    const uint32_t size = elem_size_bytes(e.op);
-    const unsigned char *tail = ep + sizeof(e);
-    ep += size;
+// value as it will be seen by a kernel of precision `f64` (constants are pooled after rounding)
+inline double as_prec(bool f64, double v) { return f64 ? v : (double)(float)v; }
+
+bool convert_group(const JGroup &jg, bool f64, std::vector<Cond> &conds, std::vector<DElem> *out,
+                   std::vector<std::vector<PhTerm>> *phn_terms, std::vector<std::pair<double, double>> *phn_base,
+                   std::string *why) {
+  for (size_t i = 0; i < jg.elems.size(); ++i) {
+    const JElem &e = jg.elems[i];
     DElem d;
-    d.mask = (e.op >> 12) & 0xffu;
-    if (e.op & kElemHasCond) {
-      uint64_t gm = e.gmask, gv = e.gval;
-      const uint32_t slot = elem_cond_slot(e.op);
-      if (slot != kCondOverflow) {
-        if (slot >= pass.conds.size()) {
-          *why = "condition slot out of range";
-          return false;
-        }
-        gm = pass.conds[slot].gmask;
-        gv = pass.conds[slot].gval;
-      }
+    if (e.gmask) {
       int found = -1;
       for (size_t c = 0; c < conds.size(); ++c)
-        if (conds[c].gmask == gm && conds[c].gval == gv) found = (int)c;
+        if (conds[c].gmask == e.gmask && conds[c].gval == e.gval) found = (int)c;
       if (found < 0) {
-        Cond c = {gm, gv};
+        Cond c = {e.gmask, e.gval};
         found = (int)conds.size();
         conds.push_back(c);
       }
       d.cond = found;
     }
-    auto load_real = [&]() {
-      for (int q = 0; q < 4; ++q) d.m[q] = (double)e.m[q];
-      d.real = true;
-    };
-    auto load_cplx = [&]() {
-      for (int q = 0; q < 8; ++q) d.m[q] = (double)e.m[q];
-      d.real = false;
-    };
-    if (id >= EC_D1R_FULL && id < EC_D1C_FULL) {
-      d.kind = DElem::D1, d.j = id - EC_D1R_FULL, d.mask = 0xf, load_real();
-    } else if (id >= EC_D1C_FULL && id < EC_D1R_MASK) {
-      d.kind = DElem::D1, d.j = id - EC_D1C_FULL, d.mask = 0xf, load_cplx();
-    } else if (id >= EC_D1R_MASK && id < EC_D1C_MASK) {
-      d.kind = DElem::D1, d.j = id - EC_D1R_MASK, load_real();
-    } else if (id >= EC_D1C_MASK && id < EC_PHASE) {
-      d.kind = DElem::D1, d.j = id - EC_D1C_MASK, load_cplx();
-    } else if (id == EC_PHASE) {
-      d.kind = DElem::PH, d.m[0] = (double)e.m[0], d.m[1] = (double)e.m[1];
-    } else if (id == EC_DENSE3) {
-      d.kind = DElem::D3;
-      d.m8.resize(128);
-      const R *w = reinterpret_cast<const R *>(tail);
-      for (int q = 0; q < 128; ++q) d.m8[q] = (double)w[q];
-    } else if (id >= EC_X_FULL && id < EC_X_MASK) {
-      d.kind = DElem::X, d.j = id - EC_X_FULL, d.mask = 0xf;
-    } else if (id >= EC_X_MASK && id < EC_PHASEN) {
-      d.kind = DElem::X, d.j = id - EC_X_MASK;
-    } else if (id == EC_PHASEN) {
-      d.kind = DElem::PHN;
-      d.slot = (uint32_t)phn_terms->size();
-      phn_base->push_back(std::make_pair((double)e.m[0], (double)e.m[1]));
-      std::vector<PhTerm> terms;
-      const uint32_t nt = (size - (uint32_t)sizeof(Elem<R>)) / (uint32_t)sizeof(PhaseTerm<R>);
-      for (uint32_t k = 0; k < nt; ++k) {
-        PhaseTerm<R> pt;
-        memcpy(&pt, tail + k * sizeof(pt), sizeof(pt));
-        PhTerm t = {pt.gmask, pt.gval, (double)pt.re, (double)pt.im};
-        terms.push_back(t);
+    switch (e.kind) {
+      case JElem::D1:
+      case JElem::X: {
+        d.kind = e.kind == JElem::X ? DElem::X : DElem::D1;
+        d.j = e.j;
+        d.lc = e.lc;
+        bool real = true;
+        for (int q = 0; q < 4; ++q) real &= as_prec(f64, e.m[q].imag()) == 0.0;
+        d.real = real;
+        for (int q = 0; q < 4; ++q) {
+          if (real) {
+            d.m[q] = as_prec(f64, e.m[q].real());
+          } else {
+            d.m[2 * q] = as_prec(f64, e.m[q].real());
+            d.m[2 * q + 1] = as_prec(f64, e.m[q].imag());
+          }
+        }
+        break;
       }
-      phn_terms->push_back(terms);
-    } else if (id >= EC_PHASE_J && id < EC_D1R_C1) {
-      d.kind = DElem::PH, d.mask = kPhaseMaskJ[id - EC_PHASE_J], d.m[0] = (double)e.m[0], d.m[1] = (double)e.m[1];
-    } else if (id >= EC_D1R_C1 && id < EC_D1R_C2) {
-      d.kind = DElem::D1, d.j = (id - EC_D1R_C1) / 2, d.mask = kPairMaskC1[(id - EC_D1R_C1) % 2], load_real();
-    } else if (id >= EC_D1R_C2 && id < EC_PHASE_2) {
-      d.kind = DElem::D1, d.j = id - EC_D1R_C2, d.mask = kPairMaskC2, load_real();
-    } else if (id >= EC_PHASE_2 && id < EC_HAD) {
-      d.kind = DElem::PH, d.mask = kPhaseMask2[id - EC_PHASE_2], d.m[0] = (double)e.m[0], d.m[1] = (double)e.m[1];
-    } else if (id >= EC_HAD && id < EC_N_CASES) {
-      d.kind = DElem::HAD, d.j = id - EC_HAD, d.mask = 0xf;
-    } else {
-      *why = "unknown elementary case id";
-      return false;
+      case JElem::HAD:
+        d.kind = DElem::HAD, d.j = e.j;
+        break;
+      case JElem::PH:
+        d.lm = e.lm, d.lv = e.lv;
+        d.m[0] = as_prec(f64, e.m[0].real()), d.m[1] = as_prec(f64, e.m[0].imag());
+        if (e.terms.empty()) {
+          d.kind = DElem::PH;
+        } else {
+          if (e.gmask) return *why = "conditional phase run under a condition", false;
+          d.kind = DElem::PHN;
+          d.slot = (uint32_t)phn_terms->size();
+          phn_base->push_back(std::make_pair(d.m[0], d.m[1]));
+          std::vector<PhTerm> terms;
+          for (size_t k = 0; k < e.terms.size(); ++k) {
+            PhTerm t = {e.terms[k].gmask, e.terms[k].gval, as_prec(f64, e.terms[k].w.real()), as_prec(f64, e.terms[k].w.imag())};
+            terms.push_back(t);
+          }
+          phn_terms->push_back(terms);
+        }
+        break;
+      case JElem::DK: {
+        d.kind = DElem::DK;
+        d.mb = e.mb;
+        if (e.mb.empty() || e.mb.size() > 3 || e.mk.size() != ((size_t)1 << (2 * e.mb.size()))) return *why = "malformed dense block", false;
+        d.mk.resize(2 * e.mk.size());
+        for (size_t q = 0; q < e.mk.size(); ++q) {
+          d.mk[2 * q] = as_prec(f64, e.mk[q].real());
+          d.mk[2 * q + 1] = as_prec(f64, e.mk[q].imag());
+        }
+        break;
+      }
     }
     out->push_back(d);
   }
@@ -198,36 +177,52 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
   const uint32_t T = h.T, L = h.L, m = h.m;
   const uint32_t low3 = f64 ? 3 : 4;
   const uint32_t amp = f64 ? 16 : 8;
-  const uint32_t kThreads = 256, kWarpBits = 3, kLaneBits = 5;
+  const uint32_t K = pass.jbits;  // bits per group: 2^K amplitudes of a group live in one thread's registers
+  if (K < 3 || K > 6 || pass.jgroups.empty()) return *why = "pass was not emitted as register groups (wide op, or generation off)", false;
   if (T < 11 || T > 14) return *why = "tile too small/large for the generated kernel", false;
   if (m < 3 || L < low3 || (1u << (L - low3)) > 256) return *why = "geometry has no TMA boxes", false;
-  if (pass.ops.empty()) return *why = "empty pass", false;
-  const uint32_t n_it_bits = T - 3 - kWarpBits - kLaneBits;
+  const uint32_t NA = 1u << K;
+  // threads per CTA: every thread owns >= 1 group per super-op; 64 data registers (K = 4 f64 / K = 5 f32) leave
+  // room for two 256-thread CTAs per SM, 32 for three
+  static const uint32_t env_threads = []() {
+    const char *e = getenv("QIPB200_JIT_CTA_THREADS");
+    const int v = e ? atoi(e) : 0;
+    return (uint32_t)(v == 128 || v == 256 ? v : 0);
+  }();
+  uint32_t kThreads = env_threads ? env_threads : 256;
+  while (kThreads > 32 && (1u << (T - K)) < kThreads) kThreads >>= 1;
+  if ((1u << (T - K)) < kThreads) return *why = "tile holds fewer groups than a warp", false;
+  const uint32_t kLaneBits = 5;
+  uint32_t kWarpBits = 0;
+  while ((32u << kWarpBits) < kThreads) ++kWarpBits;
+  const uint32_t n_it_bits = T - K - kWarpBits - kLaneBits;
   const uint32_t NIT = 1u << n_it_bits;
+  const uint32_t data_regs = NA * (f64 ? 4 : 2);
+  const uint32_t ctas_per_sm = data_regs <= 32 ? 3 : (kThreads <= 128 ? 3 : 2);
   const char *RT = f64 ? "double" : "float";
 
-  // ---- decode ----
+  // ---- convert ----
   std::vector<Cond> conds;
   std::vector<std::vector<PhTerm>> phn_terms;
   std::vector<std::pair<double, double>> phn_base;
   std::vector<std::vector<DElem>> supers;
   std::vector<uint32_t> pmask;  // tile-local bit mask of each super-op
   std::vector<std::vector<uint32_t>> pbits;
-  for (size_t i = 0; i < pass.ops.size(); ++i) {
-    const HostMicroOp &mo = pass.ops[i];
-    if (mo.h.kind != MK_SUPER || mo.h.ins_n != 3 || mo.h.lor_mask != 0 || mo.h.gmask != 0)
-      return *why = "pass holds a wide micro-op", false;
+  for (size_t i = 0; i < pass.jgroups.size(); ++i) {
+    const JGroup &jg = pass.jgroups[i];
+    if (jg.bits.size() != K) return *why = "malformed group bit list", false;
     std::vector<DElem> el;
-    const bool ok = f64 ? decode_super<double>(mo, pass, conds, &el, &phn_terms, &phn_base, why)
-                        : decode_super<float>(mo, pass, conds, &el, &phn_terms, &phn_base, why);
-    if (!ok) return false;
+    if (!convert_group(jg, f64, conds, &el, &phn_terms, &phn_base, why)) return false;
     supers.push_back(el);
-    std::vector<uint32_t> pb(mo.h.ins_pos, mo.h.ins_pos + 3);
-    pbits.push_back(pb);
-    pmask.push_back((1u << pb[0]) | (1u << pb[1]) | (1u << pb[2]));
-    if (pb[0] >= pb[1] || pb[1] >= pb[2] || pb[2] >= T) return *why = "malformed super-op bit list", false;
+    pbits.push_back(jg.bits);
+    uint32_t pm = 0;
+    for (uint32_t q = 0; q < K; ++q) {
+      if (jg.bits[q] >= T || (q && jg.bits[q] <= jg.bits[q - 1])) return *why = "malformed group bit list", false;
+      pm |= 1u << jg.bits[q];
+    }
+    pmask.push_back(pm);
   }
-  if (conds.size() > kThreads) return *why = "more than 256 CTA-uniform conditions", false;
+  if (conds.size() > 256) return *why = "more than 256 CTA-uniform conditions", false;
   const size_t S = supers.size();
   const size_t NC = conds.size(), NPH = phn_terms.size();
   size_t NPT = 0;
@@ -236,7 +231,7 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
   const size_t gsz = f64 ? sizeof(GlobalTerm<double>) : sizeof(GlobalTerm<float>);
   const size_t NG = pass.gterms.size() / gsz;
 
-  // ---- thread maps: segments of super-ops that share their three warp-id bits ----
+  // ---- thread maps: segments of super-ops that share their warp-id bits ----
   const uint32_t all_bits = (1u << T) - 1u;
   std::vector<uint32_t> wmask(S);
   std::vector<bool> cta_barrier_before(S, false);
@@ -256,24 +251,34 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
     for (uint32_t k = 0; k < n_bank_bits; ++k) n += (providers(k) & ~taken) == 0;
     return n;
   };
-  // extra conflicts (log2, summed over the super-ops s..e-1) caused by using `w` as warp bits, beyond the inherent ones
   auto extra_cost = [&](size_t s, size_t e, uint32_t w) {
     uint32_t c = 0;
     for (size_t k = s; k < e; ++k) c += lost_bank_bits(pmask[k] | w) - lost_bank_bits(pmask[k]);
     return c;
   };
   auto best_warp_bits = [&](size_t s, size_t e, uint32_t free_bits, uint32_t *cost) {
-    uint32_t best = 0, best_cost = ~0u;
+    // all kWarpBits-subsets of the free bits, highest bits first (ties go to the first hit)
     std::vector<uint32_t> fb;
     for (int b = (int)T - 1; b >= 0; --b)
       if ((free_bits >> b) & 1) fb.push_back((uint32_t)b);
-    for (size_t i = 0; i < fb.size(); ++i)
-      for (size_t j = i + 1; j < fb.size(); ++j)
-        for (size_t k = j + 1; k < fb.size(); ++k) {
-          const uint32_t w = (1u << fb[i]) | (1u << fb[j]) | (1u << fb[k]);
-          const uint32_t c = extra_cost(s, e, w);
-          if (c < best_cost) best = w, best_cost = c;  // first hit wins ties: the highest bits
-        }
+    uint32_t best = 0, best_cost = ~0u;
+    std::vector<uint32_t> idx(kWarpBits);
+    for (uint32_t i = 0; i < kWarpBits; ++i) idx[i] = i;
+    if (fb.size() < kWarpBits) {
+      *cost = ~0u;
+      return 0u;
+    }
+    for (;;) {
+      uint32_t w = 0;
+      for (uint32_t i = 0; i < kWarpBits; ++i) w |= 1u << fb[idx[i]];
+      const uint32_t c = extra_cost(s, e, w);
+      if (c < best_cost) best = w, best_cost = c;
+      int q = (int)kWarpBits - 1;
+      while (q >= 0 && idx[q] == fb.size() - kWarpBits + q) --q;
+      if (q < 0) break;
+      ++idx[q];
+      for (uint32_t r = q + 1; r < kWarpBits; ++r) idx[r] = idx[r - 1] + 1;
+    }
     *cost = best_cost;
     return best;
   };
@@ -282,9 +287,9 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
     uint32_t cost = 0;
     uint32_t w = best_warp_bits(s, s + 1, free_bits, &cost);
     size_t e = s + 1;
-    // extend the segment while three common free bits exist that cost no bank conflict: a CTA barrier is far
-    // cheaper than a 2-way conflict on every access of a super-op
-    while (e < S && __builtin_popcount(free_bits & ~pmask[e]) >= (int)kWarpBits) {
+    // extend the segment while common free bits exist that cost no bank conflict: a CTA barrier is far cheaper than
+    // a 2-way conflict on every access of a super-op
+    while (e < S && (uint32_t)__builtin_popcount(free_bits & ~pmask[e]) >= kWarpBits) {
       uint32_t c2 = 0;
       const uint32_t w2 = best_warp_bits(s, e + 1, free_bits & ~pmask[e], &c2);
       if (c2 > cost) break;
@@ -305,9 +310,7 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
     // lane / iteration bits of this super-op
     uint32_t avail = all_bits & ~pmask[s] & ~wmask[s];
     std::vector<uint32_t> lane;  // tile bit of lane bit k
-    const uint32_t n_classes = f64 ? 3 : 4;
-    for (uint32_t k = 0; k < n_classes; ++k) {
-      // bank-group bit k of a swizzled address is t_k ^ t_{k+3} (f64) / t_k (k = 0), t_k ^ t_{k+3} (f32, k >= 1)
+    for (uint32_t k = 0; k < n_bank_bits; ++k) {
       int pick = -1;
       if ((avail >> k) & 1) pick = (int)k;
       else if ((f64 || k >= 1) && k + 3 < T && ((avail >> (k + 3)) & 1)) pick = (int)(k + 3);
@@ -325,7 +328,8 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
     for (uint32_t b = 0; b < T; ++b)
       if ((avail >> b) & 1) itb.push_back(b);
     if (lane.size() != kLaneBits || itb.size() != n_it_bits) return *why = "internal: thread map", false;
-    std::vector<uint32_t> dst(8);  // tid bit -> tile bit
+    const uint32_t n_tid_bits = kLaneBits + kWarpBits;
+    std::vector<uint32_t> dst(n_tid_bits);  // tid bit -> tile bit
     for (uint32_t k = 0; k < kLaneBits; ++k) dst[k] = lane[k];
     {
       uint32_t k = 0;
@@ -333,14 +337,15 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
         if ((wmask[s] >> b) & 1) dst[kLaneBits + k++] = b;
     }
 
-    fn << "// super-op " << s << ": sub-bits {" << pbits[s][0] << "," << pbits[s][1] << "," << pbits[s][2] << "}, warp bits 0x"
-       << std::hex << wmask[s] << std::dec << "\n";
+    fn << "// super-op " << s << ": sub-bits {";
+    for (uint32_t q = 0; q < K; ++q) fn << (q ? "," : "") << pbits[s][q];
+    fn << "}, warp bits 0x" << std::hex << wmask[s] << std::dec << "\n";
     fn << "QIP_DEV void so_" << s << "(unsigned char* sm, const unsigned tid, const JP& p, const unsigned* condw, const "
        << RT << "* tbl, const " << RT << "* gt) {\n";
     fn << "  unsigned t = 0u;\n";
-    for (uint32_t k = 0; k < 8;) {
+    for (uint32_t k = 0; k < n_tid_bits;) {
       uint32_t len = 1;
-      while (k + len < 8 && dst[k + len] == dst[k] + len) ++len;
+      while (k + len < n_tid_bits && dst[k + len] == dst[k] + len) ++len;
       fn << "  t |= ((tid >> " << k << ") & " << ((1u << len) - 1u) << "u) << " << dst[k] << ";\n";
       k += len;
     }
@@ -379,12 +384,11 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
       }
       fn << "    const unsigned a = " << a << ";\n";
     }
-    // the 8 addresses: XOR part (swizzle-modified bits) + additive part
-    uint32_t soff[8], xpart[8], apart[8];
-    std::vector<uint32_t> xs;
-    for (uint32_t u = 0; u < 8; ++u) {
+    // the 2^K addresses: XOR part (swizzle-modified bits) + additive part
+    std::vector<uint32_t> soff(NA), xpart(NA), apart(NA), xs;
+    for (uint32_t u = 0; u < NA; ++u) {
       uint32_t off = 0;
-      for (uint32_t i = 0; i < 3; ++i)
+      for (uint32_t i = 0; i < K; ++i)
         if ((u >> i) & 1) off |= 1u << pbits[s][i];
       soff[u] = swz_units(f64, off) * amp;
       xpart[u] = soff[u] & 0x70u;
@@ -408,36 +412,39 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
     auto is_xlike = [](const DElem &d) {
       return d.kind == DElem::X || (d.kind == DElem::D1 && d.real && d.m[0] == 0.0 && d.m[3] == 0.0 && d.m[1] == 1.0 && d.m[2] == 1.0);
     };
-    auto pairs_list = [](uint32_t j, uint32_t mask, std::vector<std::pair<uint32_t, uint32_t>> *pr) {
-      uint32_t pidx = 0;
-      for (uint32_t c = 0; c < 8; ++c) {
+    auto pairs_list = [&](uint32_t j, uint32_t lc, std::vector<std::pair<uint32_t, uint32_t>> *pr) {
+      for (uint32_t c = 0; c < NA; ++c) {
         if ((c >> j) & 1) continue;
-        if ((mask >> pidx) & 1) pr->push_back(std::make_pair(c, c | (1u << j)));
-        ++pidx;
+        if ((c & lc) == lc) pr->push_back(std::make_pair(c, c | (1u << j)));
       }
     };
-    auto amps_of = [&](const DElem &d) -> uint32_t {
-      if (d.kind == DElem::D3) return 0xffu;
-      if (d.kind == DElem::PH || d.kind == DElem::PHN) return d.mask;
+    auto amps_of = [&](const DElem &d) -> uint64_t {
+      uint64_t a = 0;
+      if (d.kind == DElem::DK) return NA == 64 ? ~0ull : ((1ull << NA) - 1ull);
+      if (d.kind == DElem::PH || d.kind == DElem::PHN) {
+        for (uint32_t c = 0; c < NA; ++c)
+          if ((c & d.lm) == d.lv) a |= 1ull << c;
+        return a;
+      }
       std::vector<std::pair<uint32_t, uint32_t>> pr;
-      pairs_list(d.j, d.mask, &pr);
-      uint32_t a = 0;
-      for (size_t k = 0; k < pr.size(); ++k) a |= (1u << pr[k].first) | (1u << pr[k].second);
+      pairs_list(d.j, d.kind == DElem::HAD ? 0u : d.lc, &pr);
+      for (size_t k = 0; k < pr.size(); ++k) a |= (1ull << pr[k].first) | (1ull << pr[k].second);
       return a;
     };
     std::vector<char> folded(els.size(), 0);
-    int lf_cond[8], sf_cond[8];
-    uint32_t lf_other[8], sf_other[8];
-    for (uint32_t u = 0; u < 8; ++u) lf_cond[u] = sf_cond[u] = -1, lf_other[u] = sf_other[u] = u;
+    std::vector<int> lf_cond(NA, -1), sf_cond(NA, -1);
+    std::vector<uint32_t> lf_other(NA), sf_other(NA);
+    for (uint32_t u = 0; u < NA; ++u) lf_other[u] = sf_other[u] = u;
     {
-      uint32_t slot_of[8], dirty = 0;
-      for (uint32_t u = 0; u < 8; ++u) slot_of[u] = u;
+      std::vector<uint32_t> slot_of(NA);
+      uint64_t dirty = 0;
+      for (uint32_t u = 0; u < NA; ++u) slot_of[u] = u;
       for (size_t ei = 0; ei < els.size(); ++ei) {
         const DElem &d = els[ei];
-        const uint32_t am = amps_of(d);
+        const uint64_t am = amps_of(d);
         if (is_xlike(d)) {
           std::vector<std::pair<uint32_t, uint32_t>> pr;
-          pairs_list(d.j, d.mask, &pr);
+          pairs_list(d.j, d.lc, &pr);
           if (d.cond < 0) {  // static renaming: follows the names, touches nothing
             for (size_t k = 0; k < pr.size(); ++k) std::swap(slot_of[pr[k].first], slot_of[pr[k].second]);
             continue;
@@ -454,14 +461,14 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
         }
         dirty |= am;
       }
-      uint32_t later = 0;
+      uint64_t later = 0;
       for (size_t ei = els.size(); ei-- > 0;) {
         if (folded[ei]) continue;
         const DElem &d = els[ei];
-        const uint32_t am = amps_of(d);
+        const uint64_t am = amps_of(d);
         if (is_xlike(d) && d.cond >= 0 && !(am & later)) {
           std::vector<std::pair<uint32_t, uint32_t>> pr;
-          pairs_list(d.j, d.mask, &pr);
+          pairs_list(d.j, d.lc, &pr);
           for (size_t k = 0; k < pr.size(); ++k) {
             sf_cond[pr[k].first] = sf_cond[pr[k].second] = d.cond;
             sf_other[pr[k].first] = pr[k].second;
@@ -483,8 +490,8 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
       fn << "    const unsigned " << nm << " = " << cond_test(c) << " ? (" << addr(other) << ") : (" << addr(u) << ");\n";
       return nm;
     };
-    std::string vr[8], vi[8];
-    for (uint32_t u = 0; u < 8; ++u) {
+    std::vector<std::string> vr(NA), vi(NA);
+    for (uint32_t u = 0; u < NA; ++u) {
       const std::string la = sel_addr(u, lf_cond[u], lf_other[u], "la");
       const std::string q = g.fresh();
       fn << "    const QV " << q << " = *reinterpret_cast<const QV*>(sm + " << la << ");\n";
@@ -500,30 +507,17 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
         continue;
       }
       const bool cond = d.cond >= 0;
-      std::string ctest;
-      if (cond) {
-        char b[64];
-        snprintf(b, sizeof(b), "((cw%d >> %d) & 1u)", d.cond >> 5, d.cond & 31);
-        ctest = b;
-      }
+      const std::string ctest = cond ? cond_test(d.cond) : std::string();
       // new values of the amplitudes this op changes: (u, new re expr, new im expr)
       struct Upd {
         uint32_t u;
         std::string re, im;
       };
       std::vector<Upd> upd;
-      auto pairs_of = [&](uint32_t j, uint32_t mask, std::vector<std::pair<uint32_t, uint32_t>> *pr) {
-        uint32_t pidx = 0;
-        for (uint32_t c = 0; c < 8; ++c) {
-          if ((c >> j) & 1) continue;
-          if ((mask >> pidx) & 1) pr->push_back(std::make_pair(c, c | (1u << j)));
-          ++pidx;
-        }
-      };
       typedef std::vector<std::pair<double, std::string>> Terms;
-      if (d.kind == DElem::X || (d.kind == DElem::D1 && d.real && d.m[0] == 0.0 && d.m[3] == 0.0 && d.m[1] == 1.0 && d.m[2] == 1.0)) {
+      if (is_xlike(d)) {
         std::vector<std::pair<uint32_t, uint32_t>> pr;
-        pairs_of(d.j, d.mask, &pr);
+        pairs_list(d.j, d.lc, &pr);
         if (!cond) {  // pure renaming: no instruction at all, exact for every bit pattern
           for (size_t k = 0; k < pr.size(); ++k) {
             std::swap(vr[pr[k].first], vr[pr[k].second]);
@@ -539,7 +533,7 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
         }
       } else if (d.kind == DElem::HAD) {
         std::vector<std::pair<uint32_t, uint32_t>> pr;
-        pairs_of(d.j, d.mask, &pr);
+        pairs_list(d.j, 0u, &pr);
         for (size_t k = 0; k < pr.size(); ++k) {
           const uint32_t x = pr[k].first, y = pr[k].second;
           Upd a = {x, "(" + vr[x] + " + " + vr[y] + ")", "(" + vi[x] + " + " + vi[y] + ")"};
@@ -549,7 +543,7 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
         }
       } else if (d.kind == DElem::D1) {
         std::vector<std::pair<uint32_t, uint32_t>> pr;
-        pairs_of(d.j, d.mask, &pr);
+        pairs_list(d.j, d.lc, &pr);
         for (size_t k = 0; k < pr.size(); ++k) {
           const uint32_t x = pr[k].first, y = pr[k].second;
           const std::string &xr = vr[x], &xi = vi[x], &yr = vr[y], &yi = vi[y];
@@ -574,8 +568,8 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
           upd.push_back(b);
         }
       } else if (d.kind == DElem::PH) {  // QIP_PH: re' = fma(wr, re, -(wi*im)); im' = fma(wr, im, wi*re)
-        for (uint32_t c = 0; c < 8; ++c) {
-          if (!((d.mask >> c) & 1)) continue;
+        for (uint32_t c = 0; c < NA; ++c) {
+          if ((c & d.lm) != d.lv) continue;
           Upd a = {c, g.chain(Terms{{-d.m[1], vi[c]}, {d.m[0], vr[c]}}), g.chain(Terms{{d.m[1], vr[c]}, {d.m[0], vi[c]}})};
           upd.push_back(a);
         }
@@ -588,24 +582,38 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
           wr = g.fresh(), wi = g.fresh();
           fn << "    const " << RT << " " << wr << " = tbl[" << 2 * d.slot << "], " << wi << " = tbl[" << 2 * d.slot + 1 << "];\n";
         }
-        for (uint32_t c = 0; c < 8; ++c) {
-          if (!((d.mask >> c) & 1)) continue;
+        for (uint32_t c = 0; c < NA; ++c) {
+          if ((c & d.lm) != d.lv) continue;
           Upd a = {c, "QFMA(" + wr + ", " + vr[c] + ", -(" + wi + " * " + vi[c] + "))",
                    "QFMA(" + wr + ", " + vi[c] + ", (" + wi + " * " + vr[c] + "))"};
           upd.push_back(a);
         }
-      } else {  // D3: dense 8x8, rows in order, re = fma(mr, xr, re); re = fma(-mi, xi, re); im likewise
-        for (uint32_t u = 0; u < 8; ++u) {
-          Terms tr, ti;
-          for (uint32_t v = 0; v < 8; ++v) {
-            const double mr = d.m8[2 * (u * 8 + v)], mi = d.m8[2 * (u * 8 + v) + 1];
-            tr.push_back(std::make_pair(mr, vr[v]));
-            tr.push_back(std::make_pair(-mi, vi[v]));
-            ti.push_back(std::make_pair(mr, vi[v]));
-            ti.push_back(std::make_pair(mi, vr[v]));
+      } else {  // DK: dense 2^k x 2^k on the sub-bits mb, for every setting of the group's other bits; rows in
+                // order, re = fma(mr, xr, re); re = fma(-mi, xi, re); im likewise (tile_interp.cuh _QIP_D3_BODY)
+        const uint32_t kb = (uint32_t)d.mb.size(), SB = 1u << kb;
+        uint32_t mbm = 0;
+        for (uint32_t q = 0; q < kb; ++q) mbm |= 1u << d.mb[q];
+        for (uint32_t base = 0; base < NA; ++base) {
+          if (base & mbm) continue;
+          std::vector<uint32_t> idx(SB);
+          for (uint32_t r = 0; r < SB; ++r) {
+            uint32_t c = base;
+            for (uint32_t q = 0; q < kb; ++q)
+              if ((r >> q) & 1) c |= 1u << d.mb[q];
+            idx[r] = c;
           }
-          Upd a = {u, g.chain(tr), g.chain(ti)};
-          upd.push_back(a);
+          for (uint32_t u = 0; u < SB; ++u) {
+            Terms tr, ti;
+            for (uint32_t v = 0; v < SB; ++v) {
+              const double mr = d.mk[2 * (u * SB + v)], mi = d.mk[2 * (u * SB + v) + 1];
+              tr.push_back(std::make_pair(mr, vr[idx[v]]));
+              tr.push_back(std::make_pair(-mi, vi[idx[v]]));
+              ti.push_back(std::make_pair(mr, vi[idx[v]]));
+              ti.push_back(std::make_pair(mi, vr[idx[v]]));
+            }
+            Upd a = {idx[u], g.chain(tr), g.chain(ti)};
+            upd.push_back(a);
+          }
         }
       }
       // materialise (all right-hand sides refer to the OLD names)
@@ -631,23 +639,23 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
       }
     }
     if (last && NG) {  // CTA-uniform phase product, folded into the last write of every amplitude
-      std::string nr[8], ni[8];
-      for (uint32_t u = 0; u < 8; ++u) {
+      std::vector<std::string> nr(NA), ni(NA);
+      for (uint32_t u = 0; u < NA; ++u) {
         nr[u] = g.fresh();
         ni[u] = g.fresh();
         fn << "    " << RT << " " << nr[u] << " = " << vr[u] << ", " << ni[u] << " = " << vi[u] << ";\n";
       }
       fn << "    if (hasg) {\n";
-      for (uint32_t u = 0; u < 8; ++u)
+      for (uint32_t u = 0; u < NA; ++u)
         fn << "      " << nr[u] << " = QFMA(gr, " << vr[u] << ", -(gi * " << vi[u] << ")); " << ni[u] << " = QFMA(gr, " << vi[u]
            << ", (gi * " << vr[u] << "));\n";
       fn << "    }\n";
-      for (uint32_t u = 0; u < 8; ++u) {
+      for (uint32_t u = 0; u < NA; ++u) {
         vr[u] = nr[u];
         vi[u] = ni[u];
       }
     }
-    for (uint32_t u = 0; u < 8; ++u) {
+    for (uint32_t u = 0; u < NA; ++u) {
       const std::string sa = sel_addr(u, sf_cond[u], sf_other[u], "sa");
       const std::string q = g.fresh();
       fn << "    { QV " << q << "; " << q << ".x = " << vr[u] << "; " << q << ".y = " << vi[u] << "; *reinterpret_cast<QV*>(sm + "
@@ -665,6 +673,7 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
   src << "#define TILE_T " << T << "\n#define TILE_L " << L << "\n#define TILE_M " << m << "\n#define LOW3 " << low3 << "\n";
   src << "#define NBOX " << NBOX << "\n#define NC " << NC << "\n#define NPH " << NPH << "\n#define NPT " << NPT << "\n#define NG " << NG
       << "\n#define NK " << NK << "\n";
+  src << "#define CTA_THREADS " << kThreads << "\n#define CTAS_PER_SM " << ctas_per_sm << "\n";
   src << "#define TILE_BYTES " << (amp << T) << "u\n#define BOX_BYTES " << (amp << (L + 3)) << "u\n";
   const uint32_t tbl_bytes = (uint32_t)(((NPH * 2 * (f64 ? 8 : 4)) + 15) & ~(size_t)15);
   const uint32_t off_tbl = amp << T, off_gt = off_tbl + tbl_bytes, off_condw = off_gt + 16, off_mbar = off_condw + 48;
@@ -701,9 +710,10 @@ struct alignas(2 * sizeof(R)) QV { R x, y; };
   src << "QIP_DEV void prelude(unsigned char* sm, const unsigned tid, const JP& p, const u64 base) {\n";
   src << "  unsigned* condw = reinterpret_cast<unsigned*>(sm + OFF_CONDW);\n  (void)condw; (void)base; (void)tid;\n";
   if (NC) {
-    src << "  {\n    bool on = false;\n    if (tid < NC) on = (base & p.cm[tid]) == p.cv[tid];\n";
-    src << "#ifdef QIP_JIT_HOST\n    if (on) condw[tid >> 5] |= 1u << (tid & 31u);\n#else\n";
-    src << "    const unsigned bits = __ballot_sync(0xffffffffu, on);\n    if ((tid & 31u) == 0u) condw[tid >> 5] = bits;\n#endif\n  }\n";
+    src << "  for (unsigned cb = 0; cb < NC; cb += CTA_THREADS) {\n    const unsigned ci = cb + tid;\n    bool on = false;\n";
+    src << "    if (ci < NC) on = (base & p.cm[ci]) == p.cv[ci];\n";
+    src << "#ifdef QIP_JIT_HOST\n    if (on && ci < 256u) condw[ci >> 5] |= 1u << (ci & 31u);\n#else\n";
+    src << "    const unsigned bits = __ballot_sync(0xffffffffu, on);\n    if ((tid & 31u) == 0u && ci < 256u) condw[ci >> 5] = bits;\n#endif\n  }\n";
   }
   if (NPH) {
     src << "  {\n    R* tbl = reinterpret_cast<R*>(sm + OFF_TBL);\n    for (unsigned e = tid; e < NPH; e += " << kThreads << "u) {\n";
@@ -764,7 +774,7 @@ __device__ __forceinline__ void box_coords(const JP& p, u64 idx, int* c) {
   c[2] = (int)((idx >> h2) & ((1ull << (h3 - h2)) - 1ull));
   c[3] = (int)(idx >> h3);
 }
-extern "C" __global__ void __launch_bounds__(256, 3)
+extern "C" __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
 qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) unsigned char sm[];
   const unsigned tid = threadIdx.x;

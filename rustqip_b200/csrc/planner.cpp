@@ -209,6 +209,11 @@ struct Emitter {
   HostPass *pass;
   uint32_t T;
   const PlanConfig *cfg;
+  uint32_t gbits = 3;   // bits per group: 3 for the interpreter's records, cfg->jit_group_bits for the generated kernels
+  bool jmode = false;   // emit JGroups (tile.cuh) instead of serialised records
+  long jhad_group = -1; // jmode: where the last un-normalised Hadamard sits
+  size_t jhad_elem = 0;
+  bool jfail = false;   // jmode: the pass holds an op wider than a group (the interpreter's wide micro-ops serve it)
   std::vector<Group> open;
   std::vector<GlobalTerm<R>> gterms;
   // Un-normalised Hadamards: product of the scales not applied yet (a global scalar), and where the last
@@ -218,7 +223,93 @@ struct Emitter {
   size_t had_at = 0;
   uint32_t had_j = 0;
 
+  // The same group for the generated kernels: any number of bits up to gbits, ops in sub-index coordinates.
+  void emit_group_j(const Group &g) {
+    std::vector<uint32_t> P;
+    uint32_t mask = g.mask;
+    // pad with the highest unused tile-local bits that do not take a bank-group bit's last provider away
+    // (jit_codegen.cpp: bank bit k of a swizzled address needs tile bit k or k+3 outside the group)
+    for (int pass_no = 0; pass_no < 2 && (uint32_t)popc(mask) < gbits; ++pass_no)
+      for (int b = (int)T - 1; b >= 0 && (uint32_t)popc(mask) < gbits; --b) {
+        if ((mask >> b) & 1) continue;
+        if (pass_no == 0 && b < 7) {
+          const int partner = b < 3 ? b + 3 : (b < 6 ? b - 3 : -1);
+          if (partner < 0 || ((mask >> partner) & 1)) continue;  // would leave a bank bit without provider
+        }
+        mask |= 1u << b;
+      }
+    for (uint32_t b = 0; b < 32; ++b)
+      if ((mask >> b) & 1) P.push_back(b);
+    auto sub_of = [&](uint32_t lb) { return (uint32_t)(std::find(P.begin(), P.end(), lb) - P.begin()); };
+    auto sub_mask = [&](uint32_t lmask) {
+      uint32_t o = 0;
+      for (uint32_t b = 0; b < 32; ++b)
+        if ((lmask >> b) & 1) o |= 1u << sub_of(b);
+      return o;
+    };
+    JGroup jg;
+    jg.bits = P;
+    for (size_t i = 0; i < g.elems.size(); ++i) {
+      const HElem &e = g.elems[i];
+      JElem d;
+      d.gmask = e.gmask;
+      d.gval = e.gval;
+      const bool cond = e.gmask != 0;
+      if (e.type == E_DENSE1 || e.type == E_X) {
+        d.kind = e.type == E_X ? JElem::X : JElem::D1;
+        d.j = sub_of(e.lb_j);
+        d.lc = sub_mask(e.lctrl);
+        for (int q = 0; q < 4; ++q) d.m[q] = e.m[q];
+        if (e.type == E_X) {
+          d.m[0] = d.m[3] = cplx(0, 0);
+          d.m[1] = d.m[2] = cplx(1, 0);
+        } else {
+          bool real = true;
+          for (int q = 0; q < 4; ++q) real &= e.m[q].imag() == 0.0;
+          const bool everywhere = d.lc == 0 && !cond;
+          const double hs = e.m[0].real();
+          const bool is_h = real && everywhere && cfg->unnormalised_h && hs > 0.0 && e.m[1].real() == hs && e.m[2].real() == hs &&
+                            e.m[3].real() == -hs;
+          if (is_h) {  // s*[[1,1],[1,-1]]: butterfly now, the scale later (a global scalar commutes with everything)
+            d.kind = JElem::HAD;
+            pending_scale *= hs;
+            jhad_group = (long)pass->jgroups.size();
+            jhad_elem = jg.elems.size();
+          } else if (everywhere && pending_scale != 1.0) {
+            for (int q = 0; q < 4; ++q) d.m[q] *= pending_scale;
+            pending_scale = 1.0;
+            jhad_group = -1;
+          }
+        }
+      } else if (e.type == E_PHASE) {
+        d.kind = JElem::PH;
+        d.lm = sub_mask(e.lmask);
+        d.lv = sub_mask(e.lval);
+        d.m[0] = e.m[0];
+        for (size_t k = 0; k < e.terms.size(); ++k) {
+          JCondPhase t = {e.terms[k].gmask, e.terms[k].gval, e.terms[k].w};
+          d.terms.push_back(t);
+        }
+      } else {  // E_DENSE3: dense block on <= 3 of the group's bits
+        d.kind = JElem::DK;
+        for (size_t q = 0; q < e.mbits.size(); ++q) d.mb.push_back(sub_of(e.mbits[q]));
+        d.mk = e.mk;
+        if (!cond && pending_scale != 1.0) {
+          for (size_t q = 0; q < d.mk.size(); ++q) d.mk[q] *= pending_scale;
+          pending_scale = 1.0;
+          jhad_group = -1;
+        }
+      }
+      jg.elems.push_back(d);
+    }
+    pass->jgroups.push_back(jg);
+  }
+
   void emit_group(const Group &g) {
+    if (jmode) {
+      emit_group_j(g);
+      return;
+    }
     // pad the bit set to 3 with the highest unused tile-local bits (keeps the low bits for the lanes)
     std::vector<uint32_t> P;
     uint32_t mask = g.mask;
@@ -413,6 +504,16 @@ struct Emitter {
   // which becomes an ordinary real 2x2 again.
   void settle_scale() {
     if (pending_scale == 1.0) return;
+    if (jmode) {
+      JElem &d = pass->jgroups[(size_t)jhad_group].elems[jhad_elem];
+      d.kind = JElem::D1;
+      d.lc = 0;
+      d.m[0] = d.m[1] = d.m[2] = cplx(pending_scale, 0);
+      d.m[3] = cplx(-pending_scale, 0);
+      pending_scale = 1.0;
+      jhad_group = -1;
+      return;
+    }
     Elem<R> d;
     unsigned char *rec = pass->ops[(size_t)had_op].data.data() + had_at;
     memcpy(&d, rec, sizeof(d));
@@ -443,7 +544,7 @@ struct Emitter {
       for (size_t i = 0; i < out.size(); ++i) {
         bool placed = false;
         for (size_t j = 0; j < packed.size() && !placed; ++j)
-          if (popc(packed[j].mask | out[i].mask) <= 3) {
+          if ((uint32_t)popc(packed[j].mask | out[i].mask) <= gbits) {
             packed[j].mask |= out[i].mask;
             packed[j].elems.insert(packed[j].elems.end(), out[i].elems.begin(), out[i].elems.end());
             placed = true;
@@ -455,8 +556,8 @@ struct Emitter {
         // ride (disjoint bits commute; their later ops simply start a new group): their current ops cost no
         // shared-memory round trip of their own.
         for (size_t j = 0; j < packed.size(); ++j)
-          for (size_t i = 0; i < open.size() && popc(packed[j].mask) < 3;) {
-            if (popc(packed[j].mask | open[i].mask) <= 3) {
+          for (size_t i = 0; i < open.size() && (uint32_t)popc(packed[j].mask) < gbits;) {
+            if ((uint32_t)popc(packed[j].mask | open[i].mask) <= gbits) {
               packed[j].mask |= open[i].mask;
               packed[j].elems.insert(packed[j].elems.end(), open[i].elems.begin(), open[i].elems.end());
               open.erase(open.begin() + (long)i);
@@ -574,7 +675,7 @@ struct Emitter {
         hit.push_back(i);
         um |= open[i].mask;
       }
-    if (popc(um) > 3) {
+    if ((uint32_t)popc(um) > gbits) {
       flush_touching(bm, false);
       Group g;
       g.mask = bm;
@@ -703,7 +804,7 @@ struct Emitter {
 // Translate the taken ops of one pass into micro-ops.
 template <typename R>
 void emit_pass(const std::vector<FlatOp> &ops, const std::vector<size_t> &taken, const PassHeader &hdr,
-               const PlanConfig &cfg, HostPass *pass) {
+               const PlanConfig &cfg, HostPass *pass, bool jmode = false) {
   const uint32_t T = hdr.T, L = hdr.L;
   int local_of[64];  // physical bit -> tile-local bit (or -1)
   for (int b = 0; b < 64; ++b) local_of[b] = -1;
@@ -714,6 +815,8 @@ void emit_pass(const std::vector<FlatOp> &ops, const std::vector<size_t> &taken,
   em.pass = pass;
   em.T = T;
   em.cfg = &cfg;
+  em.jmode = jmode;
+  em.gbits = jmode ? std::min<uint32_t>(cfg.jit_group_bits, T) : 3;
 
   for (size_t ti = 0; ti < taken.size(); ++ti) {
     const FlatOp &f = ops[taken[ti]];
@@ -758,8 +861,10 @@ void emit_pass(const std::vector<FlatOp> &ops, const std::vector<size_t> &taken,
           g.re = (R)e.m[0].real();
           g.im = (R)e.m[0].imag();
           em.gterms.push_back(g);
-        } else if (popc(e.lmask) <= 3) {
+        } else if ((uint32_t)popc(e.lmask) <= em.gbits) {
           em.add(e);
+        } else if (jmode) {
+          em.jfail = true;
         } else {
           DiagTerm<R> t;
           t.gmask = e.gmask;
@@ -771,7 +876,7 @@ void emit_pass(const std::vector<FlatOp> &ops, const std::vector<size_t> &taken,
           wide.push_back(t);
         }
       }
-      if (!wide.empty()) {
+      if (!wide.empty() && !jmode) {
         em.flush_touching(0, true);
         em.push_wide_diag(wide);
       }
@@ -780,7 +885,7 @@ void emit_pass(const std::vector<FlatOp> &ops, const std::vector<size_t> &taken,
     if (f.cls == CLASS_BITSWAP) {
       for (size_t i = 0; i < f.swaps.size(); ++i) {
         const uint32_t a = (uint32_t)local_of[f.swaps[i].first], b = (uint32_t)local_of[f.swaps[i].second];
-        if (popc(lctrl) + 2 <= 3) {
+        if ((uint32_t)popc(lctrl) + 2 <= em.gbits) {
           HElem e;
           e.type = E_SWAP;
           e.lb_j = a;
@@ -788,6 +893,8 @@ void emit_pass(const std::vector<FlatOp> &ops, const std::vector<size_t> &taken,
           e.lctrl = lctrl;
           e.gmask = e.gval = gmask;
           em.add(e);
+        } else if (jmode) {
+          em.jfail = true;
         } else {
           em.flush_touching(0, true);
           em.push_wide_exch(std::min(a, b), std::max(a, b), lctrl, gmask);
@@ -798,7 +905,11 @@ void emit_pass(const std::vector<FlatOp> &ops, const std::vector<size_t> &taken,
     std::vector<uint32_t> ltgt;
     for (size_t i = 0; i < f.tgt_sorted.size(); ++i) ltgt.push_back((uint32_t)local_of[f.tgt_sorted[i]]);
     // local order equals physical order (low bits identity, high bits ascending), so m_sorted stays valid
-    if ((size_t)popc(lctrl) + ltgt.size() > 3) {
+    if ((size_t)popc(lctrl) + ltgt.size() > em.gbits || (ltgt.size() > 1 && (size_t)popc(lctrl) + ltgt.size() > 3)) {
+      if (jmode) {
+        em.jfail = true;
+        continue;
+      }
       em.flush_touching(0, true);
       em.push_wide_dense(f, ltgt, lctrl, gmask);
       continue;
@@ -837,6 +948,11 @@ void emit_pass(const std::vector<FlatOp> &ops, const std::vector<size_t> &taken,
   }
   em.flush_touching(0, true);
   em.settle_scale();
+  if (jmode) {
+    pass->jbits = em.jfail ? 0 : em.gbits;
+    if (em.jfail) pass->jgroups.clear();
+    return;  // global terms and conditions were produced by the record emission of the same pass
+  }
   pass->gterms.resize(em.gterms.size() * sizeof(GlobalTerm<R>));
   if (!em.gterms.empty()) memcpy(pass->gterms.data(), em.gterms.data(), pass->gterms.size());
 }
@@ -858,6 +974,9 @@ PlanConfig default_plan_config(qip_prec prec, uint32_t n_local) {
   if (const char *e = getenv("QIPB200_TILE_L")) c.L = (uint32_t)atoi(e);
   if (const char *e = getenv("QIPB200_COMPOSE")) c.compose_threshold = (uint32_t)std::max(1, atoi(e));
   if (const char *e = getenv("QIPB200_TILE_G")) c.groups_per_thread = atoi(e) == 2 ? 2 : 1;
+  // generated kernels: 2^4 (f64) / 2^5 (f32) amplitudes of a group in registers = 64 data registers per thread
+  c.jit_group_bits = prec == QIP_F32 ? 5 : 4;
+  if (const char *e = getenv("QIPB200_JIT_GROUP_BITS")) c.jit_group_bits = (uint32_t)std::min(6, std::max(3, atoi(e)));
   if (const char *e = getenv("QIPB200_NO_BLOCK_FUSION")) c.fuse_blocks = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_NO_PEEPHOLE")) c.peephole = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_SEED_SEARCH")) c.seed_search = atoi(e) != 0;
@@ -1025,6 +1144,12 @@ void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec
         emit_pass<float>(ops, taken, h, cfg, &st.pass);
       else
         emit_pass<double>(ops, taken, h, cfg, &st.pass);
+      if (cfg.jit_group_bits >= 3) {  // the same gates once more, grouped for the generated kernels
+        if (prec == QIP_F32)
+          emit_pass<float>(ops, taken, h, cfg, &st.pass, true);
+        else
+          emit_pass<double>(ops, taken, h, cfg, &st.pass, true);
+      }
       if (pass_bytes(st.pass) > kMaxPassBytes && attempt < 2) continue;  // too optimistic: retry with a smaller budget
       h.n_ops = (uint32_t)st.pass.ops.size();
       h.n_gterms = (uint32_t)(st.pass.gterms.size() / (prec == QIP_F32 ? sizeof(GlobalTerm<float>) : sizeof(GlobalTerm<double>)));

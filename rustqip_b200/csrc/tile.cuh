@@ -184,8 +184,35 @@ struct HostMicroOp {
   std::vector<unsigned char> data;
 };
 
+// ---- the same pass for the GENERATED kernels (jit_codegen.cpp): groups of up to `jbits` tile-local bits ----
+// The interpreter's records are tied to 3-bit groups (8 amplitudes, 8-bit masks); a generated kernel can keep
+// 2^4 (f64) or 2^5 (f32) amplitudes of a group in registers, and every bit more per group means fewer shared-memory
+// round trips per pass -- the resource that bounds the pass (round 2: 2 x 64 KiB through shared memory per super-op
+// and tile).  Elementary ops are given in SUB-INDEX coordinates: bit i of the sub-index <-> bits[i].
+struct JCondPhase {
+  uint64_t gmask, gval;
+  cplx w;
+};
+struct JElem {
+  enum Kind { D1 = 0, X = 1, PH = 2, DK = 3, HAD = 4 } kind = D1;
+  uint32_t j = 0;                 // D1 / X / HAD: target sub-bit
+  uint32_t lc = 0;                // D1 / X: control sub-mask (the op acts on pairs whose other bits contain lc)
+  uint32_t lm = 0, lv = 0;        // PH: acts on sub-indices c with (c & lm) == lv
+  uint64_t gmask = 0, gval = 0;   // CTA-uniform condition on the tile's base index (gmask == 0: none)
+  cplx m[4];                      // D1: m00 m01 m10 m11; PH: factor in m[0]
+  std::vector<JCondPhase> terms;  // PH: further factors, each under its own CTA-uniform condition
+  std::vector<uint32_t> mb;       // DK: the sub-bits the dense block acts on (ascending, <= 3)
+  std::vector<cplx> mk;           // DK: 2^k x 2^k, row-major, bit i of the row index <-> mb[i]
+};
+struct JGroup {
+  std::vector<uint32_t> bits;  // ascending tile-local bits, exactly jbits of them (padded)
+  std::vector<JElem> elems;
+};
+
 struct HostPass {
   PassHeader hdr{};
+  std::vector<JGroup> jgroups;  // generated-kernel view of the pass (empty: not produced)
+  uint32_t jbits = 0;
   std::vector<HostMicroOp> ops;
   std::vector<unsigned char> gterms;  // GlobalTerm<R> records
   std::vector<CondTerm> conds;        // distinct CTA-uniform conditions of the pass's elementary ops
@@ -216,6 +243,7 @@ struct PlanConfig {
   bool unnormalised_h = true;   // Hadamards as add/sub butterflies, the scale folded into another gate of the pass
   bool seed_search = false;     // tile-bit choice: also try reserving slots for bits the greedy left out (fewer passes, but
                                 // more elementary ops; measured slower on the N=30 circuit: 25 passes 309 ms vs 29 passes 302 ms)
+  uint32_t jit_group_bits = 0;     // > 0: also emit the pass as groups of this many bits for the generated kernels
   int groups_per_thread = 1;       // register-resident groups per interpreter decode (1: 3 CTAs/SM, 2: 2 CTAs/SM)
   uint32_t compose_threshold = 8;  // >= this many 2x2 gates in one group: compose them into one 8x8
 };
