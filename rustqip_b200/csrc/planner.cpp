@@ -987,6 +987,18 @@ PlanConfig default_plan_config(qip_prec prec, uint32_t n_local) {
   if (const char *e = getenv("QIPB200_X_MOVES")) c.x_as_moves = atoi(e) != 0;
   if (const char *e = getenv("QIPB200_NO_PHASEN")) c.fold_cond_phases = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_NO_TMA")) c.use_tma = atoi(e) == 0;
+  // States big enough for the generated kernels (jit_runtime.cu: from 22 local qubits): a pass costs one HBM sweep
+  // almost regardless of what it folds in, so fewer passes win (tile-bit seed search: 25 instead of 29 for the N=30
+  // circuit) and FP64 work is worth saving (phases kept out of real 2x2 gates).  Measured r2e, N=30 f64: 170 -> 152 ms.
+  // (The interpreter kernel is bound by its own instruction stream: there the same options measured slower.)
+  {
+    const char *j = getenv("QIPB200_JIT");
+    const bool jit_off = j && (!strcmp(j, "off") || !strcmp(j, "0"));
+    if (n_local >= 22 && !jit_off) {
+      if (!getenv("QIPB200_SEED_SEARCH")) c.seed_search = true;
+      if (!getenv("QIPB200_KEEP_REAL")) c.keep_real = true;
+    }
+  }
   if (n_local < c.T) c.T = n_local;
   if (c.L > c.T) c.L = c.T;
   if (c.T - c.L > kTileMaxHigh) c.L = c.T - kTileMaxHigh;
