@@ -35,6 +35,7 @@ struct DElem {
   uint32_t j = 0;          // D1 / X / HAD: target sub-bit
   uint32_t lc = 0;         // D1 / X: control sub-mask
   uint32_t lm = 0, lv = 0; // PH / PHN: acts on sub-indices c with (c & lm) == lv
+  uint32_t pm = 0, pv = 0; // PH / PHN: in the threads whose tile-local group index t has (t & pm) == pv
   int cond = -1;           // index into the program's condition list
   double m[8] = {0};       // D1: real m00 m01 m10 m11 | complex (re,im) x 4; PH: w
   std::vector<uint32_t> mb;  // DK: sub-bits of the dense block (ascending)
@@ -86,6 +87,7 @@ bool convert_group(const JGroup &jg, bool f64, std::vector<Cond> &conds, std::ve
         break;
       case JElem::PH:
         d.lm = e.lm, d.lv = e.lv;
+        d.pm = e.pm, d.pv = e.pv;
         d.m[0] = as_prec(f64, e.m[0].real()), d.m[1] = as_prec(f64, e.m[0].imag());
         if (e.terms.empty()) {
           d.kind = DElem::PH;
@@ -351,6 +353,9 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
       fn << "  t |= ((tid >> " << k << ") & " << ((1u << len) - 1u) << "u) << " << dst[k] << ";\n";
       k += len;
     }
+    bool needs_tt = false;
+    for (size_t i = 0; i < supers[s].size(); ++i) needs_tt |= supers[s][i].pm != 0;
+    if (needs_tt) fn << "  const unsigned tt0 = t;\n";  // tile-local index of this thread's group (sub-bits zero)
     fn << (f64 ? "  t ^= (t >> 3) & 7u;\n  const unsigned a0 = t << 4;\n" : "  t ^= ((t >> 4) & 7u) << 1;\n  const unsigned a0 = t << 3;\n");
     // condition words this super-op tests
     {
@@ -385,6 +390,15 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
         a += b;
       }
       fn << "    const unsigned a = " << a << ";\n";
+      if (needs_tt) {
+        std::string tt = "tt0";
+        for (uint32_t k = 0; k < n_it_bits; ++k) {
+          char b[96];
+          snprintf(b, sizeof(b), " | (((it >> %u) & 1u) << %u)", k, itb[k]);
+          tt += b;
+        }
+        fn << "    const unsigned tt = " << tt << ";\n";
+      }
     }
     // the 2^K addresses: XOR part (swizzle-modified bits) + additive part
     std::vector<uint32_t> soff(NA), xpart(NA), apart(NA), xs;
@@ -508,8 +522,13 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
         ++g.renamed;
         continue;
       }
-      const bool cond = d.cond >= 0;
-      const std::string ctest = cond ? cond_test(d.cond) : std::string();
+      const bool cond = d.cond >= 0 || d.pm != 0;
+      std::string ctest = d.cond >= 0 ? cond_test(d.cond) : std::string();
+      if (d.pm) {  // thread predicate of a phase whose bit lies outside the group
+        char b[64];
+        snprintf(b, sizeof(b), "((tt & %uu) == %uu)", d.pm, d.pv);
+        ctest = ctest.empty() ? std::string(b) : "(" + ctest + " && " + b + ")";
+      }
       // new values of the amplitudes this op changes: (u, new re expr, new im expr)
       struct Upd {
         uint32_t u;

@@ -152,6 +152,7 @@ struct HElem {
 
 struct Group {
   uint32_t mask = 0;
+  uint32_t pmask = 0;  // generated kernels only: bits outside `mask` that phases of this group are predicated on
   std::vector<HElem> elems;
 };
 
@@ -283,8 +284,10 @@ struct Emitter {
         }
       } else if (e.type == E_PHASE) {
         d.kind = JElem::PH;
-        d.lm = sub_mask(e.lmask);
-        d.lv = sub_mask(e.lval);
+        d.lm = sub_mask(e.lmask & mask);
+        d.lv = sub_mask(e.lval & mask);
+        d.pm = e.lmask & ~mask;  // bits of the phase outside the group: a predicate on the thread's tile-local index
+        d.pv = e.lval & ~mask;
         d.m[0] = e.m[0];
         for (size_t k = 0; k < e.terms.size(); ++k) {
           JCondPhase t = {e.terms[k].gmask, e.terms[k].gval, e.terms[k].w};
@@ -528,10 +531,10 @@ struct Emitter {
   // Emit the open groups that touch `lmask` (or all of them).  Groups on disjoint bits commute,
   // so the ones leaving together are first packed into as few 3-bit super-ops as possible
   // (three 1-bit groups, or a 2-bit and a 1-bit group, share one shared-memory round trip).
-  void flush_touching(uint32_t lmask, bool all) {
+  void flush_touching(uint32_t lmask, bool all, bool by_predicate = false) {
     std::vector<Group> out;
     for (size_t i = 0; i < open.size();) {
-      if (all || (open[i].mask & lmask)) {
+      if (all || ((by_predicate ? open[i].pmask : open[i].mask) & lmask)) {
         out.push_back(open[i]);
         open.erase(open.begin() + i);
       } else {
@@ -546,6 +549,7 @@ struct Emitter {
         for (size_t j = 0; j < packed.size() && !placed; ++j)
           if ((uint32_t)popc(packed[j].mask | out[i].mask) <= gbits) {
             packed[j].mask |= out[i].mask;
+            packed[j].pmask |= out[i].pmask;
             packed[j].elems.insert(packed[j].elems.end(), out[i].elems.begin(), out[i].elems.end());
             placed = true;
           }
@@ -559,6 +563,7 @@ struct Emitter {
           for (size_t i = 0; i < open.size() && (uint32_t)popc(packed[j].mask) < gbits;) {
             if ((uint32_t)popc(packed[j].mask | open[i].mask) <= gbits) {
               packed[j].mask |= open[i].mask;
+              packed[j].pmask |= open[i].pmask;
               packed[j].elems.insert(packed[j].elems.end(), open[i].elems.begin(), open[i].elems.end());
               open.erase(open.begin() + (long)i);
             } else {
@@ -668,6 +673,14 @@ struct Emitter {
       emit_group(g);
       return;
     }
+    if (jmode) {
+      // A group holding a phase predicated on bit b must run before anything that acts NON-diagonally on b
+      // (everything diagonal on b commutes with it).
+      const uint32_t ndb = nd_bits(e);
+      bool any = false;
+      for (size_t i = 0; i < open.size(); ++i) any |= (open[i].pmask & ndb) != 0;
+      if (any) flush_touching(ndb, false, true);
+    }
     uint32_t um = bm;
     std::vector<size_t> hit;
     for (size_t i = 0; i < open.size(); ++i)
@@ -675,6 +688,40 @@ struct Emitter {
         hit.push_back(i);
         um |= open[i].mask;
       }
+    if (jmode && e.type == E_PHASE && (uint32_t)popc(um) > gbits && !hit.empty()) {
+      // A diagonal op needs none of its bits in registers: instead of closing every group it touches and
+      // opening a new one, it joins the group that holds most of its bits; its other bits become per-thread
+      // predicates there (JElem::pm).  The other groups on those bits leave first: they precede it in program order.
+      size_t best = hit[0];
+      for (size_t h = 1; h < hit.size(); ++h)
+        if (popc(open[hit[h]].mask & bm) > popc(open[best].mask & bm)) best = hit[h];
+      Group host = open[best];
+      open.erase(open.begin() + (long)best);
+      const uint32_t outside = bm & ~host.mask;
+      flush_touching(outside, false);
+      bool folded = false;
+      if (cfg->peephole) {
+        std::vector<HElem> &el = host.elems;
+        for (size_t k = el.size(); k-- > 0;) {
+          HElem &prev = el[k];
+          const bool terms_ok = prev.type != E_PHASE || (prev.terms.size() < 48 && e.terms.size() < 48);
+          if (terms_ok && fold_into(prev, e, cfg->fold_cond_phases, cfg->keep_real)) {
+            folded = true;
+            if (is_identity(prev)) el.erase(el.begin() + (long)k);
+            break;
+          }
+          if (!cfg->lookback || !commute(prev, e)) break;
+        }
+      }
+      if (!folded) host.elems.push_back(e);
+      if ((uint32_t)popc(host.mask | bm) <= gbits)
+        host.mask |= bm;  // the others are gone: the bits fit after all
+      else
+        host.pmask |= outside;
+      host.pmask &= ~host.mask;
+      if (!host.elems.empty()) open.push_back(host);
+      return;
+    }
     if ((uint32_t)popc(um) > gbits) {
       flush_touching(bm, false);
       Group g;
@@ -685,8 +732,11 @@ struct Emitter {
     }
     Group merged;
     merged.mask = um;
-    for (size_t h = 0; h < hit.size(); ++h)  // disjoint groups commute: any order
+    for (size_t h = 0; h < hit.size(); ++h) {  // disjoint groups commute: any order
       merged.elems.insert(merged.elems.end(), open[hit[h]].elems.begin(), open[hit[h]].elems.end());
+      merged.pmask |= open[hit[h]].pmask;
+    }
+    merged.pmask &= ~merged.mask;
     for (size_t h = hit.size(); h-- > 0;) open.erase(open.begin() + hit[h]);
     bool folded = false;
     if (cfg->peephole) {

@@ -198,6 +198,8 @@ struct JElem {
   uint32_t j = 0;                 // D1 / X / HAD: target sub-bit
   uint32_t lc = 0;                // D1 / X: control sub-mask (the op acts on pairs whose other bits contain lc)
   uint32_t lm = 0, lv = 0;        // PH: acts on sub-indices c with (c & lm) == lv
+  uint32_t pm = 0, pv = 0;        // PH: ... in the groups whose TILE-LOCAL index t satisfies (t & pm) == pv: a diagonal op
+                                  //     needs none of its bits in registers, a bit outside the group is a per-thread predicate
   uint64_t gmask = 0, gval = 0;   // CTA-uniform condition on the tile's base index (gmask == 0: none)
   cplx m[4];                      // D1: m00 m01 m10 m11; PH: factor in m[0]
   std::vector<JCondPhase> terms;  // PH: further factors, each under its own CTA-uniform condition
