@@ -461,12 +461,15 @@ int state_alloc(qipb200_ctx *ctx, qip_prec prec, uint32_t n, int rank, int world
   s->phys_of_logical.resize(n);
   for (uint32_t b = 0; b < n; ++b) s->phys_of_logical[b] = b;
   cudaError_t e = cudaSuccess;
-  if (ctx->pool_buf && ctx->pool_bytes == s->bytes) {  // the buffer a freed state of this size left behind
+  if (world == 1 && ctx->pool_buf && ctx->pool_bytes == s->bytes) {  // the buffer a freed state of this size left behind
     s->buf = ctx->pool_buf;
     ctx->pool_buf = nullptr;
     ctx->pool_bytes = 0;
   } else {
-    e = cudaMalloc(&s->buf, s->bytes);
+    // a sharded state carries the staging area of the push exchange behind its amplitudes: one allocation, so the
+    // one CUDA-IPC handle (or peer pointer) of the shard covers both
+    s->has_stage = world > 1 && !getenv("QIPB200_NO_STAGING");
+    e = cudaMalloc(&s->buf, s->has_stage ? 2 * s->bytes : s->bytes);
   }
   if (e == cudaSuccess) e = cudaMemsetAsync(s->buf, 0, s->bytes, ctx->stream);
   if (e == cudaSuccess && world > 1) {
@@ -498,7 +501,11 @@ int check_barrier_error(qipb200_state *s) {
   return QIPB200_OK;
 }
 
-// Swap physical rank bit R (>= n_local) with local bit l: NVLink pair exchange.
+// Swap physical rank bit R (>= n_local) with local bit l.
+// Protocol (push through staging, dist.cu): [barrier] every rank pushes the half it gives away (bit l == !rb) into
+// the partner's staging area [barrier] every rank copies its own staging half into the slots it gave away.  When the
+// last tile pass before the exchange already pushed the half (s->send_stage == 2, schedule.cu) only the tail runs.
+// Without a staging area (QIPB200_NO_STAGING): the in-place pair exchange of round 1.
 int exchange_bits(qipb200_state *s, uint32_t R, uint32_t l) {
   qipb200_ctx *ctx = s->ctx;
   if (!s->ipc_ready)
@@ -506,16 +513,35 @@ int exchange_bits(qipb200_state *s, uint32_t R, uint32_t l) {
   const uint32_t r = R - s->n_local;
   const int partner = s->rank ^ (1 << r);
   const int rb = (s->rank >> r) & 1;
-  uint32_t s_bit = s->n_local - 1;
-  if (s_bit == l) s_bit = s->n_local - 2;
-  ProfileScope prof(ctx, 1);
-  CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch,
-                              s->flags + kFlagErrorSlot, ctx->stream, &ctx->launches));
-  CU(ctx, launch_pair_exchange(s->prec, s->buf, s->peer_buf[partner], s->n_local, l, s_bit, rb, ctx->stream,
-                               &ctx->launches));
-  ++ctx->exchange_launches;
-  CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch,
-                              s->flags + kFlagErrorSlot, ctx->stream, &ctx->launches));
+  {
+    ProfileScope prof(ctx, 1);
+    if (s->has_stage) {
+      const int give = 1 - rb;
+      char *my_stage = (char *)s->buf + s->bytes;
+      char *peer_stage = (char *)s->peer_buf[partner] + s->bytes;
+      if (s->send_stage && (s->send_R != R || s->send_l != l))
+        return set_err(ctx, QIPB200_ERR_COMM, "internal: the tile pass pushed a different half than the exchange needs");
+      if (s->send_stage < 1)
+        CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch,
+                                    s->flags + kFlagErrorSlot, ctx->stream, &ctx->launches));
+      if (s->send_stage < 2)
+        CU(ctx, launch_copy_half(s->prec, s->buf, peer_stage, s->n_local, l, give, true, ctx->stream, &ctx->launches));
+      s->send_stage = 0;
+      CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch,
+                                  s->flags + kFlagErrorSlot, ctx->stream, &ctx->launches));
+      CU(ctx, launch_copy_half(s->prec, my_stage, s->buf, s->n_local, l, give, false, ctx->stream, &ctx->launches));
+    } else {
+      uint32_t s_bit = s->n_local - 1;
+      if (s_bit == l) s_bit = s->n_local - 2;
+      CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch,
+                                  s->flags + kFlagErrorSlot, ctx->stream, &ctx->launches));
+      CU(ctx, launch_pair_exchange(s->prec, s->buf, s->peer_buf[partner], s->n_local, l, s_bit, rb, ctx->stream,
+                                   &ctx->launches));
+      CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch,
+                                  s->flags + kFlagErrorSlot, ctx->stream, &ctx->launches));
+    }
+    ++ctx->exchange_launches;
+  }
   s->exchange_bytes += (uint64_t)amp_bytes(s->prec) << (s->n_local - 1);
   // update the map: the logical bits living at R and l trade places
   for (uint32_t b = 0; b < s->n; ++b) {
@@ -702,6 +728,67 @@ int apply_flat_local(qipb200_state *s, const FlatOp &f_in) {
 int report_error(qipb200_state *s, int status, const std::string &msg) { return set_err(s->ctx, status, msg); }
 int report_cuda_error(qipb200_state *s, cudaError_t e, const char *what) { return cuda_fail(s->ctx, e, what); }
 
+// The local bit a migration evicts: not used by this op, next non-diagonal use furthest away.
+static int choose_victim(const qipb200_state *s, const FlatOp &f, const uint64_t *next_use) {
+  uint64_t used = f.ctrl_mask;
+  for (uint32_t j = 0; j < f.k; ++j) used |= 1ull << f.idx_bits[j];
+  int best = -1;
+  uint64_t best_key = 0;
+  for (uint32_t l = 0; l < s->n_local; ++l) {
+    if ((used >> l) & 1ull) continue;
+    uint64_t key = 1;
+    if (next_use) {
+      uint32_t logical = 0;
+      for (uint32_t b = 0; b < s->n; ++b)
+        if (s->phys_of_logical[b] == l) logical = b;
+      key = next_use[logical] + 1;
+    }
+    // prefer high bits on ties: low bits give the exchange its coalescing
+    if (best < 0 || key > best_key || (key == best_key && l > (uint32_t)best)) {
+      best = (int)l;
+      best_key = key;
+    }
+  }
+  return best;
+}
+
+// The first exchange compile_and_localize(op) would perform under the current layout (none: returns false).
+bool peek_first_exchange(const qipb200_state *s, const qip_op *op, const uint64_t *next_use, uint32_t *R, uint32_t *l) {
+  if (s->world == 1) return false;
+  FlatOp f;
+  std::string err;
+  if (compile_op(op, s->prec, s->n, &f, &err, s->phys_of_logical.data()) != QIPB200_OK) return false;
+  if (f.cls == CLASS_BITSWAP && f.ctrl_mask == 0) return false;  // a relabelling: nothing moves
+  std::vector<uint32_t> nd;
+  nondiag_bits(f, &nd);
+  for (size_t i = 0; i < nd.size(); ++i) {
+    if (nd[i] < s->n_local) continue;
+    const int v = choose_victim(s, f, next_use);
+    if (v < 0) return false;
+    *R = nd[i];
+    *l = (uint32_t)v;
+    return true;
+  }
+  return false;
+}
+
+// The flag barrier that opens an exchange (every rank has emptied its staging area), for the tile pass that pushes
+// the give-half itself; afterwards exchange_bits(R, l) only runs the tail of the protocol.
+int exchange_open_for_send(qipb200_state *s, uint32_t R, uint32_t l, void **peer_stage, int *give) {
+  qipb200_ctx *ctx = s->ctx;
+  if (!s->ipc_ready || !s->has_stage) return QIPB200_ERR_UNSUPPORTED;
+  const uint32_t r = R - s->n_local;
+  const int partner = s->rank ^ (1 << r);
+  *give = 1 - ((s->rank >> r) & 1);
+  *peer_stage = (char *)s->peer_buf[partner] + s->bytes;
+  CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch, s->flags + kFlagErrorSlot,
+                              ctx->stream, &ctx->launches));
+  s->send_stage = 1;  // the caller raises it to 2 once the pushing pass is launched
+  s->send_R = R;
+  s->send_l = l;
+  return QIPB200_OK;
+}
+
 // Compile `op` against the current layout and migrate rank-held target bits to
 // local bits if needed.  `next_use` (optional, n entries indexed by logical bit):
 // position in the schedule of the next non-diagonal use, used to pick the victim.
@@ -729,26 +816,7 @@ int compile_and_localize(qipb200_state *s, const qip_op *op, FlatOp *f, const ui
   nondiag_bits(*f, &nd);
   for (size_t i = 0; i < nd.size(); ++i) {
     if (nd[i] < s->n_local) continue;
-    // choose the local bit to evict: not used by this op, next non-diagonal use furthest away
-    uint64_t used = f->ctrl_mask;
-    for (uint32_t j = 0; j < f->k; ++j) used |= 1ull << f->idx_bits[j];
-    int best = -1;
-    uint64_t best_key = 0;
-    for (uint32_t l = 0; l < s->n_local; ++l) {
-      if ((used >> l) & 1ull) continue;
-      uint64_t key = 1;
-      if (next_use) {
-        uint32_t logical = 0;
-        for (uint32_t b = 0; b < s->n; ++b)
-          if (s->phys_of_logical[b] == l) logical = b;
-        key = next_use[logical] + 1;
-      }
-      // prefer high bits on ties: low bits give the exchange its coalescing
-      if (best < 0 || key > best_key || (key == best_key && l > (uint32_t)best)) {
-        best = (int)l;
-        best_key = key;
-      }
-    }
+    const int best = choose_victim(s, *f, next_use);
     if (best < 0) return set_err(ctx, QIPB200_ERR_UNSUPPORTED, "op touches every local bit: cannot migrate a rank bit");
     if ((st = exchange_bits(s, nd[i], (uint32_t)best)) != QIPB200_OK) return st;
     // recompile after every move so later decisions see the new layout

@@ -95,6 +95,60 @@ cudaError_t launch_pair_exchange(qip_prec prec, void *mine, void *peer, uint32_t
   return cudaGetLastError();
 }
 
+// ---- push exchange through a staging buffer -----------------------------------------------------------
+// Measured (r2f, 2 x B200): the in-place pair exchange above moves 8.6 GB per direction in 16 ms = 535 GB/s -- half of
+// the traffic of each direction are responses to the partner's remote LOADS, and more loads in flight per lane did not
+// help.  Writes are posted: every rank PUSHES the half it gives away into the partner's staging buffer (slot of the
+// amplitude it becomes there: index with bit l flipped), a flag barrier later each rank copies its staging half into
+// the slots it gave away (local HBM traffic).  The push can also be done by the last tile pass before the exchange
+// (jit_codegen: tiles of the give-half are TMA-stored to the partner's staging buffer instead of the local state).
+struct HalfArgs {
+  uint32_t pos;      // the bit l
+  uint64_t fixed;    // give_val << l
+  uint64_t flip;     // 1 << l (0 for the unstage copy)
+  uint64_t n_items;  // 2^(n_local-1)
+};
+
+template <typename V, int U>
+__global__ void __launch_bounds__(kThreads) k_copy_half(const V *__restrict__ src, V *__restrict__ dst, const HalfArgs a) {
+  const uint64_t w0 = (uint64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
+  V x[U];
+  uint64_t ii[U];
+  bool on[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const uint64_t w = w0 + (uint64_t)u * kThreads;
+    on[u] = w < a.n_items;
+    uint64_t idx = on[u] ? w : 0;
+    idx = ((idx >> a.pos) << (a.pos + 1)) | (idx & ((1ull << a.pos) - 1ull));
+    ii[u] = idx | a.fixed;
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (on[u]) x[u] = src[ii[u]];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (on[u]) dst[ii[u] ^ a.flip] = x[u];
+}
+
+// dst[i ^ flip] = src[i] for every i whose bit l equals give_val (flip_bit: push to the partner; else a plain half copy)
+cudaError_t launch_copy_half(qip_prec prec, const void *src, void *dst, uint32_t n_local, uint32_t l, int give_val, bool flip_bit,
+                             cudaStream_t s, uint64_t *launches) {
+  if (n_local < 1 || l >= n_local) return cudaErrorInvalidValue;
+  HalfArgs a;
+  a.pos = l;
+  a.fixed = (uint64_t)(give_val ? 1 : 0) << l;
+  a.flip = flip_bit ? (1ull << l) : 0ull;
+  a.n_items = 1ull << (n_local - 1);
+  const unsigned grid = (unsigned)((a.n_items + (uint64_t)kThreads * 4 - 1) / ((uint64_t)kThreads * 4));
+  if (prec == QIP_F32)
+    k_copy_half<float2, 4><<<grid, kThreads, 0, s>>>((const float2 *)src, (float2 *)dst, a);
+  else
+    k_copy_half<double2, 4><<<grid, kThreads, 0, s>>>((const double2 *)src, (double2 *)dst, a);
+  ++*launches;
+  return cudaGetLastError();
+}
+
 // ---- flag barrier -----------------------------------------------------------------
 struct BarrierArgs {
   uint32_t *peer_flags[kMaxWorld];  // peer_flags[t] = rank t's flag page (mapped), slot [rank] is ours

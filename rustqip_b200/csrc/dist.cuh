@@ -23,6 +23,11 @@ static const size_t kFlagAllocBytes = kCommOffsetBytes + (size_t)kCommDoubles * 
 cudaError_t launch_pair_exchange(qip_prec prec, void *mine, void *peer, uint32_t n_local, uint32_t l,
                                  uint32_t s_bit, int rb, cudaStream_t s, uint64_t *launches);
 
+// dst[i ^ (flip_bit ? 1<<l : 0)] = src[i] for every i of the 2^n_local amplitudes whose bit l equals give_val:
+// the push of the half a rank gives away into the partner's staging buffer, and the copy out of a rank's own staging.
+cudaError_t launch_copy_half(qip_prec prec, const void *src, void *dst, uint32_t n_local, uint32_t l, int give_val, bool flip_bit,
+                             cudaStream_t s, uint64_t *launches);
+
 // All-rank barrier through peer-mapped flag pages; stream-ordered.
 cudaError_t launch_flag_barrier(uint32_t *const *peer_flags, uint32_t *my_flags, int rank, int world,
                                 uint32_t epoch, uint32_t *error_word, cudaStream_t s, uint64_t *launches);

@@ -711,6 +711,9 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
   if (NG) src << "  R gw[2 * NG];\n";
   src << "  unsigned hi_pos[8];\n";
   if (NPH) src << "  unsigned pt_begin[NPH + 1];\n";
+  // multi-GPU: tiles whose index bit `send_bit` equals `send_val` are stored to `tmap_out` (the partner's staging
+  // area) at the index with that bit flipped -- the push half of a qubit migration; send_bit >= 64: off
+  src << "  unsigned send_bit, send_val;\n";
   src << "};\n";
   src << R"(#ifdef QIP_JIT_HOST
 #include <cmath>
@@ -796,7 +799,8 @@ __device__ __forceinline__ void box_coords(const JP& p, u64 idx, int* c) {
   c[3] = (int)(idx >> h3);
 }
 extern "C" __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM)
-qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constant__ CUtensorMap tmap) {
+qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constant__ CUtensorMap tmap,
+         const __grid_constant__ CUtensorMap tmap_out) {
   extern __shared__ __align__(1024) unsigned char sm[];
   const unsigned tid = threadIdx.x;
   const u64 base = tile_base(p, (u64)blockIdx.x);
@@ -845,13 +849,22 @@ qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constan
 #pragma unroll 1
     for (unsigned b = 0; b < NBOX; ++b) {
       int c[4];
-      box_coords(p, base + p.box_off[b], c);
-      asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(&tmap),
+      u64 idx = base + p.box_off[b];
+      const CUtensorMap* tm = &tmap;
+      if (p.send_bit < 64u && ((idx >> p.send_bit) & 1ull) == (u64)p.send_val) {
+        tm = &tmap_out;
+        idx ^= 1ull << p.send_bit;
+      }
+      box_coords(p, idx, c);
+      asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(tm),
                    "r"(smb + b * BOX_BYTES), "r"(0), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3])
                    : "memory");
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (p.send_bit < 64u)
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores to the partner: wait until they are performed
+    else
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
   (void)psi;
 }
@@ -917,6 +930,12 @@ qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constan
       at += (uint32_t)phn_terms[i].size();
     }
     put(&at, 4);
+  }
+  out->send_offset = (uint32_t)blob.size();
+  {
+    const uint32_t off_bit = 64u, val = 0u;
+    put(&off_bit, 4);
+    put(&val, 4);
   }
   while (blob.size() % 8) blob.push_back(0);  // sizeof(JP): the struct is 8-byte aligned
 

@@ -27,6 +27,7 @@ struct JitProgram {
   uint32_t smem_bytes = 0;            // dynamic shared memory of one CTA
   uint32_t threads = 256;
   uint32_t tiles_log2_sub = 0;        // grid = 1 << (n_local - T)
+  uint32_t send_offset = 0;           // byte offset of JP::send_bit / send_val in `params` (patched per launch)
   // statistics
   uint32_t n_super = 0, n_elems = 0, n_cta_barriers = 0, n_warp_syncs = 0, n_renamed = 0, n_consts = 0;
 };

@@ -232,7 +232,7 @@ void jit_wait_all(uint64_t *n_compiled, double *total_ms) {
 
 cudaError_t jit_launch(const std::shared_ptr<const JitCubin> &cubin, std::vector<std::pair<const JitCubin *, JitLoaded>> *loaded,
                        const JitProgram &prog, void *psi, uint32_t n_local, const CUtensorMap &tmap, cudaStream_t stream,
-                       std::string *err) {
+                       std::string *err, const CUtensorMap *tmap_out, uint32_t send_bit, uint32_t send_val) {
   Driver &d = driver();
   if (!d.ok || !cubin || !cubin->ok) {
     if (err) *err = !d.ok ? d.why : "no cubin";
@@ -259,7 +259,13 @@ cudaError_t jit_launch(const std::shared_ptr<const JitCubin> &cubin, std::vector
     L = &loaded->back().second;
   }
   alignas(64) CUtensorMap tm = tmap;
-  void *args[3] = {&psi, const_cast<unsigned char *>(prog.params.data()), &tm};
+  alignas(64) CUtensorMap tm_out = tmap_out ? *tmap_out : tmap;
+  std::vector<unsigned char> params = prog.params;  // the send fields are per launch
+  if (tmap_out && prog.send_offset + 8 <= params.size()) {
+    memcpy(params.data() + prog.send_offset, &send_bit, 4);
+    memcpy(params.data() + prog.send_offset + 4, &send_val, 4);
+  }
+  void *args[4] = {&psi, params.data(), &tm, &tm_out};
   const unsigned grid = 1u << (n_local - prog.tiles_log2_sub);
   const CUresult r = d.launch(L->fn, grid, 1, 1, prog.threads, 1, 1, prog.smem_bytes, (CUstream)stream, args, nullptr);
   if (r != CUDA_SUCCESS) return fail(r, "cuLaunchKernel");

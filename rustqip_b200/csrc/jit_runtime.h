@@ -45,9 +45,11 @@ std::shared_ptr<const JitCubin> jit_request(const std::string &source, bool wait
 void jit_wait_all(uint64_t *n_compiled, double *total_ms);
 
 // Load (once per context) and launch.  `loaded` is the context's module cache keyed by the cubin pointer.
+// `tmap_out` / `send_bit` / `send_val` (optional): tiles whose index bit send_bit equals send_val are stored
+// through tmap_out at the index with that bit flipped (the push half of a multi-GPU qubit migration).
 cudaError_t jit_launch(const std::shared_ptr<const JitCubin> &cubin, std::vector<std::pair<const JitCubin *, JitLoaded>> *loaded,
                        const JitProgram &prog, void *psi, uint32_t n_local, const CUtensorMap &tmap, cudaStream_t stream,
-                       std::string *err);
+                       std::string *err, const CUtensorMap *tmap_out = nullptr, uint32_t send_bit = 64, uint32_t send_val = 0);
 
 void jit_unload(std::vector<std::pair<const JitCubin *, JitLoaded>> *loaded);
 

@@ -43,8 +43,14 @@ bool needs_exchange(const qipb200_state *s, const FlatOp &f) {
   return false;
 }
 
+// The push half of the qubit migration that follows this epoch, to be done by the epoch's last tile pass.
+struct SendPlan {
+  bool on = false;
+  uint32_t R = 0, l = 0;
+};
+
 int execute_steps(qipb200_state *s, const std::vector<PlanStep> &steps, const std::vector<FlatOp> &local,
-                  const PlanConfig &cfg) {
+                  const PlanConfig &cfg, const SendPlan &send = SendPlan()) {
   qipb200_ctx *ctx = s->ctx;
   int st = QIPB200_OK;
   PassParams *pp = new PassParams();
@@ -73,10 +79,31 @@ int execute_steps(qipb200_state *s, const std::vector<PlanStep> &steps, const st
         std::shared_ptr<const JitCubin> cubin = jit_request(progs[i].source, jmode == JIT_SYNC);
         if (cubin && !cubin->ok) ctx->jit_note = "NVRTC: " + cubin->log;
         if (cubin && cubin->ok) {
+          // Last pass before a migration: the tiles of the half this rank gives away go straight to the partner's
+          // staging area (TMA stores over NVLink), provided bit l is constant within a TMA box of this pass.
+          alignas(64) CUtensorMap tmap_out;
+          const CUtensorMap *tmo = nullptr;
+          uint32_t send_bit = 64, send_val = 0;
+          const PassHeader &ph = steps[i].pass.hdr;
+          if (send.on && i + 1 == steps.size() && send.l >= ph.L && send.l != ph.hi_pos[0] && send.l != ph.hi_pos[1] &&
+              send.l != ph.hi_pos[2]) {
+            void *peer_stage = nullptr;
+            int give = 0;
+            memset(&tmap_out, 0, sizeof(tmap_out));
+            if (exchange_open_for_send(s, send.R, send.l, &peer_stage, &give) == QIPB200_OK) {
+              if (make_tile_map(&tmap_out, s->prec, peer_stage, s->n_local, ph)) {
+                tmo = &tmap_out;
+                send_bit = send.l;
+                send_val = (uint32_t)give;
+              }  // else: the opening barrier stays queued (send_stage 1), exchange_bits pushes with its own kernel
+            }
+          }
           ProfileScope prof(ctx, 0);
           std::string err;
-          cudaError_t e = jit_launch(cubin, &ctx->jit_loaded, progs[i], s->buf, s->n_local, tmap, ctx->stream, &err);
+          cudaError_t e = jit_launch(cubin, &ctx->jit_loaded, progs[i], s->buf, s->n_local, tmap, ctx->stream, &err, tmo, send_bit,
+                                     send_val);
           if (e == cudaSuccess) {
+            if (tmo) s->send_stage = 2;
             ++ctx->launches;
             ++ctx->tile_launches;
             ++ctx->jit_launches;
@@ -158,9 +185,6 @@ int run_fused(qipb200_state *s, const qip_op *ops, size_t n_ops, const std::vect
     std::vector<PlanStep> steps;
     std::vector<size_t> left;  // indices into `local`
     plan_passes(local, s->n_local, s->prec, cfg, &steps, &blocked, &left, &dep);
-    int st = execute_steps(s, steps, local, cfg);
-    if (st != QIPB200_OK) return st;
-    if (left.empty()) break;
     // the first blocked op (program order) decides the migration; identical on every rank
     size_t first_blocked = left.size();
     for (size_t i = 0; i < left.size(); ++i)
@@ -168,6 +192,19 @@ int run_fused(qipb200_state *s, const qip_op *ops, size_t n_ops, const std::vect
         first_blocked = i;
         break;
       }
+    // The migration that ends this epoch is known before the epoch runs: its last tile pass can push the half this
+    // rank gives away while it stores its tiles (each rank decides for itself; a rank whose last step cannot do it
+    // pushes with the stand-alone kernel inside exchange_bits -- the partner does not care how its staging area fills).
+    SendPlan send;
+    static const bool fused_send = !getenv("QIPB200_NO_FUSED_SEND");
+    if (fused_send && s->has_stage && first_blocked != left.size() && !steps.empty() && steps.back().is_pass) {
+      const size_t op_idx = remaining[left[first_blocked]];
+      const uint64_t *nu = next_use.empty() ? nullptr : &next_use[(op_idx + 1) * s->n];
+      send.on = peek_first_exchange(s, &ops[op_idx], nu, &send.R, &send.l);
+    }
+    int st = execute_steps(s, steps, local, cfg, send);
+    if (st != QIPB200_OK) return st;
+    if (left.empty()) break;
     if (first_blocked == left.size())
       return report_error(s, QIPB200_ERR_UNSUPPORTED, "internal: schedule made no progress");
     // Migrate the first blocked op's qubit only.  (Migrating the qubits of the other waiting

@@ -51,7 +51,11 @@ struct qipb200_state {
   uint32_t n = 0;        // qubits of the whole state
   uint32_t n_local = 0;  // index bits held by this rank
   int rank = 0, world = 1;
-  void *buf = nullptr;      // 2^n_local amplitudes
+  void *buf = nullptr;      // 2^n_local amplitudes (sharded states: followed by a staging area of the same size)
+  bool has_stage = false;   // the allocation of `buf` is 2 * bytes: [state | staging of the push exchange]
+  int send_stage = 0;       // pending exchange: 0 nothing yet, 1 its opening barrier is queued, 2 ... and the last tile
+                            // pass has pushed the give-half into the partner's staging area
+  uint32_t send_R = 0, send_l = 0;  // ... for this (rank bit, local bit) pair
   void *scratch = nullptr;  // same size, lazily allocated (out-of-place row kernel only)
   size_t bytes = 0;
   // logical index bit b (= n-1-q) -> physical index bit.  Physical bits >= n_local are
