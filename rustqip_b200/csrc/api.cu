@@ -468,7 +468,11 @@ int state_alloc(qipb200_ctx *ctx, qip_prec prec, uint32_t n, int rank, int world
   } else {
     // a sharded state carries the staging area of the push exchange behind its amplitudes: one allocation, so the
     // one CUDA-IPC handle (or peer pointer) of the shard covers both
-    s->has_stage = world > 1 && !getenv("QIPB200_NO_STAGING");
+    // (opt-in, QIPB200_STAGED_EXCHANGE=1: measured r2h on 2 x B200 -- in-place pair exchange 16.1 ms per migration,
+    // stand-alone push + copy 20.5 ms, push fused into the last pass +4.0 ms on that pass and a 14.3 ms tail: SM-issued
+    // NVLink traffic tops out near 535-600 GB/s per direction whichever way it is issued, so the variant that moves
+    // the fewest bytes locally wins)
+    s->has_stage = world > 1 && getenv("QIPB200_STAGED_EXCHANGE") != nullptr;
     e = cudaMalloc(&s->buf, s->has_stage ? 2 * s->bytes : s->bytes);
   }
   if (e == cudaSuccess) e = cudaMemsetAsync(s->buf, 0, s->bytes, ctx->stream);
@@ -505,7 +509,7 @@ int check_barrier_error(qipb200_state *s) {
 // Protocol (push through staging, dist.cu): [barrier] every rank pushes the half it gives away (bit l == !rb) into
 // the partner's staging area [barrier] every rank copies its own staging half into the slots it gave away.  When the
 // last tile pass before the exchange already pushed the half (s->send_stage == 2, schedule.cu) only the tail runs.
-// Without a staging area (QIPB200_NO_STAGING): the in-place pair exchange of round 1.
+// Default (no staging area): the in-place pair exchange (k_pair_exchange), which measured fastest (see state_alloc).
 int exchange_bits(qipb200_state *s, uint32_t R, uint32_t l) {
   qipb200_ctx *ctx = s->ctx;
   if (!s->ipc_ready)

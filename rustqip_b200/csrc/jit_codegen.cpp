@@ -41,6 +41,11 @@ struct DElem {
   std::vector<uint32_t> mb;  // DK: sub-bits of the dense block (ascending)
   std::vector<double> mk;    // DK: 2^k x 2^k complex (re,im), row-major
   uint32_t slot = 0;       // PHN: factor-table slot
+  struct TT {
+    uint32_t pm, pv;
+    double re, im;
+  };
+  std::vector<TT> tt;      // PH: thread-conditional factors (product formed in registers, applied once)
 };
 
 // value as it will be seen by a kernel of precision `f64` (constants are pooled after rounding)
@@ -89,9 +94,14 @@ bool convert_group(const JGroup &jg, bool f64, std::vector<Cond> &conds, std::ve
         d.lm = e.lm, d.lv = e.lv;
         d.pm = e.pm, d.pv = e.pv;
         d.m[0] = as_prec(f64, e.m[0].real()), d.m[1] = as_prec(f64, e.m[0].imag());
+        for (size_t k = 0; k < e.tterms.size(); ++k) {
+          DElem::TT t = {e.tterms[k].pm, e.tterms[k].pv, as_prec(f64, e.tterms[k].w.real()), as_prec(f64, e.tterms[k].w.imag())};
+          d.tt.push_back(t);
+        }
         if (e.terms.empty()) {
           d.kind = DElem::PH;
         } else {
+
           if (e.gmask) return *why = "conditional phase run under a condition", false;
           d.kind = DElem::PHN;
           d.slot = (uint32_t)phn_terms->size();
@@ -354,7 +364,7 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
       k += len;
     }
     bool needs_tt = false;
-    for (size_t i = 0; i < supers[s].size(); ++i) needs_tt |= supers[s][i].pm != 0;
+    for (size_t i = 0; i < supers[s].size(); ++i) needs_tt |= supers[s][i].pm != 0 || !supers[s][i].tt.empty();
     if (needs_tt) fn << "  const unsigned tt0 = t;\n";  // tile-local index of this thread's group (sub-bits zero)
     fn << (f64 ? "  t ^= (t >> 3) & 7u;\n  const unsigned a0 = t << 4;\n" : "  t ^= ((t >> 4) & 7u) << 1;\n  const unsigned a0 = t << 3;\n");
     // condition words this super-op tests
@@ -587,6 +597,31 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
           }
           upd.push_back(a);
           upd.push_back(b);
+        }
+      } else if ((d.kind == DElem::PH || d.kind == DElem::PHN) && !d.tt.empty()) {
+        // factor = base * product of the factors whose thread predicate holds: scalar work, then ONE application
+        const std::string wr = g.fresh(), wi = g.fresh();
+        auto lit = [&](double v) -> std::string {
+          if (v == 0.0) return f64 ? "0.0" : "0.0f";
+          if (v == 1.0) return f64 ? "1.0" : "1.0f";
+          if (v == -1.0) return f64 ? "-1.0" : "-1.0f";
+          return g.K(v);
+        };
+        if (d.kind == DElem::PHN)  // the CTA-conditional part of the product was formed once per CTA (factor table)
+          fn << "    " << RT << " " << wr << " = tbl[" << 2 * d.slot << "], " << wi << " = tbl[" << 2 * d.slot + 1 << "];\n";
+        else
+          fn << "    " << RT << " " << wr << " = " << lit(d.m[0]) << ", " << wi << " = " << lit(d.m[1]) << ";\n";
+        for (size_t k = 0; k < d.tt.size(); ++k) {
+          const std::string nr2 = g.fresh(), ni2 = g.fresh();
+          fn << "    if ((tt & " << d.tt[k].pm << "u) == " << d.tt[k].pv << "u) { const " << RT << " " << nr2 << " = "
+             << g.chain(Terms{{-d.tt[k].im, wi}, {d.tt[k].re, wr}}) << ", " << ni2 << " = "
+             << g.chain(Terms{{d.tt[k].im, wr}, {d.tt[k].re, wi}}) << "; " << wr << " = " << nr2 << "; " << wi << " = " << ni2 << "; }\n";
+        }
+        for (uint32_t c = 0; c < NA; ++c) {
+          if ((c & d.lm) != d.lv) continue;
+          Upd a = {c, "QFMA(" + wr + ", " + vr[c] + ", -(" + wi + " * " + vi[c] + "))",
+                   "QFMA(" + wr + ", " + vi[c] + ", (" + wi + " * " + vr[c] + "))"};
+          upd.push_back(a);
         }
       } else if (d.kind == DElem::PH) {  // QIP_PH: re' = fma(wr, re, -(wi*im)); im' = fma(wr, im, wi*re)
         for (uint32_t c = 0; c < NA; ++c) {

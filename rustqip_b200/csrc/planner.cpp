@@ -305,6 +305,66 @@ struct Emitter {
       }
       jg.elems.push_back(d);
     }
+    // Runs of consecutive unconditional phases (all diagonal: any order) that act on the same amplitudes of the
+    // group: one element with thread-conditional factors.
+    {
+      std::vector<JElem> out;
+      for (size_t i = 0; i < jg.elems.size();) {
+        size_t e = i;
+        auto plain_phase = [](const JElem &x) { return x.kind == JElem::PH && x.gmask == 0; };
+        while (e < jg.elems.size() && plain_phase(jg.elems[e])) ++e;
+        if (e == i) {
+          out.push_back(jg.elems[i++]);
+          continue;
+        }
+        std::vector<char> used(e - i, 0);
+        for (size_t a = i; a < e; ++a) {
+          if (used[a - i]) continue;
+          JElem head = jg.elems[a];
+          used[a - i] = 1;
+          std::vector<size_t> same;
+          for (size_t b = a + 1; b < e; ++b)
+            if (!used[b - i] && jg.elems[b].lm == head.lm && jg.elems[b].lv == head.lv) same.push_back(b);
+          if (!same.empty() && (head.pm || !same.empty())) {
+            // the unpredicated members multiply into the base factor, the predicated ones become thread terms
+            cplx base(1, 0);
+            std::vector<JElem::ThreadTerm> tt;
+            std::vector<JCondPhase> ct;
+            bool mixed = false;  // a member with CTA terms AND a thread predicate: its table factor is not unconditional
+            auto take = [&](const JElem &x) {
+              if (x.pm != 0 && !x.terms.empty()) mixed = true;
+              if (x.pm == 0) {
+                base *= x.m[0];
+                ct.insert(ct.end(), x.terms.begin(), x.terms.end());
+              } else {
+                JElem::ThreadTerm t = {x.pm, x.pv, x.m[0]};
+                tt.push_back(t);
+              }
+            };
+            take(head);
+            for (size_t q = 0; q < same.size(); ++q) {
+              take(jg.elems[same[q]]);
+              used[same[q] - i] = 1;
+            }
+            if (tt.size() <= 48 && ct.size() <= 48 && !mixed) {
+              head.m[0] = base;
+              head.pm = head.pv = 0;
+              head.tterms = tt;
+              head.terms = ct;
+              out.push_back(head);
+              continue;
+            }
+            for (size_t q = 0; q < same.size(); ++q) used[same[q] - i] = 0;  // too many: leave them as they are
+          }
+          out.push_back(jg.elems[a]);
+        }
+        i = e;
+      }
+      jg.elems.swap(out);
+      if (jhad_group == (long)pass->jgroups.size())  // the positions moved: re-locate the group's last butterfly
+        for (size_t q = 0; q < jg.elems.size(); ++q)
+          if (jg.elems[q].kind == JElem::HAD) jhad_elem = q;
+    }
     pass->jgroups.push_back(jg);
   }
 

@@ -203,6 +203,14 @@ struct JElem {
   uint64_t gmask = 0, gval = 0;   // CTA-uniform condition on the tile's base index (gmask == 0: none)
   cplx m[4];                      // D1: m00 m01 m10 m11; PH: factor in m[0]
   std::vector<JCondPhase> terms;  // PH: further factors, each under its own CTA-uniform condition
+  // PH: further factors, each under its own THREAD predicate on the tile-local index ((t & pm) == pv): a run of phases
+  // on the same amplitudes of the group that differ only in bits outside the group (QFT: the controlled phases of one
+  // target) costs one scalar product per thread and ONE application (jit_codegen forms the product in registers)
+  struct ThreadTerm {
+    uint32_t pm, pv;
+    cplx w;
+  };
+  std::vector<ThreadTerm> tterms;
   std::vector<uint32_t> mb;       // DK: the sub-bits the dense block acts on (ascending, <= 3)
   std::vector<cplx> mk;           // DK: 2^k x 2^k, row-major, bit i of the row index <-> mb[i]
 };
