@@ -528,8 +528,28 @@ int exchange_bits(qipb200_state *s, uint32_t R, uint32_t l) {
       if (s->send_stage < 1)
         CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch,
                                     s->flags + kFlagErrorSlot, ctx->stream, &ctx->launches));
-      if (s->send_stage < 2)
-        CU(ctx, launch_copy_half(s->prec, s->buf, peer_stage, s->n_local, l, give, true, ctx->stream, &ctx->launches));
+      if (s->send_stage < 2) {
+        static const bool use_ce = []() {
+          const char *e = getenv("QIPB200_STAGED_EXCHANGE");
+          return e && !strcmp(e, "ce");
+        }();
+        if (use_ce) {
+          // the give-half as a strided copy on the copy engines: rows of 2^l amplitudes every 2^(l+1)
+          const size_t ab = amp_bytes(s->prec);
+          const size_t width = ab << l, pitch = ab << (l + 1);
+          const size_t height = (size_t)1 << (s->n_local - 1 - l);
+          const char *src = (const char *)s->buf + ((size_t)give << l) * ab;
+          char *dst = peer_stage + ((size_t)(1 - give) << l) * ab;
+          if (pitch <= ((size_t)1 << 30) && height > 1) {
+            CU(ctx, cudaMemcpy2DAsync(dst, pitch, src, pitch, width, height, cudaMemcpyDeviceToDevice, ctx->stream));
+          } else {
+            for (size_t r = 0; r < height; ++r)
+              CU(ctx, cudaMemcpyAsync(dst + r * pitch, src + r * pitch, width, cudaMemcpyDeviceToDevice, ctx->stream));
+          }
+        } else {
+          CU(ctx, launch_copy_half(s->prec, s->buf, peer_stage, s->n_local, l, give, true, ctx->stream, &ctx->launches));
+        }
+      }
       s->send_stage = 0;
       CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch,
                                   s->flags + kFlagErrorSlot, ctx->stream, &ctx->launches));
