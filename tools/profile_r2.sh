@@ -15,5 +15,5 @@ $NCU --set full -k regex:qip_pass -s 8 -c 1 -o gpurun_out/r2_qip_pass_qft_f32_n2
 # per-gate kernels: CNOT (k_exchange), diagonal T (k_diag), dense 1-qubit, dense 4-qubit, dense 5-qubit
 $NCU --set full -k regex:k_exchange -s 2 -c 1 -o gpurun_out/r2_k_exchange_n28 $B --n-local 28 --depth 3 --no-fusion > /dev/null
 $NCU --set full -k regex:k_diag -s 2 -c 1 -o gpurun_out/r2_k_diag_n28 $B --n-local 28 --depth 3 --no-fusion > /dev/null
-$NCU --set full -k "regex:k_dense.*Li4" -s 2 -c 1 -o gpurun_out/r2_k_dense4_n26 $B --n-local 26 --workload dense4 --depth 6 --no-fusion > /dev/null
+$NCU --set full --kernel-name-base demangled -k "regex:k_dense<double, 4" -s 2 -c 1 -o gpurun_out/r2_k_dense4_n26 $B --n-local 26 --workload dense4 --depth 6 --no-fusion > /dev/null
 ls -la gpurun_out/*.ncu-rep
