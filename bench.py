@@ -50,6 +50,7 @@ def parse_args():
                     help="BASELINE configs[4] exactly: depth-30 random {H,CZ,CNOT}, seed 0x5EED0005 (N = n-local + log2 gpus: 33 at 8 GPUs)")
     ap.add_argument("--workload", default="random", choices=["random", "qft", "dense4"],
                     help="random: depth-D random layers (BASELINE metric / configs[1], [4]); qft: configs[2]; dense4: configs[3]")
+    ap.add_argument("--dense-k", type=int, default=4, help="qubits per dense block of --workload dense4 (4 = BASELINE configs[3]; 5..10: the wide in-place kernels)")
     ap.add_argument("--no-fusion", action="store_true", help="one kernel sweep per gate")
     ap.add_argument("--no-extras", action="store_true", help="skip the unfused / per-kernel / CPU side measurements")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
@@ -135,8 +136,9 @@ def build_workload(args, world):
         ops = circuits.qft(n)
         name = "N=%d %s textbook QFT at MatrixOp level (H, controlled phases, final swaps; BASELINE configs[2]) from |0>" % (n, args.dtype)
     elif args.workload == "dense4":
-        ops = circuits.config4(n, blocks=args.depth)
-        name = "N=%d %s H^n then %d dense 4-qubit Haar blocks on seeded random qubits (BASELINE configs[3])" % (n, args.dtype, args.depth)
+        ops = circuits.config4(n, blocks=args.depth, k=args.dense_k)
+        name = "N=%d %s H^n then %d dense %d-qubit Haar blocks on seeded random qubits (BASELINE configs[3]%s)" % (
+            n, args.dtype, args.depth, args.dense_k, "" if args.dense_k == 4 else " with wider blocks")
     else:
         ops = circuits.random_circuit(n, args.depth, args.seed, args.gate_set)
         name = "N=%d %s depth-%d random {%s} from |0>, layer 0 = H^n (SURVEY 8d generator, seed 0x%X)" % (
