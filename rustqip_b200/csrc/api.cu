@@ -233,6 +233,11 @@ extern "C" void qipb200_shutdown(qipb200_ctx *ctx) {
     }
   for (size_t i = 0; i < ctx->prof_pool.size(); ++i) cudaEventDestroy(ctx->prof_pool[i]);
   jit_unload(&ctx->jit_loaded);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_pass[i]) cudaEventDestroy(ctx->ev_pass[i]);
+    if (ctx->ev_exch[i]) cudaEventDestroy(ctx->ev_exch[i]);
+  }
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -365,7 +370,9 @@ extern "C" int qipb200_profile_read(qipb200_ctx *ctx, double *out4) {
       ctx->prof_pool.push_back(ctx->prof_events[cat][i].second);
     }
     out4[2 * cat] = ms;
-    out4[2 * cat + 1] = (double)ctx->prof_events[cat].size();
+    double n = 0.0;
+    for (size_t i = 0; i < ctx->prof_events[cat].size(); ++i) n += ctx->prof_events[cat][i].weight;
+    out4[2 * cat + 1] = n;
     ctx->prof_events[cat].clear();
   }
   return QIPB200_OK;
@@ -505,6 +512,12 @@ int check_barrier_error(qipb200_state *s) {
   return QIPB200_OK;
 }
 
+}  // namespace
+namespace qipb200 {
+int join_halves(qipb200_state *s);
+}
+namespace {
+
 // Swap physical rank bit R (>= n_local) with local bit l.
 // Protocol (push through staging, dist.cu): [barrier] every rank pushes the half it gives away (bit l == !rb) into
 // the partner's staging area [barrier] every rank copies its own staging half into the slots it gave away.  When the
@@ -514,6 +527,10 @@ int exchange_bits(qipb200_state *s, uint32_t R, uint32_t l) {
   qipb200_ctx *ctx = s->ctx;
   if (!s->ipc_ready)
     return set_err(ctx, QIPB200_ERR_COMM, "sharded state: peers not mapped (call qipb200_state_ipc_import)");
+  if (s->halves_pending) {  // an overlapped migration is still in flight on the second stream
+    int stj = join_halves(s);
+    if (stj != QIPB200_OK) return stj;
+  }
   const uint32_t r = R - s->n_local;
   const int partner = s->rank ^ (1 << r);
   const int rb = (s->rank >> r) & 1;
@@ -758,7 +775,9 @@ static int choose_victim(const qipb200_state *s, const FlatOp &f, const uint64_t
   for (uint32_t j = 0; j < f.k; ++j) used |= 1ull << f.idx_bits[j];
   int best = -1;
   uint64_t best_key = 0;
-  for (uint32_t l = 0; l < s->n_local; ++l) {
+  // the top local bit is never evicted: it splits the shard into the two halves an overlapped migration works on
+  const uint32_t l_end = s->n_local > 3 ? s->n_local - 1 : s->n_local;
+  for (uint32_t l = 0; l < l_end; ++l) {
     if ((used >> l) & 1ull) continue;
     uint64_t key = 1;
     if (next_use) {
@@ -810,6 +829,88 @@ int exchange_open_for_send(qipb200_state *s, uint32_t R, uint32_t l, void **peer
   s->send_stage = 1;  // the caller raises it to 2 once the pushing pass is launched
   s->send_R = R;
   s->send_l = l;
+  return QIPB200_OK;
+}
+
+int ensure_overlap_resources(qipb200_state *s) {
+  qipb200_ctx *ctx = s->ctx;
+  if (ctx->stream2) return QIPB200_OK;
+  CU(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CU(ctx, cudaEventCreateWithFlags(&ctx->ev_pass[i], cudaEventDisableTiming));
+    CU(ctx, cudaEventCreateWithFlags(&ctx->ev_exch[i], cudaEventDisableTiming));
+  }
+  return QIPB200_OK;
+}
+
+// The migration R <-> l as TWO half exchanges (lower / upper half of the shard = top local bit 0 / 1) on the context's
+// second stream: half v starts when ctx->ev_pass[v] (recorded by the caller on the main stream: "this half is final")
+// has fired, and ctx->ev_exch[v] fires when it is done -- the tile pass before the migration overlaps the exchange of
+// the half it finished first, the pass after it starts on the half that arrived first.  Every rank runs exactly this
+// protocol (two barrier-exchange-barrier groups); what a rank overlaps with it is its own business.
+int exchange_bits_split(qipb200_state *s, uint32_t R, uint32_t l) {
+  qipb200_ctx *ctx = s->ctx;
+  if (!s->ipc_ready) return set_err(ctx, QIPB200_ERR_COMM, "sharded state: peers not mapped (call qipb200_state_ipc_import)");
+  if (s->n_local < 4 || l >= s->n_local - 1) return set_err(ctx, QIPB200_ERR_UNSUPPORTED, "internal: split exchange on the top local bit");
+  int st0 = ensure_overlap_resources(s);
+  if (st0 != QIPB200_OK) return st0;
+  const uint32_t r = R - s->n_local;
+  const int partner = s->rank ^ (1 << r);
+  const int rb = (s->rank >> r) & 1;
+  const uint32_t nh = s->n_local - 1;  // bits of a half
+  uint32_t s_bit = nh - 1;
+  if (s_bit == l) s_bit = nh - 2;
+  const size_t half_bytes = s->bytes >> 1;
+  for (int v = 0; v < 2; ++v) {
+    CU(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_pass[v], 0));
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (ctx->profile) {
+      auto take = [&]() {
+        cudaEvent_t e = nullptr;
+        if (!ctx->prof_pool.empty()) {
+          e = ctx->prof_pool.back();
+          ctx->prof_pool.pop_back();
+        } else if (cudaEventCreate(&e) != cudaSuccess) {
+          e = nullptr;
+        }
+        return e;
+      };
+      t0 = take();
+      t1 = take();
+      if (t0) cudaEventRecord(t0, ctx->stream2);
+    }
+    CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch, s->flags + kFlagErrorSlot,
+                                ctx->stream2, &ctx->launches));
+    CU(ctx, launch_pair_exchange(s->prec, (char *)s->buf + v * half_bytes, (char *)s->peer_buf[partner] + v * half_bytes, nh, l, s_bit,
+                                 rb, ctx->stream2, &ctx->launches));
+    CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch, s->flags + kFlagErrorSlot,
+                                ctx->stream2, &ctx->launches));
+    if (t0 && t1) {
+      cudaEventRecord(t1, ctx->stream2);
+      qipb200_ctx::ProfEvent pe = {t0, t1, 0.5};
+      ctx->prof_events[1].push_back(pe);
+    }
+    CU(ctx, cudaEventRecord(ctx->ev_exch[v], ctx->stream2));
+  }
+  ++ctx->exchange_launches;
+  s->halves_pending = true;
+  s->exchange_bytes += (uint64_t)amp_bytes(s->prec) << (s->n_local - 1);
+  for (uint32_t b = 0; b < s->n; ++b) {
+    if (s->phys_of_logical[b] == R)
+      s->phys_of_logical[b] = l;
+    else if (s->phys_of_logical[b] == l)
+      s->phys_of_logical[b] = R;
+  }
+  return QIPB200_OK;
+}
+
+// Make the main stream wait for an overlapped migration (both halves).
+int join_halves(qipb200_state *s) {
+  if (!s->halves_pending) return QIPB200_OK;
+  qipb200_ctx *ctx = s->ctx;
+  CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_exch[0], 0));
+  CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_exch[1], 0));
+  s->halves_pending = false;
   return QIPB200_OK;
 }
 

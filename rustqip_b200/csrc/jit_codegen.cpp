@@ -749,6 +749,8 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
   // multi-GPU: tiles whose index bit `send_bit` equals `send_val` are stored to `tmap_out` (the partner's staging
   // area) at the index with that bit flipped -- the push half of a qubit migration; send_bit >= 64: off
   src << "  unsigned send_bit, send_val;\n";
+  // a launch may cover a contiguous part of the tile counter (half a pass around a multi-GPU migration)
+  src << "  unsigned tile_off_lo, tile_off_hi;\n";
   src << "};\n";
   src << R"(#ifdef QIP_JIT_HOST
 #include <cmath>
@@ -838,7 +840,7 @@ qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constan
          const __grid_constant__ CUtensorMap tmap_out) {
   extern __shared__ __align__(1024) unsigned char sm[];
   const unsigned tid = threadIdx.x;
-  const u64 base = tile_base(p, (u64)blockIdx.x);
+  const u64 base = tile_base(p, (u64)blockIdx.x + (((u64)p.tile_off_hi << 32) | (u64)p.tile_off_lo));
   const unsigned smb = (unsigned)__cvta_generic_to_shared(sm);
   const unsigned mbar = smb + OFF_MBAR;
   if (tid == 0) {
@@ -971,6 +973,8 @@ qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constan
     const uint32_t off_bit = 64u, val = 0u;
     put(&off_bit, 4);
     put(&val, 4);
+    put(&val, 4);  // tile_off_lo
+    put(&val, 4);  // tile_off_hi
   }
   while (blob.size() % 8) blob.push_back(0);  // sizeof(JP): the struct is 8-byte aligned
 

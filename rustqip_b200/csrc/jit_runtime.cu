@@ -232,7 +232,7 @@ void jit_wait_all(uint64_t *n_compiled, double *total_ms) {
 
 cudaError_t jit_launch(const std::shared_ptr<const JitCubin> &cubin, std::vector<std::pair<const JitCubin *, JitLoaded>> *loaded,
                        const JitProgram &prog, void *psi, uint32_t n_local, const CUtensorMap &tmap, cudaStream_t stream,
-                       std::string *err, const CUtensorMap *tmap_out, uint32_t send_bit, uint32_t send_val) {
+                       std::string *err, const CUtensorMap *tmap_out, uint32_t send_bit, uint32_t send_val, uint32_t half) {
   Driver &d = driver();
   if (!d.ok || !cubin || !cubin->ok) {
     if (err) *err = !d.ok ? d.why : "no cubin";
@@ -266,7 +266,14 @@ cudaError_t jit_launch(const std::shared_ptr<const JitCubin> &cubin, std::vector
     memcpy(params.data() + prog.send_offset + 4, &send_val, 4);
   }
   void *args[4] = {&psi, params.data(), &tm, &tm_out};
-  const unsigned grid = 1u << (n_local - prog.tiles_log2_sub);
+  unsigned grid = 1u << (n_local - prog.tiles_log2_sub);
+  if (half < 2 && grid >= 2 && prog.send_offset + 16 <= params.size()) {
+    grid >>= 1;
+    const uint64_t off = half ? (uint64_t)grid : 0ull;
+    const uint32_t lo = (uint32_t)off, hi = (uint32_t)(off >> 32);
+    memcpy(params.data() + prog.send_offset + 8, &lo, 4);
+    memcpy(params.data() + prog.send_offset + 12, &hi, 4);
+  }
   const CUresult r = d.launch(L->fn, grid, 1, 1, prog.threads, 1, 1, prog.smem_bytes, (CUstream)stream, args, nullptr);
   if (r != CUDA_SUCCESS) return fail(r, "cuLaunchKernel");
   return cudaSuccess;

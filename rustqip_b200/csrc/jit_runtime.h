@@ -49,7 +49,8 @@ void jit_wait_all(uint64_t *n_compiled, double *total_ms);
 // through tmap_out at the index with that bit flipped (the push half of a multi-GPU qubit migration).
 cudaError_t jit_launch(const std::shared_ptr<const JitCubin> &cubin, std::vector<std::pair<const JitCubin *, JitLoaded>> *loaded,
                        const JitProgram &prog, void *psi, uint32_t n_local, const CUtensorMap &tmap, cudaStream_t stream,
-                       std::string *err, const CUtensorMap *tmap_out = nullptr, uint32_t send_bit = 64, uint32_t send_val = 0);
+                       std::string *err, const CUtensorMap *tmap_out = nullptr, uint32_t send_bit = 64, uint32_t send_val = 0,
+                       uint32_t half = 2);  // half: 0 / 1 = the lower / upper half of the tile counter only, 2 = all tiles
 
 void jit_unload(std::vector<std::pair<const JitCubin *, JitLoaded>> *loaded);
 

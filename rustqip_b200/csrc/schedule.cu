@@ -45,7 +45,9 @@ bool needs_exchange(const qipb200_state *s, const FlatOp &f) {
 
 // The push half of the qubit migration that follows this epoch, to be done by the epoch's last tile pass.
 struct SendPlan {
-  bool on = false;
+  bool on = false;       // staged protocol: the last pass pushes the give-half
+  bool overlap = false;  // in-place protocol in two halves on the second stream (exchange_bits_split): the last step
+                         // records "lower / upper half final" on the context's events, preferably half by half
   uint32_t R = 0, l = 0;
 };
 
@@ -56,6 +58,7 @@ int execute_steps(qipb200_state *s, const std::vector<PlanStep> &steps, const st
   PassParams *pp = new PassParams();
   // Generated kernels (jit_codegen / jit_runtime): every pass is turned into specialised source; a pass whose
   // cubin is ready runs it, the others run the interpreter kernel while the background workers compile.
+  bool halves_recorded = false;
   const JitMode jmode = cfg.use_tma && cfg.groups_per_thread == 1 ? jit_mode_from_env(s->n_local) : JIT_OFF;
   std::vector<JitProgram> progs(steps.size());
   std::vector<char> have_prog(steps.size(), 0);
@@ -98,10 +101,33 @@ int execute_steps(qipb200_state *s, const std::vector<PlanStep> &steps, const st
               }  // else: the opening barrier stays queued (send_stage 1), exchange_bits pushes with its own kernel
             }
           }
-          ProfileScope prof(ctx, 0);
+          // A pass next to an overlapped migration runs in two halves of the tile counter (= top local bit 0 / 1,
+          // which must not be a tile bit): after a migration each half starts when its exchange is done, before one
+          // each half is reported final as soon as it is.
+          const bool top_free = ph.hi_pos[ph.m - 1] != s->n_local - 1 && s->n_local > ph.T;
+          const bool after_mig = s->halves_pending, before_mig = send.overlap && i + 1 == steps.size();
           std::string err;
-          cudaError_t e = jit_launch(cubin, &ctx->jit_loaded, progs[i], s->buf, s->n_local, tmap, ctx->stream, &err, tmo, send_bit,
-                                     send_val);
+          cudaError_t e = cudaSuccess;
+          if ((after_mig || before_mig) && top_free) {
+            for (uint32_t v = 0; v < 2 && e == cudaSuccess; ++v) {
+              if (after_mig) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_exch[v], 0);
+              if (e != cudaSuccess) break;
+              {
+                ProfileScope prof(ctx, 0, 0.5);
+                e = jit_launch(cubin, &ctx->jit_loaded, progs[i], s->buf, s->n_local, tmap, ctx->stream, &err, nullptr, 64, 0, v);
+              }
+              if (e == cudaSuccess && before_mig) e = cudaEventRecord(ctx->ev_pass[v], ctx->stream);
+            }
+            if (e == cudaSuccess) {
+              s->halves_pending = false;
+              if (before_mig) halves_recorded = true;
+              ++ctx->launches;  // two launches for this pass
+            }
+          } else {
+            if (after_mig && join_halves(s) != QIPB200_OK) return QIPB200_ERR_CUDA;
+            ProfileScope prof(ctx, 0);
+            e = jit_launch(cubin, &ctx->jit_loaded, progs[i], s->buf, s->n_local, tmap, ctx->stream, &err, tmo, send_bit, send_val);
+          }
           if (e == cudaSuccess) {
             if (tmo) s->send_stage = 2;
             ++ctx->launches;
@@ -115,6 +141,7 @@ int execute_steps(qipb200_state *s, const std::vector<PlanStep> &steps, const st
         }
       }
     }
+    if (s->halves_pending && (st = join_halves(s)) != QIPB200_OK) break;  // this step sweeps the whole shard at once
     if (steps[i].is_pass) {
       if (!serialise_pass(steps[i].pass, pp)) {
         st = report_error(s, QIPB200_ERR_UNSUPPORTED, "internal: fused pass exceeds the kernel parameter space");
@@ -131,6 +158,12 @@ int execute_steps(qipb200_state *s, const std::vector<PlanStep> &steps, const st
     }
   }
   delete pp;
+  if (st == QIPB200_OK && send.overlap && !halves_recorded) {
+    // the epoch's last step ran as one launch (or there was none): both halves are final now
+    if (s->halves_pending && (st = join_halves(s)) != QIPB200_OK) return st;
+    if (cudaEventRecord(ctx->ev_pass[0], ctx->stream) != cudaSuccess || cudaEventRecord(ctx->ev_pass[1], ctx->stream) != cudaSuccess)
+      return report_cuda_error(s, cudaGetLastError(), "cudaEventRecord");
+  }
   return st;
 }
 
@@ -146,7 +179,8 @@ int run_fused(qipb200_state *s, const qip_op *ops, size_t n_ops, const std::vect
     if (e != cudaSuccess) return report_cuda_error(s, e, "cudaFuncSetAttribute(tile pass)");
     s->ctx->tile_configured = true;
   }
-  const PlanConfig cfg = default_plan_config(s->prec, s->n_local);
+  PlanConfig cfg = default_plan_config(s->prec, s->n_local);
+  if (s->world > 1) cfg.reserve_bit = (int)s->n_local - 1;  // keeps the passes splittable in halves (overlapped migration)
   std::vector<size_t> remaining(n_ops);
   for (size_t i = 0; i < n_ops; ++i) remaining[i] = i;
   while (!remaining.empty()) {
@@ -197,13 +231,21 @@ int run_fused(qipb200_state *s, const qip_op *ops, size_t n_ops, const std::vect
     // pushes with the stand-alone kernel inside exchange_bits -- the partner does not care how its staging area fills).
     SendPlan send;
     static const bool fused_send = !getenv("QIPB200_NO_FUSED_SEND");
-    if (fused_send && s->has_stage && first_blocked != left.size() && !steps.empty() && steps.back().is_pass) {
+    static const bool overlap_exchange = !getenv("QIPB200_NO_OVERLAP_EXCHANGE");
+    if (first_blocked != left.size()) {
       const size_t op_idx = remaining[left[first_blocked]];
       const uint64_t *nu = next_use.empty() ? nullptr : &next_use[(op_idx + 1) * s->n];
-      send.on = peek_first_exchange(s, &ops[op_idx], nu, &send.R, &send.l);
+      if (s->has_stage) {
+        if (fused_send && !steps.empty() && steps.back().is_pass) send.on = peek_first_exchange(s, &ops[op_idx], nu, &send.R, &send.l);
+      } else if (overlap_exchange && s->world > 1 && s->n_local >= 8) {
+        // in-place exchange in two halves on the second stream, overlapping the passes on either side of it
+        send.overlap = peek_first_exchange(s, &ops[op_idx], nu, &send.R, &send.l) && send.l < s->n_local - 1 &&
+                       ensure_overlap_resources(s) == QIPB200_OK;
+      }
     }
     int st = execute_steps(s, steps, local, cfg, send);
     if (st != QIPB200_OK) return st;
+    if (send.overlap && (st = exchange_bits_split(s, send.R, send.l)) != QIPB200_OK) return st;
     if (left.empty()) break;
     if (first_blocked == left.size())
       return report_error(s, QIPB200_ERR_UNSUPPORTED, "internal: schedule made no progress");
@@ -247,7 +289,11 @@ int run_schedule(qipb200_state *s, const qip_op *ops, size_t n_ops, uint32_t fla
     }
   }
   const bool fuse = !(flags & QIPB200_SCHED_NO_FUSION) && s->n_local >= 6;
-  if (fuse) return run_fused(s, ops, n_ops, next_use);
+  if (fuse) {
+    const int st = run_fused(s, ops, n_ops, next_use);
+    const int stj = join_halves(s);  // whatever follows (download, measurement, the next schedule) sees one stream again
+    return st != QIPB200_OK ? st : stj;
+  }
   for (size_t i = 0; i < n_ops; ++i) {
     FlatOp f;
     const uint64_t *nu = next_use.empty() ? nullptr : &next_use[(i + 1) * s->n];

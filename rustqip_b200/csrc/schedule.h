@@ -21,6 +21,9 @@ int report_cuda_error(qipb200_state *s, cudaError_t e, const char *what);
 int compile_and_localize(qipb200_state *s, const qip_op *op, FlatOp *f, const uint64_t *next_use);
 bool peek_first_exchange(const qipb200_state *s, const qip_op *op, const uint64_t *next_use, uint32_t *R, uint32_t *l);
 int exchange_open_for_send(qipb200_state *s, uint32_t R, uint32_t l, void **peer_stage, int *give);
+int exchange_bits_split(qipb200_state *s, uint32_t R, uint32_t l);
+int join_halves(qipb200_state *s);
+int ensure_overlap_resources(qipb200_state *s);
 
 // schedule.cu: state <- ops[n-1] ... ops[0] state
 int run_schedule(qipb200_state *s, const qip_op *ops, size_t n_ops, uint32_t flags);

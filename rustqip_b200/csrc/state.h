@@ -23,6 +23,10 @@ struct qipb200_ctx {
   uint64_t jit_launches = 0;       // tile passes among `tile_launches` that ran a generated (specialised) kernel
   std::vector<std::pair<const qipb200::JitCubin *, qipb200::JitLoaded>> jit_loaded;  // modules loaded on this device
   std::string jit_note;            // why the generated-kernel path was not taken last time (diagnostics)
+  // second stream + events for the exchange that overlaps tile passes (api.cu: exchange_bits_split)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_pass[2] = {nullptr, nullptr};  // recorded on `stream`: the lower / upper half of the shard is final
+  cudaEvent_t ev_exch[2] = {nullptr, nullptr};  // recorded on `stream2`: that half has been exchanged
   // multi-device context (qipb200_init_multi): one child context per device, owned by the parent; states created
   // on the parent are sharded over the children inside this one process (peer access instead of CUDA IPC)
   std::vector<qipb200_ctx *> children;
@@ -35,7 +39,11 @@ struct qipb200_ctx {
   // optional per-category device timing (qipb200_profile_enable): CUDA-event pairs recorded on `stream`
   // around every fused tile pass [0] and every NVLink exchange incl. its two flag barriers [1]
   bool profile = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[2];
+  struct ProfEvent {
+    cudaEvent_t first, second;
+    double weight;  // 1 per launch; 0.5 for each half of a pass launched in two halves around a migration
+  };
+  std::vector<ProfEvent> prof_events[2];
   std::vector<cudaEvent_t> prof_pool;
   // staging buffers of the host-buffer drop-ins (qipb200_apply_op*)
   void *d_in = nullptr, *d_out = nullptr;
@@ -53,6 +61,7 @@ struct qipb200_state {
   int rank = 0, world = 1;
   void *buf = nullptr;      // 2^n_local amplitudes (sharded states: followed by a staging area of the same size)
   bool has_stage = false;   // the allocation of `buf` is 2 * bytes: [state | staging of the push exchange]
+  bool halves_pending = false;  // the two halves of the shard become valid at ctx->ev_exch[0/1] (an overlapped migration)
   int send_stage = 0;       // pending exchange: 0 nothing yet, 1 its opening barrier is queued, 2 ... and the last tile
                             // pass has pushed the give-half into the partner's staging area
   uint32_t send_R = 0, send_l = 0;  // ... for this (rank bit, local bit) pair
@@ -80,7 +89,8 @@ struct ProfileScope {
   qipb200_ctx *ctx;
   int cat;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  ProfileScope(qipb200_ctx *c, int category) : ctx(c), cat(category) {
+  double weight = 1.0;
+  ProfileScope(qipb200_ctx *c, int category, double w = 1.0) : ctx(c), cat(category), weight(w) {
     if (!ctx->profile) return;
     auto take = [&]() {
       cudaEvent_t e = nullptr;
@@ -99,7 +109,8 @@ struct ProfileScope {
   ~ProfileScope() {
     if (!e0 || !e1) return;
     cudaEventRecord(e1, ctx->stream);
-    ctx->prof_events[cat].push_back(std::make_pair(e0, e1));
+    qipb200_ctx::ProfEvent pe = {e0, e1, weight};
+    ctx->prof_events[cat].push_back(pe);
   }
 };
 

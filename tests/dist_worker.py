@@ -24,8 +24,11 @@ def main():
     g = (world - 1).bit_length()
     ctx = Context(local_rank)
     failures = 0
-    for n, dtype, fusion in [(12, np.complex128, False), (14, np.complex128, True), (15, np.complex64, True),
-                             (17, np.complex128, True)]:
+    for n, dtype, fusion, jit in [(12, np.complex128, False, "off"), (14, np.complex128, True, "off"), (15, np.complex64, True, "off"),
+                                  (17, np.complex128, True, "off"), (18, np.complex128, True, "sync"), (19, np.complex64, True, "sync")]:
+        # "sync": the generated kernels even at these sizes -- passes next to a migration run in two halves that
+        # overlap the two halves of the exchange (schedule.cu / exchange_bits_split)
+        os.environ["QIPB200_JIT"] = jit
         # gates on rank-held qubits (0..g-1) of every kind + random circuits touching them repeatedly
         ops = circuits.sharded_parity_circuit(n, g)
         st = init_sharded_state(n, dtype, ctx)
@@ -73,8 +76,8 @@ def main():
             ok = all(checks.values())
             if not ok:
                 print("  failed checks:", [k for k, v in checks.items() if not v], "samples", samples, flush=True)
-            print("n=%d %s fusion=%s world=%d: max err %.3e, norm %.12f, probs/samples/collapse checked, exchanged %.1f MiB/rank -> %s" % (
-                n, np.dtype(dtype).name, fusion, world, err, norm_all, exch / 2 ** 20, "OK" if ok else "FAIL"), flush=True)
+            print("n=%d %s fusion=%s jit=%s world=%d: max err %.3e, norm %.12f, probs/samples/collapse checked, exchanged %.1f MiB/rank -> %s" % (
+                n, np.dtype(dtype).name, fusion, jit, world, err, norm_all, exch / 2 ** 20, "OK" if ok else "FAIL"), flush=True)
             failures += 0 if ok else 1
     flag = [failures]
     dist.broadcast_object_list(flag, src=0)
