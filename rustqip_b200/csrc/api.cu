@@ -835,7 +835,10 @@ int exchange_open_for_send(qipb200_state *s, uint32_t R, uint32_t l, void **peer
 int ensure_overlap_resources(qipb200_state *s) {
   qipb200_ctx *ctx = s->ctx;
   if (ctx->stream2) return QIPB200_OK;
-  CU(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  // highest priority: the exchange needs few resident warps but must not queue behind the pass's thousands of CTAs
+  int prio_lo = 0, prio_hi = 0;
+  CU(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CU(ctx, cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_hi));
   for (int i = 0; i < 2; ++i) {
     CU(ctx, cudaEventCreateWithFlags(&ctx->ev_pass[i], cudaEventDisableTiming));
     CU(ctx, cudaEventCreateWithFlags(&ctx->ev_exch[i], cudaEventDisableTiming));

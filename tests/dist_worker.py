@@ -55,7 +55,8 @@ def main():
         if rank == 0:
             want = qo.run_pipeline(n, ops, 5, dtype)
             tol = 1e-10 if dtype == np.complex128 else 1e-5
-            ptol = 1e-12 if dtype == np.complex128 else 1e-5
+            # f32: the oracle (like the reference) accumulates the probabilities in f32, the device in f64
+            ptol = 1e-12 if dtype == np.complex128 else 1e-4
             err = float(np.max(np.abs(got.astype(np.complex128) - want.astype(np.complex128))))
             wprobs = qo.measure_probs(n, [0, n - 1, 3], want).astype(np.float64)
             wpost = np.zeros_like(got)
