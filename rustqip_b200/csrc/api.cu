@@ -884,8 +884,12 @@ int exchange_bits_split(qipb200_state *s, uint32_t R, uint32_t l) {
     }
     CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch, s->flags + kFlagErrorSlot,
                                 ctx->stream2, &ctx->launches));
+    static const unsigned split_ctas = []() {
+      const char *e = getenv("QIPB200_EXCH_CTAS");
+      return (unsigned)(e ? atoi(e) : 296);
+    }();
     CU(ctx, launch_pair_exchange(s->prec, (char *)s->buf + v * half_bytes, (char *)s->peer_buf[partner] + v * half_bytes, nh, l, s_bit,
-                                 rb, ctx->stream2, &ctx->launches));
+                                 rb, ctx->stream2, &ctx->launches, split_ctas));
     CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch, s->flags + kFlagErrorSlot,
                                 ctx->stream2, &ctx->launches));
     if (t0 && t1) {

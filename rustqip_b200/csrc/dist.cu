@@ -34,7 +34,8 @@ struct ExArgs {
 template <typename V, int U>
 __global__ void __launch_bounds__(kThreads)
     k_pair_exchange(V *__restrict__ mine, V *__restrict__ peer, const ExArgs a) {
-  const uint64_t w0 = (uint64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
+  for (uint64_t blk = blockIdx.x; blk * (uint64_t)(kThreads * U) < a.n_items; blk += gridDim.x) {  // grid-stride over CTA chunks
+  const uint64_t w0 = blk * (kThreads * U) + threadIdx.x;
   uint64_t ii[U], jj[U];
   V x[U], y[U];
   bool on[U];
@@ -60,10 +61,11 @@ __global__ void __launch_bounds__(kThreads)
       mine[ii[u]] = y[u];
       peer[jj[u]] = x[u];  // NVLink store (posted)
     }
+  }
 }
 
 cudaError_t launch_pair_exchange(qip_prec prec, void *mine, void *peer, uint32_t n_local, uint32_t l,
-                                 uint32_t s_bit, int rb, cudaStream_t s, uint64_t *launches) {
+                                 uint32_t s_bit, int rb, cudaStream_t s, uint64_t *launches, unsigned max_ctas) {
   if (n_local < 2 || l == s_bit || l >= n_local || s_bit >= n_local) return cudaErrorInvalidValue;
   ExArgs a;
   a.pos_lo = l < s_bit ? l : s_bit;
@@ -78,7 +80,8 @@ cudaError_t launch_pair_exchange(qip_prec prec, void *mine, void *peer, uint32_t
   }();
 #define QIP_EXCH(UU)                                                                                        \
   {                                                                                                         \
-    const unsigned grid = (unsigned)((a.n_items + (uint64_t)kThreads * UU - 1) / ((uint64_t)kThreads * UU)); \
+    unsigned grid = (unsigned)((a.n_items + (uint64_t)kThreads * UU - 1) / ((uint64_t)kThreads * UU));       \
+    if (max_ctas && grid > max_ctas) grid = max_ctas;                                                       \
     if (prec == QIP_F32)                                                                                    \
       k_pair_exchange<float2, UU><<<grid, kThreads, 0, s>>>((float2 *)mine, (float2 *)peer, a);             \
     else                                                                                                    \
