@@ -180,7 +180,7 @@ int run_fused(qipb200_state *s, const qip_op *ops, size_t n_ops, const std::vect
     s->ctx->tile_configured = true;
   }
   PlanConfig cfg = default_plan_config(s->prec, s->n_local);
-  if (s->world > 1) cfg.reserve_bit = (int)s->n_local - 1;  // keeps the passes splittable in halves (overlapped migration)
+  if (s->world > 1 && overlap_exchange_enabled()) cfg.reserve_bit = (int)s->n_local - 1;  // passes splittable in halves
   std::vector<size_t> remaining(n_ops);
   for (size_t i = 0; i < n_ops; ++i) remaining[i] = i;
   while (!remaining.empty()) {
@@ -231,7 +231,7 @@ int run_fused(qipb200_state *s, const qip_op *ops, size_t n_ops, const std::vect
     // pushes with the stand-alone kernel inside exchange_bits -- the partner does not care how its staging area fills).
     SendPlan send;
     static const bool fused_send = !getenv("QIPB200_NO_FUSED_SEND");
-    static const bool overlap_exchange = !getenv("QIPB200_NO_OVERLAP_EXCHANGE");
+    const bool overlap_exchange = overlap_exchange_enabled();
     if (first_blocked != left.size()) {
       const size_t op_idx = remaining[left[first_blocked]];
       const uint64_t *nu = next_use.empty() ? nullptr : &next_use[(op_idx + 1) * s->n];

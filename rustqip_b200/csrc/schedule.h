@@ -24,6 +24,7 @@ int exchange_open_for_send(qipb200_state *s, uint32_t R, uint32_t l, void **peer
 int exchange_bits_split(qipb200_state *s, uint32_t R, uint32_t l);
 int join_halves(qipb200_state *s);
 int ensure_overlap_resources(qipb200_state *s);
+bool overlap_exchange_enabled();
 
 // schedule.cu: state <- ops[n-1] ... ops[0] state
 int run_schedule(qipb200_state *s, const qip_op *ops, size_t n_ops, uint32_t flags);
