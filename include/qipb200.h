@@ -131,10 +131,15 @@ int qipb200_apply_op_overwrite(qipb200_ctx *ctx, qip_prec prec, uint32_t n_qubit
 /* qip_iterators::matrix_ops::apply_ops (matrix_ops.rs:158-219).
  *   n_ops == 0 : copy of the overlapping index range (matrix_ops.rs:170-183);
  *   n_ops == 1 : apply_op;
- *   n_ops  > 1 : output += (ops[n_ops-1] ... ops[0]) . input, the sequential
- *                product on the full state (requires zero offsets and full-length
- *                buffers).  The reference's multi-op row iterator is NOT
- *                reproduced: SURVEY.md section 8 quirk Q5, "parity unpinned". */
+ *   n_ops  > 1 : output += the reference's multi-op row sum (matrix_ops.rs:184-217 with
+ *                sum_for_ops_cols, iterators/iterator_mapper.rs:8-31, and MultiOpIterator,
+ *                qubit_multi_iterator.rs:38-78), restated AS IT IS: op i reads its row from
+ *                the low bits left of the sub-row while columns are composed first-op-high
+ *                (SURVEY.md section 8 quirk Q5), so for ops that are not all alike the
+ *                result is not their tensor product -- exactly what the reference returns.
+ *                Offsets and ragged windows as in apply_op.  2..8 ops, at most 40 indices
+ *                in total (else QIPB200_ERR_UNSUPPORTED).  To apply gates one after the
+ *                other use a state + qipb200_state_apply_schedule. */
 int qipb200_apply_ops(qipb200_ctx *ctx, qip_prec prec, uint32_t n_qubits, const qip_op *ops,
                       size_t n_ops, const void *input, uint64_t input_len, void *output,
                       uint64_t output_len, uint64_t input_offset, uint64_t output_offset);

@@ -64,6 +64,25 @@ int qo_apply_op_f32(uint64_t n, const qip_op *op, const float *input, uint64_t i
                     float *output, uint64_t output_len, uint64_t input_offset,
                     uint64_t output_offset, int accumulate);
 
+/* apply_ops (matrix_ops.rs:158-219): [] = copy of the overlapping window, [op] = apply_op, several ops = the
+ * multi-op row iterator (iterators/iterator_mapper.rs:8-31 + qubit_multi_iterator.rs:13-79), accumulated into
+ * `output`.  Restated AS IT IS, including SURVEY.md quirk Q5 (row bits are peeled low-first per op while columns are
+ * composed first-op-high: for ops that are not all alike the result is not their tensor product).  Pinned by the six
+ * MultiOpIterator known-answer tests of the reference (qubit_multi_iterator.rs:82-205, ported in
+ * tests/test_oracle_reference_kat.py) through qo_multi_op_iterator_*.  At most QO_MAX_MULTI_OPS ops. */
+#define QO_MAX_MULTI_OPS 16
+int qo_apply_ops_f64(uint64_t n, const qip_op *ops, uint64_t n_ops, const double *input, uint64_t input_len,
+                     double *output, uint64_t output_len, uint64_t input_offset, uint64_t output_offset);
+int qo_apply_ops_f32(uint64_t n, const qip_op *ops, uint64_t n_ops, const float *input, uint64_t input_len,
+                     float *output, uint64_t output_len, uint64_t input_offset, uint64_t output_offset);
+/* MultiOpIterator::new(ns, lists).collect(): list i = lens[i] entries (cols[i][e], vals[i][2e..2e+1]). */
+uint64_t qo_multi_op_iterator_f64(const uint64_t *ns, const uint64_t *const *cols, const double *const *vals,
+                                  const uint64_t *lens, uint64_t n_lists, uint64_t *out_cols, double *out_vals,
+                                  uint64_t cap);
+uint64_t qo_multi_op_iterator_f32(const uint64_t *ns, const uint64_t *const *cols, const float *const *vals,
+                                  const uint64_t *lens, uint64_t n_lists, uint64_t *out_cols, float *out_vals,
+                                  uint64_t cap);
+
 /* qip/src/state_ops/measurement_ops.rs:11-13 */
 double qo_prob_magnitude_f64(const double *input, uint64_t len);
 float qo_prob_magnitude_f32(const float *input, uint64_t len);

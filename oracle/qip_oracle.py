@@ -38,6 +38,12 @@ def lib():
             f = getattr(L, "qo_apply_op_" + sfx)
             f.restype = C.c_int
             f.argtypes = [u64, opp, p, u64, p, u64, u64, u64, C.c_int]
+            f = getattr(L, "qo_apply_ops_" + sfx)
+            f.restype = C.c_int
+            f.argtypes = [u64, opp, u64, p, u64, p, u64, u64, u64]
+            f = getattr(L, "qo_multi_op_iterator_" + sfx)
+            f.restype = u64
+            f.argtypes = [p, p, p, p, u64, p, p, u64]
             real = C.c_double if sfx == "f64" else C.c_float
             g = getattr(L, "qo_prob_magnitude_" + sfx)
             g.restype, g.argtypes = real, [p, u64]
@@ -136,6 +142,37 @@ def apply_op(n, op, inp, out, input_offset=0, output_offset=0):
 def apply_op_overwrite(n, op, inp, out, input_offset=0, output_offset=0):
     """qip_iterators::matrix_ops::apply_op_overwrite, matrix_ops.rs:127-152."""
     _apply(n, op, inp, out, input_offset, output_offset, False)
+
+
+def apply_ops(n, ops, inp, out, input_offset=0, output_offset=0):
+    """qip_iterators::matrix_ops::apply_ops (matrix_ops.rs:158-219), accumulating into `out`."""
+    from rustqip_b200._abi import marshal_ops
+    prec = prec_of(inp.dtype)
+    assert inp.dtype == cdtype(prec) and out.dtype == inp.dtype
+    arr, keep = marshal_ops(ops, prec)
+    f = lib().qo_apply_ops_f64 if prec == QIP_F64 else lib().qo_apply_ops_f32
+    if f(n, arr, len(ops), inp.ctypes.data, inp.shape[0], out.ctypes.data, out.shape[0], input_offset, output_offset) != 0:
+        raise ValueError("oracle: malformed op list")
+
+
+def multi_op_iterator(ns, lists, dtype=np.complex128):
+    """MultiOpIterator::new(ns, lists).collect() (qubit_multi_iterator.rs:13-79); lists[i] = [(col, val), ...]."""
+    prec = prec_of(dtype)
+    cols = [np.ascontiguousarray(np.array([c for c, _ in l], dtype=np.uint64)) for l in lists]
+    vals = [np.ascontiguousarray(np.array([v for _, v in l], dtype=dtype)) for l in lists]
+    cp = (C.c_void_p * len(lists))(*[c.ctypes.data for c in cols])
+    vp = (C.c_void_p * len(lists))(*[v.ctypes.data for v in vals])
+    lens = _u64arr([len(l) for l in lists])
+    nsa = _u64arr(ns)
+    cap = 1
+    for l in lists:
+        cap *= max(len(l), 1)
+    oc = np.zeros(cap, dtype=np.uint64)
+    ov = np.zeros(cap, dtype=dtype)
+    f = lib().qo_multi_op_iterator_f64 if prec == QIP_F64 else lib().qo_multi_op_iterator_f32
+    cnt = int(f(nsa.ctypes.data, C.cast(cp, C.c_void_p), C.cast(vp, C.c_void_p), lens.ctypes.data, len(lists),
+                oc.ctypes.data, ov.ctypes.data, cap))
+    return [(int(oc[i]), complex(ov[i])) for i in range(min(cnt, cap))]
 
 
 def apply_op_raw(n, cop, state, dtype=np.complex128):

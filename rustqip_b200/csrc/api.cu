@@ -1288,31 +1288,38 @@ extern "C" int qipb200_apply_ops(qipb200_ctx *ctx, qip_prec prec, uint32_t n, co
   }
   if (n_ops == 1)  // matrix_ops.rs:167
     return qipb200_apply_op(ctx, prec, n, ops, input, input_len, output, output_len, input_offset, output_offset);
-  // Sequential product on the full state, accumulated into `output` (see header: Q5).
-  if (n > 40 || input_offset != 0 || output_offset != 0 || input_len != (1ull << n) || output_len != (1ull << n))
-    return set_err(ctx, QIPB200_ERR_UNSUPPORTED, "apply_ops with several ops needs full-length buffers and zero offsets");
+  // Several ops: the reference's multi-op row iterator (matrix_ops.rs:184-217), restated as it is -- including
+  // SURVEY.md quirk Q5 -- by k_multi_gather; accumulates into `output` like the reference (:212).
   return guarded(ctx, [&]() -> int {
-    qipb200_state *s = nullptr;
-    int st = qipb200_state_new(ctx, prec, n, &s);
-    if (st != QIPB200_OK) return st;
-    st = qipb200_state_upload(s, input, 0, input_len);
-    if (st == QIPB200_OK) st = qipb200_state_apply_schedule(s, ops, n_ops, QIPB200_SCHED_DEFAULT);
-    std::vector<char> tmp;
-    if (st == QIPB200_OK) {
-      tmp.resize(output_len * ab);
-      st = qipb200_state_download(s, tmp.data(), 0, output_len);
+    qipb200_ctx *c = ctx->children.empty() ? ctx : ctx->children[0];
+    if ((!input && input_len) || (!output && output_len)) return set_err(ctx, QIPB200_ERR_INVALID_ARG, "apply_ops: NULL amplitude buffer");
+    if (n > 40 || input_len > (1ull << 40) || output_len > (1ull << 40))
+      return set_err(ctx, QIPB200_ERR_SIZE_MISMATCH, "apply_ops: buffer length out of range");
+    if (n_ops > 8) return set_err(ctx, QIPB200_ERR_UNSUPPORTED, "apply_ops: more than 8 ops in one multi-op sweep");
+    std::vector<FlatOp> fs(n_ops);
+    uint32_t ktot = 0;
+    for (size_t i = 0; i < n_ops; ++i) {
+      std::string err;
+      int st = compile_op(&ops[i], prec, n, &fs[i], &err);
+      if (st != QIPB200_OK) return set_err(ctx, st, err);
+      ktot += fs[i].k;
     }
-    qipb200_state_free(s);
-    if (st != QIPB200_OK) return st;
-    if (prec == QIP_F32) {
-      float *o = (float *)output;
-      const float *t = (const float *)tmp.data();
-      for (uint64_t i = 0; i < 2 * output_len; ++i) o[i] += t[i];
-    } else {
-      double *o = (double *)output;
-      const double *t = (const double *)tmp.data();
-      for (uint64_t i = 0; i < 2 * output_len; ++i) o[i] += t[i];
+    if (ktot > 40) return set_err(ctx, QIPB200_ERR_UNSUPPORTED, "apply_ops: more than 40 indices over all ops");
+    if (cudaSetDevice(c->device) != cudaSuccess) return set_err(ctx, QIPB200_ERR_CUDA, "cudaSetDevice");
+    int st;
+    if ((st = grow(c, &c->d_in, &c->d_in_bytes, std::max<size_t>(input_len * ab, 16))) != QIPB200_OK ||
+        (st = grow(c, &c->d_out, &c->d_out_bytes, std::max<size_t>(output_len * ab, 16))) != QIPB200_OK) {
+      if (c != ctx) ctx->err = c->err;
+      return st;
     }
+    cudaError_t e = cudaSuccess;
+    if (input_len) e = cudaMemcpyAsync(c->d_in, input, input_len * ab, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && output_len) e = cudaMemcpyAsync(c->d_out, output, output_len * ab, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess)
+      e = launch_multi_gather(prec, fs, c->d_in, input_len, input_offset, c->d_out, output_len, output_offset, c->stream, &c->launches);
+    if (e == cudaSuccess && output_len) e = cudaMemcpyAsync(output, c->d_out, output_len * ab, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return set_err(ctx, QIPB200_ERR_CUDA, std::string("apply_ops: ") + cudaGetErrorString(e));
     return (int)QIPB200_OK;
   });
 }

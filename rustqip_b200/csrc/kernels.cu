@@ -749,6 +749,209 @@ static cudaError_t launch_gather_t(const FlatOp &f, const R *in, uint64_t in_len
   return e;
 }
 
+// ---------------------------------------------------------------------------------
+// apply_ops with several ops (qip-iterators/src/matrix_ops.rs:184-217): one thread == one output row of
+// sum_for_ops_cols (iterators/iterator_mapper.rs:8-31) over the MultiOpIterator (qubit_multi_iterator.rs:38-78),
+// restated as the reference computes it -- op i reads its row from the LOW bits of what is left of matrow
+// (iterator_mapper.rs:17-18,24), the column is composed first-op-high (qubit_multi_iterator.rs:48-52), the value is
+// ((one * v0) * v1) ..., the cursor of the last op moves fastest and the items are summed from zero in that order
+// (SURVEY.md quirk Q5 included: for ops that are not all alike this is not their tensor product).  Same never-
+// contracted arithmetic as k_gather, so results are bit-identical to the oracle's restatement.
+// ---------------------------------------------------------------------------------
+constexpr uint32_t kMultiMaxOps = 8;
+
+struct MultiOpDesc {
+  uint32_t k, kop;
+  int base_kind;
+  uint64_t thr;
+  const void *dense;
+  const uint64_t *sp_rowptr, *sp_col;
+  const void *sp_val;
+};
+
+struct MultiGatherArgs {
+  uint32_t n_ops, ktot;
+  uint64_t all_mask;
+  uint32_t idx_bits[40];  // concatenated, reference order: idx_bits[j] <-> sub-index bit ktot-1-j
+  MultiOpDesc op[kMultiMaxOps];
+  uint64_t in_len, in_off, out_len, out_off;
+};
+
+template <typename R>
+__global__ void __launch_bounds__(kThreads)
+    k_multi_gather(const R *__restrict__ in, R *__restrict__ out, const __grid_constant__ MultiGatherArgs a) {
+  const uint64_t o = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (o >= a.out_len) return;
+  const uint64_t row = a.out_off + o;
+  uint64_t matrow = 0;
+  for (uint32_t j = 0; j < a.ktot; ++j) matrow |= ((row >> a.idx_bits[j]) & 1ull) << (a.ktot - 1 - j);
+  const uint64_t row_cleared = row & ~a.all_mask;
+
+  uint64_t op_row[kMultiMaxOps], cur[kMultiMaxOps], pcol[kMultiMaxOps + 1];
+  R pr[kMultiMaxOps + 1], pi[kMultiMaxOps + 1];
+  {
+    uint64_t acc_row = matrow;
+    for (uint32_t i = 0; i < a.n_ops; ++i) {
+      op_row[i] = acc_row & ((1ull << a.op[i].k) - 1ull);
+      acc_row >>= a.op[i].k;
+    }
+  }
+  // next entry of op i's row at or after cursor cur[i] (cursor semantics per kind); false when the row is exhausted
+  auto next_entry = [&](uint32_t i, uint64_t *col, R *vr, R *vi) -> bool {
+    const MultiOpDesc &d = a.op[i];
+    if (op_row[i] < d.thr) {  // identity row of a control op: the single entry (row, 1)
+      if (cur[i]) return false;
+      cur[i] = 1;
+      *col = op_row[i];
+      *vr = (R)1;
+      *vi = (R)0;
+      return true;
+    }
+    const uint64_t r = op_row[i] - d.thr;
+    if (d.base_kind == QIP_OP_MATRIX) {
+      const R *m = static_cast<const R *>(d.dense) + 2 * (r << d.kop);
+      const uint64_t side = 1ull << d.kop;
+      for (uint64_t c = cur[i]; c < side; ++c) {
+        const R x = m[2 * c], y = m[2 * c + 1];
+        if (x == (R)0 && y == (R)0) continue;
+        cur[i] = c + 1;
+        *col = c + d.thr;
+        *vr = x;
+        *vi = y;
+        return true;
+      }
+      return false;
+    }
+    if (d.base_kind == QIP_OP_SPARSE) {
+      const uint64_t e = d.sp_rowptr[r] + cur[i];
+      if (e >= d.sp_rowptr[r + 1]) return false;
+      const R *v = static_cast<const R *>(d.sp_val);
+      cur[i] += 1;
+      *col = d.sp_col[e] + d.thr;
+      *vr = v[2 * e];
+      *vi = v[2 * e + 1];
+      return true;
+    }
+    if (cur[i]) return false;  // swap
+    cur[i] = 1;
+    const uint32_t half = d.kop >> 1;
+    const uint64_t lower_mask = ~(~0ull << half);
+    *col = (((r & lower_mask) << half) + (r >> half)) + d.thr;
+    *vr = (R)1;
+    *vi = (R)0;
+    return true;
+  };
+
+  R ar = (R)0, ai = (R)0;
+  pcol[0] = 0;
+  pr[0] = (R)1;  // P::one()
+  pi[0] = (R)0;
+  int lvl = 0;
+  cur[0] = 0;
+  while (lvl >= 0) {
+    uint64_t col;
+    R vr, vi;
+    if (!next_entry((uint32_t)lvl, &col, &vr, &vi)) {
+      --lvl;
+      continue;
+    }
+    pcol[lvl + 1] = (pcol[lvl] << a.op[lvl].k) | col;
+    pr[lvl + 1] = Arith<R>::sub(Arith<R>::mul(pr[lvl], vr), Arith<R>::mul(pi[lvl], vi));  // acc_val * val
+    pi[lvl + 1] = Arith<R>::add(Arith<R>::mul(pr[lvl], vi), Arith<R>::mul(pi[lvl], vr));
+    if ((uint32_t)lvl + 1 < a.n_ops) {
+      ++lvl;
+      cur[lvl] = 0;
+      continue;
+    }
+    const uint64_t c = pcol[lvl + 1];
+    uint64_t colbits = row_cleared;
+    for (uint32_t j = 0; j < a.ktot; ++j) colbits |= ((c >> (a.ktot - 1 - j)) & 1ull) << a.idx_bits[j];
+    R tr = (R)0, ti = (R)0;
+    if (colbits >= a.in_off && colbits - a.in_off < a.in_len) {
+      const R xr = in[2 * (colbits - a.in_off)], xi = in[2 * (colbits - a.in_off) + 1];
+      tr = Arith<R>::sub(Arith<R>::mul(pr[lvl + 1], xr), Arith<R>::mul(pi[lvl + 1], xi));
+      ti = Arith<R>::add(Arith<R>::mul(pr[lvl + 1], xi), Arith<R>::mul(pi[lvl + 1], xr));
+    }
+    ar = Arith<R>::add(ar, tr);
+    ai = Arith<R>::add(ai, ti);
+  }
+  out[2 * o] = Arith<R>::add(out[2 * o], ar);  // *outputloc += ... (matrix_ops.rs:212)
+  out[2 * o + 1] = Arith<R>::add(out[2 * o + 1], ai);
+}
+
+template <typename R>
+static cudaError_t launch_multi_gather_t(const std::vector<FlatOp> &fs, const R *in, uint64_t in_len, uint64_t in_off, R *out,
+                                         uint64_t out_len, uint64_t out_off, cudaStream_t s, uint64_t *launches) {
+  if (out_len == 0) return cudaSuccess;
+  if (fs.size() < 2 || fs.size() > kMultiMaxOps) return cudaErrorInvalidValue;
+  MultiGatherArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_ops = (uint32_t)fs.size();
+  a.in_len = in_len;
+  a.in_off = in_off;
+  a.out_len = out_len;
+  a.out_off = out_off;
+  std::vector<void *> owned;
+  cudaError_t e = cudaSuccess;
+  auto dev_copy = [&](const void *src, size_t bytes, const void **dst) {
+    void *d = nullptr;
+    if (e != cudaSuccess) return;
+    if ((e = cudaMallocAsync(&d, bytes + 16, s)) != cudaSuccess) return;
+    owned.push_back(d);
+    if (bytes) e = cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s);
+    *dst = d;
+  };
+  for (size_t i = 0; i < fs.size() && e == cudaSuccess; ++i) {
+    const FlatOp &f = fs[i];
+    if (a.ktot + f.k > 40) {
+      e = cudaErrorInvalidValue;
+      break;
+    }
+    for (uint32_t j = 0; j < f.k; ++j) {
+      a.idx_bits[a.ktot++] = f.idx_bits[j];
+      a.all_mask |= 1ull << f.idx_bits[j];
+    }
+    MultiOpDesc &d = a.op[i];
+    d.k = f.k;
+    d.kop = f.kop;
+    d.base_kind = f.base_kind;
+    d.thr = f.nc ? ((1ull << f.k) - (1ull << f.kop)) : 0;
+    std::vector<R> tmp;
+    if (f.base_kind == QIP_OP_MATRIX || (f.base_kind == QIP_OP_SPARSE && f.has_dense)) {
+      d.base_kind = QIP_OP_MATRIX;
+      tmp.resize(2 * f.dense.size());
+      for (size_t t = 0; t < f.dense.size(); ++t) {
+        tmp[2 * t] = (R)f.dense[t].real();
+        tmp[2 * t + 1] = (R)f.dense[t].imag();
+      }
+      dev_copy(tmp.data(), tmp.size() * sizeof(R), &d.dense);
+    } else if (f.base_kind == QIP_OP_SPARSE) {
+      tmp.resize(2 * f.sp_val.size());
+      for (size_t t = 0; t < f.sp_val.size(); ++t) {
+        tmp[2 * t] = (R)f.sp_val[t].real();
+        tmp[2 * t + 1] = (R)f.sp_val[t].imag();
+      }
+      dev_copy(tmp.data(), tmp.size() * sizeof(R), &d.sp_val);
+      dev_copy(f.sp_rowptr.data(), f.sp_rowptr.size() * 8, (const void **)&d.sp_rowptr);
+      dev_copy(f.sp_col.data(), f.sp_col.size() * 8, (const void **)&d.sp_col);
+    }
+  }
+  if (e == cudaSuccess) {
+    k_multi_gather<R><<<grid_for(out_len), kThreads, 0, s>>>(in, out, a);
+    ++*launches;
+    e = cudaGetLastError();
+  }
+  for (size_t i = 0; i < owned.size(); ++i) cudaFreeAsync(owned[i], s);
+  return e;
+}
+
+cudaError_t launch_multi_gather(qip_prec prec, const std::vector<FlatOp> &fs, const void *in, uint64_t in_len, uint64_t in_off,
+                                void *out, uint64_t out_len, uint64_t out_off, cudaStream_t s, uint64_t *launches) {
+  return prec == QIP_F32 ? launch_multi_gather_t<float>(fs, (const float *)in, in_len, in_off, (float *)out, out_len, out_off, s, launches)
+                         : launch_multi_gather_t<double>(fs, (const double *)in, in_len, in_off, (double *)out, out_len, out_off, s,
+                                                         launches);
+}
+
 cudaError_t launch_gather(qip_prec prec, const FlatOp &f, uint32_t, const void *in, uint64_t in_len,
                           uint64_t in_off, void *out, uint64_t out_len, uint64_t out_off, bool accumulate,
                           cudaStream_t s, uint64_t *launches) {

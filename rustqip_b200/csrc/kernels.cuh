@@ -40,6 +40,9 @@ cudaError_t launch_bitswap(qip_prec prec, void *psi, uint32_t n_local, uint64_t 
 cudaError_t launch_gather(qip_prec prec, const FlatOp &f, uint32_t n_qubits, const void *in,
                           uint64_t in_len, uint64_t in_off, void *out, uint64_t out_len,
                           uint64_t out_off, bool accumulate, cudaStream_t s, uint64_t *launches);
+// apply_ops with several ops as the reference computes it (multi-op row iterator, accumulating; 2..8 ops).
+cudaError_t launch_multi_gather(qip_prec prec, const std::vector<FlatOp> &fs, const void *in, uint64_t in_len, uint64_t in_off,
+                                void *out, uint64_t out_len, uint64_t out_off, cudaStream_t s, uint64_t *launches);
 
 // sum |a|^2 into *d_out (a device double, zeroed by the launcher).
 cudaError_t launch_norm2(qip_prec prec, const void *psi, uint64_t len, double *d_out, cudaStream_t s,

@@ -1090,6 +1090,7 @@ PlanConfig default_plan_config(qip_prec prec, uint32_t n_local) {
   if (const char *e = getenv("QIPB200_NO_BLOCK_FUSION")) c.fuse_blocks = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_NO_PEEPHOLE")) c.peephole = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_SEED_SEARCH")) c.seed_search = atoi(e) != 0;
+  if (const char *e = getenv("QIPB200_PLAN_LOOKAHEAD")) c.lookahead = (uint32_t)std::max(0, atoi(e));
   if (const char *e = getenv("QIPB200_NO_HAD")) c.unnormalised_h = atoi(e) == 0;
   if (const char *e = getenv("QIPB200_KEEP_REAL")) c.keep_real = atoi(e) != 0;
   if (const char *e = getenv("QIPB200_NO_LOOKBACK")) c.lookback = atoi(e) == 0;
@@ -1115,6 +1116,160 @@ PlanConfig default_plan_config(qip_prec prec, uint32_t n_local) {
   if (prec == QIP_F32 && c.L == 0 && c.T >= 1) c.L = 1;  // a 16-byte unit holds two f32 amplitudes
   return c;
 }
+
+// ---- tile-bit selection -----------------------------------------------------------------
+// One greedy selection in program order, the tile's high bits pre-seeded with `seed`.
+struct Pick {
+  uint64_t S_high = 0;
+  std::vector<size_t> taken, left;
+  double unfused = 0.0;
+  long single = -1;  // first op that may run alone right now: not blocked, commutes past EVERY earlier op
+  size_t n_nd = 0;   // non-diagonal gates absorbed (diagonal ones ride along in any pass)
+};
+
+struct Selector {
+  const std::vector<OpInfo> &info;
+  const std::vector<char> *blocked;
+  bool can_tile;
+  uint64_t low_mask;
+  uint32_t m;
+  uint64_t budget;
+
+  Pick select(const std::vector<size_t> &remaining, uint64_t seed) const {
+    Pick pk;
+    pk.S_high = seed;
+    uint64_t pend_d = 0, pend_nd = 0, bytes = 0, seen_d = 0, seen_nd = 0;
+    for (size_t r = 0; r < remaining.size(); ++r) {
+      const size_t idx = remaining[r];
+      const OpInfo &o = info[idx];
+      const bool is_blocked = blocked && (*blocked)[idx];
+      const bool conflict = (o.nd & (pend_d | pend_nd)) || (o.dg & pend_nd);
+      if (pk.single < 0 && !is_blocked && !((o.nd & (seen_d | seen_nd)) || (o.dg & seen_nd))) pk.single = (long)r;
+      seen_d |= o.dg;
+      seen_nd |= o.nd;
+      if (can_tile && !conflict && o.tile_ok && bytes + o.est_bytes <= budget) {
+        const uint64_t need = o.need_tile & ~low_mask & ~pk.S_high;
+        if ((uint32_t)popc(pk.S_high | need) <= m) {
+          pk.S_high |= need;
+          pk.taken.push_back(idx);
+          pk.unfused += o.unfused_cost;
+          pk.n_nd += o.nd ? 1 : 0;
+          bytes += o.est_bytes;
+          continue;
+        }
+      }
+      pend_d |= o.dg;
+      pend_nd |= o.nd;
+      pk.left.push_back(idx);
+    }
+    return pk;
+  }
+
+  uint64_t candidate_bits(const Pick &pk) const {
+    uint64_t cand = 0;
+    for (size_t r = 0; r < pk.left.size() && r < 64; ++r) cand |= info[pk.left[r]].need_tile & ~low_mask;
+    return cand & ~pk.S_high;
+  }
+
+  // The plain greedy fills the tile with the bits of the first gates it meets.  Try reserving slots for bits that
+  // gates left behind need (forward selection, one bit at a time): keep whichever selection absorbs the most
+  // non-diagonal gates.
+  Pick seed_search(const std::vector<size_t> &remaining, Pick best, std::vector<Pick> *chain = nullptr) const {
+    uint64_t seeds = 0;
+    for (uint32_t round = 0; round < m && !best.left.empty(); ++round) {
+      const uint64_t cand = candidate_bits(best);
+      uint64_t best_bit = 0;
+      for (uint32_t bit = 0; bit < 64; ++bit) {
+        if (!((cand >> bit) & 1)) continue;
+        Pick alt = select(remaining, seeds | (1ull << bit));
+        if (alt.n_nd > best.n_nd) {
+          if (chain) chain->push_back(best);
+          best = std::move(alt);
+          best_bit = 1ull << bit;
+        }
+      }
+      if (!best_bit) break;
+      seeds |= best_bit;
+    }
+    return best;
+  }
+
+  // Sweeps the plain greedy needs for `remaining` (what is left when it gets stuck behind blocked ops is charged at
+  // the average rate of a pass).
+  double rollout(std::vector<size_t> remaining) const {
+    double cost = 0.0;
+    while (!remaining.empty()) {
+      Pick pk = select(remaining, 0);
+      if (pk.taken.empty() || pk.unfused <= 1.05) {
+        if (pk.single < 0) {
+          size_t nd = 0;
+          for (size_t r = 0; r < remaining.size(); ++r) nd += info[remaining[r]].nd ? 1 : 0;
+          return cost + nd / 24.0;
+        }
+        cost += std::min(1.0, info[remaining[(size_t)pk.single]].unfused_cost);
+        remaining.erase(remaining.begin() + pk.single);
+        continue;
+      }
+      cost += 1.0;
+      remaining.swap(pk.left);
+    }
+    return cost;
+  }
+
+  // Look-ahead: a pass that absorbs the most gates NOW is not always the one that leaves the cheapest rest.  Score
+  // candidate tile-bit sets by 1 + the sweeps a plain greedy needs for what they leave behind.
+  Pick lookahead(const std::vector<size_t> &remaining, Pick incumbent, uint32_t width) const {
+    std::vector<Pick> cands;
+    cands.push_back(select(remaining, 0));
+    (void)seed_search(remaining, cands[0], &cands);
+    double best_cost = rollout(incumbent.left);
+    std::vector<uint64_t> tried;
+    tried.push_back(incumbent.S_high);
+    // beam over seed sets: each round extends the best `width` seed sets by one more reserved bit
+    struct Node {
+      uint64_t seeds;
+      double cost;
+      size_t n_nd;
+    };
+    std::vector<Node> frontier(1, Node{0, 0.0, 0});
+    Pick best = std::move(incumbent);
+    for (size_t c = 0; c < cands.size(); ++c) {
+      const double cost = rollout(cands[c].left);
+      if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && cands[c].n_nd > best.n_nd)) {
+        best_cost = cost;
+        best = cands[c];
+      }
+    }
+    for (uint32_t round = 0; round < m; ++round) {
+      std::vector<Node> next;
+      for (size_t f = 0; f < frontier.size(); ++f) {
+        const Pick base = select(remaining, frontier[f].seeds);
+        const uint64_t cand = candidate_bits(base);
+        for (uint32_t bit = 0; bit < 64; ++bit) {
+          if (!((cand >> bit) & 1)) continue;
+          const uint64_t seeds = frontier[f].seeds | (1ull << bit);
+          if ((uint32_t)popc(seeds) > m) continue;
+          bool dup = false;
+          for (size_t t = 0; t < next.size(); ++t) dup = dup || next[t].seeds == seeds;
+          if (dup) continue;
+          Pick alt = select(remaining, seeds);
+          if (alt.taken.empty()) continue;
+          const double cost = rollout(alt.left);
+          next.push_back(Node{seeds, cost, alt.n_nd});
+          if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && alt.n_nd > best.n_nd)) {
+            best_cost = cost;
+            best = std::move(alt);
+          }
+        }
+      }
+      if (next.empty()) break;
+      std::sort(next.begin(), next.end(), [](const Node &a, const Node &b) { return a.cost != b.cost ? a.cost < b.cost : a.n_nd > b.n_nd; });
+      if (next.size() > width) next.resize(width);
+      frontier.swap(next);
+    }
+    return best;
+  }
+};
 
 void op_dependency_masks(const FlatOp &f, DepMasks *out) {
   const OpInfo o = analyse(f);
@@ -1165,66 +1320,10 @@ void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec
     bool done = false, stuck = false;
     for (int attempt = 0; attempt < 3 && !done; ++attempt) {
       const uint64_t budget = (uint64_t)byte_budget * kBudgetScale[attempt];
-      // One greedy selection in program order, the tile's high bits pre-seeded with `seed`.
-      struct Pick {
-        uint64_t S_high = 0;
-        std::vector<size_t> taken, left;
-        double unfused = 0.0;
-        long single = -1;  // first op that may run alone right now: not blocked, commutes past EVERY earlier op
-        size_t n_nd = 0;   // non-diagonal gates absorbed (diagonal ones ride along in any pass)
-      };
-      auto select = [&](uint64_t seed) {
-        Pick pk;
-        pk.S_high = seed;
-        uint64_t pend_d = 0, pend_nd = 0, bytes = 0, seen_d = 0, seen_nd = 0;
-        for (size_t r = 0; r < remaining.size(); ++r) {
-          const size_t idx = remaining[r];
-          const OpInfo &o = info[idx];
-          const bool is_blocked = blocked && (*blocked)[idx];
-          const bool conflict = (o.nd & (pend_d | pend_nd)) || (o.dg & pend_nd);
-          if (pk.single < 0 && !is_blocked && !((o.nd & (seen_d | seen_nd)) || (o.dg & seen_nd))) pk.single = (long)r;
-          seen_d |= o.dg;
-          seen_nd |= o.nd;
-          if (can_tile && !conflict && o.tile_ok && bytes + o.est_bytes <= budget) {
-            const uint64_t need = o.need_tile & ~low_mask & ~pk.S_high;
-            if ((uint32_t)popc(pk.S_high | need) <= m) {
-              pk.S_high |= need;
-              pk.taken.push_back(idx);
-              pk.unfused += o.unfused_cost;
-              pk.n_nd += o.nd ? 1 : 0;
-              bytes += o.est_bytes;
-              continue;
-            }
-          }
-          pend_d |= o.dg;
-          pend_nd |= o.nd;
-          pk.left.push_back(idx);
-        }
-        return pk;
-      };
-      Pick best = select(0);
-      if (cfg.seed_search && can_tile) {
-        // The plain greedy fills the tile with the bits of the first gates it meets.  Try reserving slots
-        // for bits that gates left behind need (forward selection, one bit at a time): keep whichever
-        // selection absorbs the most non-diagonal gates.
-        uint64_t seeds = 0;
-        for (uint32_t round = 0; round < m && !best.left.empty(); ++round) {
-          uint64_t cand = 0;
-          for (size_t r = 0; r < best.left.size() && r < 64; ++r) cand |= info[best.left[r]].need_tile & ~low_mask;
-          cand &= ~best.S_high;
-          uint64_t best_bit = 0;
-          for (uint32_t bit = 0; bit < 64; ++bit) {
-            if (!((cand >> bit) & 1)) continue;
-            Pick alt = select(seeds | (1ull << bit));
-            if (alt.n_nd > best.n_nd) {
-              best = std::move(alt);
-              best_bit = 1ull << bit;
-            }
-          }
-          if (!best_bit) break;
-          seeds |= best_bit;
-        }
-      }
+      Selector sel{info, blocked, can_tile, low_mask, m, budget};
+      Pick best = sel.select(remaining, 0);
+      if (cfg.seed_search && can_tile) best = sel.seed_search(remaining, std::move(best));
+      if (cfg.lookahead && can_tile && !best.left.empty()) best = sel.lookahead(remaining, std::move(best), cfg.lookahead);
       uint64_t S_high = best.S_high;
       std::vector<size_t> &taken = best.taken, &left = best.left;
       const double unfused = best.unfused;

@@ -55,7 +55,8 @@ def apply_op_overwrite(n: int, op: MatrixOp, input: np.ndarray, output: np.ndarr
 
 def apply_ops(n: int, ops: Sequence[MatrixOp], input: np.ndarray, output: np.ndarray,
               input_offset: int = 0, output_offset: int = 0, ctx: Optional[Context] = None) -> None:
-    """matrix_ops.rs:158-219 ([] = overlap copy, [op] = apply_op, else sequential product; Q5)."""
+    """matrix_ops.rs:158-219 ([] = overlap copy, [op] = apply_op, else the reference's multi-op row iterator,
+    quirk Q5 included; accumulates into `output`)."""
     ctx = ctx or default_context()
     prec = _bufs(input, output)
     arr, keep = marshal_ops(ops, prec)

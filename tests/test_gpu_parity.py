@@ -179,12 +179,46 @@ def test_dropin_apply_ops(ctx):
     got = np.zeros_like(psi)
     mo.apply_ops(n, [op], psi, got, ctx=ctx)
     assert np.array_equal(got, want)
-    # several ops: sequential product, accumulated
+    # several ops: the reference's multi-op row iterator (quirk Q5 included), accumulated: bit-identical to the oracle
     ops = [gates.x(0), gates.x(3), gates.h(1)]
-    want = qo.run_pipeline(n, ops, state=psi)
-    got = np.zeros_like(psi)
+    want = psi.copy()
+    qo.apply_ops(n, ops, psi, want)
+    got = psi.copy()
     mo.apply_ops(n, ops, psi, got, ctx=ctx)
-    assert np.allclose(got, want, atol=1e-14)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_dropin_apply_ops_multi_op_iterator_bit_identical(ctx, dtype):
+    """matrix_ops.rs:184-217 + iterator_mapper.rs:8-31 + qubit_multi_iterator.rs:38-78 on the device (k_multi_gather):
+    every op kind in the list, offsets and ragged windows, accumulation into a non-zero output."""
+    rng = np.random.default_rng(77)
+    n = 9
+    psi = rand_state(n, dtype, 8)
+    sparse = MatrixOp.new_sparse([6, 7], [[(0, 1.0), (3, 0.5j)], [(1, -1.0)], [(2, 1j), (3, 2.0)], [(0, 0.25)]])
+    lists = [
+        [gates.h(0), gates.t(4)],
+        [gates.cnot(1, 5), make_matrix_op([2, 3], rand_unitary(2, rng).reshape(-1)), gates.x(8)],
+        [make_swap_op([0, 1], [4, 5]), sparse, gates.toffoli(2, 3, 8)],
+        [make_control_op([7], make_control_op([1], gates.h(3))), make_matrix_op([0, 5, 6], rand_unitary(3, rng).reshape(-1))],
+        [gates.h(q) for q in (8, 2, 5, 0)],
+        [gates.x(q) for q in range(8)],
+    ]
+    for ops in lists:
+        want = rand_state(n, dtype, 9)
+        got = want.copy()
+        qo.apply_ops(n, ops, psi, want)
+        mo.apply_ops(n, ops, psi, got, ctx=ctx)
+        assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), [repr(o) for o in ops]
+    # windows: input [40, 400), output [100, 500)
+    ops = lists[1]
+    want = np.zeros(400, dtype=dtype)
+    got = np.zeros(400, dtype=dtype)
+    qo.apply_ops(n, ops, np.ascontiguousarray(psi[40:400]), want, 40, 100)
+    mo.apply_ops(n, ops, np.ascontiguousarray(psi[40:400]), got, 40, 100, ctx=ctx)
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8)) and np.any(got != 0)
+    with pytest.raises(Exception):
+        mo.apply_ops(n, [gates.x(0)] * 9, psi, got, ctx=ctx)  # more than 8 ops in one sweep: UNSUPPORTED, not a wrong answer
 
 
 # ---------------------------------------------------------------------------------------

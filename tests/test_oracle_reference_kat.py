@@ -80,6 +80,102 @@ def test_c_iterator():  # :355-379
     assert np.array_equal(_row_matrix(op, 2), [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]])
 
 
+# ---- qip-iterators/src/iterators/qubit_multi_iterator.rs:82-205 (MultiOpIterator) -------------------
+def test_multi_iter_trivial():  # :87-98
+    assert qo.multi_op_iterator([1, 1], [[(1, 1.0)], [(0, 1.0)]]) == [(2, 1 + 0j)]
+
+
+def test_multi_iter_nontrivial():  # :100-112
+    assert qo.multi_op_iterator([1, 1], [[(0, 1.0), (1, 1.0)], [(0, 1.0)]]) == [(0, 1 + 0j), (2, 1 + 0j)]
+
+
+def test_multi_iter_nontrivial_other():  # :114-126
+    assert qo.multi_op_iterator([1, 1], [[(0, 1.0)], [(0, 1.0), (1, 1.0)]]) == [(0, 1 + 0j), (1, 1 + 0j)]
+
+
+def _multi_iter_matrix(n, lists_of_row, ns):
+    m = np.zeros((1 << n, 1 << n))
+    for i in range(1 << n):
+        for col, _ in qo.multi_op_iterator(ns, lists_of_row(i)):
+            m[i, col] = 1.0
+    return m
+
+
+def test_multi_iter_mat_iterator():  # :128-149
+    assert np.array_equal(_multi_iter_matrix(1, lambda i: [[(1 - i, 1.0)]], [1]), [[0, 1], [1, 0]])
+
+
+def test_multi_iter_double_mat_identity():  # :151-177
+    m = _multi_iter_matrix(2, lambda i: [[((i & 2) >> 1, 1.0)], [(i & 1, 1.0)]], [1, 1])
+    assert np.array_equal(m, np.eye(4))
+
+
+def test_multi_iter_double_mat_swap():  # :179-205
+    m = _multi_iter_matrix(2, lambda i: [[((~i & 2) >> 1, 1.0)], [(~i & 1, 1.0)]], [1, 1])
+    assert np.array_equal(m, np.eye(4)[::-1])
+
+
+def test_apply_ops_empty_and_single():  # matrix_ops.rs:167-183
+    rng = np.random.default_rng(5)
+    n = 4
+    psi = (rng.standard_normal(16) + 1j * rng.standard_normal(16)).astype(np.complex128)
+    out = np.zeros(10, dtype=np.complex128)
+    qo.apply_ops(n, [], psi[2:14].copy(), out, input_offset=2, output_offset=5)  # window [5, 14)
+    assert np.array_equal(out[:9], psi[5:14]) and out[9] == 0
+    op = MatrixOp.new_matrix([1], from_reals([0.0, 1.0, 1.0, 0.0]))
+    a = np.zeros(16, dtype=np.complex128)
+    b = np.zeros(16, dtype=np.complex128)
+    qo.apply_ops(n, [op], psi, a)
+    qo.apply_op(n, op, psi, b)
+    assert np.array_equal(a, b)
+
+
+def test_apply_ops_identical_single_qubit_ops():
+    """What the reference's benches do (state_bench.rs:226-236): the same 1-qubit gate on several qubits.  Op i takes
+    its ROW bit from the qubit of op (last - i) and writes its COLUMN bit at its own qubit (quirk Q5), so the result is
+    the tensor product applied to the input with those qubits in reversed order."""
+    rng = np.random.default_rng(6)
+    n = 5
+    psi = (rng.standard_normal(32) + 1j * rng.standard_normal(32)).astype(np.complex128)
+    h = [x / np.sqrt(2) for x in (1.0, 1.0, 1.0, -1.0)]
+    qs = (0, 2, 3)
+    ops = [MatrixOp.new_matrix([q], from_reals(h)) for q in qs]
+    out = np.zeros(32, dtype=np.complex128)
+    qo.apply_ops(n, ops, psi, out)
+    rev = np.zeros_like(psi)
+    for i in range(32):
+        j = i
+        for a, b in zip(qs, qs[::-1]):
+            j = (j & ~(1 << (n - 1 - a))) | (((i >> (n - 1 - b)) & 1) << (n - 1 - a))
+        rev[j] = psi[i]
+    assert np.allclose(out, qo.run_pipeline(n, ops, state=rev), atol=1e-14)
+    assert not np.allclose(out, qo.run_pipeline(n, ops, state=psi), atol=1e-3)
+
+
+def test_apply_ops_quirk_q5():
+    """SURVEY.md Q5, restated as the reference computes it: row bits are peeled low-first per op
+    (iterator_mapper.rs:16-25), columns composed first-op-high (qubit_multi_iterator.rs:48-52): [X(q0), I(q1)] on
+    two qubits is a 4-cycle, not X (x) I."""
+    x = MatrixOp.new_matrix([0], from_reals([0.0, 1.0, 1.0, 0.0]))
+    i2 = MatrixOp.new_matrix([1], from_reals([1.0, 0.0, 0.0, 1.0]))
+    m = np.zeros((4, 4))
+    for col in range(4):
+        e = np.zeros(4, dtype=np.complex128)
+        e[col] = 1
+        out = np.zeros(4, dtype=np.complex128)
+        qo.apply_ops(2, [x, i2], e, out)
+        m[:, col] = out.real
+    # row r = (b1 b0): op 0 (X) sees b0, op 1 (I) sees b1; column = (X-col << 1) | I-col = ((1 - b0) << 1) | b1
+    expect = np.zeros((4, 4))
+    for r in range(4):
+        b1, b0 = r >> 1, r & 1
+        expect[r, ((1 - b0) << 1) | b1] = 1
+    assert np.array_equal(m, expect)
+    assert not np.array_equal(m, np.kron([[0, 1], [1, 0]], np.eye(2)))
+    p = np.linalg.matrix_power(m, 4)
+    assert np.array_equal(p, np.eye(4)) and not np.array_equal(np.linalg.matrix_power(m, 2), np.eye(4))
+
+
 # ---- qip/src/state_ops/matrix_ops.rs:265-377 ---------------------------------------------
 def test_get_bit_set_bit():  # :265-275
     assert not qo.get_bit(1, 1)
