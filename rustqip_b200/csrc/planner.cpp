@@ -1194,8 +1194,9 @@ struct Selector {
     return best;
   }
 
-  // Sweeps the plain greedy needs for `remaining` (what is left when it gets stuck behind blocked ops is charged at
-  // the average rate of a pass).
+  // Sweeps the plain greedy needs for `remaining`; what is left when it gets stuck behind blocked ops is charged at
+  // the average rate of a pass.  (Rollouts cut off after a few passes or a window of ops were tried: the estimate of
+  // the cut-off tail misleads the search -- 29..48 sweeps instead of 25 on the N=30 circuit.)
   double rollout(std::vector<size_t> remaining) const {
     double cost = 0.0;
     while (!remaining.empty()) {

@@ -253,8 +253,11 @@ struct PlanConfig {
   bool unnormalised_h = true;   // Hadamards as add/sub butterflies, the scale folded into another gate of the pass
   bool seed_search = false;     // tile-bit choice: also try reserving slots for bits the greedy left out (fewer passes, but
                                 // more elementary ops; measured slower on the N=30 circuit: 25 passes 309 ms vs 29 passes 302 ms)
-  uint32_t lookahead = 0;       // tile-bit choice: beam width of the look-ahead search (0 = off): candidate bit sets are scored
-                                // by the sweeps a plain greedy needs for the gates they leave behind
+  uint32_t lookahead = 0;       // tile-bit choice: beam width of the look-ahead search (0 = off, env QIPB200_PLAN_LOOKAHEAD): candidate
+                                // bit sets are scored by the sweeps a plain greedy needs for the gates they leave behind.  CPU
+                                // measurements (tests/native emulator): N=30 d40 circuits 25/23/25 -> 24/22/22 sweeps, config 2
+                                // 22 -> 20, at 50-70 ms of planning instead of < 5 ms: worth it only for a circuit run many
+                                // times, hence opt-in
   uint32_t jit_group_bits = 0;     // > 0: also emit the pass as groups of this many bits for the generated kernels
   int reserve_bit = -1;            // a local bit the tile-bit padding avoids (sharded states keep their top local bit out
                                    // of the tiles so that a pass can be run in two halves around a migration)

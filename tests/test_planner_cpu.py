@@ -102,6 +102,7 @@ def test_planner_matches_oracle_mixed(emul, n, T, Lo, fuse):
     {"QIPB200_SEED_SEARCH": "1"}, {"QIPB200_KEEP_REAL": "1"}, {"QIPB200_NO_HAD": "1"}, {"QIPB200_NO_LOOKBACK": "1"},
     {"QIPB200_NO_FILL": "1"}, {"QIPB200_NO_PEEPHOLE": "1"}, {"QIPB200_NO_PHASEN": "1"}, {"QIPB200_X_MOVES": "1"},
     {"QIPB200_COMPOSE": "3"}, {"QIPB200_SEED_SEARCH": "1", "QIPB200_KEEP_REAL": "1", "QIPB200_NO_FILL": "1"},
+    {"QIPB200_PLAN_LOOKAHEAD": "2"}, {"QIPB200_PLAN_LOOKAHEAD": "1", "QIPB200_SEED_SEARCH": "1"},
 ])
 def test_planner_knobs_keep_parity(emul, monkeypatch, knobs):
     """Every planner switch (read from the environment at plan time) must leave the amplitudes alone."""
