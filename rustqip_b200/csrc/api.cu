@@ -322,6 +322,11 @@ extern "C" int qipb200_jit_precompile(qip_prec prec, uint32_t n_qubits, const qi
     }
   }
   out5[3] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (getenv("QIPB200_JIT_CACHE_DIR") && log && log_len && !log[0]) {
+    uint64_t n_disk = 0;
+    jit_wait_all(nullptr, nullptr, &n_disk);
+    snprintf(log, log_len, "disk cache: %llu programs loaded from QIPB200_JIT_CACHE_DIR so far in this process", (unsigned long long)n_disk);
+  }
   return QIPB200_OK;
 }
 

@@ -3,9 +3,11 @@
 
 #include <dlfcn.h>
 #include <nvrtc.h>
+#include <unistd.h>
 
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -27,6 +29,7 @@ struct Nvrtc {
   nvrtcResult (*log_size)(nvrtcProgram, size_t *) = nullptr;
   nvrtcResult (*log)(nvrtcProgram, char *) = nullptr;
   nvrtcResult (*destroy)(nvrtcProgram *) = nullptr;
+  nvrtcResult (*version)(int *, int *) = nullptr;  // optional
   std::string why;
   bool ok = false;
 };
@@ -56,6 +59,7 @@ Nvrtc &nvrtc() {
     QIP_SYM(log, "nvrtcGetProgramLog")
     QIP_SYM(destroy, "nvrtcDestroyProgram")
 #undef QIP_SYM
+    *(void **)(&n.version) = dlsym(n.h, "nvrtcVersion");
     n.ok = true;
   });
   return n;
@@ -129,6 +133,94 @@ std::shared_ptr<JitCubin> compile_now(const std::string &source) {
   return out;
 }
 
+// ---- optional on-disk cache of cubins (QIPB200_JIT_CACHE_DIR) ---------------------------------------------
+// A program is keyed by its source text (two independent 64-bit FNV-1a hashes + the length) and the compiler
+// identity (NVRTC version, target, options).  Files are written to a temporary name and renamed, so concurrent
+// processes sharing the directory never see a partial file; anything that does not check out is recompiled.
+uint64_t fnv1a(const std::string &s, uint64_t seed) {
+  uint64_t h = 1469598103934665603ull ^ seed;
+  for (size_t i = 0; i < s.size(); ++i) {
+    h ^= (unsigned char)s[i];
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+struct DiskHeader {
+  char magic[8];
+  uint64_t source_len, hash_a, hash_b, image_len;
+};
+
+std::string disk_path(const std::string &source, uint64_t *ha, uint64_t *hb) {
+  const char *dir = getenv("QIPB200_JIT_CACHE_DIR");
+  if (!dir || !*dir) return std::string();
+  int major = 0, minor = 0;
+  Nvrtc &n = nvrtc();
+  if (n.ok && n.version) n.version(&major, &minor);
+  const std::string ident = "nvrtc " + std::to_string(major) + "." + std::to_string(minor) + " sm_100a c++17 fmad=false lineinfo|";
+  *ha = fnv1a(ident + source, 0);
+  *hb = fnv1a(ident + source, 0x9E3779B97F4A7C15ull);
+  char name[96];
+  snprintf(name, sizeof(name), "/qip_%016llx_%zu.cubin", (unsigned long long)*ha, source.size());
+  return std::string(dir) + name;
+}
+
+bool disk_load(const std::string &source, JitCubin *out) {
+  uint64_t ha = 0, hb = 0;
+  const std::string path = disk_path(source, &ha, &hb);
+  if (path.empty()) return false;
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  DiskHeader h;
+  bool ok = fread(&h, sizeof(h), 1, f) == 1 && !memcmp(h.magic, "QIPJIT1", 8) && h.source_len == source.size() && h.hash_a == ha &&
+            h.hash_b == hb && h.image_len > 0 && h.image_len < (1ull << 28);
+  if (ok) {
+    out->image.resize(h.image_len);
+    ok = fread(out->image.data(), 1, h.image_len, f) == h.image_len && fgetc(f) == EOF;
+  }
+  fclose(f);
+  if (!ok) out->image.clear();
+  return ok;
+}
+
+void disk_store(const std::string &source, const JitCubin &c) {
+  uint64_t ha = 0, hb = 0;
+  const std::string path = disk_path(source, &ha, &hb);
+  if (path.empty() || !c.ok) return;
+  char suffix[64];
+  snprintf(suffix, sizeof(suffix), ".tmp.%ld.%llx", (long)getpid(), (unsigned long long)(uintptr_t)&c);
+  const std::string tmp = path + suffix;
+  FILE *f = fopen(tmp.c_str(), "wb");
+  if (!f) return;  // an unwritable cache directory is not an error: the program was compiled anyway
+  DiskHeader h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, "QIPJIT1", 8);
+  h.source_len = source.size();
+  h.hash_a = ha;
+  h.hash_b = hb;
+  h.image_len = c.image.size();
+  const bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && fwrite(c.image.data(), 1, c.image.size(), f) == c.image.size();
+  if (fclose(f) != 0 || !ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+}
+
+std::shared_ptr<JitCubin> compile_or_load(const std::string &source, bool *from_disk) {
+  *from_disk = false;
+  if (getenv("QIPB200_JIT_CACHE_DIR")) {
+    const auto t0 = std::chrono::steady_clock::now();
+    std::shared_ptr<JitCubin> hit = std::make_shared<JitCubin>();
+    if (disk_load(source, hit.get())) {
+      hit->ok = true;
+      hit->log = "loaded from QIPB200_JIT_CACHE_DIR";
+      hit->compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      *from_disk = true;
+      return hit;
+    }
+  }
+  std::shared_ptr<JitCubin> c = compile_now(source);
+  disk_store(source, *c);
+  return c;
+}
+
 // ---- process-wide cache + background workers ----
 struct Entry {
   std::shared_ptr<const JitCubin> cubin;  // null while pending
@@ -142,7 +234,7 @@ struct Cache {
   std::deque<std::string> queue;
   std::vector<std::thread> workers;
   unsigned in_flight = 0;
-  uint64_t n_compiled = 0;
+  uint64_t n_compiled = 0, n_from_disk = 0;
   double total_ms = 0.0;
   bool stop = false;
 
@@ -163,15 +255,20 @@ struct Cache {
         src.swap(queue.front());
         queue.pop_front();
       }
-      std::shared_ptr<JitCubin> c = compile_now(src);
+      bool from_disk = false;
+      std::shared_ptr<JitCubin> c = compile_or_load(src, &from_disk);
       {
         std::lock_guard<std::mutex> lk(mu);
         Entry &e = map[src];
         e.cubin = c;
         e.pending = false;
         --in_flight;
-        ++n_compiled;
-        total_ms += c->compile_ms;
+        if (from_disk) {
+          ++n_from_disk;
+        } else {
+          ++n_compiled;
+          total_ms += c->compile_ms;
+        }
       }
       cv.notify_all();
     }
@@ -222,12 +319,13 @@ std::shared_ptr<const JitCubin> jit_request(const std::string &source, bool wait
   return c.map[source].cubin;
 }
 
-void jit_wait_all(uint64_t *n_compiled, double *total_ms) {
+void jit_wait_all(uint64_t *n_compiled, double *total_ms, uint64_t *n_from_disk) {
   Cache &c = cache();
   std::unique_lock<std::mutex> lk(c.mu);
   c.cv.wait(lk, [&]() { return c.in_flight == 0; });
   if (n_compiled) *n_compiled = c.n_compiled;
   if (total_ms) *total_ms = c.total_ms;
+  if (n_from_disk) *n_from_disk = c.n_from_disk;
 }
 
 cudaError_t jit_launch(const std::shared_ptr<const JitCubin> &cubin, std::vector<std::pair<const JitCubin *, JitLoaded>> *loaded,

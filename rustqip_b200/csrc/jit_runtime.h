@@ -40,9 +40,10 @@ bool jit_available(std::string *why);
 // background; with wait = true blocks until the compilation finishes.  Thread-safe.
 std::shared_ptr<const JitCubin> jit_request(const std::string &source, bool wait);
 
-// Block until the background queue is empty; returns the number of programs compiled so far and the
-// total compile time spent (sum over programs, ms).
-void jit_wait_all(uint64_t *n_compiled, double *total_ms);
+// Block until the background queue is empty; returns the number of programs compiled so far, the total compile
+// time spent (sum over programs, ms) and the number of programs taken from the on-disk cache instead
+// (QIPB200_JIT_CACHE_DIR: cubins keyed by source text + compiler identity, shared between processes).
+void jit_wait_all(uint64_t *n_compiled, double *total_ms, uint64_t *n_from_disk = nullptr);
 
 // Load (once per context) and launch.  `loaded` is the context's module cache keyed by the cubin pointer.
 // `tmap_out` / `send_bit` / `send_val` (optional): tiles whose index bit send_bit equals send_val are stored

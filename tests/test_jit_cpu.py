@@ -143,3 +143,50 @@ def test_nvrtc_compiles_every_pass_of_the_bench_workloads():
         rc = L.qipb200_jit_precompile(prec_of(dtype), n, arr, len(ops), out, log, 4000)
         assert rc == 0, log.value
         assert out[0] >= 7 and out[1] == out[0] and out[2] == out[0], (list(out), log.value)
+
+
+_CACHE_PROBE = r"""
+import ctypes as C, json, sys
+import numpy as np
+from rustqip_b200 import _lib, circuits
+from rustqip_b200._abi import marshal_ops, prec_of
+L = _lib.lib()
+ops = circuits.qft(24)
+arr, keep = marshal_ops(ops, prec_of(np.complex64))
+out = (C.c_double * 5)()
+log = C.create_string_buffer(4000)
+rc = L.qipb200_jit_precompile(prec_of(np.complex64), 24, arr, len(ops), out, log, 4000)
+print(json.dumps({"rc": rc, "out": list(out), "log": log.value.decode()}))
+"""
+
+
+def test_jit_disk_cache_between_processes(tmp_path):
+    """QIPB200_JIT_CACHE_DIR: the second PROCESS planning the same circuit loads every cubin from disk instead of
+    calling NVRTC; a corrupted file is ignored and rewritten."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QIPB200_JIT_CACHE_DIR=str(tmp_path), PYTHONPATH=root)
+
+    def probe():
+        r = subprocess.run([sys.executable, "-c", _CACHE_PROBE], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        return json.loads(r.stdout.strip().splitlines()[-1])
+
+    first = probe()
+    assert first["rc"] == 0 and first["out"][2] == first["out"][0] >= 3, first
+    assert "disk cache: 0 programs" in first["log"], first
+    files = sorted(p for p in os.listdir(tmp_path) if p.endswith(".cubin"))
+    assert 1 <= len(files) <= int(first["out"][0]) and not [p for p in os.listdir(tmp_path) if ".tmp." in p]
+    second = probe()
+    assert second["out"][2] == first["out"][2] and ("disk cache: %d programs" % len(files)) in second["log"], second
+    assert second["out"][3] < first["out"][3]
+    # a damaged entry must not be trusted
+    victim = os.path.join(tmp_path, files[0])
+    blob = bytearray(open(victim, "rb").read())
+    blob[16] ^= 0xFF  # inside the header's first hash
+    open(victim, "wb").write(bytes(blob))
+    third = probe()
+    assert third["out"][2] == first["out"][2] and ("disk cache: %d programs" % (len(files) - 1)) in third["log"], third
+    assert open(victim, "rb").read() != bytes(blob)  # recompiled and rewritten
