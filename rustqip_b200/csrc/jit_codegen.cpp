@@ -751,6 +751,9 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
   src << "  unsigned send_bit, send_val;\n";
   // a launch may cover a contiguous part of the tile counter (half a pass around a multi-GPU migration)
   src << "  unsigned tile_off_lo, tile_off_hi;\n";
+  // tiles of this launch: a CTA walks the tile counter with stride gridDim.x (grid == tile count: one tile per CTA;
+  // a grid of a few CTAs per SM: persistent CTAs, no CTA exit / launch / barrier init between tiles)
+  src << "  unsigned tile_cnt_lo, tile_cnt_hi;\n";
   src << "};\n";
   src << R"(#ifdef QIP_JIT_HOST
 #include <cmath>
@@ -840,7 +843,6 @@ qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constan
          const __grid_constant__ CUtensorMap tmap_out) {
   extern __shared__ __align__(1024) unsigned char sm[];
   const unsigned tid = threadIdx.x;
-  const u64 base = tile_base(p, (u64)blockIdx.x + (((u64)p.tile_off_hi << 32) | (u64)p.tile_off_lo));
   const unsigned smb = (unsigned)__cvta_generic_to_shared(sm);
   const unsigned mbar = smb + OFF_MBAR;
   if (tid == 0) {
@@ -848,7 +850,12 @@ qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constan
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0) {
+  const u64 tile_off = ((u64)p.tile_off_hi << 32) | (u64)p.tile_off_lo, tile_cnt = ((u64)p.tile_cnt_hi << 32) | (u64)p.tile_cnt_lo;
+  unsigned parity = 0u;
+#pragma unroll 1
+  for (u64 tile = blockIdx.x; tile < tile_cnt; tile += gridDim.x, parity ^= 1u) {
+  const u64 base = tile_base(p, tile + tile_off);
+  if (tid == 0) {  // the tile buffer is free: this thread waited for the previous tile's stores to have read it
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(TILE_BYTES) : "memory");
 #pragma unroll 1
     for (unsigned b = 0; b < NBOX; ++b) {
@@ -863,10 +870,12 @@ qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constan
   }
 )";
   src << "  prelude(sm, tid, p, base);\n";
+  // (always needed with persistent CTAs: the previous tile's super-ops read what the prelude overwrites -- they are
+  // all past the barrier before the stores -- and the prelude's results must be visible before the super-ops)
   if (has_prelude) src << "  __syncthreads();\n";
   src << "  const unsigned* condw = reinterpret_cast<const unsigned*>(sm + OFF_CONDW);\n";
   src << "  const R* tbl = reinterpret_cast<const R*>(sm + OFF_TBL);\n  const R* gt = reinterpret_cast<const R*>(sm + OFF_GT);\n";
-  src << "  mbar_wait(mbar, 0u);\n";
+  src << "  mbar_wait(mbar, parity);\n";
   uint32_t n_bar = 0, n_ws = 0;
   for (size_t s = 0; s < S; ++s) {
     if (s) {
@@ -903,6 +912,7 @@ qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constan
     else
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
+  }  // tile loop
   (void)psi;
 }
 #endif
@@ -975,6 +985,8 @@ qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constan
     put(&val, 4);
     put(&val, 4);  // tile_off_lo
     put(&val, 4);  // tile_off_hi
+    put(&val, 4);  // tile_cnt_lo (set per launch)
+    put(&val, 4);  // tile_cnt_hi
   }
   while (blob.size() % 8) blob.push_back(0);  // sizeof(JP): the struct is 8-byte aligned
 

@@ -5,6 +5,7 @@
 #include <nvrtc.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
@@ -364,14 +365,23 @@ cudaError_t jit_launch(const std::shared_ptr<const JitCubin> &cubin, std::vector
     memcpy(params.data() + prog.send_offset + 4, &send_val, 4);
   }
   void *args[4] = {&psi, params.data(), &tm, &tm_out};
-  unsigned grid = 1u << (n_local - prog.tiles_log2_sub);
-  if (half < 2 && grid >= 2 && prog.send_offset + 16 <= params.size()) {
-    grid >>= 1;
-    const uint64_t off = half ? (uint64_t)grid : 0ull;
-    const uint32_t lo = (uint32_t)off, hi = (uint32_t)(off >> 32);
-    memcpy(params.data() + prog.send_offset + 8, &lo, 4);
-    memcpy(params.data() + prog.send_offset + 12, &hi, 4);
+  uint64_t tiles = 1ull << (n_local - prog.tiles_log2_sub), off = 0;
+  if (prog.send_offset + 24 > params.size()) return cudaErrorInvalidValue;
+  if (half < 2 && tiles >= 2) {
+    tiles >>= 1;
+    off = half ? tiles : 0ull;
   }
+  {
+    const uint32_t w[4] = {(uint32_t)off, (uint32_t)(off >> 32), (uint32_t)tiles, (uint32_t)(tiles >> 32)};
+    memcpy(params.data() + prog.send_offset + 8, w, 16);
+  }
+  // QIPB200_JIT_PERSISTENT=<CTAs>: a fixed grid of persistent CTAs walking the tile counter instead of one CTA per tile
+  static const unsigned persistent_ctas = []() {
+    const char *e = getenv("QIPB200_JIT_PERSISTENT");
+    return e ? (unsigned)std::max(0, atoi(e)) : 0u;
+  }();
+  unsigned grid = (unsigned)std::min<uint64_t>(tiles, 0x7fffffffull);
+  if (persistent_ctas && grid > persistent_ctas) grid = persistent_ctas;
   const CUresult r = d.launch(L->fn, grid, 1, 1, prog.threads, 1, 1, prog.smem_bytes, (CUstream)stream, args, nullptr);
   if (r != CUDA_SUCCESS) return fail(r, "cuLaunchKernel");
   return cudaSuccess;

@@ -16,7 +16,7 @@ ap.add_argument("--dtype", default="f64")
 ap.add_argument("--out", default="/tmp/jit/p")
 ap.add_argument("--nvcc", action="store_true")
 a = ap.parse_args()
-so = os.path.join(ROOT, "tests", "native", "_build", "libplan_emul.so")
+so = os.environ.get("EMUL_SO") or os.path.join(ROOT, "tests", "native", "_build", "libplan_emul.so")
 L = C.CDLL(so)
 L.emul_dump_jit.restype = C.c_int
 L.emul_dump_jit.argtypes = [C.c_int, C.c_uint32, C.POINTER(QipOp), C.c_size_t, C.c_char_p]
