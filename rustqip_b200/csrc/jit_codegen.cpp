@@ -754,6 +754,9 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
   // tiles of this launch: a CTA walks the tile counter with stride gridDim.x (grid == tile count: one tile per CTA;
   // a grid of a few CTAs per SM: persistent CTAs, no CTA exit / launch / barrier init between tiles)
   src << "  unsigned tile_cnt_lo, tile_cnt_hi;\n";
+  // > 0: ask the TMA unit to pull the tile `prefetch_dist` places ahead in the tile counter into L2 while this one is
+  // processed (DRAM reads in flight are then no longer bounded by the shared memory of the resident CTAs)
+  src << "  unsigned prefetch_dist, pad_;\n";
   src << "};\n";
   src << R"(#ifdef QIP_JIT_HOST
 #include <cmath>
@@ -866,6 +869,17 @@ qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constan
               smb + b * BOX_BYTES),
           "l"(&tmap), "r"(mbar), "r"(0), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3])
           : "memory");
+    }
+  }
+  if (p.prefetch_dist && tid == 32u && tile + p.prefetch_dist < tile_cnt) {
+    const u64 nbase = tile_base(p, tile + p.prefetch_dist + tile_off);
+#pragma unroll 1
+    for (unsigned b = 0; b < NBOX; ++b) {
+      int c[4];
+      box_coords(p, nbase + p.box_off[b], c);
+      asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global [%0, {%1, %2, %3, %4, %5}];" ::"l"(&tmap), "r"(0), "r"(c[0]), "r"(c[1]),
+                   "r"(c[2]), "r"(c[3])
+                   : "memory");
     }
   }
 )";
@@ -987,6 +1001,8 @@ qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constan
     put(&val, 4);  // tile_off_hi
     put(&val, 4);  // tile_cnt_lo (set per launch)
     put(&val, 4);  // tile_cnt_hi
+    put(&val, 4);  // prefetch_dist (set per launch)
+    put(&val, 4);  // pad_
   }
   while (blob.size() % 8) blob.push_back(0);  // sizeof(JP): the struct is 8-byte aligned
 

@@ -366,7 +366,7 @@ cudaError_t jit_launch(const std::shared_ptr<const JitCubin> &cubin, std::vector
   }
   void *args[4] = {&psi, params.data(), &tm, &tm_out};
   uint64_t tiles = 1ull << (n_local - prog.tiles_log2_sub), off = 0;
-  if (prog.send_offset + 24 > params.size()) return cudaErrorInvalidValue;
+  if (prog.send_offset + 32 > params.size()) return cudaErrorInvalidValue;
   if (half < 2 && tiles >= 2) {
     tiles >>= 1;
     off = half ? tiles : 0ull;
@@ -382,6 +382,12 @@ cudaError_t jit_launch(const std::shared_ptr<const JitCubin> &cubin, std::vector
   }();
   unsigned grid = (unsigned)std::min<uint64_t>(tiles, 0x7fffffffull);
   if (persistent_ctas && grid > persistent_ctas) grid = persistent_ctas;
+  // QIPB200_JIT_PREFETCH=<tiles>: L2 prefetch distance in the tile counter (0 = off)
+  static const unsigned prefetch_dist = []() {
+    const char *e = getenv("QIPB200_JIT_PREFETCH");
+    return e ? (unsigned)std::max(0, atoi(e)) : 0u;
+  }();
+  memcpy(params.data() + prog.send_offset + 24, &prefetch_dist, 4);
   const CUresult r = d.launch(L->fn, grid, 1, 1, prog.threads, 1, 1, prog.smem_bytes, (CUstream)stream, args, nullptr);
   if (r != CUDA_SUCCESS) return fail(r, "cuLaunchKernel");
   return cudaSuccess;
