@@ -325,6 +325,121 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---------------------------------------------------------------------------------
+// f64 dense blocks on 5 / 6 target bits on the FP64 TENSOR pipe (DMMA, mma.sync.m8n8k4.f64 -- the only tensor path
+// for f64: tcgen05 has no f64 kind).  Y(S x G) = U(S x S) X(S x G) over G groups, complex as four real products:
+//   Yr += Ur Xr;  Yr += (-Ui) Xi;  Yi += Ui Xr;  Yi += Ur Xi.
+// A warp owns 8 * NT groups: it loads their amplitudes straight into B fragments (lane <-> sub-index v = 4 ks + lane % 4
+// of group 8 nt + lane / 4: one 16-byte load yields the re and the im operand; neighbouring lanes cover neighbouring
+// v, neighbouring quads neighbouring groups, so every 32-byte sector of a warp load is used whole), walks the matrix
+// from shared memory (one conflict-free LDS.128 per 4 * NT DMMAs: rows padded by 4 entries) and stores the D fragments
+// (rows 8 mt + lane / 4 of groups 8 nt + 2 (lane % 4) + {0, 1}) in place -- all its inputs are in registers by then.
+// ---------------------------------------------------------------------------------
+struct DmmaArgs {
+  InsArgs ins;
+  uint64_t ctrl_mask;
+  uint64_t n_items;    // groups (a power of two >= 8 * NT)
+  uint64_t off_lo[8];  // amplitude offset of sub-index v, v < 8
+  uint64_t off_k[16];  // ... of v = 4 ks
+  uint64_t off_m[8];   // ... of v = 8 mt
+};
+
+__device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int K, int NT>
+__global__ void __launch_bounds__(128)
+    k_dense_dmma(double *__restrict__ psi, const double *__restrict__ mat, const __grid_constant__ DmmaArgs a) {
+  constexpr int S = 1 << K, LD = S + 4, MT = S / 8, KS = S / 4;
+  extern __shared__ __align__(16) unsigned char smem_dmma[];
+  double2 *U = reinterpret_cast<double2 *>(smem_dmma);
+  for (int i = threadIdx.x; i < S * S; i += 128) U[(i >> K) * LD + (i & (S - 1))] = reinterpret_cast<const double2 *>(mat)[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, q = lane >> 2, r = lane & 3;
+  const uint64_t w0 = ((uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5)) * (8 * NT);
+  if (w0 >= a.n_items) return;
+  // B fragments: the warp's inputs
+  double xr[KS][NT], xi[KS][NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const uint64_t base = (expand_index(w0 + 8 * nt + q, a.ins) | a.ctrl_mask) + a.off_lo[r];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const double2 v = *reinterpret_cast<const double2 *>(psi + 2 * (base + a.off_k[ks]));
+      xr[ks][nt] = v.x;
+      xi[ks][nt] = v.y;
+    }
+  }
+  uint64_t obase[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) obase[nt][j] = (expand_index(w0 + 8 * nt + 2 * r + j, a.ins) | a.ctrl_mask) + a.off_lo[q];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    double yr[NT][2], yi[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) yr[nt][0] = yr[nt][1] = yi[nt][0] = yi[nt][1] = 0.0;
+    const double2 *urow = U + (8 * mt + q) * LD + r;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const double2 u = urow[4 * ks];
+      const double nui = -u.y;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        dmma_8x8x4(yr[nt][0], yr[nt][1], u.x, xr[ks][nt]);
+        dmma_8x8x4(yr[nt][0], yr[nt][1], nui, xi[ks][nt]);
+        dmma_8x8x4(yi[nt][0], yi[nt][1], u.y, xr[ks][nt]);
+        dmma_8x8x4(yi[nt][0], yi[nt][1], u.x, xi[ks][nt]);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double2 o;
+        o.x = yr[nt][j];
+        o.y = yi[nt][j];
+        *reinterpret_cast<double2 *>(psi + 2 * (obase[nt][j] + a.off_m[mt])) = o;
+      }
+  }
+}
+
+template <int K, int NT>
+static cudaError_t launch_dense_dmma(double *psi, uint32_t n_local, const FlatOp &f, const double *d_mat, cudaStream_t s) {
+  constexpr int S = 1 << K;
+  DmmaArgs a;
+  memset(&a, 0, sizeof(a));
+  if (!build_ins(f.ctrl_mask, f.tgt_sorted.data(), K, &a.ins)) return cudaErrorInvalidValue;
+  a.ctrl_mask = f.ctrl_mask;
+  a.n_items = 1ull << (n_local - a.ins.n_ins);
+  auto off_of = [&](uint32_t v) {
+    uint64_t off = 0;
+    for (uint32_t i = 0; i < (uint32_t)K; ++i)
+      if ((v >> i) & 1) off |= 1ull << f.tgt_sorted[i];
+    return off;
+  };
+  for (uint32_t v = 0; v < 8; ++v) a.off_lo[v] = off_of(v);
+  for (uint32_t ks = 0; ks < (uint32_t)S / 4; ++ks) a.off_k[ks] = off_of(4 * ks);
+  for (uint32_t mt = 0; mt < (uint32_t)S / 8; ++mt) a.off_m[mt] = off_of(8 * mt);
+  const size_t smem = (size_t)S * (S + 4) * sizeof(double2);
+  cudaError_t e = cudaFuncSetAttribute((const void *)k_dense_dmma<K, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const uint64_t per_cta = 4ull * 8 * NT;
+  k_dense_dmma<K, NT><<<(unsigned)((a.n_items + per_cta - 1) / per_cta), 128, smem, s>>>(psi, d_mat, a);
+  return cudaGetLastError();
+}
+
+// QIPB200_DENSE_DMMA=0: f64 blocks on 5 / 6 bits on the FMA kernels (k_dense5 / k_dense_big) instead of the tensor pipe
+static bool dense_dmma_enabled() {
+  static const bool on = []() {
+    const char *e = getenv("QIPB200_DENSE_DMMA");
+    return !e || atoi(e) != 0;
+  }();
+  return on;
+}
+
 template <typename R>
 static cudaError_t launch_dense_wide_t(R *psi, uint32_t n_local, const FlatOp &f, cudaStream_t s, uint64_t *launches) {
   const uint32_t K = (uint32_t)f.tgt_sorted.size();
@@ -345,6 +460,13 @@ static cudaError_t launch_dense_wide_t(R *psi, uint32_t n_local, const FlatOp &f
     return e;
   }
   const uint32_t n_ins = K + (uint32_t)__builtin_popcountll(f.ctrl_mask);
+  if (sizeof(R) == 8 && (K == 5 || K == 6) && n_local >= n_ins + 4 && dense_dmma_enabled()) {
+    e = K == 5 ? launch_dense_dmma<5, 2>((double *)psi, n_local, f, (const double *)d_mat, s)
+               : launch_dense_dmma<6, 1>((double *)psi, n_local, f, (const double *)d_mat, s);
+    ++*launches;
+    cudaFreeAsync(d_mat, s);
+    return e;
+  }
   if (K == 5) {
     WideArgs a;
     if (!build_ins(f.ctrl_mask, f.tgt_sorted.data(), K, &a.ins)) return cudaFreeAsync(d_mat, s), cudaErrorInvalidValue;

@@ -46,3 +46,18 @@ def test_wide_dense_and_diagonal_in_place(ctx, dtype):
             st.apply_op(op)
             assert ctx.kernel_launches() - l0 == 1
             assert_close(st.download(), want, dtype)
+
+
+def test_wide_dense_f64_smallest_states(ctx):
+    """The f64 5/6-qubit blocks go to the tensor pipe (k_dense_dmma) from 16 groups per shard on; below that the FMA
+    kernels take over.  Both sides of the switch, and the env override, against the oracle."""
+    rng = np.random.default_rng(78)
+    for n, k in [(9, 5), (8, 5), (7, 5), (10, 6), (9, 6), (11, 6), (12, 5)]:
+        psi = rand_state(n, np.complex128, 16 + n)
+        qs = [int(q) for q in rng.choice(n, k, replace=False)]
+        op = make_matrix_op(qs, rand_unitary(k, rng).reshape(-1))
+        want = oracle_apply(n, op, psi)
+        with State(n, np.complex128, ctx) as st:
+            st.upload(psi)
+            st.apply_op(op)
+            assert_close(st.download(), want, np.complex128)
