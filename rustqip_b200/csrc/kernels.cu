@@ -197,17 +197,9 @@ static cudaError_t launch_dense_t(R *psi, uint32_t n_local, const FlatOp &f, cud
   return cudaGetLastError();
 }
 
-static bool dense_dmma_enabled();
-static cudaError_t launch_dense4_dmma(double *psi, uint32_t n_local, const FlatOp &f, cudaStream_t s);
-
 cudaError_t launch_dense(qip_prec prec, void *psi, uint32_t n_local, const FlatOp &f, cudaStream_t s,
                          uint64_t *launches) {
   const int K = (int)f.tgt_sorted.size();
-  // f64 blocks on 4 bits: FP64 tensor pipe (k_dense_dmma<4>) from 32 groups per shard on
-  if (K == 4 && prec == QIP_F64 && n_local >= 4 + (uint32_t)__builtin_popcountll(f.ctrl_mask) + 5 && dense_dmma_enabled()) {
-    ++*launches;
-    return launch_dense4_dmma((double *)psi, n_local, f, s);
-  }
 #define DISPATCH(KK)                                                                              \
   case KK:                                                                                        \
     return prec == QIP_F32 ? launch_dense_t<float, KK>((float *)psi, n_local, f, s, launches)     \
@@ -351,25 +343,18 @@ struct DmmaArgs {
   uint64_t off_k[16];  // ... of v = 4 ks
   uint64_t off_m[8];   // ... of v = 8 mt
 };
-struct DmmaArgs4 : DmmaArgs {  // K = 4: the 16 x 16 matrix travels in the kernel parameters (no device allocation per gate)
-  double2 m[256];
-};
 
 __device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-template <int K, int NT, typename A>
+template <int K, int NT>
 __global__ void __launch_bounds__(128)
-    k_dense_dmma(double *__restrict__ psi, const double *__restrict__ mat, const __grid_constant__ A a) {
+    k_dense_dmma(double *__restrict__ psi, const double *__restrict__ mat, const __grid_constant__ DmmaArgs a) {
   constexpr int S = 1 << K, LD = S + 4, MT = S / 8, KS = S / 4;
   extern __shared__ __align__(16) unsigned char smem_dmma[];
   double2 *U = reinterpret_cast<double2 *>(smem_dmma);
-  if constexpr (K == 4) {
-    for (int i = threadIdx.x; i < S * S; i += 128) U[(i >> K) * LD + (i & (S - 1))] = a.m[i];
-  } else {
-    for (int i = threadIdx.x; i < S * S; i += 128) U[(i >> K) * LD + (i & (S - 1))] = reinterpret_cast<const double2 *>(mat)[i];
-  }
+  for (int i = threadIdx.x; i < S * S; i += 128) U[(i >> K) * LD + (i & (S - 1))] = reinterpret_cast<const double2 *>(mat)[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, q = lane >> 2, r = lane & 3;
   const uint64_t w0 = ((uint64_t)blockIdx.x * 4 + (threadIdx.x >> 5)) * (8 * NT);
@@ -424,8 +409,7 @@ __global__ void __launch_bounds__(128)
 template <int K, int NT>
 static cudaError_t launch_dense_dmma(double *psi, uint32_t n_local, const FlatOp &f, const double *d_mat, cudaStream_t s) {
   constexpr int S = 1 << K;
-  typedef typename std::conditional<K == 4, DmmaArgs4, DmmaArgs>::type A;
-  A a;
+  DmmaArgs a;
   memset(&a, 0, sizeof(a));
   if (!build_ins(f.ctrl_mask, f.tgt_sorted.data(), K, &a.ins)) return cudaErrorInvalidValue;
   a.ctrl_mask = f.ctrl_mask;
@@ -439,29 +423,20 @@ static cudaError_t launch_dense_dmma(double *psi, uint32_t n_local, const FlatOp
   for (uint32_t v = 0; v < 8; ++v) a.off_lo[v] = off_of(v);
   for (uint32_t ks = 0; ks < (uint32_t)S / 4; ++ks) a.off_k[ks] = off_of(4 * ks);
   for (uint32_t mt = 0; mt < (uint32_t)S / 8; ++mt) a.off_m[mt] = off_of(8 * mt);
-  if constexpr (K == 4) {
-    for (int i = 0; i < S * S; ++i) a.m[i] = make_double2(f.m_sorted[(size_t)i].real(), f.m_sorted[(size_t)i].imag());
-  }
   const size_t smem = (size_t)S * (S + 4) * sizeof(double2);
   if (smem > 48 * 1024) {  // a per-device opt-in: set it on the current device every time (cheap)
-    cudaError_t e = cudaFuncSetAttribute((const void *)k_dense_dmma<K, NT, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute((const void *)k_dense_dmma<K, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
   const uint64_t per_cta = 4ull * 8 * NT;
-  k_dense_dmma<K, NT, A><<<(unsigned)((a.n_items + per_cta - 1) / per_cta), 128, smem, s>>>(psi, d_mat, a);
+  k_dense_dmma<K, NT><<<(unsigned)((a.n_items + per_cta - 1) / per_cta), 128, smem, s>>>(psi, d_mat, a);
   return cudaGetLastError();
 }
 
-static cudaError_t launch_dense4_dmma(double *psi, uint32_t n_local, const FlatOp &f, cudaStream_t s) {
-  static const int nt = []() {
-    const char *e = getenv("QIPB200_DENSE4_NT");  // groups per warp / 8 (A/B knob)
-    return e ? atoi(e) : 4;
-  }();
-  return nt == 2 ? launch_dense_dmma<4, 2>(psi, n_local, f, nullptr, s) : launch_dense_dmma<4, 4>(psi, n_local, f, nullptr, s);
-}
-
-// QIPB200_DENSE_DMMA=0: f64 blocks on 4 / 5 / 6 bits on the FMA kernels (k_dense / k_dense5 / k_dense_big) instead of the
-// tensor pipe
+// QIPB200_DENSE_DMMA=0: f64 blocks on 5 / 6 bits on the FMA kernels (k_dense5 / k_dense_big) instead of the tensor pipe.
+// (4-bit blocks stay on k_dense<4>: they are HBM-bound, and the fragment layout's half-sector stores cost more than the
+// tensor pipe saves -- measured on B200, N=26, 200 blocks: 88.0 ms (8 * 2 groups per warp) / 105.9 ms (8 * 4) vs 73.9 ms,
+// profiles/r2s_dense4_dmma_ab.txt.)
 static bool dense_dmma_enabled() {
   static const bool on = []() {
     const char *e = getenv("QIPB200_DENSE_DMMA");
