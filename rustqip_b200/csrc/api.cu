@@ -666,9 +666,14 @@ static void nondiag_bits(const FlatOp &f, std::vector<uint32_t> *out) {
 // by the rank index select a slice of the diagonal.  No communication.  *skip = true when
 // the op is the identity on this rank.
 int restrict_to_rank(const qipb200_state *s, const FlatOp &f_in, FlatOp *out, bool *skip) {
+  return restrict_to_rank_as(s, s->rank, f_in, out, skip);
+}
+
+// ... as rank `rank` of this state's world would see the op (rank == world - 1: every rank-held bit is 1)
+int restrict_to_rank_as(const qipb200_state *s, int rank, const FlatOp &f_in, FlatOp *out, bool *skip) {
   const uint32_t nl = s->n_local;
   const uint64_t lo_mask = (nl >= 64) ? ~0ull : ((1ull << nl) - 1ull);
-  const uint64_t rank_val = (uint64_t)s->rank << nl;
+  const uint64_t rank_val = (uint64_t)rank << nl;
   *skip = false;
   *out = f_in;
   if (f_in.cls == CLASS_IDENTITY) {
@@ -916,6 +921,57 @@ int exchange_bits_split(qipb200_state *s, uint32_t R, uint32_t l) {
   }
   ++ctx->exchange_launches;
   s->halves_pending = true;
+  s->exchange_bytes += (uint64_t)amp_bytes(s->prec) << (s->n_local - 1);
+  for (uint32_t b = 0; b < s->n; ++b) {
+    if (s->phys_of_logical[b] == R)
+      s->phys_of_logical[b] = l;
+    else if (s->phys_of_logical[b] == l)
+      s->phys_of_logical[b] = R;
+  }
+  return QIPB200_OK;
+}
+
+// ---- migration fused into a tile pass, in place (paired send) ----
+void paired_partner(const qipb200_state *s, uint32_t R, int *partner, int *give) {
+  const uint32_t r = R - s->n_local;
+  *partner = s->rank ^ (1 << r);
+  *give = 1 - ((s->rank >> r) & 1);
+}
+
+// The rank's part of the per-tile protocol by a stand-alone kernel (its last pass ran without the send).
+int paired_send_standin(qipb200_state *s, uint32_t R, uint32_t l, uint32_t cbit, uint32_t seq, const PassHeader &hdr) {
+  qipb200_ctx *ctx = s->ctx;
+  int partner = 0, give = 0;
+  paired_partner(s, R, &partner, &give);
+  PairedSendArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mine = s->buf;
+  a.peer = s->peer_buf[partner];
+  a.my_flags = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(s->flags) + kPairFlagOffsetBytes);
+  a.peer_flags = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(s->peer_flags[partner]) + kPairFlagOffsetBytes);
+  a.error_word = s->flags + kFlagErrorSlot;
+  a.seq = seq;
+  a.n_local = s->n_local;
+  a.T = hdr.T;
+  a.L = hdr.L;
+  a.m = hdr.m;
+  a.l = l;
+  a.cbit = cbit;
+  a.give = (uint32_t)give;
+  for (uint32_t i = 0; i < 8; ++i) a.hi_pos[i] = hdr.hi_pos[i];
+  ProfileScope prof(ctx, 1);
+  CU(ctx, launch_paired_send(s->prec, a, ctx->stream, &ctx->launches));
+  return QIPB200_OK;
+}
+
+int finish_paired_exchange(qipb200_state *s, uint32_t R, uint32_t l) {
+  qipb200_ctx *ctx = s->ctx;
+  {
+    ProfileScope prof(ctx, 1);
+    CU(ctx, launch_flag_barrier(s->peer_flags.data(), s->flags, s->rank, s->world, ++s->epoch, s->flags + kFlagErrorSlot,
+                                ctx->stream, &ctx->launches));
+  }
+  ++ctx->exchange_launches;
   s->exchange_bytes += (uint64_t)amp_bytes(s->prec) << (s->n_local - 1);
   for (uint32_t b = 0; b < s->n; ++b) {
     if (s->phys_of_logical[b] == R)

@@ -200,6 +200,66 @@ cudaError_t launch_flag_barrier(uint32_t *const *peer_flags, uint32_t *my_flags,
   return cudaGetLastError();
 }
 
+// ---- stand-in for the fused (paired) migration ------------------------------------------------------------------
+// One CTA per tile of the give-half; 2^T amplitudes through the registers of 256 threads.
+template <typename V, int PER>
+__global__ void __launch_bounds__(256) k_paired_send(const PairedSendArgs a) {
+  const V *mine = static_cast<const V *>(a.mine);
+  V *peer = static_cast<V *>(a.peer);
+  // tile counter of this CTA: blockIdx with the give value inserted at counter bit `cbit`
+  const uint64_t c = blockIdx.x;
+  const uint64_t t = ((c >> a.cbit) << (a.cbit + 1)) | ((uint64_t)a.give << a.cbit) | (c & ((1ull << a.cbit) - 1ull));
+  uint64_t base = t << a.L;
+  for (uint32_t i = 0; i < a.m; ++i) {
+    const uint32_t q = a.hi_pos[i];
+    base = ((base >> q) << (q + 1)) | (base & ((1ull << q) - 1ull));
+  }
+  V x[PER];  // PER = 2^T / 256 amplitudes per thread
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const uint32_t e = threadIdx.x + (uint32_t)j * 256u;
+    uint64_t idx = base + (e & ((1u << a.L) - 1u));
+    for (uint32_t i = 0; i < a.m; ++i)
+      if ((e >> (a.L + i)) & 1u) idx |= 1ull << a.hi_pos[i];
+    x[j] = mine[idx];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flags + (t ^ (1ull << a.cbit))), "r"(a.seq) : "memory");
+    const uint64_t t0 = globaltimer_ns();
+    uint32_t v;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.my_flags + t) : "memory");
+      if ((int32_t)(v - a.seq) >= 0) break;
+      if (globaltimer_ns() - t0 > 20ull * 1000ull * 1000ull * 1000ull) {
+        *a.error_word = 1u;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const uint32_t e = threadIdx.x + (uint32_t)j * 256u;
+    uint64_t idx = base + (e & ((1u << a.L) - 1u));
+    for (uint32_t i = 0; i < a.m; ++i)
+      if ((e >> (a.L + i)) & 1u) idx |= 1ull << a.hi_pos[i];
+    peer[idx ^ (1ull << a.l)] = x[j];
+  }
+}
+
+cudaError_t launch_paired_send(qip_prec prec, const PairedSendArgs &a, cudaStream_t s, uint64_t *launches) {
+  if (a.T != (prec == QIP_F32 ? 13u : 12u) || a.n_local <= a.T || a.m > 8) return cudaErrorInvalidValue;  // full-size tiles only
+  const unsigned grid = 1u << (a.n_local - a.T - 1);
+  if (prec == QIP_F32)
+    k_paired_send<float2, 32><<<grid, 256, 0, s>>>(a);
+  else
+    k_paired_send<double2, 16><<<grid, 256, 0, s>>>(a);
+  ++*launches;
+  return cudaGetLastError();
+}
+
 // ---- small all-reduce through the peers' reduction slots ----------------------------------
 struct CommSumArgs {
   const double *comm[kMaxWorld];

@@ -181,7 +181,7 @@ uint32_t swz_units(bool f64, uint32_t t) { return f64 ? (t ^ ((t >> 3) & 7u)) : 
 
 }  // namespace
 
-bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::string *why) {
+bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::string *why, bool paired) {
   std::string dummy;
   if (!why) why = &dummy;
   const PassHeader &h = pass.hdr;
@@ -735,6 +735,7 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
   const uint32_t off_tbl = amp << T, off_gt = off_tbl + tbl_bytes, off_condw = off_gt + 16, off_mbar = off_condw + 48;
   src << "#define OFF_TBL " << off_tbl << "u\n#define OFF_GT " << off_gt << "u\n#define OFF_CONDW " << off_condw << "u\n#define OFF_MBAR "
       << off_mbar << "u\n";
+  src << "#define QIP_PAIRED " << (paired ? 1 : 0) << "\n";
   src << "typedef " << RT << " R;\n";
   src << "struct JP {\n  u64 box_off[NBOX];\n";
   if (NC) src << "  u64 cm[NC], cv[NC];\n";
@@ -757,6 +758,11 @@ bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::str
   // > 0: ask the TMA unit to pull the tile `prefetch_dist` places ahead in the tile counter into L2 while this one is
   // processed (DRAM reads in flight are then no longer bounded by the shared memory of the resident CTAs)
   src << "  unsigned prefetch_dist, pad_;\n";
+  // migration fused into this pass, in place ("paired send", multi-GPU): a tile of the half this rank gives away
+  // (tile counter bit pair_cbit == send_val) is announced to the partner as soon as it sits in shared memory (partner's
+  // flag word of the paired tile := pair_seq) and stored into the PARTNER's shard (tmap_out, index bit send_bit
+  // flipped) once the partner has announced the tile it gives in return -- the slot being overwritten.  pair_my == 0: off
+  src << "  unsigned pair_cbit, pair_seq, pair_my_lo, pair_my_hi, pair_peer_lo, pair_peer_hi, pair_err_lo, pair_err_hi;\n";
   src << "};\n";
   src << R"(#ifdef QIP_JIT_HOST
 #include <cmath>
@@ -890,6 +896,18 @@ qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constan
   src << "  const unsigned* condw = reinterpret_cast<const unsigned*>(sm + OFF_CONDW);\n";
   src << "  const R* tbl = reinterpret_cast<const R*>(sm + OFF_TBL);\n  const R* gt = reinterpret_cast<const R*>(sm + OFF_GT);\n";
   src << "  mbar_wait(mbar, parity);\n";
+  src << R"(#if QIP_PAIRED
+  const u64 pair_my = ((u64)p.pair_my_hi << 32) | (u64)p.pair_my_lo;
+  const bool pair_give = pair_my != 0ull && (((tile + tile_off) >> p.pair_cbit) & 1ull) == (u64)p.send_val;
+  if (pair_give && tid == 0) {  // my copy of the tile is in shared memory: the partner may overwrite the slot
+    const u64 peer_flags = ((u64)p.pair_peer_hi << 32) | (u64)p.pair_peer_lo;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags + 4ull * ((tile + tile_off) ^ (1ull << p.pair_cbit))),
+                 "r"(p.pair_seq)
+                 : "memory");
+  }
+#endif
+)";
   uint32_t n_bar = 0, n_ws = 0;
   for (size_t s = 0; s < S; ++s) {
     if (s) {
@@ -906,6 +924,22 @@ qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constan
   src << R"(  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   if (tid == 0) {
+#if QIP_PAIRED
+    if (pair_give) {  // wait for the partner's copy of the tile this one replaces
+      unsigned v;
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(pair_my + 4ull * (tile + tile_off)) : "memory");
+        if ((int)(v - p.pair_seq) >= 0) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 20000000000ull) {  // 20 s: the partner is gone
+          *reinterpret_cast<unsigned*>(((u64)p.pair_err_hi << 32) | (u64)p.pair_err_lo) = 1u;
+          break;
+        }
+      }
+    }
+#endif
 #pragma unroll 1
     for (unsigned b = 0; b < NBOX; ++b) {
       int c[4];
@@ -921,7 +955,7 @@ qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constan
                    : "memory");
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    if (p.send_bit < 64u)
+    if (p.send_bit < 64u && ((base >> p.send_bit) & 1ull) == (u64)p.send_val)  // (bit send_bit is constant within a tile)
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores to the partner: wait until they are performed
     else
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -1003,6 +1037,7 @@ qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constan
     put(&val, 4);  // tile_cnt_hi
     put(&val, 4);  // prefetch_dist (set per launch)
     put(&val, 4);  // pad_
+    for (int i = 0; i < 8; ++i) put(&val, 4);  // pair_* (set per launch)
   }
   while (blob.size() % 8) blob.push_back(0);  // sizeof(JP): the struct is 8-byte aligned
 

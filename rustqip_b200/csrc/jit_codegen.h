@@ -34,6 +34,7 @@ struct JitProgram {
 
 // Returns false (and says why) when the pass holds something the generator does not cover (wide micro-ops,
 // geometry without TMA boxes, > 256 CTA-uniform conditions ...): the caller then runs the interpreter kernel.
-bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::string *why);
+// `paired`: the kernel can also play the per-tile handshake of a migration fused into the pass (multi-GPU, JP::pair_*).
+bool jit_generate(const HostPass &pass, qip_prec prec, JitProgram *out, std::string *why, bool paired = false);
 
 }  // namespace qipb200

@@ -331,7 +331,8 @@ void jit_wait_all(uint64_t *n_compiled, double *total_ms, uint64_t *n_from_disk)
 
 cudaError_t jit_launch(const std::shared_ptr<const JitCubin> &cubin, std::vector<std::pair<const JitCubin *, JitLoaded>> *loaded,
                        const JitProgram &prog, void *psi, uint32_t n_local, const CUtensorMap &tmap, cudaStream_t stream,
-                       std::string *err, const CUtensorMap *tmap_out, uint32_t send_bit, uint32_t send_val, uint32_t half) {
+                       std::string *err, const CUtensorMap *tmap_out, uint32_t send_bit, uint32_t send_val, uint32_t half,
+                       const JitPair *pair) {
   Driver &d = driver();
   if (!d.ok || !cubin || !cubin->ok) {
     if (err) *err = !d.ok ? d.why : "no cubin";
@@ -366,7 +367,7 @@ cudaError_t jit_launch(const std::shared_ptr<const JitCubin> &cubin, std::vector
   }
   void *args[4] = {&psi, params.data(), &tm, &tm_out};
   uint64_t tiles = 1ull << (n_local - prog.tiles_log2_sub), off = 0;
-  if (prog.send_offset + 32 > params.size()) return cudaErrorInvalidValue;
+  if (prog.send_offset + 64 > params.size()) return cudaErrorInvalidValue;
   if (half < 2 && tiles >= 2) {
     tiles >>= 1;
     off = half ? tiles : 0ull;
@@ -388,6 +389,13 @@ cudaError_t jit_launch(const std::shared_ptr<const JitCubin> &cubin, std::vector
     return e ? (unsigned)std::max(0, atoi(e)) : 0u;
   }();
   memcpy(params.data() + prog.send_offset + 24, &prefetch_dist, 4);
+  if (pair && tmap_out) {
+    const uint64_t mf = (uint64_t)(uintptr_t)pair->my_flags, pf = (uint64_t)(uintptr_t)pair->peer_flags,
+                   ew = (uint64_t)(uintptr_t)pair->error_word;
+    const uint32_t w[8] = {pair->cbit, pair->seq, (uint32_t)mf, (uint32_t)(mf >> 32), (uint32_t)pf, (uint32_t)(pf >> 32),
+                           (uint32_t)ew, (uint32_t)(ew >> 32)};
+    memcpy(params.data() + prog.send_offset + 32, w, 32);
+  }
   const CUresult r = d.launch(L->fn, grid, 1, 1, prog.threads, 1, 1, prog.smem_bytes, (CUstream)stream, args, nullptr);
   if (r != CUDA_SUCCESS) return fail(r, "cuLaunchKernel");
   return cudaSuccess;

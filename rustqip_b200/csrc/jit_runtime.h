@@ -48,10 +48,20 @@ void jit_wait_all(uint64_t *n_compiled, double *total_ms, uint64_t *n_from_disk 
 // Load (once per context) and launch.  `loaded` is the context's module cache keyed by the cubin pointer.
 // `tmap_out` / `send_bit` / `send_val` (optional): tiles whose index bit send_bit equals send_val are stored
 // through tmap_out at the index with that bit flipped (the push half of a multi-GPU qubit migration).
+// `pair` (optional, with tmap_out over the partner's SHARD): the migration is done in place, tile by tile, under a
+// per-tile flag handshake with the partner's pass (jit_codegen.cpp: pair_*).
+struct JitPair {
+  uint32_t cbit = 0;              // position of index bit send_bit in the tile counter
+  uint32_t seq = 0;               // value of this migration in the flag words
+  uint32_t *my_flags = nullptr;   // this rank's per-tile flag words (polled locally)
+  uint32_t *peer_flags = nullptr; // the partner's (written over NVLink)
+  uint32_t *error_word = nullptr;
+};
 cudaError_t jit_launch(const std::shared_ptr<const JitCubin> &cubin, std::vector<std::pair<const JitCubin *, JitLoaded>> *loaded,
                        const JitProgram &prog, void *psi, uint32_t n_local, const CUtensorMap &tmap, cudaStream_t stream,
                        std::string *err, const CUtensorMap *tmap_out = nullptr, uint32_t send_bit = 64, uint32_t send_val = 0,
-                       uint32_t half = 2);  // half: 0 / 1 = the lower / upper half of the tile counter only, 2 = all tiles
+                       uint32_t half = 2,  // half: 0 / 1 = the lower / upper half of the tile counter only, 2 = all tiles
+                       const JitPair *pair = nullptr);
 
 void jit_unload(std::vector<std::pair<const JitCubin *, JitLoaded>> *loaded);
 

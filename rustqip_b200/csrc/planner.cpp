@@ -1278,6 +1278,22 @@ void op_dependency_masks(const FlatOp &f, DepMasks *out) {
   out->dg = o.dg;
 }
 
+void op_uniform_info(const FlatOp &f, DepMasks *out) {
+  out->has_uniform = true;
+  if (f.cls == CLASS_IDENTITY) {  // nothing to do on the virtual rank: rides along in any pass
+    out->u_tile_ok = true;
+    out->u_need_tile = 0;
+    out->u_unfused_cost = 0.0;
+    out->u_est_bytes = 0;
+    return;
+  }
+  const OpInfo o = analyse(f);
+  out->u_tile_ok = o.tile_ok;
+  out->u_need_tile = o.need_tile;
+  out->u_unfused_cost = o.unfused_cost;
+  out->u_est_bytes = o.est_bytes;
+}
+
 void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec, const PlanConfig &cfg_in,
                  std::vector<PlanStep> *steps, const std::vector<char> *blocked, std::vector<size_t> *leftover,
                  const std::vector<DepMasks> *dep) {
@@ -1289,8 +1305,21 @@ void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec
   const bool can_tile = cfg.T >= 3;
   std::vector<OpInfo> info(ops.size());
   std::vector<size_t> remaining;
+  const bool uniform = dep && !dep->empty() && (*dep)[0].has_uniform;
   for (size_t i = 0; i < ops.size(); ++i) {
     const bool is_blocked = blocked && (*blocked)[i];
+    if (uniform) {  // nothing rank-specific may steer the selection
+      const DepMasks &d = (*dep)[i];
+      info[i] = OpInfo();
+      info[i].nd = d.nd;
+      info[i].dg = d.dg;
+      info[i].need_tile = d.u_need_tile;
+      info[i].tile_ok = d.u_tile_ok && !is_blocked;
+      info[i].unfused_cost = d.u_unfused_cost;
+      info[i].est_bytes = d.u_est_bytes;
+      remaining.push_back(i);
+      continue;
+    }
     if (ops[i].cls == CLASS_IDENTITY && !is_blocked) {
       if (!dep) continue;  // a plain identity gate: nothing to do, nothing to order
       // identity ON THIS RANK under the current layout (e.g. a rank-held control is 0): it emits
@@ -1319,7 +1348,7 @@ void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec
   static const uint32_t kBudgetScale[3] = {4, 2, 1};
   while (!remaining.empty()) {
     bool done = false, stuck = false;
-    for (int attempt = 0; attempt < 3 && !done; ++attempt) {
+    for (int attempt = uniform ? 2 : 0; attempt < 3 && !done; ++attempt) {  // uniform: the guaranteed budget only
       const uint64_t budget = (uint64_t)byte_budget * kBudgetScale[attempt];
       Selector sel{info, blocked, can_tile, low_mask, m, budget};
       Pick best = sel.select(remaining, 0);

@@ -10,12 +10,15 @@
 // when a rank-held qubit has to be migrated; an exchange is a fusion barrier.
 #include "schedule.h"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
 #include <vector>
 
 #include "../../include/qipb200.h"
+#include "dist.cuh"
 #include "jit_codegen.h"
 #include "jit_runtime.h"
 #include "tile.cuh"
@@ -48,6 +51,9 @@ struct SendPlan {
   bool on = false;       // staged protocol: the last pass pushes the give-half
   bool overlap = false;  // in-place protocol in two halves on the second stream (exchange_bits_split): the last step
                          // records "lower / upper half final" on the context's events, preferably half by half
+  bool pair = false;     // in-place protocol fused into the last pass (paired send): tiles of the give-half go straight into
+                         // the partner's shard under a per-tile flag handshake; a rank whose last pass cannot do it runs
+                         // the pass normally and then the stand-in kernel -- the partner does not see the difference
   uint32_t R = 0, l = 0;
 };
 
@@ -58,7 +64,15 @@ int execute_steps(qipb200_state *s, const std::vector<PlanStep> &steps, const st
   PassParams *pp = new PassParams();
   // Generated kernels (jit_codegen / jit_runtime): every pass is turned into specialised source; a pass whose
   // cubin is ready runs it, the others run the interpreter kernel while the background workers compile.
-  bool halves_recorded = false;
+  bool halves_recorded = false, paired_done = false;
+  uint32_t pair_cbit = 0, pair_seq = 0;
+  if (send.pair && !steps.empty() && steps.back().is_pass) {
+    const PassHeader &lh = steps.back().pass.hdr;
+    pair_cbit = send.l - lh.L;
+    for (uint32_t k = 0; k < lh.m; ++k)
+      if (lh.hi_pos[k] < send.l) --pair_cbit;
+    pair_seq = ++s->pair_seq;  // one value per migration, the same on every rank
+  }
   const JitMode jmode = cfg.use_tma && cfg.groups_per_thread == 1 ? jit_mode_from_env(s->n_local) : JIT_OFF;
   std::vector<JitProgram> progs(steps.size());
   std::vector<char> have_prog(steps.size(), 0);
@@ -66,7 +80,7 @@ int execute_steps(qipb200_state *s, const std::vector<PlanStep> &steps, const st
     for (size_t i = 0; i < steps.size(); ++i) {
       if (!steps[i].is_pass) continue;
       std::string why;
-      if (jit_generate(steps[i].pass, s->prec, &progs[i], &why)) {
+      if (jit_generate(steps[i].pass, s->prec, &progs[i], &why, send.pair && i + 1 == steps.size())) {
         have_prog[i] = 1;
         (void)jit_request(progs[i].source, false);  // all compilations of this schedule start now, in parallel
       } else {
@@ -101,6 +115,26 @@ int execute_steps(qipb200_state *s, const std::vector<PlanStep> &steps, const st
               }  // else: the opening barrier stays queued (send_stage 1), exchange_bits pushes with its own kernel
             }
           }
+          // Paired send: the give-half tiles go into the partner's shard, tile by tile under the flag handshake.
+          JitPair pair;
+          // (test hook QIPB200_PAIRED_STANDIN_RANK=<rank | -1 for all>: that rank never fuses the send into its pass)
+          static const int standin_rank = getenv("QIPB200_PAIRED_STANDIN_RANK") ? atoi(getenv("QIPB200_PAIRED_STANDIN_RANK")) : -2;
+          const bool pair_here = send.pair && i + 1 == steps.size() && standin_rank != -1 && standin_rank != s->rank;
+          if (pair_here) {
+            int partner = 0, give = 0;
+            paired_partner(s, send.R, &partner, &give);
+            memset(&tmap_out, 0, sizeof(tmap_out));
+            if (make_tile_map(&tmap_out, s->prec, s->peer_buf[partner], s->n_local, ph)) {
+              tmo = &tmap_out;
+              send_bit = send.l;
+              send_val = (uint32_t)give;
+              pair.cbit = pair_cbit;
+              pair.seq = pair_seq;
+              pair.my_flags = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(s->flags) + kPairFlagOffsetBytes);
+              pair.peer_flags = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(s->peer_flags[partner]) + kPairFlagOffsetBytes);
+              pair.error_word = s->flags + kFlagErrorSlot;
+            }
+          }
           // A pass next to an overlapped migration runs in two halves of the tile counter (= top local bit 0 / 1,
           // which must not be a tile bit): after a migration each half starts when its exchange is done, before one
           // each half is reported final as soon as it is.
@@ -126,10 +160,14 @@ int execute_steps(qipb200_state *s, const std::vector<PlanStep> &steps, const st
           } else {
             if (after_mig && join_halves(s) != QIPB200_OK) return QIPB200_ERR_CUDA;
             ProfileScope prof(ctx, 0);
-            e = jit_launch(cubin, &ctx->jit_loaded, progs[i], s->buf, s->n_local, tmap, ctx->stream, &err, tmo, send_bit, send_val);
+            e = jit_launch(cubin, &ctx->jit_loaded, progs[i], s->buf, s->n_local, tmap, ctx->stream, &err, tmo, send_bit, send_val, 2,
+                           pair_here && tmo ? &pair : nullptr);
           }
           if (e == cudaSuccess) {
-            if (tmo) s->send_stage = 2;
+            if (pair_here && tmo)
+              paired_done = true;
+            else if (tmo)
+              s->send_stage = 2;
             ++ctx->launches;
             ++ctx->tile_launches;
             ++ctx->jit_launches;
@@ -158,6 +196,11 @@ int execute_steps(qipb200_state *s, const std::vector<PlanStep> &steps, const st
     }
   }
   delete pp;
+  if (st == QIPB200_OK && send.pair && !paired_done)  // the last pass ran without the send: play the protocol separately
+    st = paired_send_standin(s, send.R, send.l, pair_cbit, pair_seq, steps.back().pass.hdr);
+  if (send.pair && getenv("QIPB200_PAIRED_DEBUG"))
+    fprintf(stderr, "paired send: rank %d migration %u (R=%u l=%u) %s\n", s->rank, pair_seq, send.R, send.l,
+            paired_done ? "fused into the pass" : "stand-in kernel");
   if (st == QIPB200_OK && send.overlap && !halves_recorded) {
     // the epoch's last step ran as one launch (or there was none): both halves are final now
     if (s->halves_pending && (st = join_halves(s)) != QIPB200_OK) return st;
@@ -181,6 +224,13 @@ int run_fused(qipb200_state *s, const qip_op *ops, size_t n_ops, const std::vect
   }
   PlanConfig cfg = default_plan_config(s->prec, s->n_local);
   if (s->world > 1 && overlap_exchange_enabled()) cfg.reserve_bit = (int)s->n_local - 1;  // passes splittable in halves
+  // Paired send (QIPB200_PAIRED_SEND=1): the migration that ends an epoch is fused into the epoch's last tile pass and done
+  // in place, tile by tile, against the partner's copy of the same pass.  Tiles pair up across GPUs, so every rank must
+  // choose the same tile bits: the planner then selects from rank-independent data only (op_uniform_info).
+  static const bool paired_env = getenv("QIPB200_PAIRED_SEND") != nullptr && atoi(getenv("QIPB200_PAIRED_SEND")) != 0;
+  const bool paired_mode = paired_env && s->world > 1 && !s->has_stage && !overlap_exchange_enabled() && cfg.use_tma &&
+                           cfg.groups_per_thread == 1 && jit_mode_from_env(s->n_local) != JIT_OFF &&
+                           cfg.T == (s->prec == QIP_F32 ? 13u : 12u) && s->n_local > cfg.T && s->n_local - cfg.T <= kPairFlagLog2;
   std::vector<size_t> remaining(n_ops);
   for (size_t i = 0; i < n_ops; ++i) remaining[i] = i;
   while (!remaining.empty()) {
@@ -204,6 +254,16 @@ int run_fused(qipb200_state *s, const qip_op *ops, size_t n_ops, const std::vect
         return report_error(s, st, err);
       }
       op_dependency_masks(f, &dep[r]);
+      if (paired_mode) {  // what the op looks like on the rank whose rank-held bits are all 1: the same on every rank
+        FlatOp fv;
+        bool skipv = false;
+        if ((st = restrict_to_rank_as(s, s->world - 1, f, &fv, &skipv)) != QIPB200_OK) return st;
+        if (skipv) {
+          fv = FlatOp();
+          fv.cls = CLASS_IDENTITY;
+        }
+        op_uniform_info(fv, &dep[r]);
+      }
       if (needs_exchange(s, f)) {
         blocked[r] = 1;
         local[r] = f;
@@ -235,7 +295,14 @@ int run_fused(qipb200_state *s, const qip_op *ops, size_t n_ops, const std::vect
     if (first_blocked != left.size()) {
       const size_t op_idx = remaining[left[first_blocked]];
       const uint64_t *nu = next_use.empty() ? nullptr : &next_use[(op_idx + 1) * s->n];
-      if (s->has_stage) {
+      if (paired_mode) {
+        if (!steps.empty() && steps.back().is_pass && peek_first_exchange(s, &ops[op_idx], nu, &send.R, &send.l)) {
+          const PassHeader &ph = steps.back().pass.hdr;  // rank-independent geometry: bit l must be constant within a tile
+          bool ok = send.l >= ph.L && ph.T == cfg.T;
+          for (uint32_t k = 0; k < ph.m; ++k) ok = ok && ph.hi_pos[k] != send.l;
+          send.pair = ok;
+        }
+      } else if (s->has_stage) {
         if (fused_send && !steps.empty() && steps.back().is_pass) send.on = peek_first_exchange(s, &ops[op_idx], nu, &send.R, &send.l);
       } else if (overlap_exchange && s->world > 1 && s->n_local >= 8) {
         // in-place exchange in two halves on the second stream, overlapping the passes on either side of it
@@ -246,6 +313,7 @@ int run_fused(qipb200_state *s, const qip_op *ops, size_t n_ops, const std::vect
     int st = execute_steps(s, steps, local, cfg, send);
     if (st != QIPB200_OK) return st;
     if (send.overlap && (st = exchange_bits_split(s, send.R, send.l)) != QIPB200_OK) return st;
+    if (send.pair && (st = finish_paired_exchange(s, send.R, send.l)) != QIPB200_OK) return st;
     if (left.empty()) break;
     if (first_blocked == left.size())
       return report_error(s, QIPB200_ERR_UNSUPPORTED, "internal: schedule made no progress");

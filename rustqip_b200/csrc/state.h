@@ -61,6 +61,7 @@ struct qipb200_state {
   int rank = 0, world = 1;
   void *buf = nullptr;      // 2^n_local amplitudes (sharded states: followed by a staging area of the same size)
   bool has_stage = false;   // the allocation of `buf` is 2 * bytes: [state | staging of the push exchange]
+  uint32_t pair_seq = 0;        // migrations fused into a tile pass so far (value written into the per-tile flag words)
   bool halves_pending = false;  // the two halves of the shard become valid at ctx->ev_exch[0/1] (an overlapped migration)
   int send_stage = 0;       // pending exchange: 0 nothing yet, 1 its opening barrier is queued, 2 ... and the last tile
                             // pass has pushed the give-half into the partner's staging area

@@ -275,8 +275,17 @@ struct PlanConfig {
 // (rank-held controls dropped) but the ordering must respect the unrestricted bits.
 struct DepMasks {
   uint64_t nd = 0, dg = 0;
+  // Optional RANK-INDEPENDENT selection data (sharded states whose ranks must choose the same tile bits for every pass:
+  // migrations fused into a pass pair up tiles across GPUs).  Filled by op_uniform_info from the op as restricted to a
+  // virtual rank whose rank-held bits are all 1; when present, the planner selects with these instead of anything
+  // derived from `ops` (which differ from rank to rank), and uses the guaranteed byte budget only (no size-driven retry).
+  bool has_uniform = false, u_tile_ok = false;
+  uint64_t u_need_tile = 0;
+  double u_unfused_cost = 0.0;
+  uint32_t u_est_bytes = 0;
 };
 void op_dependency_masks(const FlatOp &f, DepMasks *out);
+void op_uniform_info(const FlatOp &restricted_to_virtual_rank, DepMasks *out);
 void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec, const PlanConfig &cfg,
                  std::vector<PlanStep> *steps, const std::vector<char> *blocked = nullptr,
                  std::vector<size_t> *leftover = nullptr, const std::vector<DepMasks> *dep = nullptr);

@@ -24,8 +24,13 @@ def main():
     g = (world - 1).bit_length()
     ctx = Context(local_rank)
     failures = 0
-    for n, dtype, fusion, jit in [(12, np.complex128, False, "off"), (14, np.complex128, True, "off"), (15, np.complex64, True, "off"),
-                                  (17, np.complex128, True, "off"), (18, np.complex128, True, "sync"), (19, np.complex64, True, "sync")]:
+    cases = [(12, np.complex128, False, "off"), (14, np.complex128, True, "off"), (15, np.complex64, True, "off"),
+             (17, np.complex128, True, "off"), (18, np.complex128, True, "sync"), (19, np.complex64, True, "sync")]
+    if os.environ.get("QIPB200_PAIRED_SEND"):
+        # migrations fused into the last tile pass of an epoch (schedule.cu: paired send) need the generated kernels
+        cases = [(18, np.complex128, True, "sync"), (19, np.complex64, True, "sync"), (20, np.complex128, True, "sync"),
+                 (18, np.complex128, True, "async")]
+    for n, dtype, fusion, jit in cases:
         # "sync": the generated kernels even at these sizes -- passes next to a migration run in two halves that
         # overlap the two halves of the exchange (schedule.cu / exchange_bits_split)
         os.environ["QIPB200_JIT"] = jit

@@ -585,7 +585,7 @@ extern "C" int emul_dump_jit(int prec, uint32_t n, const qip_op *ops, size_t n_o
     JitProgram prog;
     std::string why;
     char name[512];
-    if (!jit_generate(steps[s].pass, (qip_prec)prec, &prog, &why)) {
+    if (!jit_generate(steps[s].pass, (qip_prec)prec, &prog, &why, getenv("JIT_DUMP_PAIRED") != nullptr)) {
       fprintf(stderr, "pass %zu declined: %s\n", s, why.c_str());
       continue;
     }

@@ -26,6 +26,32 @@ def test_sharded_state_matches_oracle(world):
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
 
 
+@pytest.mark.parametrize("standin", ["none", "0", "-1"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_paired_send_matches_oracle(world, standin):
+    """QIPB200_PAIRED_SEND=1: the migration that ends an epoch is fused into the epoch's last generated tile pass and done
+    in place, tile by tile, under a per-tile flag handshake with the partner's pass (one kernel = compute + NVLink
+    transfer).  `standin`: which rank plays the protocol with the stand-alone kernel instead (none / rank 0 / all) --
+    every mix must give the oracle's amplitudes."""
+    if _gpu_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    env = dict(os.environ, QIPB200_PAIRED_SEND="1", QIPB200_PAIRED_DEBUG="1")
+    if standin != "none":
+        env["QIPB200_PAIRED_STANDIN_RANK"] = standin
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29640 + world), os.path.join(ROOT, "tests", "dist_worker.py")]
+    p = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    sys.stdout.write(p.stdout[-4000:])
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    fused, alone = p.stderr.count("fused into the pass"), p.stderr.count("stand-in kernel")
+    print("paired migrations: %d fused, %d stand-in" % (fused, alone))
+    assert fused + alone > 0, p.stderr[-2000:]
+    if standin == "none":
+        assert fused > 0
+    if standin == "-1":
+        assert fused == 0
+
+
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_single_process_multi_device_context(world):
     """qipb200_init_multi: ONE process, one context over `world` devices (the shape a Rust B200Builder replacing
