@@ -206,9 +206,14 @@ template <typename V, int PER>
 __global__ void __launch_bounds__(256) k_paired_send(const PairedSendArgs a) {
   const V *mine = static_cast<const V *>(a.mine);
   V *peer = static_cast<V *>(a.peer);
-  // tile counter of this CTA: blockIdx with the give value inserted at counter bit `cbit`
-  const uint64_t c = blockIdx.x;
-  const uint64_t t = ((c >> a.cbit) << (a.cbit + 1)) | ((uint64_t)a.give << a.cbit) | (c & ((1ull << a.cbit) - 1ull));
+  // tile counter of this CTA: the j-th tile of the give-half IN THE ORDER THE FUSED PASS WALKS THEM (launch position
+  // 2 j + give with bits 0 and cbit exchanged, jit_codegen.cpp) -- both sides of a pair must come up in the same order, or
+  // the two bounded sets of resident CTAs can wait for each other
+  uint64_t t = 2ull * blockIdx.x + a.give;
+  if (a.cbit != 0u) {
+    const uint64_t b0 = t & 1ull, bc = (t >> a.cbit) & 1ull;
+    t = (t & ~(1ull | (1ull << a.cbit))) | bc | (b0 << a.cbit);
+  }
   uint64_t base = t << a.L;
   for (uint32_t i = 0; i < a.m; ++i) {
     const uint32_t q = a.hi_pos[i];
@@ -232,8 +237,8 @@ __global__ void __launch_bounds__(256) k_paired_send(const PairedSendArgs a) {
     for (;;) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.my_flags + t) : "memory");
       if ((int32_t)(v - a.seq) >= 0) break;
-      if (globaltimer_ns() - t0 > 20ull * 1000ull * 1000ull * 1000ull) {
-        *a.error_word = 1u;
+      if (globaltimer_ns() - t0 > 20ull * 1000ull * 1000ull * 1000ull || *(volatile uint32_t *)a.error_word != 0u) {
+        *a.error_word = 1u;  // the partner is gone; later tiles give up at once
         break;
       }
     }

@@ -861,9 +861,24 @@ qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constan
   __syncthreads();
   const u64 tile_off = ((u64)p.tile_off_hi << 32) | (u64)p.tile_off_lo, tile_cnt = ((u64)p.tile_cnt_hi << 32) | (u64)p.tile_cnt_lo;
   unsigned parity = 0u;
+#if QIP_PAIRED
+  const u64 pair_my = ((u64)p.pair_my_hi << 32) | (u64)p.pair_my_lo;
+#endif
 #pragma unroll 1
   for (u64 tile = blockIdx.x; tile < tile_cnt; tile += gridDim.x, parity ^= 1u) {
-  const u64 base = tile_base(p, tile + tile_off);
+#if QIP_PAIRED
+  // paired send: walk the tile counter with its bits 0 and pair_cbit exchanged, so that tiles this rank keeps and tiles it
+  // gives away alternate (HBM and NVLink traffic overlap) and both ranks reach a pair of tiles at about the same time
+  u64 tpos = tile;
+  if (pair_my != 0ull && p.pair_cbit != 0u) {
+    const u64 b0 = tpos & 1ull, bc = (tpos >> p.pair_cbit) & 1ull;
+    tpos = (tpos & ~(1ull | (1ull << p.pair_cbit))) | bc | (b0 << p.pair_cbit);
+  }
+  const u64 tt = tpos + tile_off;
+#else
+  const u64 tt = tile + tile_off;
+#endif
+  const u64 base = tile_base(p, tt);
   if (tid == 0) {  // the tile buffer is free: this thread waited for the previous tile's stores to have read it
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(TILE_BYTES) : "memory");
 #pragma unroll 1
@@ -897,12 +912,11 @@ qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constan
   src << "  const R* tbl = reinterpret_cast<const R*>(sm + OFF_TBL);\n  const R* gt = reinterpret_cast<const R*>(sm + OFF_GT);\n";
   src << "  mbar_wait(mbar, parity);\n";
   src << R"(#if QIP_PAIRED
-  const u64 pair_my = ((u64)p.pair_my_hi << 32) | (u64)p.pair_my_lo;
-  const bool pair_give = pair_my != 0ull && (((tile + tile_off) >> p.pair_cbit) & 1ull) == (u64)p.send_val;
+  const bool pair_give = pair_my != 0ull && ((tt >> p.pair_cbit) & 1ull) == (u64)p.send_val;
   if (pair_give && tid == 0) {  // my copy of the tile is in shared memory: the partner may overwrite the slot
     const u64 peer_flags = ((u64)p.pair_peer_hi << 32) | (u64)p.pair_peer_lo;
     __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags + 4ull * ((tile + tile_off) ^ (1ull << p.pair_cbit))),
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags + 4ull * (tt ^ (1ull << p.pair_cbit))),
                  "r"(p.pair_seq)
                  : "memory");
   }
@@ -930,11 +944,12 @@ qip_pass(R* __restrict__ psi, const __grid_constant__ JP p, const __grid_constan
       unsigned long long t0, t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
       for (;;) {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(pair_my + 4ull * (tile + tile_off)) : "memory");
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(pair_my + 4ull * tt) : "memory");
         if ((int)(v - p.pair_seq) >= 0) break;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 20000000000ull) {  // 20 s: the partner is gone
-          *reinterpret_cast<unsigned*>(((u64)p.pair_err_hi << 32) | (u64)p.pair_err_lo) = 1u;
+        volatile unsigned* errw = reinterpret_cast<volatile unsigned*>(((u64)p.pair_err_hi << 32) | (u64)p.pair_err_lo);
+        if (t1 - t0 > 20000000000ull || *errw != 0u) {  // 20 s: the partner is gone (later tiles give up at once)
+          *errw = 1u;
           break;
         }
       }
