@@ -671,43 +671,7 @@ int restrict_to_rank(const qipb200_state *s, const FlatOp &f_in, FlatOp *out, bo
 
 // ... as rank `rank` of this state's world would see the op (rank == world - 1: every rank-held bit is 1)
 int restrict_to_rank_as(const qipb200_state *s, int rank, const FlatOp &f_in, FlatOp *out, bool *skip) {
-  const uint32_t nl = s->n_local;
-  const uint64_t lo_mask = (nl >= 64) ? ~0ull : ((1ull << nl) - 1ull);
-  const uint64_t rank_val = (uint64_t)rank << nl;
-  *skip = false;
-  *out = f_in;
-  if (f_in.cls == CLASS_IDENTITY) {
-    *skip = true;
-    return QIPB200_OK;
-  }
-  const uint64_t hc = f_in.ctrl_mask & ~lo_mask;
-  if ((rank_val & hc) != hc) {  // a control held by the rank index is 0 here
-    *skip = true;
-    return QIPB200_OK;
-  }
-  out->ctrl_mask = f_in.ctrl_mask & lo_mask;
-  if (f_in.cls == CLASS_DIAGONAL) {
-    std::vector<cplx> d = f_in.diag;
-    std::vector<uint32_t> all = f_in.diag_bits;
-    for (int i = (int)all.size() - 1; i >= 0; --i) {  // highest first keeps indices valid
-      if (all[i] < nl) continue;
-      const int v = (int)((rank_val >> all[i]) & 1ull);
-      std::vector<cplx> nd;
-      for (uint64_t u = 0; u < d.size(); ++u)
-        if ((int)((u >> i) & 1) == v) nd.push_back(d[u]);
-      d.swap(nd);
-      all.erase(all.begin() + i);
-    }
-    bool all_one = true;
-    for (size_t u = 0; u < d.size(); ++u)
-      if (!(d[u].real() == 1.0 && d[u].imag() == 0.0)) all_one = false;
-    if (all_one) {
-      *skip = true;
-      return QIPB200_OK;
-    }
-    out->diag_bits = all;
-    out->diag = d;
-  }
+  restrict_flat_op(f_in, s->n_local, rank, out, skip);  // opcompile.cpp
   return QIPB200_OK;
 }
 

@@ -278,4 +278,44 @@ int compile_op(const qip_op *op, qip_prec prec, uint32_t n_qubits, FlatOp *out, 
   return QIPB200_OK;
 }
 
+void restrict_flat_op(const FlatOp &f_in, uint32_t n_local, int rank, FlatOp *out, bool *skip) {
+  const uint32_t nl = n_local;
+  const uint64_t lo_mask = (nl >= 64) ? ~0ull : ((1ull << nl) - 1ull);
+  const uint64_t rank_val = (uint64_t)rank << nl;
+  *skip = false;
+  *out = f_in;
+  if (f_in.cls == CLASS_IDENTITY) {
+    *skip = true;
+    return;
+  }
+  const uint64_t hc = f_in.ctrl_mask & ~lo_mask;
+  if ((rank_val & hc) != hc) {  // a control held by the rank index is 0 here
+    *skip = true;
+    return;
+  }
+  out->ctrl_mask = f_in.ctrl_mask & lo_mask;
+  if (f_in.cls == CLASS_DIAGONAL) {
+    std::vector<cplx> d = f_in.diag;
+    std::vector<uint32_t> all = f_in.diag_bits;
+    for (int i = (int)all.size() - 1; i >= 0; --i) {  // highest first keeps indices valid
+      if (all[i] < nl) continue;
+      const int v = (int)((rank_val >> all[i]) & 1ull);
+      std::vector<cplx> nd;
+      for (uint64_t u = 0; u < d.size(); ++u)
+        if ((int)((u >> i) & 1) == v) nd.push_back(d[u]);
+      d.swap(nd);
+      all.erase(all.begin() + i);
+    }
+    bool all_one = true;
+    for (size_t u = 0; u < d.size(); ++u)
+      if (!(d[u].real() == 1.0 && d[u].imag() == 0.0)) all_one = false;
+    if (all_one) {
+      *skip = true;
+      return;
+    }
+    out->diag_bits = all;
+    out->diag = d;
+  }
+}
+
 }  // namespace qipb200

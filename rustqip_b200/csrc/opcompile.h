@@ -62,6 +62,11 @@ struct FlatOp {
 int compile_op(const qip_op *op, qip_prec prec, uint32_t n_qubits, FlatOp *out, std::string *err,
                const uint32_t *phys_of_logical = nullptr);
 
+// Restrict a compiled op (physical bits, non-diagonal targets all below n_local) to rank `rank` of a state sharded by
+// the index bits >= n_local: controls held by the rank index either vanish or switch the op off; diagonal bits held by
+// the rank index select a slice of the diagonal.  *skip = true when the op is the identity on that rank.
+void restrict_flat_op(const FlatOp &f_in, uint32_t n_local, int rank, FlatOp *out, bool *skip);
+
 // Validation only (what the reference's make_*_op constructors check + index range/distinctness).
 int validate_op(const qip_op *op, qip_prec prec, uint32_t n_qubits, std::string *err);
 

@@ -422,6 +422,178 @@ extern "C" int emul_schedule_blocked(int prec, uint32_t n, const qip_op *ops, si
   return 0;
 }
 
+// A 2^g-way SHARDED state with rank-independent planning (schedule.cu: run_fused in paired-send mode): every epoch,
+// every virtual rank restricts the remaining ops to itself (opcompile.cpp: restrict_flat_op), plans with the uniform
+// selection data (op_uniform_info of the all-ones rank) and must arrive at the SAME steps -- same tile bits, same ops
+// taken, same single steps, same leftovers -- because a migration fused into a pass pairs up tiles across GPUs.  The
+// passes are then executed per rank on its shard (what each rank emitted for ITSELF, ops that are the identity on a rank
+// included), single steps and migrations on the whole vector.  Returns -10 when two ranks plan differently.
+// stats: [0] passes, [1] epochs, [2] migrations, [3] ops that were the identity on at least one rank but not on all.
+static void swap_index_bits(std::vector<cd> &psi, uint32_t a, uint32_t b) {
+  if (a == b) return;
+  for (uint64_t i = 0; i < psi.size(); ++i)
+    if (((i >> a) & 1ull) == 0 && ((i >> b) & 1ull) == 1) std::swap(psi[i], psi[i ^ (1ull << a) ^ (1ull << b)]);
+}
+
+extern "C" int emul_sharded_uniform(int prec, uint32_t n, uint32_t g, const qip_op *ops, size_t n_ops, double *state, uint32_t T,
+                                    uint32_t L, uint64_t *stats, char *errbuf, size_t errlen) {
+  const uint32_t nl = n - g, world = 1u << g;
+  std::vector<uint32_t> phys(n);
+  for (uint32_t b = 0; b < n; ++b) phys[b] = b;
+  PlanConfig cfg = default_plan_config((qip_prec)prec, nl);
+  if (T) cfg.T = T;
+  if (L) cfg.L = L;
+  g_decode_errors = 0;
+  std::vector<cd> psi(1ull << n);
+  for (uint64_t i = 0; i < (1ull << n); ++i) psi[i] = cd(state[2 * i], state[2 * i + 1]);
+  std::vector<size_t> remaining(n_ops);
+  for (size_t i = 0; i < n_ops; ++i) remaining[i] = i;
+  uint64_t epochs = 0, n_pass = 0, n_mig = 0, n_mixed = 0;
+  auto fail = [&](int code, const std::string &msg) {
+    if (errbuf && errlen) snprintf(errbuf, errlen, "%s", msg.c_str());
+    return code;
+  };
+  while (!remaining.empty()) {
+    ++epochs;
+    std::vector<FlatOp> flat(remaining.size());
+    std::vector<char> blocked(remaining.size(), 0);
+    std::vector<DepMasks> dep(remaining.size());
+    for (size_t r = 0; r < remaining.size(); ++r) {
+      std::string err;
+      int st = compile_op(&ops[remaining[r]], (qip_prec)prec, n, &flat[r], &err, phys.data());
+      if (st != QIPB200_OK) return fail(st, err);
+      op_dependency_masks(flat[r], &dep[r]);
+      blocked[r] = (dep[r].nd >> nl) ? 1 : 0;
+      FlatOp fv;
+      bool skipv = false;
+      restrict_flat_op(flat[r], nl, (int)world - 1, &fv, &skipv);
+      if (skipv) {
+        fv = FlatOp();
+        fv.cls = CLASS_IDENTITY;
+      }
+      if (!getenv("EMUL_NO_UNIFORM")) op_uniform_info(fv, &dep[r]);
+    }
+    std::vector<std::vector<PlanStep>> steps(world);
+    std::vector<std::vector<FlatOp>> local(world, std::vector<FlatOp>(remaining.size()));
+    std::vector<size_t> left0;
+    for (uint32_t rk = 0; rk < world; ++rk) {
+      std::vector<size_t> left;
+      for (size_t r = 0; r < remaining.size(); ++r) {
+        if (blocked[r]) {
+          local[rk][r] = flat[r];
+          continue;
+        }
+        bool skip = false;
+        restrict_flat_op(flat[r], nl, (int)rk, &local[rk][r], &skip);
+        if (skip) {
+          local[rk][r] = FlatOp();
+          local[rk][r].cls = CLASS_IDENTITY;
+        }
+      }
+      plan_passes(local[rk], nl, (qip_prec)prec, cfg, &steps[rk], &blocked, &left, &dep);
+      if (rk == 0) {
+        left0 = left;
+      } else {
+        if (left != left0 || steps[rk].size() != steps[0].size()) return fail(-10, "ranks disagree on the number of steps / leftovers");
+        for (size_t s = 0; s < steps[0].size(); ++s) {
+          const PlanStep &a = steps[0][s], &b = steps[rk][s];
+          if (a.is_pass != b.is_pass) return fail(-10, "ranks disagree on the kind of a step");
+          if (!a.is_pass && a.op_index != b.op_index) return fail(-10, "ranks disagree on a single step");
+          if (a.is_pass && (memcmp(a.pass.hdr.hi_pos, b.pass.hdr.hi_pos, sizeof(a.pass.hdr.hi_pos)) != 0 || a.pass.hdr.T != b.pass.hdr.T ||
+                            a.pass.hdr.L != b.pass.hdr.L || a.pass.n_gates != b.pass.n_gates))
+            return fail(-10, "ranks disagree on the tile bits / the gates of a pass");
+        }
+      }
+    }
+    for (size_t r = 0; r < remaining.size(); ++r) {
+      if (blocked[r]) continue;
+      bool any = false, all = true;
+      for (uint32_t rk = 0; rk < world; ++rk) {
+        const bool id = local[rk][r].cls == CLASS_IDENTITY;
+        any = any || id;
+        all = all && id;
+      }
+      if (any && !all) ++n_mixed;
+    }
+    for (size_t s = 0; s < steps[0].size(); ++s) {
+      if (!steps[0][s].is_pass) {
+        if (blocked[steps[0][s].op_index]) return fail(-4, "a blocked op was scheduled");
+        apply_single(flat[steps[0][s].op_index], n, psi);  // == every rank applying its restriction to its shard
+        continue;
+      }
+      for (uint32_t rk = 0; rk < world; ++rk) {
+        PassParams pp;
+        if (!serialise_pass(steps[rk][s].pass, &pp)) return fail(-2, "pass exceeds the parameter space");
+        std::vector<cd> shard(psi.begin() + ((uint64_t)rk << nl), psi.begin() + ((uint64_t)(rk + 1) << nl));
+        if (prec == QIP_F32)
+          run_pass_params<float>(pp, nl, shard);
+        else
+          run_pass_params<double>(pp, nl, shard);
+        std::copy(shard.begin(), shard.end(), psi.begin() + ((uint64_t)rk << nl));
+      }
+      ++n_pass;
+    }
+    if (left0.empty()) break;
+    size_t fb = left0.size();
+    for (size_t i = 0; i < left0.size(); ++i)
+      if (blocked[left0[i]]) {
+        fb = i;
+        break;
+      }
+    if (fb == left0.size()) return fail(-5, "no progress and nothing to migrate for");
+    // migrate: every rank-held non-diagonal bit of the first blocked op trades places with the highest free local bit
+    const FlatOp &f = flat[left0[fb]];
+    uint64_t used = dep[left0[fb]].nd | dep[left0[fb]].dg;
+    for (uint32_t R = nl; R < n; ++R) {
+      if (!((dep[left0[fb]].nd >> R) & 1ull)) continue;
+      int l = -1;
+      for (int b = (int)nl - 1; b >= 0; --b)
+        if (!((used >> b) & 1ull)) {
+          l = b;
+          break;
+        }
+      if (l < 0) return fail(-6, "op touches every local bit");
+      swap_index_bits(psi, R, (uint32_t)l);
+      for (uint32_t b = 0; b < n; ++b) {
+        if (phys[b] == R)
+          phys[b] = (uint32_t)l;
+        else if (phys[b] == (uint32_t)l)
+          phys[b] = R;
+      }
+      used |= 1ull << l;
+      ++n_mig;
+    }
+    (void)f;
+    std::vector<size_t> next;
+    for (size_t i = 0; i < left0.size(); ++i) next.push_back(remaining[left0[i]]);
+    remaining.swap(next);
+  }
+  // restore the canonical layout: logical bit b back at physical bit b
+  for (uint32_t b = 0; b < n; ++b) {
+    if (phys[b] == b) continue;
+    const uint32_t where = phys[b];
+    swap_index_bits(psi, b, where);
+    for (uint32_t c = 0; c < n; ++c) {
+      if (phys[c] == b)
+        phys[c] = where;
+      else if (phys[c] == where)
+        phys[c] = b;
+    }
+  }
+  for (uint64_t i = 0; i < (1ull << n); ++i) {
+    state[2 * i] = psi[i].real();
+    state[2 * i + 1] = psi[i].imag();
+  }
+  if (stats) {
+    stats[0] = n_pass;
+    stats[1] = epochs;
+    stats[2] = n_mig;
+    stats[3] = n_mixed;
+  }
+  if (g_decode_errors) return fail(-3, "decode errors");
+  return 0;
+}
+
 // plan only (no amplitudes): pass / single-step counts for big circuits
 extern "C" int emul_plan_stats(int prec, uint32_t n, const qip_op *ops, size_t n_ops, uint32_t T, uint32_t L,
                                int fuse_blocks, uint32_t max_k, uint64_t *stats) {

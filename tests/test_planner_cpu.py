@@ -39,6 +39,9 @@ def emul():
     L.emul_schedule_blocked.restype = C.c_int
     L.emul_schedule_blocked.argtypes = [C.c_int, C.c_uint32, C.POINTER(QipOp), C.c_size_t, C.c_void_p, C.c_uint32,
                                         C.c_uint32, C.c_uint64, C.c_void_p, C.c_char_p, C.c_size_t]
+    L.emul_sharded_uniform.restype = C.c_int
+    L.emul_sharded_uniform.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(QipOp), C.c_size_t, C.c_void_p, C.c_uint32,
+                                       C.c_uint32, C.c_void_p, C.c_char_p, C.c_size_t]
     L.emul_plan_stats.restype = C.c_int
     L.emul_plan_stats.argtypes = [C.c_int, C.c_uint32, C.POINTER(QipOp), C.c_size_t, C.c_uint32, C.c_uint32,
                                   C.c_int, C.c_uint32, C.c_void_p]
@@ -234,3 +237,39 @@ def test_plan_stats_bench_circuits(emul):
         sweeps = int(stats[0] + stats[1])
         assert sweeps < len(ops) / 4, (name, sweeps)
     print(out)
+
+
+@pytest.mark.parametrize("n,g,T,Lo", [(11, 1, 6, 2), (12, 2, 6, 2), (12, 3, 5, 2), (13, 2, 7, 3)])
+def test_sharded_ranks_plan_alike_with_uniform_selection(emul, n, g, T, Lo):
+    """Paired send (schedule.cu) pairs up tiles across GPUs: with the rank-independent selection data (op_uniform_info)
+    every virtual rank of a 2^g-way sharded state must plan the same steps from ITS restriction of the ops (controls and
+    diagonal bits held by the rank index differ from rank to rank), and executing what each rank emitted for itself on
+    its shard must give the oracle's amplitudes -- epochs, migrations and layout restore included."""
+    for seed in (1, 2):
+        ops = circuits.sharded_parity_circuit(n, g, seed) + circuits.random_circuit(n, 5, 40 + seed, "H,T,CNOT") + circuits.qft(n)[:40]
+        psi = rand_state(n, 30 + seed)
+        want = qo.run_pipeline(n, ops, state=psi)
+        arr, keep = marshal_ops(ops, prec_of(np.complex128))
+        st = np.ascontiguousarray(psi.astype(np.complex128))
+        stats = np.zeros(8, dtype=np.uint64)
+        err = C.create_string_buffer(256)
+        rc = emul.emul_sharded_uniform(prec_of(np.complex128), n, g, arr, len(ops), st.ctypes.data, T, Lo, stats.ctypes.data, err, 256)
+        assert rc == 0, (rc, err.value)
+        assert np.max(np.abs(st - want)) < 1e-12
+        assert stats[0] > 0 and stats[2] > 0 and stats[3] > 0  # passes ran, qubits migrated, some ops were rank-dependent
+
+
+def test_sharded_ranks_plan_differently_without_uniform_selection(emul, monkeypatch):
+    """Negative control of the test above: planned from each rank's own restriction of the ops, two ranks of an 8-way
+    sharded state choose different steps (return code -10) -- the reason the paired send needs op_uniform_info."""
+    monkeypatch.setenv("EMUL_NO_UNIFORM", "1")
+    n, g = 12, 3
+    seen = set()
+    for seed in (1, 2):
+        ops = circuits.sharded_parity_circuit(n, g, seed) + circuits.random_circuit(n, 5, 40 + seed, "H,T,CNOT") + circuits.qft(n)[:40]
+        arr, keep = marshal_ops(ops, prec_of(np.complex128))
+        st = np.ascontiguousarray(rand_state(n, 30 + seed).astype(np.complex128))
+        stats = np.zeros(8, dtype=np.uint64)
+        err = C.create_string_buffer(256)
+        seen.add(emul.emul_sharded_uniform(prec_of(np.complex128), n, g, arr, len(ops), st.ctypes.data, 5, 2, stats.ctypes.data, err, 256))
+    assert -10 in seen, seen
