@@ -415,8 +415,8 @@ def run_b200(args):
                                     "double" if args.dtype == "f64" else "float"), args.dtype, fused_gates / tile_passes),
                             "achieved": local_bytes / (avg_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                             "frac": local_bytes / (avg_ms / 1e3) / 1e9 / peak, "peak_source": peak_src,
-                            "traffic": (ncu_traffic("k_tile_pass", local_bytes) or {}).get("bytes"),
-                            "traffic_source": (ncu_traffic("k_tile_pass", local_bytes) or {}).get("source"),
+                            "traffic": (ncu_traffic("qip_pass" if gen else "k_tile_pass", local_bytes) or {}).get("bytes"),
+                            "traffic_source": (ncu_traffic("qip_pass" if gen else "k_tile_pass", local_bytes) or {}).get("source"),
                             "algorithmic_bytes_per_launch": local_bytes, "avg_launch_ms": avg_ms,
                             "frac_of_nominal_8TBps": local_bytes / (avg_ms / 1e3) / 1e9 / 8000.0,
                             "share_of_step": prof["tile_ms"] / max(1e-9, ms),
