@@ -190,3 +190,24 @@ def test_jit_disk_cache_between_processes(tmp_path):
     third = probe()
     assert third["out"][2] == first["out"][2] and ("disk cache: %d programs" % (len(files) - 1)) in third["log"], third
     assert open(victim, "rb").read() != bytes(blob)  # recompiled and rewritten
+
+
+def test_jit_disk_cache_concurrent_writers(tmp_path):
+    """Two processes filling the same cache directory at the same time (temporary name + rename): both succeed, no
+    temporary file is left behind, and a third process finds every program on disk."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QIPB200_JIT_CACHE_DIR=str(tmp_path), PYTHONPATH=root)
+    procs = [subprocess.Popen([sys.executable, "-c", _CACHE_PROBE], env=env, cwd=root, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for _ in range(2)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    res = [json.loads(o[0].strip().splitlines()[-1]) for o in outs]
+    assert all(p.returncode == 0 for p in procs), [o[1][-500:] for o in outs]
+    assert all(r["rc"] == 0 and r["out"][2] == r["out"][0] for r in res), res
+    assert not [f for f in os.listdir(tmp_path) if ".tmp." in f]
+    r = subprocess.run([sys.executable, "-c", _CACHE_PROBE], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    third = json.loads(r.stdout.strip().splitlines()[-1])
+    n_files = len([f for f in os.listdir(tmp_path) if f.endswith(".cubin")])
+    assert ("disk cache: %d programs" % n_files) in third["log"], third

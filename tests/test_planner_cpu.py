@@ -239,8 +239,9 @@ def test_plan_stats_bench_circuits(emul):
     print(out)
 
 
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
 @pytest.mark.parametrize("n,g,T,Lo", [(11, 1, 6, 2), (12, 2, 6, 2), (12, 3, 5, 2), (13, 2, 7, 3)])
-def test_sharded_ranks_plan_alike_with_uniform_selection(emul, n, g, T, Lo):
+def test_sharded_ranks_plan_alike_with_uniform_selection(emul, n, g, T, Lo, dtype):
     """Paired send (schedule.cu) pairs up tiles across GPUs: with the rank-independent selection data (op_uniform_info)
     every virtual rank of a 2^g-way sharded state must plan the same steps from ITS restriction of the ops (controls and
     diagonal bits held by the rank index differ from rank to rank), and executing what each rank emitted for itself on
@@ -249,13 +250,13 @@ def test_sharded_ranks_plan_alike_with_uniform_selection(emul, n, g, T, Lo):
         ops = circuits.sharded_parity_circuit(n, g, seed) + circuits.random_circuit(n, 5, 40 + seed, "H,T,CNOT") + circuits.qft(n)[:40]
         psi = rand_state(n, 30 + seed)
         want = qo.run_pipeline(n, ops, state=psi)
-        arr, keep = marshal_ops(ops, prec_of(np.complex128))
+        arr, keep = marshal_ops(ops, prec_of(dtype))  # f32: the gate constants are rounded to f32, the emulator computes in f64
         st = np.ascontiguousarray(psi.astype(np.complex128))
         stats = np.zeros(8, dtype=np.uint64)
         err = C.create_string_buffer(256)
-        rc = emul.emul_sharded_uniform(prec_of(np.complex128), n, g, arr, len(ops), st.ctypes.data, T, Lo, stats.ctypes.data, err, 256)
+        rc = emul.emul_sharded_uniform(prec_of(dtype), n, g, arr, len(ops), st.ctypes.data, T, Lo, stats.ctypes.data, err, 256)
         assert rc == 0, (rc, err.value)
-        assert np.max(np.abs(st - want)) < 1e-12
+        assert np.max(np.abs(st - want)) < (1e-12 if dtype == np.complex128 else 2e-5)
         assert stats[0] > 0 and stats[2] > 0 and stats[3] > 0  # passes ran, qubits migrated, some ops were rank-dependent
 
 
