@@ -96,9 +96,16 @@ int each_shard(qipb200_state *p, F f) {
     }
   };
   std::vector<std::thread> th;
-  for (size_t r = 1; r < G; ++r) th.emplace_back(run, r);
-  run(0);
+  bool spawn_failed = false;
+  try {
+    th.reserve(G);
+    for (size_t r = 1; r < G; ++r) th.emplace_back(run, r);
+  } catch (const std::exception &) {  // no thread for some device: the started ones run into the flag barriers' timeout
+    spawn_failed = true;
+  }
+  if (!spawn_failed) run(0);
   for (std::thread &t : th) t.join();
+  if (spawn_failed) return set_err(p->ctx, QIPB200_ERR_OOM, "could not start one host thread per device");
   for (size_t r = 0; r < G; ++r)
     if (st[r] != QIPB200_OK) return set_err(p->ctx, st[r], p->shards[r]->ctx->err);
   return QIPB200_OK;
