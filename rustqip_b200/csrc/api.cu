@@ -633,6 +633,9 @@ int swap_physical_bits(qipb200_state *s, uint32_t p, uint32_t q) {
 }
 
 int restore_layout(qipb200_state *s) {
+  // an unsharded state whose qubits were rotated through the low positions (schedule.cu: run_rotating): many displaced
+  // bits -- swap-only tile passes instead of one half-sweep per transposition
+  if (s->world == 1 && s->n_local >= 6 && rotate_enabled()) return restore_layout_planned(s);
   for (int p = (int)s->n - 1; p >= 0; --p) {
     const uint32_t where = s->phys_of_logical[p];
     if (where == (uint32_t)p) continue;

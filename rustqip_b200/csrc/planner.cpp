@@ -16,6 +16,7 @@
 // on disjoint bit sets commute, so several stay open at once; an op whose bits span
 // groups merges them (if <= 3 bits in total) or closes them.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -1413,6 +1414,427 @@ void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec
     if (stuck) break;
   }
   if (leftover) *leftover = remaining;
+}
+
+// ---- planning with qubit rotation (tile.cuh: RotatePlan) -------------------------------------------------------
+namespace {
+
+// Greedy selection over LOGICAL qubits: a tile is any set S of <= T qubits with at most m of them from outside `prev`
+// (the previous tile): the L low positions are filled from the previous tile by the swaps that end the previous pass.
+struct RotSelector {
+  const std::vector<OpInfo> &info;
+  uint32_t T, m;
+  uint64_t prev, budget;
+
+  bool fits(uint64_t S) const { return (uint32_t)popc(S) <= T && (uint32_t)popc(S & ~prev) <= m; }
+
+  Pick select(const std::vector<size_t> &remaining, uint64_t seed) const {
+    Pick pk;
+    pk.S_high = seed;  // here: the whole tile set
+    uint64_t pend_d = 0, pend_nd = 0, bytes = 0, seen_d = 0, seen_nd = 0;
+    for (size_t r = 0; r < remaining.size(); ++r) {
+      const size_t idx = remaining[r];
+      const OpInfo &o = info[idx];
+      const bool conflict = (o.nd & (pend_d | pend_nd)) || (o.dg & pend_nd);
+      if (pk.single < 0 && !((o.nd & (seen_d | seen_nd)) || (o.dg & seen_nd))) pk.single = (long)r;
+      seen_d |= o.dg;
+      seen_nd |= o.nd;
+      if (!conflict && o.tile_ok && bytes + o.est_bytes <= budget && fits(pk.S_high | o.need_tile)) {
+        pk.S_high |= o.need_tile;
+        pk.taken.push_back(idx);
+        pk.unfused += o.unfused_cost;
+        pk.n_nd += o.nd ? 1 : 0;
+        bytes += o.est_bytes;
+        continue;
+      }
+      pend_d |= o.dg;
+      pend_nd |= o.nd;
+      pk.left.push_back(idx);
+    }
+    return pk;
+  }
+
+  Pick seed_search(const std::vector<size_t> &remaining, Pick best) const {
+    uint64_t seeds = 0;
+    for (uint32_t round = 0; round < T && !best.left.empty(); ++round) {
+      uint64_t cand = 0;
+      for (size_t r = 0; r < best.left.size() && r < 64; ++r) cand |= info[best.left[r]].need_tile;
+      cand &= ~best.S_high;
+      uint64_t best_bit = 0;
+      for (uint32_t bit = 0; bit < 64; ++bit) {
+        if (!((cand >> bit) & 1) || !fits(seeds | (1ull << bit))) continue;
+        Pick alt = select(remaining, seeds | (1ull << bit));
+        if (alt.n_nd > best.n_nd) {
+          best = std::move(alt);
+          best_bit = 1ull << bit;
+        }
+      }
+      if (!best_bit) break;
+      seeds |= best_bit;
+    }
+    return best;
+  }
+};
+
+FlatOp make_bitswap(uint32_t p, uint32_t q, uint32_t n) {
+  FlatOp f;
+  f.base_kind = QIP_OP_SWAP;
+  f.n = n;
+  f.k = 2;
+  f.kop = 2;
+  f.nc = 0;
+  f.idx_bits.push_back(p);
+  f.idx_bits.push_back(q);
+  f.cls = CLASS_BITSWAP;
+  f.ctrl_mask = 0;
+  f.swaps.push_back(std::make_pair(std::min(p, q), std::max(p, q)));
+  return f;
+}
+
+// One pass over the physical tile bits low L + `S_high`, holding exactly `pops` (compiled under the current layout).
+void build_forced_pass(const std::vector<FlatOp> &pops, uint64_t S_high, const PlanConfig &cfg, qip_prec prec, uint32_t n_gates,
+                       PlanStep *st) {
+  const uint32_t m = cfg.T - cfg.L;
+  st->is_pass = true;
+  PassHeader &h = st->pass.hdr;
+  memset(&h, 0, sizeof(h));
+  h.T = cfg.T;
+  h.L = cfg.L;
+  h.m = m;
+  uint32_t c = 0;
+  for (uint32_t b = 0; b < 64; ++b)
+    if ((S_high >> b) & 1) h.hi_pos[c++] = b;
+  for (uint32_t ch = 0; ch < (1u << m); ++ch) {
+    uint64_t off = 0;
+    for (uint32_t i = 0; i < m; ++i)
+      if ((ch >> i) & 1) off |= 1ull << h.hi_pos[i];
+    h.chunk_off[ch] = off;
+  }
+  std::vector<size_t> all(pops.size());
+  for (size_t i = 0; i < pops.size(); ++i) all[i] = i;
+  for (int jm = 0; jm < (cfg.jit_group_bits >= 3 ? 2 : 1); ++jm) {
+    if (prec == QIP_F32)
+      emit_pass<float>(pops, all, h, cfg, &st->pass, jm == 1);
+    else
+      emit_pass<double>(pops, all, h, cfg, &st->pass, jm == 1);
+  }
+  h.n_ops = (uint32_t)st->pass.ops.size();
+  h.n_gterms = (uint32_t)(st->pass.gterms.size() / (prec == QIP_F32 ? sizeof(GlobalTerm<float>) : sizeof(GlobalTerm<double>)));
+  st->pass.n_gates = n_gates;
+}
+
+}  // namespace
+
+static int plan_rotating_scaled(const qip_op *ops, size_t n_ops, qip_prec prec, uint32_t n, const PlanConfig &cfg_in,
+                                uint32_t budget_scale, RotatePlan *out, std::string *err, std::vector<uint32_t> *layout, bool restore);
+
+// transpositions that bring `phys` home, packed into swap-only steps by the fixed-layout planner
+static int append_restore(qip_prec prec, uint32_t n, const PlanConfig &cfg, std::vector<uint32_t> &phys, RotatePlan *out,
+                          std::string *err) {
+  std::vector<FlatOp> back;
+  for (int b = (int)n - 1; b >= 0; --b) {
+    if (phys[(size_t)b] == (uint32_t)b) continue;
+    const uint32_t where = phys[(size_t)b];
+    back.push_back(make_bitswap((uint32_t)b, where, n));
+    for (uint32_t c = 0; c < n; ++c) {
+      if (phys[c] == (uint32_t)b)
+        phys[c] = where;
+      else if (phys[c] == where)
+        phys[c] = (uint32_t)b;
+    }
+  }
+  if (back.empty()) return QIPB200_OK;
+  std::vector<PlanStep> steps;
+  std::vector<size_t> left;
+  plan_passes(back, n, prec, cfg, &steps, nullptr, &left);
+  if (!left.empty()) {
+    if (err) *err = "internal: layout restore left ops behind";
+    return QIPB200_ERR_UNSUPPORTED;
+  }
+  for (size_t i = 0; i < steps.size(); ++i) {
+    if (!steps[i].is_pass) {
+      out->singles.push_back(back[steps[i].op_index]);
+      steps[i].op_index = out->singles.size() - 1;
+    }
+    out->steps.push_back(steps[i]);
+    ++out->n_restore_steps;
+  }
+  return QIPB200_OK;
+}
+
+int plan_layout_restore(qip_prec prec, uint32_t n, const PlanConfig &cfg, uint32_t *layout, RotatePlan *out, std::string *err) {
+  out->steps.clear();
+  out->singles.clear();
+  out->n_swaps = out->n_restore_steps = 0;
+  std::vector<uint32_t> phys(layout, layout + n);
+  int st = append_restore(prec, n, cfg, phys, out, err);
+  if (st == QIPB200_OK)
+    for (uint32_t b = 0; b < n; ++b) layout[b] = phys[b];
+  return st;
+}
+
+int plan_rotating(const qip_op *ops, size_t n_ops, qip_prec prec, uint32_t n, const PlanConfig &cfg, RotatePlan *out,
+                  std::string *err, uint32_t *layout, bool restore) {
+  std::vector<uint32_t> start(n);
+  for (uint32_t b = 0; b < n; ++b) start[b] = layout ? layout[b] : b;
+  // the per-op byte estimates are upper bounds: optimistic budgets first, as plan_passes does
+  static const uint32_t kScale[3] = {4, 2, 1};
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    std::vector<uint32_t> phys = start;
+    int st = plan_rotating_scaled(ops, n_ops, prec, n, cfg, kScale[attempt], out, err, &phys, restore);
+    if (st != QIPB200_OK) return st;
+    bool fits = true;
+    for (size_t i = 0; i < out->steps.size(); ++i)
+      if (out->steps[i].is_pass && pass_bytes(out->steps[i].pass) > kMaxPassBytes) fits = false;
+    if (fits || attempt == 2) {
+      if (layout)
+        for (uint32_t b = 0; b < n; ++b) layout[b] = phys[b];
+      return QIPB200_OK;
+    }
+  }
+  return QIPB200_OK;
+}
+
+static int plan_rotating_scaled(const qip_op *ops, size_t n_ops, qip_prec prec, uint32_t n, const PlanConfig &cfg_in,
+                                uint32_t budget_scale, RotatePlan *out, std::string *err, std::vector<uint32_t> *layout, bool restore) {
+  out->steps.clear();
+  out->singles.clear();
+  out->n_swaps = out->n_restore_steps = 0;
+  PlanConfig cfg = cfg_in;
+  if (cfg.T > n) cfg.T = n;
+  if (cfg.L > cfg.T) cfg.L = cfg.T;
+  const uint32_t T = cfg.T, L = cfg.L, m = T - L;
+  if (T < 3 || n > 62) {
+    if (err) *err = "rotating plan: state too small / too large";
+    return QIPB200_ERR_UNSUPPORTED;
+  }
+  // logical view: every op compiled under the identity layout
+  std::vector<OpInfo> info(n_ops);
+  std::vector<size_t> remaining;
+  for (size_t i = 0; i < n_ops; ++i) {
+    FlatOp f;
+    int st = compile_op(&ops[i], prec, n, &f, err);
+    if (st != QIPB200_OK) return st;
+    if (f.cls == CLASS_IDENTITY) continue;
+    info[i] = analyse(f);
+    remaining.push_back(i);
+  }
+  std::vector<uint32_t> &phys = *layout;  // logical bit -> physical bit
+  auto logical_at = [&](uint32_t p) {
+    for (uint32_t b = 0; b < n; ++b)
+      if (phys[b] == p) return b;
+    return 0u;
+  };
+  auto compile_now = [&](size_t i, FlatOp *f) { return compile_op(&ops[i], prec, n, f, err, phys.data()); };
+  const uint64_t byte_budget = (uint64_t)(kMaxPassBytes - 2048) * budget_scale;
+
+  // the pass that is selected but not emitted yet (its end swaps depend on the NEXT selection)
+  bool have_pending = false;
+  uint64_t pend_tile = 0;           // logical qubits of the pending pass (exactly T)
+  std::vector<size_t> pend_taken;
+  uint64_t prev = 0;                // logical qubits the next tile may take its low positions from
+  for (uint32_t p = 0; p < L; ++p) prev |= 1ull << logical_at(p);
+
+  // emit the pending pass; `want_low` (logical, exactly L qubits of pend_tile) must sit in the low positions afterwards
+  auto flush_pending = [&](uint64_t want_low, const std::vector<std::pair<uint32_t, uint32_t>> &extra_swaps) -> int {
+    std::vector<FlatOp> pops(pend_taken.size());
+    for (size_t i = 0; i < pend_taken.size(); ++i) {
+      int st = compile_now(pend_taken[i], &pops[i]);
+      if (st != QIPB200_OK) return st;
+    }
+    uint64_t S_high = 0;
+    for (uint32_t b = 0; b < n; ++b)
+      if (((pend_tile >> b) & 1) && phys[b] >= L) S_high |= 1ull << phys[b];
+    if ((uint32_t)popc(S_high) != m) {
+      if (err) *err = "internal: rotating plan lost track of the tile";
+      return QIPB200_ERR_UNSUPPORTED;
+    }
+    // The pass may end with ANY permutation of its tile positions.  Target: the wanted qubits in the low positions (at
+    // their own low position when they have one), every other tile qubit at its own position when that one is a high
+    // position of this tile, the rest wherever is left (staying put when possible) -- the layout never drifts far from the
+    // canonical one, which keeps the final restore short.
+    auto do_swap = [&](uint32_t p, uint32_t q) {
+      pops.push_back(make_bitswap(p, q, n));
+      const uint32_t a = logical_at(p), b = logical_at(q);
+      phys[a] = q;
+      phys[b] = p;
+      ++out->n_swaps;
+    };
+    {
+      std::vector<uint32_t> pos;  // the tile's positions
+      for (uint32_t p = 0; p < L; ++p) pos.push_back(p);
+      for (uint32_t p = L; p < n; ++p)
+        if ((S_high >> p) & 1) pos.push_back(p);
+      std::vector<int> target(n, -1);       // target[position] = logical qubit
+      std::vector<char> placed(n, 0);       // by logical qubit
+      auto in_tile_pos = [&](uint32_t p) { return p < L || ((S_high >> p) & 1); };
+      // 1. wanted-low qubits whose own position is low
+      for (uint32_t b = 0; b < L; ++b)
+        if ((want_low >> b) & 1) {
+          target[b] = (int)b;
+          placed[b] = 1;
+        }
+      // 2. the other wanted-low qubits: stay where they are if that is a free low position, else any free low position
+      for (int round = 0; round < 2; ++round)
+        for (uint32_t b = 0; b < n; ++b) {
+          if (!((want_low >> b) & 1) || placed[b]) continue;
+          if (round == 0) {
+            if (phys[b] < L && target[phys[b]] < 0) {
+              target[phys[b]] = (int)b;
+              placed[b] = 1;
+            }
+            continue;
+          }
+          for (uint32_t p = 0; p < L; ++p)
+            if (target[p] < 0) {
+              target[p] = (int)b;
+              placed[b] = 1;
+              break;
+            }
+        }
+      // 3. the remaining tile qubits: home if home is a high tile position, else stay put if still free, else anything
+      std::vector<uint32_t> rest;
+      for (size_t i = 0; i < pos.size(); ++i) {
+        const uint32_t b = logical_at(pos[i]);
+        if (!placed[b]) rest.push_back(b);
+      }
+      for (int round = 0; round < 3; ++round)
+        for (size_t i = 0; i < rest.size(); ++i) {
+          const uint32_t b = rest[i];
+          if (placed[b]) continue;
+          if (round == 0) {
+            if (b >= L && in_tile_pos(b) && target[b] < 0) {
+              target[b] = (int)b;
+              placed[b] = 1;
+            }
+          } else if (round == 1) {
+            if (phys[b] >= L && target[phys[b]] < 0) {
+              target[phys[b]] = (int)b;
+              placed[b] = 1;
+            }
+          } else {
+            for (size_t k = 0; k < pos.size(); ++k)
+              if (pos[k] >= L && target[pos[k]] < 0) {
+                target[pos[k]] = (int)b;
+                placed[b] = 1;
+                break;
+              }
+          }
+        }
+      // realise it: put the right qubit into every position in turn (a transposition each)
+      for (size_t i = 0; i < pos.size(); ++i) {
+        const uint32_t p = pos[i];
+        if (target[p] < 0) {
+          if (err) *err = "internal: rotating plan: tile position without a qubit";
+          return QIPB200_ERR_UNSUPPORTED;
+        }
+        const uint32_t want = (uint32_t)target[p];
+        if (logical_at(p) != want) do_swap(p, phys[want]);
+      }
+    }
+    for (size_t i = 0; i < extra_swaps.size(); ++i) do_swap(extra_swaps[i].first, extra_swaps[i].second);
+    PlanStep st;
+    build_forced_pass(pops, S_high, cfg, prec, (uint32_t)pend_taken.size(), &st);
+    out->steps.push_back(st);
+    have_pending = false;
+    return QIPB200_OK;
+  };
+
+  while (!remaining.empty()) {
+    RotSelector sel{info, T, m, prev, byte_budget};
+    Pick best = sel.select(remaining, 0);
+    if (cfg.seed_search) best = sel.seed_search(remaining, std::move(best));
+    if (best.taken.empty() || best.unfused <= 1.05) {
+      // not worth a sweep: one op with its per-gate kernel, under the layout left by the pending pass
+      if (best.single < 0) {
+        if (err) *err = "internal: rotating plan made no progress";
+        return QIPB200_ERR_UNSUPPORTED;
+      }
+      if (have_pending) {
+        uint64_t keep = 0;  // nothing to prepare: the low positions stay as they are
+        for (uint32_t p = 0; p < L; ++p) keep |= 1ull << logical_at(p);
+        int st = flush_pending(keep, {});
+        if (st != QIPB200_OK) return st;
+      }
+      FlatOp f;
+      int st = compile_now(remaining[(size_t)best.single], &f);
+      if (st != QIPB200_OK) return st;
+      out->singles.push_back(f);
+      PlanStep ps;
+      ps.is_pass = false;
+      ps.op_index = out->singles.size() - 1;
+      out->steps.push_back(ps);
+      remaining.erase(remaining.begin() + best.single);
+      continue;
+    }
+    // the tile of this pass: the selected qubits, padded to T (first from the previous tile: they cost nothing)
+    uint64_t tile = best.S_high;
+    for (int round = 0; round < 2 && (uint32_t)popc(tile) < T; ++round)
+      for (int b = (int)n - 1; b >= 0 && (uint32_t)popc(tile) < T; --b) {
+        const uint64_t bit = 1ull << b;
+        if (tile & bit) continue;
+        if (round == 0 ? ((prev & bit) != 0) : ((uint32_t)popc((tile | bit) & ~prev) <= m)) tile |= bit;
+      }
+    if ((uint32_t)popc(tile) != T || (uint32_t)popc(tile & ~prev) > m) {
+      if (err) *err = "internal: rotating plan could not complete a tile";
+      return QIPB200_ERR_UNSUPPORTED;
+    }
+    // its low positions: L qubits of tile & prev, preferring the ones that already sit low
+    uint64_t want_low = 0;
+    for (int round = 0; round < 2 && (uint32_t)popc(want_low) < L; ++round)
+      for (uint32_t b = 0; b < n && (uint32_t)popc(want_low) < L; ++b) {
+        const uint64_t bit = 1ull << b;
+        if (!(tile & prev & bit) || (want_low & bit)) continue;
+        if (round == 1 || phys[b] < L) want_low |= bit;
+      }
+    if ((uint32_t)popc(want_low) != L) {
+      if (err) *err = "internal: rotating plan: fewer than L carried qubits";
+      return QIPB200_ERR_UNSUPPORTED;
+    }
+    if (have_pending) {
+      int st = flush_pending(want_low, {});
+      if (st != QIPB200_OK) return st;
+    }  // else: first pass -- prev is exactly the L qubits sitting low, so want_low == prev
+    have_pending = true;
+    pend_tile = tile;
+    pend_taken = best.taken;
+    prev = tile;
+    remaining.swap(best.left);
+  }
+  if (have_pending) {
+    // last pass: fold in every restoring transposition whose two positions are tile bits of this pass, in an order
+    // that keeps the low positions filled from the tile; the rest is restored by swap-only passes below
+    uint64_t keep = 0;
+    for (uint32_t p = 0; p < L; ++p) keep |= 1ull << logical_at(p);
+    uint64_t tile_phys = (1ull << L) - 1ull;
+    for (uint32_t b = 0; b < n; ++b)
+      if ((pend_tile >> b) & 1) tile_phys |= 1ull << phys[b];
+    std::vector<std::pair<uint32_t, uint32_t>> extra;
+    if (restore) {
+      std::vector<uint32_t> sim = phys;  // simulate the transpositions b <-> home within the tile
+      bool progress = true;
+      while (progress) {
+        progress = false;
+        for (uint32_t b = 0; b < n; ++b) {
+          const uint32_t where = sim[b];
+          if (where == b || !((tile_phys >> where) & 1) || !((tile_phys >> b) & 1)) continue;
+          extra.push_back(std::make_pair(b, where));  // physical positions b (home) and where
+          for (uint32_t c = 0; c < n; ++c) {
+            if (sim[c] == b)
+              sim[c] = where;
+            else if (c != b && sim[c] == where)
+              sim[c] = b;
+          }
+          sim[b] = b;
+          progress = true;
+        }
+      }
+    }
+    int st = flush_pending(keep, extra);
+    if (st != QIPB200_OK) return st;
+  }
+  if (restore) return append_restore(prec, n, cfg_in, phys, out, err);
+  return QIPB200_OK;
 }
 
 bool serialise_pass(const HostPass &p, PassParams *out) {

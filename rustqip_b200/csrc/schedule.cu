@@ -340,6 +340,46 @@ int run_fused(qipb200_state *s, const qip_op *ops, size_t n_ops, const std::vect
 
 }  // namespace
 
+bool rotate_enabled() {
+  static const bool on = getenv("QIPB200_ROTATE") != nullptr && atoi(getenv("QIPB200_ROTATE")) != 0;
+  return on;
+}
+
+// Unsharded state, qubit rotation: the whole schedule planned in one go over LOGICAL qubits; the state keeps the layout
+// of the last pass (restored lazily by the API).  Returns false when the plan could not be made (the caller then takes the
+// plain path, which also owns the error reporting for malformed ops).
+static bool run_rotating(qipb200_state *s, const qip_op *ops, size_t n_ops, int *status) {
+  if (!s->ctx->tile_configured) {
+    if (tile_pass_configure() != cudaSuccess) return false;
+    s->ctx->tile_configured = true;
+  }
+  const PlanConfig cfg = default_plan_config(s->prec, s->n_local);
+  RotatePlan plan;
+  std::string err;
+  std::vector<uint32_t> layout = s->phys_of_logical;
+  if (plan_rotating(ops, n_ops, s->prec, s->n_local, cfg, &plan, &err, layout.data(), false) != QIPB200_OK) return false;
+  s->phys_of_logical = layout;
+  *status = execute_steps(s, plan.steps, plan.singles, cfg);
+  return true;
+}
+
+int restore_layout_planned(qipb200_state *s) {
+  if (!s->ctx->tile_configured) {
+    cudaError_t e = tile_pass_configure();
+    if (e != cudaSuccess) return report_cuda_error(s, e, "cudaFuncSetAttribute(tile pass)");
+    s->ctx->tile_configured = true;
+  }
+  const PlanConfig cfg = default_plan_config(s->prec, s->n_local);
+  RotatePlan plan;
+  std::string err;
+  std::vector<uint32_t> layout = s->phys_of_logical;
+  int st = plan_layout_restore(s->prec, s->n_local, cfg, layout.data(), &plan, &err);
+  if (st != QIPB200_OK) return report_error(s, st, err);
+  st = execute_steps(s, plan.steps, plan.singles, cfg);
+  if (st == QIPB200_OK) s->phys_of_logical = layout;
+  return st;
+}
+
 int run_schedule(qipb200_state *s, const qip_op *ops, size_t n_ops, uint32_t flags) {
   std::vector<uint64_t> next_use;  // [i * n + logical_bit]
   if (s->world > 1 && n_ops) {
@@ -357,6 +397,10 @@ int run_schedule(qipb200_state *s, const qip_op *ops, size_t n_ops, uint32_t fla
     }
   }
   const bool fuse = !(flags & QIPB200_SCHED_NO_FUSION) && s->n_local >= 6;
+  if (fuse && s->world == 1 && rotate_enabled() && n_ops) {
+    int st = QIPB200_OK;
+    if (run_rotating(s, ops, n_ops, &st)) return st;
+  }
   if (fuse) {
     const int st = run_fused(s, ops, n_ops, next_use);
     const int stj = join_halves(s);  // whatever follows (download, measurement, the next schedule) sees one stream again

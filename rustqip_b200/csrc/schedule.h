@@ -33,6 +33,11 @@ void paired_partner(const qipb200_state *s, uint32_t R, int *partner, int *give)
 int paired_send_standin(qipb200_state *s, uint32_t R, uint32_t l, uint32_t cbit, uint32_t seq, const PassHeader &hdr);
 int finish_paired_exchange(qipb200_state *s, uint32_t R, uint32_t l);
 
+// qubit rotation (opt-in, QIPB200_ROTATE=1, unsharded states; planner.cpp: plan_rotating): is it on / run swap-only steps
+// that bring the state's layout back to the canonical one (api.cu: restore_layout)
+bool rotate_enabled();
+int restore_layout_planned(qipb200_state *s);
+
 // schedule.cu: state <- ops[n-1] ... ops[0] state
 int run_schedule(qipb200_state *s, const qip_op *ops, size_t n_ops, uint32_t flags);
 

@@ -290,6 +290,29 @@ void plan_passes(const std::vector<FlatOp> &ops, uint32_t n_local, qip_prec prec
                  std::vector<PlanStep> *steps, const std::vector<char> *blocked = nullptr,
                  std::vector<size_t> *leftover = nullptr, const std::vector<DepMasks> *dep = nullptr);
 
+// Planning with QUBIT ROTATION (single shard, opt-in: QIPB200_ROTATE=1).  The L lowest
+// index bits are in every tile, so with a fixed layout the qubits living there are in EVERY pass although a pass leaves
+// its qubits blocked on partners outside the tile -- those slots mostly idle.  Here a pass may END with a permutation of
+// its own tile bits (Swap elements inside register groups: pure renaming in the generated kernels), so the low
+// positions of the next tile can hold ANY L qubits of the previous tile: the selection runs over logical qubits with the
+// only constraint that a pass brings in at most T - L qubits from outside the previous tile.  The logical -> physical
+// map is tracked, every pass is emitted from its ops compiled under the layout of the moment, and the inverse permutation
+// is folded into the last pass / appended as swap-only passes: the state ends in the canonical layout and the results
+// are those of the plain schedule.  Headline circuit: 19 + restore instead of 25 sweeps (all 12 tile bits free: 16).
+struct RotatePlan {
+  std::vector<PlanStep> steps;   // PlanStep::op_index of a single step indexes `singles`
+  std::vector<FlatOp> singles;
+  uint32_t n_swaps = 0, n_restore_steps = 0;
+};
+// `layout` (n entries, logical bit -> physical bit, or NULL = canonical): the layout the state is in; on return the
+// layout it is left in.  restore = true: the plan ends in the canonical layout (inverse permutation folded into the last
+// pass + swap-only passes); false: the state keeps the layout of the last pass (the API restores it lazily, like the
+// migrated qubits of a sharded state: before a download, never between schedules).
+int plan_rotating(const qip_op *ops, size_t n_ops, qip_prec prec, uint32_t n, const PlanConfig &cfg, RotatePlan *out,
+                  std::string *err, uint32_t *layout = nullptr, bool restore = true);
+// Swap-only steps that bring `layout` back to the canonical one (layout is updated to the identity).
+int plan_layout_restore(qip_prec prec, uint32_t n, const PlanConfig &cfg, uint32_t *layout, RotatePlan *out, std::string *err);
+
 // Serialise a pass: header + micro-op records + global terms.  Returns false if the
 // records do not fit kMaxPassBytes (the planner bounds passes so that they do).
 bool serialise_pass(const HostPass &p, PassParams *out);

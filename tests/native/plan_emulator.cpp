@@ -594,6 +594,82 @@ extern "C" int emul_sharded_uniform(int prec, uint32_t n, uint32_t g, const qip_
   return 0;
 }
 
+// Planning with qubit rotation (planner.cpp: plan_rotating): passes that end with a permutation of their tile bits, tracked
+// layout, restore folded into the last pass / swap-only passes (restore != 0) or left to the caller (restore == 0: the
+// layout the state is left in comes back in `layout`, n entries logical -> physical, also the layout it starts in;
+// unpermute != 0 brings the amplitudes back to the canonical order here, for the comparison with the oracle).
+// Executed on the CPU; the result must be the plain schedule's.  state == NULL: plan only.
+// stats: [0] passes, [1] single steps, [2] relabelling swaps, [3] restore steps, [4] gates in passes
+extern "C" int emul_schedule_rotate(int prec, uint32_t n, const qip_op *ops, size_t n_ops, double *state, uint32_t T, uint32_t L,
+                                    int restore, uint32_t *layout, int unpermute, uint64_t *stats, char *errbuf, size_t errlen) {
+  PlanConfig cfg = default_plan_config((qip_prec)prec, n);
+  if (T) cfg.T = T;
+  if (L) cfg.L = L;
+  RotatePlan plan;
+  std::string err;
+  std::vector<uint32_t> lay(n);
+  for (uint32_t b = 0; b < n; ++b) lay[b] = layout ? layout[b] : b;
+  int st = plan_rotating(ops, n_ops, (qip_prec)prec, n, cfg, &plan, &err, lay.data(), restore != 0);
+  if (st != QIPB200_OK) {
+    if (errbuf && errlen) snprintf(errbuf, errlen, "%s", err.c_str());
+    return st;
+  }
+  uint64_t n_pass = 0, n_single = 0, n_gates = 0;
+  if (state) {
+    g_decode_errors = 0;
+    std::vector<cd> psi(1ull << n);
+    for (uint64_t i = 0; i < (1ull << n); ++i) psi[i] = cd(state[2 * i], state[2 * i + 1]);
+    auto run_steps = [&](const RotatePlan &pl) -> int {
+      for (size_t s = 0; s < pl.steps.size(); ++s) {
+        if (pl.steps[s].is_pass) {
+          PassParams pp;
+          if (!serialise_pass(pl.steps[s].pass, &pp)) return -2;
+          if (prec == QIP_F32)
+            run_pass_params<float>(pp, n, psi);
+          else
+            run_pass_params<double>(pp, n, psi);
+        } else {
+          apply_single(pl.singles[pl.steps[s].op_index], n, psi);
+        }
+      }
+      return 0;
+    };
+    int rc = run_steps(plan);
+    if (rc) return rc;
+    if (unpermute) {  // what the API does before a download: planned swap-only steps (planner.cpp: plan_layout_restore)
+      RotatePlan back;
+      st = plan_layout_restore((qip_prec)prec, n, cfg, lay.data(), &back, &err);
+      if (st != QIPB200_OK) return st;
+      rc = run_steps(back);
+      if (rc) return rc;
+      plan.n_restore_steps += back.n_restore_steps;
+    }
+    for (uint64_t i = 0; i < (1ull << n); ++i) {
+      state[2 * i] = psi[i].real();
+      state[2 * i + 1] = psi[i].imag();
+    }
+    if (g_decode_errors) return -3;
+  }
+  if (layout)
+    for (uint32_t b = 0; b < n; ++b) layout[b] = lay[b];
+  for (size_t s = 0; s < plan.steps.size(); ++s) {
+    if (plan.steps[s].is_pass) {
+      ++n_pass;
+      n_gates += plan.steps[s].pass.n_gates;
+    } else {
+      ++n_single;
+    }
+  }
+  if (stats) {
+    stats[0] = n_pass;
+    stats[1] = n_single;
+    stats[2] = plan.n_swaps;
+    stats[3] = plan.n_restore_steps;
+    stats[4] = n_gates;
+  }
+  return 0;
+}
+
 // plan only (no amplitudes): pass / single-step counts for big circuits
 extern "C" int emul_plan_stats(int prec, uint32_t n, const qip_op *ops, size_t n_ops, uint32_t T, uint32_t L,
                                int fuse_blocks, uint32_t max_k, uint64_t *stats) {
@@ -674,7 +750,19 @@ extern "C" int emul_schedule_jit(int prec, uint32_t n, const qip_op *ops, size_t
   if (T) cfg.T = T;
   if (L) cfg.L = L;
   std::vector<PlanStep> steps;
-  plan_passes(flat, n, (qip_prec)prec, cfg, &steps);
+  RotatePlan rplan;
+  if (getenv("EMUL_ROTATE")) {  // the rotating planner's passes (end-of-pass swaps = renaming) through the generated kernels
+    std::string err;
+    int st = plan_rotating(ops, n_ops, (qip_prec)prec, n, cfg, &rplan, &err);
+    if (st != QIPB200_OK) {
+      if (errbuf && errlen) snprintf(errbuf, errlen, "%s", err.c_str());
+      return st;
+    }
+    steps = rplan.steps;
+    flat = rplan.singles;  // single steps index the plan's own op list
+  } else {
+    plan_passes(flat, n, (qip_prec)prec, cfg, &steps);
+  }
   const uint64_t N = 1ull << n;
   uint64_t st_[8] = {0};
   for (size_t s = 0; s < steps.size(); ++s) {

@@ -211,3 +211,16 @@ def test_jit_disk_cache_concurrent_writers(tmp_path):
     third = json.loads(r.stdout.strip().splitlines()[-1])
     n_files = len([f for f in os.listdir(tmp_path) if f.endswith(".cubin")])
     assert ("disk cache: %d programs" % n_files) in third["log"], third
+
+
+def test_generated_kernels_run_rotating_plans(emul, monkeypatch):
+    """Passes of the rotating planner (planner.cpp: plan_rotating) end with swaps among their tile bits -- register
+    renaming in the generated kernels: the host-compiled generated source of every such pass against the oracle."""
+    monkeypatch.setenv("EMUL_ROTATE", "1")
+    for n, seed, dtype, tol in [(14, 3, np.complex128, 1e-12), (15, 4, np.complex64, 2e-5)]:
+        ops = circuits.random_circuit(n, 10, 70 + seed, "H,T,CNOT") + circuits.qft(n)[:30]
+        psi = rand_state(n, seed, dtype)
+        want = qo.run_pipeline(n, ops, state=psi, dtype=dtype)
+        got, stats = run_jit(emul, n, ops, psi, dtype)
+        assert np.max(np.abs(got.astype(np.complex128) - want.astype(np.complex128))) <= tol * max(1.0, np.max(np.abs(want)))
+        assert stats[0] > 0 and stats[5] > 0  # passes ran through generated code, some ops were pure renaming

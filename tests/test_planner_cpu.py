@@ -42,6 +42,9 @@ def emul():
     L.emul_sharded_uniform.restype = C.c_int
     L.emul_sharded_uniform.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(QipOp), C.c_size_t, C.c_void_p, C.c_uint32,
                                        C.c_uint32, C.c_void_p, C.c_char_p, C.c_size_t]
+    L.emul_schedule_rotate.restype = C.c_int
+    L.emul_schedule_rotate.argtypes = [C.c_int, C.c_uint32, C.POINTER(QipOp), C.c_size_t, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int,
+                                       C.c_void_p, C.c_int, C.c_void_p, C.c_char_p, C.c_size_t]
     L.emul_plan_stats.restype = C.c_int
     L.emul_plan_stats.argtypes = [C.c_int, C.c_uint32, C.POINTER(QipOp), C.c_size_t, C.c_uint32, C.c_uint32,
                                   C.c_int, C.c_uint32, C.c_void_p]
@@ -274,3 +277,56 @@ def test_sharded_ranks_plan_differently_without_uniform_selection(emul, monkeypa
         err = C.create_string_buffer(256)
         seen.add(emul.emul_sharded_uniform(prec_of(np.complex128), n, g, arr, len(ops), st.ctypes.data, 5, 2, stats.ctypes.data, err, 256))
     assert -10 in seen, seen
+
+
+def run_rotate(L, n, ops, st, dtype=np.complex128, T=0, Lo=0, restore=True, layout=None, unpermute=False):
+    arr, keep = marshal_ops(ops, prec_of(dtype))
+    stats = np.zeros(8, dtype=np.uint64)
+    err = C.create_string_buffer(256)
+    rc = L.emul_schedule_rotate(prec_of(dtype), n, arr, len(ops), st.ctypes.data if st is not None else None, T, Lo, int(restore),
+                                layout.ctypes.data if layout is not None else None, int(unpermute), stats.ctypes.data, err, 256)
+    assert rc == 0, (rc, err.value)
+    return [int(x) for x in stats[:5]]  # passes, single steps, relabelling swaps, restore steps, gates in passes
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("n,T,Lo", [(10, 7, 3), (9, 6, 2), (12, 7, 3), (11, 6, 3), (12, 8, 2)])
+def test_rotating_plan_matches_oracle(emul, n, T, Lo, dtype):
+    """Qubit rotation (planner.cpp: plan_rotating, opt-in QIPB200_ROTATE): passes that end with a permutation of their
+    own tile bits, every pass emitted under the layout of the moment.  (1) With the inverse permutation inside the plan the
+    amplitudes are the oracle's; (2) lazily: a schedule leaves the state in a permuted layout, the next schedule starts
+    from it, and the planned restore (what the API runs before a download) brings the canonical order back."""
+    seed = n + T
+    a = mixed_circuit(n, 120, 2000 + seed) + circuits.random_circuit(n, 12, 90 + seed, "H,T,CNOT")
+    b = circuits.qft(n)[:40] + circuits.random_circuit(n, 6, 190 + seed, "H,T,CNOT")
+    psi = rand_state(n, seed)
+    want = qo.run_pipeline(n, a + b, state=psi)
+    tol = 1e-12 if dtype == np.complex128 else 2e-5
+    st = np.ascontiguousarray(psi.astype(np.complex128))
+    stats = run_rotate(emul, n, a + b, st, dtype, T, Lo, restore=True)
+    assert np.max(np.abs(st - want)) < tol and stats[2] > 0
+    st = np.ascontiguousarray(psi.astype(np.complex128))
+    layout = np.arange(n, dtype=np.uint32)
+    run_rotate(emul, n, a, st, dtype, T, Lo, restore=False, layout=layout)
+    assert np.any(layout != np.arange(n)) and sorted(layout) == list(range(n))  # a permutation, not the identity
+    run_rotate(emul, n, b, st, dtype, T, Lo, restore=False, layout=layout, unpermute=True)
+    assert np.all(layout == np.arange(n))
+    assert np.max(np.abs(st - want)) < tol
+
+
+def test_rotating_plan_needs_fewer_sweeps(emul):
+    """The point of the rotation: with the state left in the layout of the last pass, the N=30 headline circuit and
+    BASELINE configs[1] need clearly fewer HBM sweeps than with the fixed layout (plan only, no amplitudes)."""
+    out = {}
+    for name, n, ops in [("n30_d40", 30, circuits.random_circuit(30, 40, 0x5EED0002)), ("cfg2_n28", 28, circuits.config2())]:
+        arr, keep = marshal_ops(ops, prec_of(np.complex128))
+        stats = np.zeros(64, dtype=np.uint64)
+        assert emul.emul_plan_stats(prec_of(np.complex128), n, arr, len(ops), 0, 0, 1, 0, stats.ctypes.data) == 0
+        fixed = int(stats[0] + stats[1])
+        rot = run_rotate(emul, n, ops, None, restore=False)
+        lazy = rot[0] + rot[1]
+        rot = run_rotate(emul, n, ops, None, restore=True)
+        full = rot[0] + rot[1]
+        out[name] = (fixed, lazy, full)
+        assert lazy <= fixed - 4 and full <= fixed, out
+    print(out)
