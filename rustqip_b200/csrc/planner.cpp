@@ -1661,6 +1661,7 @@ static int plan_rotating_scaled(const qip_op *ops, size_t n_ops, qip_prec prec, 
       ++out->n_swaps;
     };
     {
+      static const bool homing = !getenv("QIPB200_ROTATE_NO_HOMING");
       std::vector<uint32_t> pos;  // the tile's positions
       for (uint32_t p = 0; p < L; ++p) pos.push_back(p);
       for (uint32_t p = L; p < n; ++p)
@@ -1703,7 +1704,7 @@ static int plan_rotating_scaled(const qip_op *ops, size_t n_ops, qip_prec prec, 
           const uint32_t b = rest[i];
           if (placed[b]) continue;
           if (round == 0) {
-            if (b >= L && in_tile_pos(b) && target[b] < 0) {
+            if (homing && b >= L && in_tile_pos(b) && target[b] < 0) {
               target[b] = (int)b;
               placed[b] = 1;
             }

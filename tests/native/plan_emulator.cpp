@@ -670,6 +670,44 @@ extern "C" int emul_schedule_rotate(int prec, uint32_t n, const qip_op *ops, siz
   return 0;
 }
 
+// Generated-kernel statistics of a whole plan (no amplitudes): rotate != 0: the rotating planner (lazy layout).
+// stats: [0] passes, [1] passes the generator declined, [2] super-ops (shared-memory round trips), [3] elementary ops,
+//        [4] CTA barriers, [5] warp syncs, [6] renamed (instruction-free) ops
+extern "C" int emul_jit_plan_stats(int prec, uint32_t n, const qip_op *ops, size_t n_ops, int rotate, uint64_t *stats) {
+  PlanConfig cfg = default_plan_config((qip_prec)prec, n);
+  std::vector<PlanStep> steps;
+  RotatePlan rplan;
+  if (rotate) {
+    std::string err;
+    if (plan_rotating(ops, n_ops, (qip_prec)prec, n, cfg, &rplan, &err, nullptr, false) != QIPB200_OK) return -1;
+    steps = rplan.steps;
+  } else {
+    std::vector<FlatOp> flat(n_ops);
+    for (size_t i = 0; i < n_ops; ++i) {
+      std::string err;
+      if (compile_op(&ops[i], (qip_prec)prec, n, &flat[i], &err) != QIPB200_OK) return -1;
+    }
+    plan_passes(flat, n, (qip_prec)prec, cfg, &steps);
+  }
+  for (int i = 0; i < 8; ++i) stats[i] = 0;
+  for (size_t s = 0; s < steps.size(); ++s) {
+    if (!steps[s].is_pass) continue;
+    ++stats[0];
+    JitProgram prog;
+    std::string why;
+    if (!jit_generate(steps[s].pass, (qip_prec)prec, &prog, &why)) {
+      ++stats[1];
+      continue;
+    }
+    stats[2] += prog.n_super;
+    stats[3] += prog.n_elems;
+    stats[4] += prog.n_cta_barriers;
+    stats[5] += prog.n_warp_syncs;
+    stats[6] += prog.n_renamed;
+  }
+  return 0;
+}
+
 // plan only (no amplitudes): pass / single-step counts for big circuits
 extern "C" int emul_plan_stats(int prec, uint32_t n, const qip_op *ops, size_t n_ops, uint32_t T, uint32_t L,
                                int fuse_blocks, uint32_t max_k, uint64_t *stats) {
